@@ -1,0 +1,227 @@
+"""CPU oracle for the b200seg hot path.  TEST INFRASTRUCTURE ONLY.
+
+`oracle/oracle.c` restates the reference algorithms (each function cites the reference
+file:line it follows); this module builds it with gcc and wraps it with numpy signatures that
+mirror the reference call sites.  `oracle/_ref/` holds the reference's own Cython/CUDA code built
+by `oracle/build_ref.py` (validation of the restatement, and `cpu_baseline.kind == "reference"`).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs
+may import this package -- as the checker or the reported CPU baseline, never as the product.
+"""
+import ctypes
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def build(force=False):
+    """gcc-compile oracle.c -> liboracle.so (baseline x86-64, no FMA contraction)."""
+    src = os.path.join(HERE, "oracle.c")
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= os.path.getmtime(src)):
+        return LIB_PATH
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99",
+                           src, "-o", LIB_PATH, "-lm"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        L.oracle_nms_3d.restype = c.c_long
+        L.oracle_nms_3d.argtypes = [c.c_void_p, c.c_long, c.c_float, c.c_int, c.c_void_p]
+        L.oracle_argsort_desc.restype = None
+        L.oracle_argsort_desc.argtypes = [c.c_void_p, c.c_long, c.c_void_p]
+        L.oracle_bbox_overlaps_3d.restype = None
+        L.oracle_bbox_overlaps_3d.argtypes = [c.c_void_p, c.c_long, c.c_void_p, c.c_long, c.c_void_p]
+        for name in ("oracle_roialign3d_fwd", "oracle_roialign3d_bwd"):
+            f = getattr(L, name)
+            f.restype = None
+            f.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int,
+                          c.c_int, c.c_int, c.c_int, c.c_float, c.c_int, c.c_void_p]
+        L.oracle_peak_stimulation.restype = c.c_long
+        L.oracle_peak_stimulation.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
+                                              c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_long,
+                                              c.c_void_p, c.c_void_p]
+        L.oracle_otsu_2d_fast.restype = c.c_int
+        L.oracle_otsu_2d_fast.argtypes = [c.c_void_p, c.c_void_p, c.c_long, c.c_void_p,
+                                          c.POINTER(c.c_int), c.c_void_p, c.POINTER(c.c_int)]
+        L.oracle_paste_labels.restype = None
+        L.oracle_paste_labels.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p,
+                                          c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+# ------------------------------------------------------------------------------- boxes
+def nms_3d(dets, thresh, by_volume=False):
+    """cython_nms_3d.pyx:39-96 / :102-159 -> int64 kept indices, ascending."""
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    n = dets.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    m = lib().oracle_nms_3d(_p(dets), n, np.float32(thresh), int(by_volume), _p(keep))
+    return keep[:m].copy()
+
+
+def nms_3d_volume(dets, thresh):
+    return nms_3d(dets, thresh, by_volume=True)
+
+
+def argsort_desc(keys):
+    keys = np.ascontiguousarray(keys, dtype=np.float32)
+    out = np.empty(keys.shape[0], dtype=np.int64)
+    lib().oracle_argsort_desc(_p(keys), keys.shape[0], _p(out))
+    return out
+
+
+def bbox_overlaps_3d(boxes, query_boxes):
+    """cython_bbox_3d.pyx:32-80 -> [N,K] fp32."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+    query_boxes = np.ascontiguousarray(query_boxes, dtype=np.float32)
+    out = np.empty((boxes.shape[0], query_boxes.shape[0]), dtype=np.float32)
+    lib().oracle_bbox_overlaps_3d(_p(boxes), boxes.shape[0], _p(query_boxes), query_boxes.shape[0], _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------- RoIAlign3D
+def roialign3d_fwd(features, rois, P, scale, sr):
+    """roi_align_kernel_3d.cu:81-151; returns [R,C,P,P,P] holding the reference's (H,W,S) bin order."""
+    features = np.ascontiguousarray(features, dtype=np.float32)
+    rois = np.ascontiguousarray(rois, dtype=np.float32)
+    B, C, S, H, W = features.shape
+    Ps, Ph, Pw = (P, P, P) if np.isscalar(P) else P
+    out = np.empty((rois.shape[0], C, Ps, Ph, Pw), dtype=np.float32)
+    lib().oracle_roialign3d_fwd(_p(features), B, C, S, H, W, _p(rois), rois.shape[0], Ps, Ph, Pw,
+                                np.float32(scale), int(sr), _p(out))
+    return out
+
+
+def roialign3d_bwd(grad_out, rois, feat_shape, scale, sr):
+    """roi_align_kernel_3d.cu:238-338 with sequential (deterministic) adds."""
+    grad_out = np.ascontiguousarray(grad_out, dtype=np.float32)
+    rois = np.ascontiguousarray(rois, dtype=np.float32)
+    B, C, S, H, W = feat_shape
+    _, _, Ps, Ph, Pw = grad_out.shape
+    gi = np.empty(feat_shape, dtype=np.float32)
+    lib().oracle_roialign3d_bwd(_p(grad_out), B, C, S, H, W, _p(rois), rois.shape[0], Ps, Ph, Pw,
+                                np.float32(scale), int(sr), _p(gi))
+    return gi
+
+
+# ------------------------------------------------------------------------------- peaks
+def peak_stimulation_3d(inp, win_size=3, filter_mode="median", thresholds=None, return_aggregation=True):
+    """peak_stimulation_3d.py:9-41.  filter_mode: None | 'median' | 'given' (thresholds [B,A])."""
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    B, A, S, H, W = inp.shape
+    mode = {None: 0, "none": 0, "median": 1, "given": 2}[filter_mode]
+    thr_in = None
+    if mode == 2:
+        thr_in = np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, dtype=np.float32).reshape(-1), (B * A,)))
+    cap = max(int(inp.size), 1)
+    cap = min(cap, 1 << 22)
+    peaks = np.empty((cap, 5), dtype=np.int64)
+    agg = np.empty((B, A), dtype=np.float32)
+    thr = np.empty((B, A), dtype=np.float32)
+    n = lib().oracle_peak_stimulation(_p(inp), B, A, S, H, W, int(win_size), mode, _p(thr_in),
+                                      _p(peaks), cap, _p(agg), _p(thr))
+    if n > cap:
+        peaks = np.empty((n, 5), dtype=np.int64)
+        lib().oracle_peak_stimulation(_p(inp), B, A, S, H, W, int(win_size), mode, _p(thr_in),
+                                      _p(peaks), n, _p(agg), _p(thr))
+    peaks = peaks[:n].copy()
+    if return_aggregation:
+        return peaks, agg, thr
+    return peaks
+
+
+# ------------------------------------------------------------------------------- Otsu
+class OtsuNoThreshold(UnboundLocalError):
+    """The reference raises NameError/UnboundLocalError on k_max when no b wins (otsu.py:277)."""
+
+
+def otsu_py_2d_fast(image, prm, want_hist=False):
+    """tools/otsu.py:199-284 -> (uint8 mask {0,255}, k_max=-1, b_max[, hist.T])."""
+    shape = image.shape
+    img = np.ascontiguousarray(image, dtype=np.uint16).ravel()
+    pr = np.ascontiguousarray(prm, dtype=np.uint16).ravel()
+    mask = np.empty(img.size, dtype=np.uint8)
+    b = ctypes.c_int(0)
+    G = ctypes.c_int(0)
+    hist = None
+    if want_hist:
+        g = int(img.max()) - int(img.min()) + 1
+        hist = np.empty((g, g), dtype=np.float64)
+    st = lib().oracle_otsu_2d_fast(_p(img), _p(pr), img.size, _p(mask), ctypes.byref(b), _p(hist), ctypes.byref(G))
+    if st == -1:
+        raise ValueError("gray range too large for the oracle")
+    if st == 1:
+        raise OtsuNoThreshold("local variable 'k_max' referenced before assignment")
+    out = (mask.reshape(shape), -1, int(b.value))
+    return out + (hist,) if want_hist else out
+
+
+def soma_normalise(box_img, box_prm):
+    """binarization_soma.py:85-91: image -> uint16 in [30,330], prm -> uint16 round(prm/max*300+30)."""
+    gray_max = np.max(box_img)
+    f = box_img.astype(float)
+    with np.errstate(all="ignore"):
+        f = np.clip(f / gray_max * 300, 0, 300) + 30
+        img = f.astype(np.uint16)
+        p = box_prm.astype(float)
+        p = np.round(p / np.max(p) * 300 + 30).astype(np.uint16)
+    return img, p
+
+
+# ------------------------------------------------------------------------------- paste
+def paste_labels(seg, boxes, ids, masks):
+    """binarization_soma.py:100-104.  seg uint16 [S,H,W] updated in place; boxes int [n,6]
+    (x1,y1,z1,x2,y2,z2 inclusive); masks = list of uint8/bool crops [sz,sy,sx].  Returns survive[n]."""
+    assert seg.dtype == np.uint16 and seg.flags.c_contiguous
+    n = len(masks)
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(n, 6)
+    ids = np.ascontiguousarray(ids, dtype=np.uint16)
+    off = np.zeros(n + 1, dtype=np.int64)
+    for i, m in enumerate(masks):
+        b = boxes[i]
+        assert m.shape == (b[5] - b[2] + 1, b[4] - b[1] + 1, b[3] - b[0] + 1), (m.shape, b)
+        off[i + 1] = off[i] + m.size
+    flat = np.empty(max(int(off[-1]), 1), dtype=np.uint8)
+    for i, m in enumerate(masks):
+        flat[off[i]:off[i + 1]] = (np.asarray(m) != 0).ravel()
+    S, H, W = seg.shape
+    surv = np.zeros(max(n, 1), dtype=np.uint8)
+    lib().oracle_paste_labels(_p(seg), S, H, W, n, _p(boxes), _p(ids), _p(flat), _p(off), _p(surv))
+    return surv[:n].astype(bool)
+
+
+# ------------------------------------------------------------------------------- reference builds
+def ref_module(name):
+    """Import a reference Cython module built into oracle/_ref (None when it is not there)."""
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        return importlib.import_module(name)
+    except ImportError:
+        return None
+
+
+def ref_roialign_lib():
+    p = os.path.join(REF_DIR, "libref_roialign3d.so")
+    return ctypes.CDLL(p) if os.path.exists(p) else None
