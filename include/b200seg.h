@@ -1,0 +1,204 @@
+/*
+ * b200seg.h -- C ABI of the B200-native 3D instance-segmentation operator layer.
+ *
+ * One shared library (libb200seg.so, hand-written CUDA for sm_100a) exposes the hot path of
+ * MeowMeowLady/InstanceSeg-Without-Voxelwise-Labeling behind plain-C entry points: raw pointers,
+ * sizes and a CUDA stream, no torch types.  Each entry point names the reference interface it
+ * replaces (path:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a positive cudaError_t value when the CUDA runtime
+ *     reported an error, or a negative B200SEG_E* code for invalid arguments.  Nothing calls
+ *     exit() (the reference launcher does: roi_align_kernel_3d.cu:165-169).
+ *     b200seg_last_error() returns a thread-local human-readable message.
+ *   - "_dev" entry points take DEVICE pointers, enqueue work on `stream` and never synchronise;
+ *     data-dependent counts are written to device memory.
+ *   - "_host" entry points take HOST pointers, perform the H2D/D2H copies themselves on an
+ *     internal stream with grow-only device scratch, and return when the result is in host memory.
+ *     They are what the reference's numpy call sites bind to.
+ *   - Boxes are (x1,y1,z1,x2,y2,z2) with inclusive "+1" extents, as in the reference.
+ *   - Tie rule for equal sort keys (scores / volumes): key descending, then original index
+ *     ascending (numpy's default argsort, cython_nms_3d.pyx:49, is unstable and platform dependent).
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_EINVAL   (-1)   /* bad argument (null pointer, negative size, unsupported value) */
+#define B200SEG_EWORKSPACE (-2) /* workspace too small */
+#define B200SEG_EUNSUPPORTED (-3)
+
+typedef void* b200seg_stream_t;   /* cudaStream_t */
+
+/* dtype codes for feature / gradient tensors */
+#define B200SEG_F32  0
+#define B200SEG_BF16 1
+
+const char* b200seg_last_error(void);
+int b200seg_version(void);
+/* Number of kernels launched by this library in the calling process so far (all entry points). */
+long long b200seg_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * 3D NMS  -- replaces lib/utils/cython_nms_3d.pyx:39-96 (nms_3d) and :102-159 (nms_3d_volume),
+ *            reached through lib/utils/boxes_3d.py:364-374.
+ * Batched: `batch` independent detection sets stored back to back in dets[total,7]
+ * (x1,y1,z1,x2,y2,z2,score fp32); set b owns rows [offsets[b], offsets[b+1]).
+ *   keep        [total] int64: for set b, keep[offsets[b] + i], i < keep_count[b], are the kept
+ *               ORIGINAL (set-local) indices in ascending order (== np.where(suppressed==0)[0]).
+ *   keep_count  [batch] int32.
+ *   rank_order  [total] int32 or NULL: the same kept indices in VISIT order (key descending),
+ *               i.e. the order tools/binarization_soma.py:60-62 sorts them into.
+ * n_max = upper bound of the per-set size (host-known, sizes the grid and the workspace).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_nms3d_workspace_bytes(int batch, int n_max);
+int b200seg_nms3d_dev(const float* dets, const int32_t* offsets, int batch, int n_max,
+                      float thresh, int by_volume,
+                      int64_t* keep, int32_t* keep_count, int32_t* rank_order,
+                      void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+/* numpy seam: dets on the host, keep[n] on the host, *n_keep returned. */
+int b200seg_nms3d_host(const float* dets, int n, float thresh, int by_volume,
+                       int64_t* keep, int* n_keep);
+
+/* ----------------------------------------------------------------------------------------------
+ * 3D box IoU matrix -- replaces lib/utils/cython_bbox_3d.pyx:32-80 (alias boxes_3d.py:55).
+ * boxes [N,6], query [K,6] fp32 -> overlaps [N,K] fp32, with the reference's mixed fp32/fp64
+ * arithmetic reproduced bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_iou3d_dev(const float* boxes, long long N, const float* query, long long K,
+                      float* overlaps, b200seg_stream_t stream);
+int b200seg_iou3d_host(const float* boxes, long long N, const float* query, long long K,
+                       float* overlaps);
+
+/* ----------------------------------------------------------------------------------------------
+ * RoIAlign3D -- replaces roi_align_forward_cuda_3d / roi_align_backward_cuda_3d
+ * (lib/modeling/roi_xfrom/roi_align_3d/src/roi_align_cuda_3d.h:1-5, kernels in
+ * src/roi_align_kernel_3d.cu:81-151 and :238-338).
+ * features [B,C,S,H,W] contiguous (fp32 or bf16), rois [R,7] fp32 (batch,x1,y1,z1,x2,y2,z2),
+ * output [R,C,Ps,Ph,Pw] of the feature dtype.  Outputs need NOT be pre-zeroed.
+ * layout: 0 = reference (forward emits bins in (H,W,S) order into the [.,.,Ps,Ph,Pw] tensor,
+ *             backward reads grad_out in (S,H,W) order and uses the z guard -0.1; this is what the
+ *             reference computes, quirks included),
+ *         1 = "shw": forward emits (S,H,W) order and backward is its exact adjoint.
+ * The backward is deterministic and atomics-free: every grad_in element is written exactly once.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_roialign3d_workspace_bytes(int R);
+int b200seg_roialign3d_fwd_dev(const void* features, int dtype, const float* rois, void* output,
+                               int B, int C, int S, int H, int W, int R,
+                               int Ps, int Ph, int Pw, float spatial_scale, int sampling_ratio,
+                               int layout, b200seg_stream_t stream);
+int b200seg_roialign3d_bwd_dev(const void* grad_out, int dtype, const float* rois, void* grad_in,
+                               int B, int C, int S, int H, int W, int R,
+                               int Ps, int Ph, int Pw, float spatial_scale, int sampling_ratio,
+                               int layout, void* workspace, size_t workspace_bytes,
+                               b200seg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * PRM peak stimulation -- replaces lib/prm/peak_stimulation_3d.py:9-41 (forward) with the
+ * median threshold of lib/prm/peak_response_mapping_3d.py:45-49 fused in.
+ * input [B,A,S,H,W] fp32.  A voxel is a peak when it is the arg-max of its own win^3 window under
+ * ATen max_pool3d rules (first maximum in z,y,x scan order wins, -inf padding).
+ * filter_mode: 0 none, 1 lower median of the (b,a) volume (torch.median), 2 thresholds given in
+ *              thr_in[B*A] (the caller evaluated an arbitrary peak_filter callable).
+ * peaks [cap,5] int64 rows (b,a,z,y,x) in lexicographic order (torch.nonzero order);
+ * *n_peaks (device int32) = total number of peaks (may exceed cap; extra rows are dropped).
+ * agg [B*A] fp32 or NULL: sum(input*peak)/sum(peak) (NaN when a map has no peak).
+ * thr_out [B*A] fp32 or NULL: thresholds used.   win must be odd, 3 <= win <= 7.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_peaks3d_workspace_bytes(int B, int A, int S, int H, int W);
+int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int H, int W, int win,
+                        int filter_mode, const float* thr_in,
+                        int64_t* peaks, int cap, int32_t* n_peaks, float* agg, float* thr_out,
+                        void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+/* backward of the aggregation (peak_stimulation_3d.py:43-48): grad_in = peak_map * grad_agg[b,a],
+ * peaks as produced by the forward; grad_in [B,A,S,H,W] is fully written (zeros elsewhere). */
+int b200seg_peaks3d_bwd_dev(const int64_t* peaks, const int32_t* n_peaks, int cap,
+                            const float* grad_agg, float* grad_in,
+                            int B, int A, int S, int H, int W, b200seg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * 2D-Otsu binarization -- replaces tools/otsu.py:199-284 (otsu_py_2d_fast, k = -1), batched over
+ * instance crops.  Crop i owns samples [crop_off[i], crop_off[i+1]) of image/prm (uint16, the
+ * dtype both binarization scripts pass).  Outputs per crop: mask (0/255 uint8, same packing),
+ * b_max[i], g_info[i*4..] = {g_min, g_max, prm_min, prm_max}, status[i]: 0 ok, 1 = no b wins
+ * (the reference raises on k_max, otsu.py:277; mask is then all 255), 2 = empty crop.
+ * hist (optional, may be NULL): uint32 counts of hist.T ([prm_bin][img_bin], G*G per crop) at
+ * hist_off[i] (int64 element offsets, caller sized from G = g_max-g_min+1).
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_otsu2d_dev(const uint16_t* image, const uint16_t* prm, const int64_t* crop_off,
+                       int n_crops, uint8_t* mask, int32_t* b_max, int32_t* g_info, int32_t* status,
+                       uint32_t* hist, const int64_t* hist_off, b200seg_stream_t stream);
+/* numpy seam: one crop on the host (image, prm uint16[n]) -> mask uint8[n], *b_max; returns 0, or
+ * 1 when no threshold exists (caller raises, like the reference). */
+int b200seg_otsu2d_host(const uint16_t* image, const uint16_t* prm, long long n,
+                        uint8_t* mask, int* b_max);
+
+/* ----------------------------------------------------------------------------------------------
+ * Per-instance binarization straight from the raw volume (tools/binarization_soma.py:78-94):
+ * crop by the int()-truncated box, normalise image and PRM (:85-91), 2D-Otsu (:94).
+ *   volume [S,H,W] uint8; boxes [n,6] int32 inclusive voxel coords inside the volume;
+ *   prm: raw uint8 PRM crops (box-shaped, [sz,sy,sx]) packed at crop_off[i];
+ *   order [n] int32 or NULL: process instance order[i] as i-th (visit order from NMS);
+ *   n_valid (device int32) or NULL: only the first *n_valid instances are processed.
+ * Outputs as b200seg_otsu2d_dev, plus status 3 = PRM crop has no positive voxel (skipped,
+ * binarization_soma.py:74-76, mask all 0).  Masks are written in the packing of `prm`.
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_soma_binarize_dev(const uint8_t* volume, int S, int H, int W,
+                              const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,
+                              int n, const int32_t* order, const int32_t* n_valid,
+                              uint8_t* mask, int32_t* b_max, int32_t* status,
+                              b200seg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Label paste-back -- replaces the inline numpy of tools/binarization_soma.py:100-104 (and
+ * binarization_nuclei.py:141-149): instances are visited in order, instance i writes label
+ * ids[i] where its mask is set and the label volume is still 0.  seg [S,H,W] uint16 is written
+ * exactly once per voxel (zero-fill folded in; no pre-clear needed).
+ *   order / n_valid as above (instance order[i] is visited i-th); ids [n] indexed by visit rank.
+ *   survive [n] uint8 (by visit rank): 1 when the label is present in the volume
+ *   (`mask_id in np.unique(seg)`, :103).
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_paste_labels_dev(uint16_t* seg, int S, int H, int W, int n,
+                             const int32_t* boxes, const uint16_t* ids,
+                             const uint8_t* masks, const int64_t* mask_off,
+                             const int32_t* order, const int32_t* n_valid,
+                             uint8_t* survive, b200seg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Post-processing chain of tools/binarization_soma.py:57-104 for a batch of volumes, device
+ * resident: 3D NMS (:57) -> visit in descending score (:60-62) -> per-instance crop + normalise +
+ * 2D-Otsu (:78-94) -> label paste-back + survivor test (:100-104).
+ *   volumes [nv,S,H,W] uint8; detection set b = rows [det_off[b], det_off[b+1]) of dets[total,7];
+ *   det_off is given twice: device copy (kernels) and host copy (launch geometry);
+ *   boxes [total,6] int32 = int()-truncated detections clipped to the volume (:78);
+ *   prm = raw uint8 PRM crops, crop i ([sz,sy,sx] of box i) at crop_off[i] (int64 [total+1], device).
+ * Outputs: seg [nv,S,H,W] uint16 (label = visit rank + 1, :67), keep / keep_count / rank_order as
+ * b200seg_nms3d_dev, masks (packing of prm), b_max[total], status[total] (-1 = suppressed by NMS,
+ * else as b200seg_soma_binarize_dev), survive[total] (set b, visit rank r at det_off[b] + r).
+ * The largest-connected-component step (:97-99) is not part of the chain.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max);
+int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
+                              const float* dets, const int32_t* det_off_dev, const int32_t* det_off_host,
+                              const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,
+                              float nms_thresh,
+                              uint16_t* seg, int64_t* keep, int32_t* keep_count, int32_t* rank_order,
+                              uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive,
+                              void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+/* One volume, HOST buffers in and out (H2D / D2H inside; returns when seg is in host memory). */
+int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
+                               const float* dets, int n, const int32_t* boxes,
+                               const uint8_t* prm, const int64_t* crop_off, float nms_thresh,
+                               uint16_t* seg, int* n_keep, int32_t* rank_order,
+                               int32_t* b_max, int32_t* status, uint8_t* survive);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

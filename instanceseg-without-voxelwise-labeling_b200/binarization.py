@@ -1,0 +1,132 @@
+"""Per-volume post-processing of tools/binarization_soma.py:57-104 on the GPU.
+
+`soma_binarize`, `paste_labels` expose the two steps; `SomaPostproc` runs the whole chain
+(3D NMS -> visit order -> per-instance crop/normalise/2D-Otsu -> label paste-back) for a batch of
+volumes without leaving the device, and `postproc_soma_host` is the host-buffer (numpy) call a
+drop-in binarization script makes."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def dets_to_boxes(dets, shape):
+    """int()-truncated, volume-clipped boxes (binarization_soma.py:78; numpy slicing clips the end)."""
+    S, H, W = shape
+    b = np.asarray(dets)[:, :6].astype(np.int64)          # astype(int): truncation toward zero
+    b[:, 0] = np.clip(b[:, 0], 0, W - 1); b[:, 3] = np.clip(b[:, 3], 0, W - 1)
+    b[:, 1] = np.clip(b[:, 1], 0, H - 1); b[:, 4] = np.clip(b[:, 4], 0, H - 1)
+    b[:, 2] = np.clip(b[:, 2], 0, S - 1); b[:, 5] = np.clip(b[:, 5], 0, S - 1)
+    b[:, 3] = np.maximum(b[:, 3], b[:, 0]); b[:, 4] = np.maximum(b[:, 4], b[:, 1]); b[:, 5] = np.maximum(b[:, 5], b[:, 2])
+    return b.astype(np.int32)
+
+
+def crop_offsets(boxes):
+    b = np.asarray(boxes, dtype=np.int64)
+    sizes = (b[:, 3] - b[:, 0] + 1) * (b[:, 4] - b[:, 1] + 1) * (b[:, 5] - b[:, 2] + 1)
+    off = np.zeros(b.shape[0] + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    return off
+
+
+def soma_binarize(volume, boxes, prm, crop_off, order=None, n_valid=None):
+    """Device op (torch cuda tensors): volume uint8 [S,H,W], boxes int32 [n,6], prm uint8 packed crops,
+    crop_off int64 [n+1].  Returns (mask uint8 packed, b_max int32 [n], status int32 [n])."""
+    import torch
+    S, H, W = volume.shape
+    n = boxes.shape[0]
+    dev = volume.device
+    mask = torch.zeros(max(prm.numel(), 1), dtype=torch.uint8, device=dev)
+    b_max = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    status = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().b200seg_soma_binarize_dev(
+        _lib.ptr(volume), S, H, W, _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off), n, _lib.ptr(order),
+        _lib.ptr(n_valid), _lib.ptr(mask), _lib.ptr(b_max), _lib.ptr(status), _lib.current_stream()), "soma_binarize")
+    return mask, b_max[:n], status[:n]
+
+
+def paste_labels(seg, boxes, ids, masks, mask_off, order=None, n_valid=None):
+    """Device op: seg uint16 [S,H,W] is (over)written once; returns survive uint8 [n] by visit rank."""
+    import torch
+    S, H, W = seg.shape
+    n = boxes.shape[0]
+    survive = torch.zeros(max(n, 1), dtype=torch.uint8, device=seg.device)
+    _lib.check(_lib.lib().b200seg_paste_labels_dev(
+        _lib.ptr(seg), S, H, W, n, _lib.ptr(boxes), _lib.ptr(ids), _lib.ptr(masks), _lib.ptr(mask_off),
+        _lib.ptr(order), _lib.ptr(n_valid), _lib.ptr(survive), _lib.current_stream()), "paste_labels")
+    return survive[:n]
+
+
+class SomaPostproc(object):
+    """Device-resident chain for a batch of equally shaped volumes (buffers allocated once)."""
+
+    def __init__(self, n_volumes, shape, det_counts, prm_bytes, device="cuda"):
+        import torch
+        self.torch = torch
+        self.nv = int(n_volumes)
+        self.S, self.H, self.W = [int(v) for v in shape]
+        self.det_off_host = np.zeros(self.nv + 1, dtype=np.int32)
+        self.det_off_host[1:] = np.cumsum(det_counts)
+        total = int(self.det_off_host[-1])
+        self.total = total
+        self.n_max = int(max(det_counts)) if len(det_counts) else 0
+        dev = torch.device(device)
+        self.det_off_dev = torch.from_numpy(self.det_off_host).to(dev)
+        t = max(total, 1)
+        self.seg = torch.empty((self.nv, self.S, self.H, self.W), dtype=torch.uint16, device=dev)
+        self.keep = torch.empty(t, dtype=torch.int64, device=dev)
+        self.keep_count = torch.zeros(max(self.nv, 1), dtype=torch.int32, device=dev)
+        self.rank_order = torch.empty(t, dtype=torch.int32, device=dev)
+        self.masks = torch.empty(max(int(prm_bytes), 1) + 16, dtype=torch.uint8, device=dev)
+        self.b_max = torch.zeros(t, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(t, dtype=torch.int32, device=dev)
+        self.survive = torch.zeros(t, dtype=torch.uint8, device=dev)
+        self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(self.nv, self.n_max)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+    def launches_per_call(self):
+        """Kernels launched by one run(): 3 NMS + iota + per volume (binarize + paste)."""
+        nz = int(np.count_nonzero(np.diff(self.det_off_host)))
+        return (3 + 1 if self.n_max > 0 else 0) + nz + self.nv
+
+    def run(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
+        """All arguments are cuda tensors (volumes uint8 [nv,S,H,W], dets f32 [total,7], boxes int32
+        [total,6], prm uint8 packed, crop_off int64 [total+1]).  Enqueues on the current stream."""
+        _lib.check(_lib.lib().b200seg_postproc_soma_dev(
+            _lib.ptr(volumes), self.nv, self.S, self.H, self.W, _lib.ptr(dets), _lib.ptr(self.det_off_dev),
+            _lib.ptr(self.det_off_host), _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off),
+            float(np.float32(nms_thresh)), _lib.ptr(self.seg), _lib.ptr(self.keep), _lib.ptr(self.keep_count),
+            _lib.ptr(self.rank_order), _lib.ptr(self.masks), _lib.ptr(self.b_max), _lib.ptr(self.status),
+            _lib.ptr(self.survive), _lib.ptr(self.ws), self.ws_bytes, _lib.current_stream()), "postproc_soma_dev")
+        return self.seg
+
+
+def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=None):
+    """numpy in / numpy out for ONE volume (H2D and D2H happen inside the C call).
+    Returns dict(seg uint16 [S,H,W], n_keep, rank_order, b_max, status, survive, scores [[id, score]])."""
+    volume = np.ascontiguousarray(volume, dtype=np.uint8)
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32)
+    prm = np.ascontiguousarray(prm, dtype=np.uint8)
+    crop_off = np.ascontiguousarray(crop_off, dtype=np.int64)
+    S, H, W = volume.shape
+    n = dets.shape[0]
+    seg = seg_out if seg_out is not None else np.empty((S, H, W), dtype=np.uint16)
+    nn = max(n, 1)
+    rank = np.zeros(nn, dtype=np.int32)
+    b_max = np.zeros(nn, dtype=np.int32)
+    status = np.zeros(nn, dtype=np.int32)
+    survive = np.zeros(nn, dtype=np.uint8)
+    cnt = C.c_int(0)
+    _lib.check(_lib.lib().b200seg_postproc_soma_host(
+        _lib.ptr(volume), S, H, W, _lib.ptr(dets), n, _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off),
+        float(np.float32(nms_thresh)), _lib.ptr(seg), C.byref(cnt), _lib.ptr(rank), _lib.ptr(b_max),
+        _lib.ptr(status), _lib.ptr(survive)), "postproc_soma_host")
+    k = cnt.value
+    order = rank[:k]
+    alive = survive[:k].astype(bool)
+    scores = np.stack([np.arange(1, k + 1, dtype=np.float32)[alive], dets[order, 6][alive]], axis=1) if k else \
+        np.zeros((0, 2), dtype=np.float32)
+    return dict(seg=seg, n_keep=k, rank_order=order.copy(), b_max=b_max[:n], status=status[:n],
+                survive=alive, scores=scores.astype(np.float32))

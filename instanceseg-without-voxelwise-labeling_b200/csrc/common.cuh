@@ -1,0 +1,92 @@
+// common.cuh -- shared helpers for the b200seg CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+
+#include "../../include/b200seg.h"
+
+#define B200SEG_VERSION 100
+
+namespace b200seg {
+
+// thread-local error text + global launch counter (api.cu)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_cuda(cudaError_t e, const char* what);
+int num_sms();
+
+#define B200_CHECK_ARG(cond, ...)                         \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            ::b200seg::set_error(__VA_ARGS__);            \
+            return B200SEG_EINVAL;                        \
+        }                                                 \
+    } while (0)
+
+#define B200_CUDA(call)                                              \
+    do {                                                             \
+        int _e = ::b200seg::check_cuda((call), #call);               \
+        if (_e) return _e;                                           \
+    } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                      \
+    do {                                                             \
+        ::b200seg::count_launch();                                   \
+        int _e = ::b200seg::check_cuda(cudaGetLastError(), name);    \
+        if (_e) return _e;                                           \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// grow-only device arena + private stream used by the HOST-buffer entry points (api.cu owns it)
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    char* buf = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    int ensure(size_t bytes);
+};
+HostCtx& host_ctx();
+
+struct Carver {
+    char* p;
+    explicit Carver(char* base) : p(base) {}
+    template <typename T> T* take(size_t n) { T* r = (T*)p; p += align_up(n * sizeof(T), 256); return r; }
+    static size_t need(size_t bytes) { return align_up(bytes, 256); }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+
+// Monotone map float -> uint32 such that a < b  <=>  key(a) < key(b); -0.0 and +0.0 map to the
+// same key; every NaN maps to the largest key.
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+    if (f != f) return 0xFFFFFFFFu;
+    if (f == 0.0f) f = 0.0f;                       // canonicalise -0
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// streaming (evict-first) 128-bit global accesses for data touched exactly once
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace b200seg

@@ -1,0 +1,299 @@
+// nms3d.cu -- batched 3D greedy NMS on the GPU (replaces lib/utils/cython_nms_3d.pyx:39-159).
+//
+// Three launches per batch of detection sets, no host round trip:
+//   1. nms_rank_kernel   rank sort: rank(i) = #{j : key_j > key_i or (key_j == key_i and j < i)}
+//                        (O(n^2) compares, trivially parallel, deterministic, stable tie rule) and
+//                        scatter of {box, volume, original index} into visit order.
+//   2. nms_mask_kernel   upper-triangular 64x64 tiles of the suppression relation; one warp owns a
+//                        32-row strip, lane = column box, one __ballot_sync per row builds the 32-bit
+//                        word (warp-ballot bitmask).  IoU uses the exact fp32 operation order of the
+//                        reference (cython_nms_3d.pyx:82-93) through __f*_rn intrinsics (never
+//                        contracted into FMA).
+//   3. nms_reduce_kernel one CTA per set walks the 64-row chunks: warp 0 resolves the chunk's
+//                        diagonal tile in registers (ffs over the alive word), then all threads OR the
+//                        kept rows' mask words into the removed bitset held in shared memory.  Emits the
+//                        kept ORIGINAL indices ascending (np.where(suppressed==0)) and, optionally, in
+//                        visit order.
+#include "common.cuh"
+
+namespace b200seg {
+
+struct __align__(16) SortedBox {
+    float x1, y1, z1, x2;
+    float y2, z2, vol;
+    int orig;
+};
+
+__device__ __forceinline__ float box_volume_f32(const float* d) {
+    // numpy fp32: (x2 - x1 + 1) * (y2 - y1 + 1) * (z2 - z1 + 1)      cython_nms_3d.pyx:48
+    float a = __fadd_rn(__fsub_rn(d[3], d[0]), 1.0f);
+    float b = __fadd_rn(__fsub_rn(d[4], d[1]), 1.0f);
+    float c = __fadd_rn(__fsub_rn(d[5], d[2]), 1.0f);
+    return __fmul_rn(__fmul_rn(a, b), c);
+}
+
+__device__ __forceinline__ float ref_max(float a, float b) { return a >= b ? a : b; }   // pyx:30-31
+__device__ __forceinline__ float ref_min(float a, float b) { return a <= b ? a : b; }   // pyx:33-34
+
+// true when box j must be suppressed by box i (cython_nms_3d.pyx:82-95)
+__device__ __forceinline__ bool suppresses(const SortedBox& bi, const SortedBox& bj, float thresh) {
+    float xx1 = ref_max(bi.x1, bj.x1);
+    float yy1 = ref_max(bi.y1, bj.y1);
+    float zz1 = ref_max(bi.z1, bj.z1);
+    float xx2 = ref_min(bi.x2, bj.x2);
+    float yy2 = ref_min(bi.y2, bj.y2);
+    float zz2 = ref_min(bi.z2, bj.z2);
+    float w = ref_max(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    float h = ref_max(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+    float s = ref_max(0.0f, __fadd_rn(__fsub_rn(zz2, zz1), 1.0f));
+    float inter = __fmul_rn(__fmul_rn(w, h), s);
+    float uni = __fsub_rn(__fadd_rn(bi.vol, bj.vol), inter);
+    float ovr = __fdiv_rn(inter, uni);
+    return ovr >= thresh;
+}
+
+constexpr int RANK_THREADS = 128;
+
+__global__ void __launch_bounds__(RANK_THREADS)
+nms_rank_kernel(const float* __restrict__ dets, const int32_t* __restrict__ offsets,
+                int by_volume, int n_max, SortedBox* __restrict__ sorted_all) {
+    const int b = blockIdx.y;
+    const int off = offsets[b];
+    const int n = offsets[b + 1] - off;
+    const int i0 = blockIdx.x * RANK_THREADS;
+    if (i0 >= n) return;
+    const float* d = dets + (size_t)off * 7;
+    SortedBox* sorted = sorted_all + (size_t)b * n_max;
+
+    __shared__ uint32_t s_key[RANK_THREADS];
+    const int i = i0 + threadIdx.x;
+    float my[7];
+    uint32_t ki = 0;
+    float vi = 0.f;
+    if (i < n) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) my[k] = d[(size_t)i * 7 + k];
+        vi = box_volume_f32(my);
+        ki = ordered_key(by_volume ? vi : my[6]);
+    }
+    int rank = 0;
+    for (int j0 = 0; j0 < n; j0 += RANK_THREADS) {
+        const int j = j0 + threadIdx.x;
+        uint32_t kj = 0;
+        if (j < n) {
+            if (by_volume) {
+                float t[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) t[k] = d[(size_t)j * 7 + k];
+                kj = ordered_key(box_volume_f32(t));
+            } else {
+                kj = ordered_key(d[(size_t)j * 7 + 6]);
+            }
+        }
+        __syncthreads();
+        s_key[threadIdx.x] = kj;
+        __syncthreads();
+        const int lim = min(RANK_THREADS, n - j0);
+        if (i < n) {
+            for (int t = 0; t < lim; ++t) {
+                const uint32_t k = s_key[t];
+                rank += (k > ki) || (k == ki && (j0 + t) < i);
+            }
+        }
+    }
+    if (i < n) {
+        SortedBox sb;
+        sb.x1 = my[0]; sb.y1 = my[1]; sb.z1 = my[2]; sb.x2 = my[3]; sb.y2 = my[4]; sb.z2 = my[5];
+        sb.vol = vi; sb.orig = i;
+        sorted[rank] = sb;
+    }
+}
+
+// grid (W64, W64, batch), 64 threads: warp w owns rows rb*64 + 32*w .. +31, both warps share the
+// 64 column boxes staged in shared memory.  mask[row][cb] (uint64) bit c set <=> row suppresses
+// column cb*64+c (only columns later in visit order).
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const SortedBox* __restrict__ sorted_all, const int32_t* __restrict__ offsets,
+                int n_max, int w64, float thresh, unsigned long long* __restrict__ mask_all) {
+    const int b = blockIdx.z;
+    const int n = offsets[b + 1] - offsets[b];
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+    const SortedBox* sorted = sorted_all + (size_t)b * n_max;
+    unsigned long long* mask = mask_all + (size_t)b * n_max * w64;
+
+    __shared__ SortedBox s_row[64];
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const int col = cb * 64 + t;
+    const int row = rb * 64 + t;
+    SortedBox cbox0, cbox1;       // lane's two column boxes: columns cb*64+lane and cb*64+32+lane
+    {
+        SortedBox z; z.x1 = z.y1 = z.z1 = 0.f; z.x2 = z.y2 = z.z2 = -1.f; z.vol = 0.f; z.orig = -1;
+        s_row[t] = row < n ? sorted[row] : z;
+        const int c0 = cb * 64 + lane, c1 = c0 + 32;
+        cbox0 = c0 < n ? sorted[c0] : z;
+        cbox1 = c1 < n ? sorted[c1] : z;
+        (void)col;
+    }
+    __syncthreads();
+    const int c0 = cb * 64 + lane, c1 = c0 + 32;
+    unsigned long long my_word = 0ull;
+    // each warp walks its 32 rows; the row box is a shared-memory broadcast, the predicate is
+    // evaluated by 32 lanes at once and gathered with one ballot per 32 columns
+    for (int r = 0; r < 32; ++r) {
+        const int rl = warp * 32 + r;
+        const int rg = rb * 64 + rl;
+        if (rg >= n) break;                                   // warp-uniform
+        const SortedBox rbox = s_row[rl];
+        const bool p0 = (c0 < n) && (c0 > rg) && suppresses(rbox, cbox0, thresh);
+        const bool p1 = (c1 < n) && (c1 > rg) && suppresses(rbox, cbox1, thresh);
+        const unsigned lo = __ballot_sync(0xffffffffu, p0);
+        const unsigned hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == r) my_word = ((unsigned long long)hi << 32) | lo;
+    }
+    const int my_row = rb * 64 + warp * 32 + lane;
+    if (my_row < n) mask[(size_t)my_row * w64 + cb] = my_word;
+}
+
+constexpr int REDUCE_THREADS = 256;
+
+// dynamic smem: removed[w64] u64 | flags[w64] u64 (bit = original index kept)
+__global__ void __launch_bounds__(REDUCE_THREADS)
+nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long long* __restrict__ mask_all,
+                  const int32_t* __restrict__ offsets, int n_max, int w64,
+                  int64_t* __restrict__ keep, int32_t* __restrict__ keep_count,
+                  int32_t* __restrict__ rank_order) {
+    extern __shared__ unsigned long long s_dyn[];
+    unsigned long long* removed = s_dyn;
+    unsigned long long* flags = s_dyn + w64;
+    __shared__ int s_rows[64];
+    __shared__ int s_nk;
+    __shared__ int s_scan[REDUCE_THREADS];
+
+    const int b = blockIdx.x;
+    const int off = offsets[b];
+    const int n = offsets[b + 1] - off;
+    const SortedBox* sorted = sorted_all + (size_t)b * n_max;
+    const unsigned long long* mask = mask_all + (size_t)b * n_max * w64;
+    const int nw = (n + 63) >> 6;
+    const int tid = threadIdx.x;
+
+    for (int w = tid; w < nw; w += REDUCE_THREADS) { removed[w] = 0ull; flags[w] = 0ull; }
+    __syncthreads();
+
+    int n_kept = 0;    // uniform across the CTA
+    for (int c = 0; c < nw; ++c) {
+        if (tid < 32) {
+            const int r0 = c * 64 + tid, r1 = r0 + 32;
+            const unsigned long long d0 = r0 < n ? mask[(size_t)r0 * w64 + c] : 0ull;
+            const unsigned long long d1 = r1 < n ? mask[(size_t)r1 * w64 + c] : 0ull;
+            const int rows = min(64, n - c * 64);
+            unsigned long long alive = ~removed[c];
+            if (rows < 64) alive &= ((1ull << rows) - 1ull);
+            int nk = 0;
+            while (alive) {                                    // warp-uniform loop
+                const int r = __ffsll((long long)alive) - 1;
+                const unsigned long long lo = __shfl_sync(0xffffffffu, d0, r & 31);
+                const unsigned long long hi = __shfl_sync(0xffffffffu, d1, r & 31);
+                const unsigned long long d = (r < 32) ? lo : hi;
+                alive &= ~d;
+                alive &= ~(1ull << r);
+                if (tid == 0) s_rows[nk] = c * 64 + r;
+                ++nk;
+            }
+            if (tid == 0) s_nk = nk;
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        const int rest = nw - c - 1;
+        for (int item = tid; item < nk * rest; item += REDUCE_THREADS) {
+            const int k = item / rest, w = c + 1 + item % rest;
+            const unsigned long long m = mask[(size_t)s_rows[k] * w64 + w];
+            if (m) atomicOr(&removed[w], m);
+        }
+        for (int k = tid; k < nk; k += REDUCE_THREADS) {
+            const int orig = sorted[s_rows[k]].orig;
+            atomicOr(&flags[orig >> 6], 1ull << (orig & 63));
+            if (rank_order) rank_order[off + n_kept + k] = orig;
+        }
+        n_kept += nk;
+        __syncthreads();
+    }
+    if (tid == 0) keep_count[b] = n_kept;
+
+    // ascending original indices: exclusive scan of popcounts over the flag words
+    int base = 0;
+    for (int w0 = 0; w0 < nw; w0 += REDUCE_THREADS) {
+        const int w = w0 + tid;
+        const unsigned long long f = w < nw ? flags[w] : 0ull;
+        const int cnt = __popcll(f);
+        s_scan[tid] = cnt;
+        __syncthreads();
+        for (int d = 1; d < REDUCE_THREADS; d <<= 1) {         // Hillis-Steele inclusive scan
+            const int v = tid >= d ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        int pos = base + s_scan[tid] - cnt;
+        unsigned long long g = f;
+        while (g) {
+            const int bit = __ffsll((long long)g) - 1;
+            g &= g - 1;
+            keep[off + pos++] = (int64_t)(w * 64 + bit);
+        }
+        base += s_scan[REDUCE_THREADS - 1];
+        __syncthreads();
+    }
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" size_t b200seg_nms3d_workspace_bytes(int batch, int n_max) {
+    if (batch <= 0 || n_max <= 0) return 256;
+    const size_t w64 = (size_t)(n_max + 63) / 64;
+    size_t per = align_up((size_t)n_max * sizeof(SortedBox), 256) + align_up((size_t)n_max * w64 * 8, 256);
+    return per * batch + 256;
+}
+
+extern "C" int b200seg_nms3d_dev(const float* dets, const int32_t* offsets, int batch, int n_max,
+                                 float thresh, int by_volume, int64_t* keep, int32_t* keep_count,
+                                 int32_t* rank_order, void* workspace, size_t workspace_bytes,
+                                 b200seg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200_CHECK_ARG(batch >= 0 && n_max >= 0, "nms3d: negative batch/n_max");
+    if (batch == 0) return 0;
+    B200_CHECK_ARG(offsets && keep_count, "nms3d: null offsets/keep_count");
+    if (n_max == 0) {
+        B200_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t) * batch, stream));
+        return 0;
+    }
+    B200_CHECK_ARG(dets && keep && workspace, "nms3d: null pointer");
+    if (workspace_bytes < b200seg_nms3d_workspace_bytes(batch, n_max)) {
+        set_error("nms3d: workspace too small (%zu < %zu)", workspace_bytes,
+                  b200seg_nms3d_workspace_bytes(batch, n_max));
+        return B200SEG_EWORKSPACE;
+    }
+    const int w64 = (n_max + 63) / 64;
+    B200_CHECK_ARG(2 * (size_t)w64 * 8 <= 200 * 1024, "nms3d: n_max=%d too large", n_max);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    SortedBox* sorted = (SortedBox*)ws;
+    unsigned long long* mask = (unsigned long long*)(ws + align_up((size_t)n_max * sizeof(SortedBox), 256) * batch);
+
+    dim3 g1((n_max + RANK_THREADS - 1) / RANK_THREADS, batch);
+    nms_rank_kernel<<<g1, RANK_THREADS, 0, stream>>>(dets, offsets, by_volume, n_max, sorted);
+    B200_LAUNCH_CHECK("nms_rank_kernel");
+    dim3 g2(w64, w64, batch);
+    nms_mask_kernel<<<g2, 64, 0, stream>>>(sorted, offsets, n_max, w64, thresh, mask);
+    B200_LAUNCH_CHECK("nms_mask_kernel");
+    const size_t smem = 2 * (size_t)w64 * 8;
+    if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_reduce_kernel<<<batch, REDUCE_THREADS, smem, stream>>>(sorted, mask, offsets, n_max, w64, keep,
+                                                              keep_count, rank_order);
+    B200_LAUNCH_CHECK("nms_reduce_kernel");
+    return 0;
+}

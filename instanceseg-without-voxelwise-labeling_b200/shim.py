@@ -1,0 +1,60 @@
+"""Make the reference's import names resolve to this package, so that lib/modeling/model_builder.py,
+lib/utils/boxes_3d.py, lib/prm/*, tools/binarization_*.py and tools/infer_simple.py keep working
+unchanged.
+
+    import b200seg.shim; b200seg.shim.install()
+
+registers these modules in sys.modules:
+    utils.cython_nms_3d          -> nms_3d, nms_3d_volume
+    utils.cython_bbox_3d         -> bbox_overlaps_3d
+    modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d -> RoIAlignFunction_3d
+    modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d   -> RoIAlign_3d, RoIAlignAvg_3d, RoIAlignMax_3d
+    prm.peak_stimulation_3d      -> peak_stimulation_3d, PeakStimulation
+    otsu                         -> otsu_py_2d_fast
+"""
+import sys
+import types
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__b200seg_shim__ = True
+    return m
+
+
+def install(overwrite=True):
+    from . import boxes_3d, roi_align_3d, peak_stimulation_3d, otsu
+    mods = {
+        "utils.cython_nms_3d": _module("utils.cython_nms_3d", nms_3d=boxes_3d._nms_numpy and
+                                       (lambda dets, thresh: boxes_3d._nms_numpy(dets, thresh, False)),
+                                       nms_3d_volume=lambda dets, thresh: boxes_3d._nms_numpy(dets, thresh, True)),
+        "utils.cython_bbox_3d": _module("utils.cython_bbox_3d", bbox_overlaps_3d=boxes_3d.bbox_overlaps_3d),
+        "modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d":
+            _module("modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d",
+                    RoIAlignFunction_3d=roi_align_3d.RoIAlignFunction_3d),
+        "modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d":
+            _module("modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d",
+                    RoIAlign_3d=roi_align_3d.RoIAlign_3d, RoIAlignAvg_3d=roi_align_3d.RoIAlignAvg_3d,
+                    RoIAlignMax_3d=roi_align_3d.RoIAlignMax_3d),
+        "prm.peak_stimulation_3d": _module("prm.peak_stimulation_3d",
+                                           peak_stimulation_3d=peak_stimulation_3d.peak_stimulation_3d,
+                                           PeakStimulation=peak_stimulation_3d.PeakStimulation),
+        "otsu": _module("otsu", otsu_py_2d_fast=otsu.otsu_py_2d_fast),
+    }
+    installed = []
+    for name, mod in mods.items():
+        if overwrite or name not in sys.modules:
+            sys.modules[name] = mod
+            installed.append(name)
+            # make `import a.b.c` work when the parents are absent: create empty parent packages
+            parts = name.split(".")
+            for i in range(1, len(parts)):
+                parent = ".".join(parts[:i])
+                if parent not in sys.modules:
+                    pm = types.ModuleType(parent)
+                    pm.__path__ = []
+                    pm.__b200seg_shim__ = True
+                    sys.modules[parent] = pm
+                setattr(sys.modules[parent], parts[i], sys.modules.get(".".join(parts[:i + 1]), None) or mod)
+    return installed

@@ -1,0 +1,166 @@
+"""Generate the golden vectors under tests/golden/ by running THE REFERENCE'S OWN CODE.
+
+Run in the authoring container only (needs /root/reference and oracle/_ref built by
+oracle/build_ref.py):   python tests/golden/make_golden.py
+
+  nms_iou.npz   cython_nms_3d.nms_3d / nms_3d_volume / cython_bbox_3d.bbox_overlaps_3d
+                (reference .pyx built unmodified except the 2-token numpy-2 patch)
+  otsu.npz      tools/otsu.py:otsu_py_2d_fast imported with matplotlib/skimage stubbed and
+                np.float = float (the module imports but never uses them)
+  peaks.npz     lib/prm/peak_stimulation_3d.py:peak_stimulation_3d on CPU torch, with the median
+                filter of lib/prm/peak_response_mapping_3d.py:45-49
+  rle.npz       lib/utils/mask_3d.py literal of :75-79 (the only known-answer in the reference)
+The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
+what the `-m gpu` tests pin the CUDA path against on the GPU box (no /root/reference there).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+import oracle  # noqa: E402
+from b200seg import synth  # noqa: E402
+
+
+def load_ref_otsu():
+    for m in ("matplotlib", "matplotlib.pyplot", "skimage", "skimage.io", "skimage.exposure"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["skimage"].io = sys.modules["skimage.io"]
+    sys.modules["skimage"].exposure = sys.modules["skimage.exposure"]
+    np.float = float
+    spec = importlib.util.spec_from_file_location("ref_otsu", os.path.join(REF, "tools", "otsu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_ref_peaks():
+    spec = importlib.util.spec_from_file_location("ref_peak", os.path.join(REF, "lib", "prm", "peak_stimulation_3d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_nms_iou():
+    nms = oracle.ref_module("cython_nms_3d")
+    bb = oracle.ref_module("cython_bbox_3d")
+    assert nms is not None and bb is not None, "run oracle/build_ref.py first"
+    rng = np.random.default_rng(1001)
+    out = {}
+    cases = [(0, 1, 100, 0.23, False), (1, 2, 100, 0.5, False), (2, 50, 120, 0.23, False), (3, 50, 60, 0.23, True),
+             (4, 200, 150, 0.15, False), (5, 200, 150, 0.15, True), (6, 1000, 300, 0.23, False),
+             (7, 1000, 250, 0.7, True), (8, 333, 80, 0.3, False)]
+    for cid, n, ext, thr, integer in cases:
+        d = synth.random_dets(rng, n, extent=(ext, ext, ext // 2 + 8), integer=integer)
+        out["nms%d_dets" % cid] = d
+        out["nms%d_thr" % cid] = np.float32(thr)
+        out["nms%d_keep" % cid] = nms.nms_3d(d, np.float32(thr)).astype(np.int64)
+        # volume-ordered variant only where volumes are distinct (ties are platform dependent)
+        vol = (d[:, 3] - d[:, 0] + 1) * (d[:, 4] - d[:, 1] + 1) * (d[:, 5] - d[:, 2] + 1)
+        if len(np.unique(vol)) == n:
+            out["nms%d_keepvol" % cid] = nms.nms_3d_volume(d, np.float32(thr)).astype(np.int64)
+    for cid, (N, K, integer) in enumerate([(1, 1, False), (40, 7, False), (300, 50, True), (257, 33, False)]):
+        b = synth.random_dets(rng, N, extent=(120, 120, 60), integer=integer)[:, :6].copy()
+        q = synth.random_dets(rng, K, extent=(120, 120, 60), integer=integer)[:, :6].copy()
+        q[: min(N, K) // 2] = b[: min(N, K) // 2]            # identical boxes: IoU 0.9999999, not 1.0
+        out["iou%d_boxes" % cid] = b
+        out["iou%d_query" % cid] = q
+        out["iou%d_out" % cid] = bb.bbox_overlaps_3d(b, q)
+    np.savez_compressed(os.path.join(HERE, "nms_iou.npz"), **out)
+    print("nms_iou.npz", len(out), "arrays")
+
+
+def make_otsu():
+    ro = load_ref_otsu()
+    rng = np.random.default_rng(1003)
+    out = {}
+    n = 0
+    for cid in range(14):
+        shape = tuple(int(v) for v in rng.integers(6, 30, 3))
+        vol, boxes, blobs = synth.blob_volume(rng, shape, 1, sigma_xy=(shape[1] / 6, shape[1] / 3),
+                                              sigma_z=(shape[0] / 6, shape[0] / 3))
+        prm = synth.prm_crop(blobs[0], (0, 0, 0, shape[2] - 1, shape[1] - 1, shape[0] - 1))
+        if prm.max() == 0:
+            continue
+        if cid % 2 == 0:
+            img16, prm16 = oracle.soma_normalise(vol, prm)       # soma call-site normalisation (uint16, ~301 levels)
+        else:
+            img16, prm16 = vol.astype(np.uint16), prm.astype(np.uint16)   # raw uint8 levels
+        if cid == 5:
+            prm16[:] = 77                                          # constant PRM axis (edge expansion +-0.5)
+        mask, k, b = ro.otsu_py_2d_fast(img16, prm16)
+        g = int(img16.max()) - int(img16.min()) + 1
+        hist = np.histogram2d(img16.ravel(), prm16.ravel(), bins=g)[0].T
+        out["otsu%d_img" % n] = img16
+        out["otsu%d_prm" % n] = prm16
+        out["otsu%d_b" % n] = np.int64(b)
+        out["otsu%d_k" % n] = np.int64(k)
+        out["otsu%d_mask" % n] = np.packbits(mask.ravel() > 0)
+        out["otsu%d_hist" % n] = hist.astype(np.uint32)
+        n += 1
+    out["count"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "otsu.npz"), **out)
+    print("otsu.npz", n, "crops")
+
+
+def make_peaks():
+    import torch
+    rp = load_ref_peaks()
+
+    def median_filter(input):                     # lib/prm/peak_response_mapping_3d.py:45-49
+        b, c, s, h, w = input.size()
+        thr, _ = torch.median(input.view(b, c, s * h * w), dim=2)
+        return thr.contiguous().view(b, c, 1, 1, 1)
+
+    rng = np.random.default_rng(1005)
+    out = {}
+    cases = [((1, 2, 8, 16, 16), 3, "smooth"), ((2, 3, 5, 9, 11), 3, "ties"), ((1, 1, 6, 10, 33), 5, "noise"),
+             ((1, 2, 4, 7, 40), 3, "plateau"), ((1, 1, 9, 12, 12), 7, "noise"), ((1, 14, 8, 20, 20), 3, "smooth")]
+    for cid, (shape, win, kind) in enumerate(cases):
+        if kind == "smooth":
+            x = np.concatenate([synth.response_map(rng, shape[2:], n_peaks=6, channels=shape[1]) for _ in range(shape[0])], 0)
+        elif kind == "ties":
+            x = (np.round(rng.normal(size=shape) * 2) / 2).astype(np.float32)
+        elif kind == "plateau":
+            x = np.zeros(shape, np.float32); x[..., 1:3, 2:4, 5:9] = 1.0; x[..., 0, 0, 0] = 1.0
+        else:
+            x = rng.normal(size=shape).astype(np.float32)
+        out["pk%d_in" % cid] = x
+        out["pk%d_win" % cid] = np.int64(win)
+        t = torch.from_numpy(x)
+        pl, agg = rp.peak_stimulation_3d(t, win_size=win, peak_filter=median_filter)
+        out["pk%d_peaks_med" % cid] = pl.numpy().astype(np.int64)
+        out["pk%d_agg_med" % cid] = agg.numpy()
+        pl0, agg0 = rp.peak_stimulation_3d(t, win_size=win, peak_filter=None)
+        out["pk%d_peaks_none" % cid] = pl0.numpy().astype(np.int64)
+        out["pk%d_agg_none" % cid] = agg0.numpy()
+    out["count"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "peaks.npz"), **out)
+    print("peaks.npz", len(cases), "cases")
+
+
+def make_rle():
+    sys.path.insert(0, os.path.join(REF, "lib", "utils"))
+    spec = importlib.util.spec_from_file_location("ref_mask_3d", os.path.join(REF, "lib", "utils", "mask_3d.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    a = np.array([[[1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0]], [[1, 1, 1, 1, 1, 0], [1, 1, 1, 0, 0, 0]]])
+    r = m.binary_mask_to_rle(a)
+    np.savez_compressed(os.path.join(HERE, "rle.npz"), mask=a.astype(np.uint8),
+                        counts=np.asarray(r["counts"], dtype=np.int64), size=np.asarray(r["size"], dtype=np.int64))
+    print("rle.npz", r)
+
+
+if __name__ == "__main__":
+    make_nms_iou()
+    make_otsu()
+    make_peaks()
+    make_rle()

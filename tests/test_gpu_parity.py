@@ -1,0 +1,476 @@
+"""GPU parity tests proper: every CUDA path, called through the C ABI (ctypes), against the oracle
+on seeded inputs and against the committed golden vectors produced by the reference's own code.
+Bit-exact for integer/index/byte results; RoIAlign3D within 1e-5 relative (fp32)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import oracle_chain
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b2(built_lib, cuda):
+    import b200seg
+    return b200seg
+
+
+@pytest.fixture(scope="module")
+def torch_(cuda):
+    import torch
+    return torch
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def test_nms_golden(b2, golden):
+    g = golden("nms_iou.npz")
+    ids = sorted({int(k[3:].split("_")[0]) for k in g.files if k.startswith("nms")})
+    for i in ids:
+        d, thr = g["nms%d_dets" % i], g["nms%d_thr" % i]
+        keep = b2.nms_3d(d, thr)
+        assert keep.dtype == np.int64 and np.array_equal(keep, g["nms%d_keep" % i]), i
+        if "nms%d_keepvol" % i in g.files:
+            assert np.array_equal(b2.nms_3d_volume(d, thr), g["nms%d_keepvol" % i]), i
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 127, 200, 1000, 2500, 6000])
+def test_nms_vs_oracle_sizes(b2, n):
+    from b200seg import synth
+    rng = np.random.default_rng(100 + n)
+    for rep in range(3 if n <= 1000 else 1):
+        d = synth.random_dets(rng, n, extent=(60 + 3 * rep * 40, 200, 64), integer=(rep == 1))
+        for thr in (0.15, 0.23, 0.7):
+            assert np.array_equal(b2.nms_3d(d, thr), oracle.nms_3d(d, thr)), (n, rep, thr)
+        assert np.array_equal(b2.nms_3d_volume(d, 0.15), oracle.nms_3d_volume(d, 0.15)), (n, rep)
+
+
+def test_nms_ties_and_degenerate(b2):
+    rng = np.random.default_rng(5)
+    from b200seg import synth
+    d = synth.random_dets(rng, 300, extent=(80, 80, 40), integer=True)
+    d[:, 6] = (rng.integers(0, 4, 300) / 4).astype(np.float32)           # heavy score ties: documented tie rule
+    assert np.array_equal(b2.nms_3d(d, 0.23), oracle.nms_3d(d, 0.23))
+    d2 = np.repeat(d[:1], 70, axis=0)                                    # identical boxes and scores
+    assert np.array_equal(b2.nms_3d(d2, 0.5), oracle.nms_3d(d2, 0.5)) and len(b2.nms_3d(d2, 0.5)) == 1
+    d3 = d.copy(); d3[:, 3:6] = d3[:, :3] - 5                            # inverted boxes (negative extents)
+    assert np.array_equal(b2.nms_3d(d3, 0.23), oracle.nms_3d(d3, 0.23))
+    assert b2.nms_3d(np.zeros((0, 7), np.float32), 0.3) == []
+
+
+def test_nms_batched_device_and_rank_order(b2, torch_):
+    from b200seg import synth
+    rng = np.random.default_rng(77)
+    sets = [synth.random_dets(rng, n, extent=(150, 150, 60)) for n in (800, 0, 1, 257, 800, 64)]
+    off = np.zeros(len(sets) + 1, np.int32); off[1:] = np.cumsum([s.shape[0] for s in sets])
+    dets = torch_.from_numpy(np.concatenate(sets)).cuda()
+    keep, cnt, rank = b2.nms_3d_batched(dets, torch_.from_numpy(off).cuda(), 800, 0.23, want_rank_order=True)
+    keep, cnt, rank = keep.cpu().numpy(), cnt.cpu().numpy(), rank.cpu().numpy()
+    for b, s in enumerate(sets):
+        ok = oracle.nms_3d(s, 0.23)
+        assert cnt[b] == len(ok)
+        assert np.array_equal(keep[off[b]:off[b] + cnt[b]], ok)
+        exp_rank = ok[oracle.argsort_desc(s[ok, 6])] if len(ok) else ok
+        assert np.array_equal(rank[off[b]:off[b] + cnt[b]], exp_rank)
+    # tensor seam
+    k2 = b2.nms_3d(torch_.from_numpy(sets[0]).cuda(), 0.23)
+    assert np.array_equal(k2.cpu().numpy(), oracle.nms_3d(sets[0], 0.23))
+
+
+# ------------------------------------------------------------------------------------------ IoU
+def test_iou_golden_and_random(b2, golden, torch_):
+    g = golden("nms_iou.npz")
+    for i in range(4):
+        out = b2.bbox_overlaps_3d(g["iou%d_boxes" % i], g["iou%d_query" % i])
+        assert out.dtype == np.float32
+        assert np.array_equal(out.view(np.uint32), g["iou%d_out" % i].view(np.uint32)), i
+    from b200seg import synth
+    rng = np.random.default_rng(9)
+    for (N, K, integer) in [(1, 1, False), (5, 3, True), (1000, 50, False), (4097, 7, True), (33, 1025, False)]:
+        b = synth.random_dets(rng, N, extent=(120, 120, 50), integer=integer)[:, :6].copy()
+        q = synth.random_dets(rng, K, extent=(120, 120, 50), integer=integer)[:, :6].copy()
+        q[: min(N, K)] = b[: min(N, K)]
+        o = oracle.bbox_overlaps_3d(b, q)
+        assert np.array_equal(b2.bbox_overlaps_3d(b, q).view(np.uint32), o.view(np.uint32)), (N, K)
+        t = b2.bbox_overlaps_3d(torch_.from_numpy(b).cuda(), torch_.from_numpy(q).cuda())
+        assert np.array_equal(t.cpu().numpy().view(np.uint32), o.view(np.uint32))
+    assert b2.bbox_overlaps_3d(np.zeros((0, 6), np.float32), np.zeros((4, 6), np.float32)).shape == (0, 4)
+
+
+def test_iou_anchor_sized_properties(b2, torch_):
+    """BASELINE-sized call (917 504 anchors x 50 gt): sampled rows equal the oracle, result is symmetric."""
+    from b200seg import synth
+    rng = np.random.default_rng(10)
+    N, K = 917504, 50
+    b = synth.random_dets(rng, N, extent=(256, 256, 64), side=(8, 64))[:, :6].copy()
+    q = synth.random_dets(rng, K, extent=(256, 256, 64), side=(10, 40))[:, :6].copy()
+    out = b2.bbox_overlaps_3d(torch_.from_numpy(b).cuda(), torch_.from_numpy(q).cuda())
+    rows = rng.choice(N, 2000, replace=False)
+    assert np.array_equal(out[torch_.from_numpy(rows).cuda()].cpu().numpy().view(np.uint32),
+                          oracle.bbox_overlaps_3d(b[rows], q).view(np.uint32))
+    outT = b2.bbox_overlaps_3d(torch_.from_numpy(q).cuda(), torch_.from_numpy(b[:4096]).cuda())
+    ref = oracle.bbox_overlaps_3d(q, b[:4096])
+    assert np.array_equal(outT.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    assert float(out.max()) <= 1.0 and float(out.min()) >= 0.0
+
+
+# ------------------------------------------------------------------------------------------ Otsu
+def test_otsu_golden(b2, golden):
+    g = golden("otsu.npz")
+    for i in range(int(g["count"])):
+        img, prm = g["otsu%d_img" % i], g["otsu%d_prm" % i]
+        mask, k, b = b2.otsu_py_2d_fast(img, prm)
+        assert (k, b) == (-1, int(g["otsu%d_b" % i])), i
+        assert mask.dtype == np.uint8 and mask.shape == img.shape
+        assert np.array_equal(np.packbits(mask.ravel() > 0), g["otsu%d_mask" % i]), i
+
+
+def _random_crops(rng, n, lo=4, hi=36, u16=True):
+    from b200seg import synth
+    crops = []
+    while len(crops) < n:
+        shape = tuple(int(v) for v in rng.integers(lo, hi, 3))
+        vol, _, blobs = synth.blob_volume(rng, shape, 1, sigma_xy=(shape[1] / 6 + .5, shape[1] / 3 + 1),
+                                          sigma_z=(shape[0] / 6 + .5, shape[0] / 3 + 1), noise=int(rng.integers(5, 60)))
+        prm = synth.prm_crop(blobs[0], (0, 0, 0, shape[2] - 1, shape[1] - 1, shape[0] - 1))
+        if prm.max() == 0:
+            continue
+        crops.append((vol, prm))
+    return crops
+
+
+def test_otsu_batch_vs_oracle_hist_threshold_mask(b2, torch_):
+    rng = np.random.default_rng(2024)
+    raw = _random_crops(rng, 160)
+    imgs, prms = [], []
+    for i, (v, p) in enumerate(raw):
+        if i % 3 == 0:
+            a, b = v.astype(np.uint16), p.astype(np.uint16)
+        else:
+            a, b = oracle.soma_normalise(v, p)
+        if i % 17 == 0:
+            b = np.full_like(b, 123)                    # constant second attribute
+        if i % 23 == 0:
+            a = a * 3 + 1000                            # wider, offset gray range
+        imgs.append(a); prms.append(b)
+    imgs.append(np.full((3, 4, 5), 42, np.uint16)); prms.append(np.full((3, 4, 5), 7, np.uint16))   # constant crop
+    off = np.zeros(len(imgs) + 1, np.int64); off[1:] = np.cumsum([a.size for a in imgs])
+    I = torch_.from_numpy(np.concatenate([a.ravel() for a in imgs])).cuda()
+    P = torch_.from_numpy(np.concatenate([a.ravel() for a in prms])).cuda()
+    out = b2.otsu_2d_batch(I, P, torch_.from_numpy(off).cuda(), want_hist=True)
+    mask, bmax, status = out["mask"].cpu().numpy(), out["b_max"].cpu().numpy(), out["status"].cpu().numpy()
+    for i, (a, p) in enumerate(zip(imgs, prms)):
+        try:
+            om, _, ob, oh = oracle.otsu_py_2d_fast(a, p, want_hist=True)
+        except UnboundLocalError:
+            assert status[i] == 1 and (mask[off[i]:off[i + 1]] == 255).all(), i
+            continue
+        assert status[i] == 0 and bmax[i] == ob, (i, bmax[i], ob)
+        assert np.array_equal(mask[off[i]:off[i + 1]].reshape(a.shape), om), i
+        assert np.array_equal(out["hist"][i].astype(np.int64), oh.astype(np.int64)), i
+    assert status[-1] == 1
+    with pytest.raises(UnboundLocalError):
+        b2.otsu_py_2d_fast(imgs[-1], prms[-1])
+
+
+def test_soma_binarize_vs_oracle(b2, torch_):
+    from b200seg import synth
+    case = synth.postproc_case(31, shape=(40, 128, 160), n_blobs=20, n_dup=5, n_false=5)
+    case["prm"][case["crop_off"][3]:case["crop_off"][4]] = 0                 # instance with empty PRM (skipped)
+    vol = torch_.from_numpy(case["volume"]).cuda()
+    mask, bmax, status = b2.soma_binarize(vol, torch_.from_numpy(case["boxes"]).cuda(), torch_.from_numpy(case["prm"]).cuda(),
+                                          torch_.from_numpy(case["crop_off"]).cuda())
+    mask, bmax, status = mask.cpu().numpy(), bmax.cpu().numpy(), status.cpu().numpy()
+    off = case["crop_off"]
+    for i, b in enumerate(case["boxes"]):
+        img = case["volume"][b[2]:b[5] + 1, b[1]:b[4] + 1, b[0]:b[3] + 1]
+        p = case["prm"][off[i]:off[i + 1]].reshape(img.shape)
+        if p.max() == 0:
+            assert status[i] == 3 and not mask[off[i]:off[i + 1]].any()
+            continue
+        i16, p16 = oracle.soma_normalise(img, p)
+        try:
+            om, _, ob = oracle.otsu_py_2d_fast(i16, p16)
+        except UnboundLocalError:
+            assert status[i] == 1
+            continue
+        assert status[i] == 0 and bmax[i] == ob, i
+        assert np.array_equal(mask[off[i]:off[i + 1]].reshape(img.shape), om), i
+
+
+# ------------------------------------------------------------------------------------------ paste + chain
+def test_paste_vs_oracle_overlapping(b2, torch_):
+    rng = np.random.default_rng(3)
+    S, H, W = 20, 50, 77                                                     # W not a multiple of 8: scalar store path
+    n = 120                                                                  # > PASTE_MAXL in one tile: overflow path
+    boxes = np.zeros((n, 6), np.int32)
+    masks = []
+    for i in range(n):
+        sz, sy, sx = rng.integers(1, 12), rng.integers(1, 30), rng.integers(1, 40)
+        z1, y1, x1 = rng.integers(0, S - sz + 1), rng.integers(0, H - sy + 1), rng.integers(0, W - sx + 1)
+        boxes[i] = [x1, y1, z1, x1 + sx - 1, y1 + sy - 1, z1 + sz - 1]
+        masks.append((rng.random((sz, sy, sx)) < 0.6).astype(np.uint8) * 255)
+    ids = np.arange(1, n + 1, dtype=np.uint16)
+    off = np.zeros(n + 1, np.int64); off[1:] = np.cumsum([m.size for m in masks])
+    seg_o = np.zeros((S, H, W), np.uint16)
+    surv_o = oracle.paste_labels(seg_o, boxes, ids, masks)
+    seg = torch_.full((S, H, W), 999, dtype=torch_.uint16, device="cuda")   # no pre-clear needed
+    surv = b2.paste_labels(seg, torch_.from_numpy(boxes).cuda(), torch_.from_numpy(ids).cuda(),
+                           torch_.from_numpy(np.concatenate([m.ravel() for m in masks])).cuda(), torch_.from_numpy(off).cuda())
+    assert np.array_equal(seg.cpu().numpy(), seg_o)
+    assert np.array_equal(surv.cpu().numpy().astype(bool), surv_o)
+
+
+@pytest.mark.parametrize("seed,shape,nb", [(1001, (64, 256, 256), 35), (7, (33, 100, 130), 12)])
+def test_postproc_chain_host_vs_oracle(b2, seed, shape, nb):
+    """BASELINE config 1: one 64x256x256 uint8 volume, exactly 50 boxes, NMS 0.23 + per-instance Otsu + paste."""
+    from b200seg import synth
+    case = synth.postproc_case(seed, shape=shape, n_blobs=nb)
+    out = b2.postproc_soma_host(case["volume"], case["dets"], case["boxes"], case["prm"], case["crop_off"], 0.23)
+    ref = oracle_chain(case, 0.23)
+    assert out["n_keep"] == len(ref["order"]) and np.array_equal(out["rank_order"], ref["order"])
+    for i, st in ref["status"].items():
+        assert out["status"][i] == st, i
+    for i, bm in ref["b_max"].items():
+        assert out["b_max"][i] == bm, i
+    assert np.array_equal(out["seg"], ref["seg"])
+    assert np.array_equal(out["survive"], ref["survive"])
+    assert (out["status"][np.setdiff1d(np.arange(len(case["dets"])), ref["order"])] == -1).all()
+
+
+def test_postproc_batched_device_and_fullsize_properties(b2, torch_):
+    """Two 128x512x512 volumes (BASELINE config 3/5 size) through the device chain:
+    volume 0 is checked voxel-exact against the oracle, both against size-independent properties."""
+    from b200seg import synth
+    shape = (128, 512, 512)
+    cases = [synth.postproc_case(2000 + i, shape=shape, n_blobs=60, n_dup=20, n_false=10) for i in range(2)]
+    counts = [c["dets"].shape[0] for c in cases]
+    prm = np.concatenate([c["prm"] for c in cases])
+    offs, base = [], 0
+    for c in cases:
+        offs.append(c["crop_off"][:-1] + base); base += c["crop_off"][-1]
+    crop_off = np.concatenate(offs + [np.array([base], np.int64)])
+    pp = b2.SomaPostproc(2, shape, counts, prm.size)
+    vols = torch_.from_numpy(np.stack([c["volume"] for c in cases])).cuda()
+    seg = pp.run(vols, torch_.from_numpy(np.concatenate([c["dets"] for c in cases])).cuda(),
+                 torch_.from_numpy(np.concatenate([c["boxes"] for c in cases])).cuda(),
+                 torch_.from_numpy(prm).cuda(), torch_.from_numpy(crop_off).cuda(), 0.23)
+    torch_.cuda.synchronize()
+    seg = seg.cpu().numpy()
+    cnt = pp.keep_count.cpu().numpy()
+    ref0 = oracle_chain(cases[0], 0.23)
+    assert cnt[0] == len(ref0["order"]) and np.array_equal(seg[0], ref0["seg"])
+    for v in range(2):
+        labels = np.unique(seg[v])
+        surv = pp.survive.cpu().numpy()[pp.det_off_host[v]:pp.det_off_host[v] + cnt[v]].astype(bool)
+        assert np.array_equal(labels[labels > 0], np.nonzero(surv)[0] + 1)      # survivors == labels present
+        order = pp.rank_order.cpu().numpy()[pp.det_off_host[v]:pp.det_off_host[v] + cnt[v]]
+        for lab in labels[labels > 0][:10]:                                     # every label lies inside its own box
+            b = cases[v]["boxes"][order[lab - 1]]
+            zz, yy, xx = np.nonzero(seg[v] == lab)
+            assert zz.min() >= b[2] and zz.max() <= b[5] and yy.min() >= b[1] and yy.max() <= b[4] and xx.min() >= b[0] and xx.max() <= b[3]
+    # idempotence: running the chain again gives the same volume
+    seg2 = pp.run(vols, torch_.from_numpy(np.concatenate([c["dets"] for c in cases])).cuda(),
+                  torch_.from_numpy(np.concatenate([c["boxes"] for c in cases])).cuda(),
+                  torch_.from_numpy(prm).cuda(), torch_.from_numpy(crop_off).cuda(), 0.23).cpu().numpy()
+    assert np.array_equal(seg, seg2)
+
+
+# ------------------------------------------------------------------------------------------ peaks
+def test_peaks_golden(b2, golden, torch_):
+    from b200seg.peak_stimulation_3d import peak_stimulation_3d, median_filter
+    g = golden("peaks.npz")
+    for i in range(int(g["count"])):
+        x, win = torch_.from_numpy(g["pk%d_in" % i]).cuda(), int(g["pk%d_win" % i])
+        pl, agg = peak_stimulation_3d(x, win_size=win, peak_filter=median_filter)
+        assert pl.dtype == torch_.int64 and np.array_equal(pl.cpu().numpy(), g["pk%d_peaks_med" % i]), i
+        np.testing.assert_allclose(agg.cpu().numpy(), g["pk%d_agg_med" % i], rtol=1e-5, atol=1e-6, equal_nan=True)
+        pl0, agg0 = peak_stimulation_3d(x, win_size=win, peak_filter=None)
+        assert np.array_equal(pl0.cpu().numpy(), g["pk%d_peaks_none" % i]), i
+        np.testing.assert_allclose(agg0.cpu().numpy(), g["pk%d_agg_none" % i], rtol=1e-5, atol=1e-6, equal_nan=True)
+        only = peak_stimulation_3d(x, return_aggregation=False, win_size=win, peak_filter="median")
+        assert np.array_equal(only.cpu().numpy(), g["pk%d_peaks_med" % i])
+
+
+def test_peaks_vs_oracle_random_edge_cases(b2, torch_):
+    from b200seg.peak_stimulation_3d import peaks_forward, peak_stimulation_3d
+    rng = np.random.default_rng(11)
+    for t in range(24):
+        B, A = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        S, H, W = [int(v) for v in rng.integers(1, 40, 3)]
+        x = rng.normal(size=(B, A, S, H, W)).astype(np.float32)
+        if t % 4 == 1:
+            x = np.round(x * 2) / 2                                    # plateaus / ties
+        if t % 4 == 2:
+            x[...] = 0.125                                             # constant map: only the first voxel... none
+        if t % 6 == 3:
+            x.flat[rng.integers(0, x.size, 3)] = -np.inf
+        if t % 6 == 5:
+            x.flat[rng.integers(0, x.size, 2)] = np.nan                # NaN: median becomes NaN -> no peaks
+        if t % 5 == 0:
+            x[x < 0] = -0.0                                            # signed zeros
+        win = int(rng.choice([3, 3, 5, 7]))
+        for mode, name in ((0, None), (1, "median")):
+            p, agg, thr = peaks_forward(torch_.from_numpy(x).cuda(), win, mode)
+            op, oagg, othr = oracle.peak_stimulation_3d(x, win_size=win, filter_mode=name)
+            assert np.array_equal(p.cpu().numpy(), op), (t, mode, x.shape, win)
+            np.testing.assert_allclose(agg.cpu().numpy(), oagg, rtol=1e-5, atol=1e-6, equal_nan=True)
+            if mode == 1:
+                assert np.array_equal(thr.cpu().numpy(), othr, equal_nan=True), (t, thr, othr)
+        # arbitrary callable filter (mean), constant filter
+        xt = torch_.from_numpy(x).cuda()
+        if not np.isnan(x).any() and not np.isinf(x).any():
+            mean = lambda inp: inp.view(inp.size(0), inp.size(1), -1).mean(2).view(inp.size(0), inp.size(1), 1, 1, 1)
+            pl, _ = peak_stimulation_3d(xt, win_size=win, peak_filter=mean)
+            thr_np = mean(xt).reshape(B, A).cpu().numpy()
+            op = oracle.peak_stimulation_3d(x, win_size=win, filter_mode="given", thresholds=thr_np, return_aggregation=False)
+            assert np.array_equal(pl.cpu().numpy(), op)
+
+
+def test_peaks_config3_size_and_backward(b2, torch_):
+    """(1,14,32,128,128) fp32 response map (BASELINE config 3 @stride 4): exact peaks vs oracle; backward."""
+    from b200seg import synth
+    from b200seg.peak_stimulation_3d import peak_stimulation_3d
+    rng = np.random.default_rng(1003)
+    x = synth.response_map(rng, (32, 128, 128), n_peaks=60, channels=14)
+    xt = torch_.from_numpy(x).cuda().requires_grad_(True)
+    pl, agg = peak_stimulation_3d(xt, win_size=3, peak_filter="median")
+    op, oagg, _ = oracle.peak_stimulation_3d(x, win_size=3, filter_mode="median")
+    assert np.array_equal(pl.cpu().numpy(), op)
+    np.testing.assert_allclose(agg.detach().cpu().numpy(), oagg, rtol=1e-5, atol=1e-6)
+    w = torch_.arange(1, 15, dtype=torch_.float32, device="cuda").view(1, 14)
+    (agg * w).sum().backward()
+    gi = xt.grad.cpu().numpy()
+    ref = np.zeros_like(x)
+    ref[op[:, 0], op[:, 1], op[:, 2], op[:, 3], op[:, 4]] = (op[:, 1] + 1).astype(np.float32)    # peak_map * grad (:43-48)
+    assert np.array_equal(gi, ref)
+
+
+# ------------------------------------------------------------------------------------------ RoIAlign3D
+def _ref_cuda_roialign(torch_, feat, rois, P, scale, sr, grad=None):
+    """The reference's own CUDA kernels (oracle/_ref/libref_roialign3d.so), called through ctypes."""
+    L = oracle.ref_roialign_lib()
+    if L is None:
+        return None
+    f = torch_.from_numpy(feat).cuda(); r = torch_.from_numpy(rois).cuda()
+    B, C, S, H, W = feat.shape
+    R = rois.shape[0]
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    out = torch_.zeros((R, C, P, P, P), dtype=torch_.float32, device="cuda")
+    L.ROIAlignForwardLaucher_3d.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.ROIAlignForwardLaucher_3d(vp(f.data_ptr()), cf(scale), R, S, H, W, C, P, P, P, sr, vp(r.data_ptr()), vp(out.data_ptr()),
+                                vp(torch_.cuda.current_stream().cuda_stream))
+    gi = None
+    if grad is not None:
+        g = torch_.from_numpy(grad).cuda()
+        gi = torch_.zeros((B, C, S, H, W), dtype=torch_.float32, device="cuda")
+        L.ROIAlignBackwardLaucher_3d.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+        L.ROIAlignBackwardLaucher_3d(vp(g.data_ptr()), cf(scale), B, R, S, H, W, C, P, P, P, sr, vp(r.data_ptr()), vp(gi.data_ptr()),
+                                     vp(torch_.cuda.current_stream().cuda_stream))
+    torch_.cuda.synchronize()
+    return out.cpu().numpy(), (gi.cpu().numpy() if gi is not None else None)
+
+
+def _close(a, b, rel=1e-5):
+    """|a-b| <= rel * max(|b|, typical magnitude): 1e-5 relative in fp32, robust to cancellation to ~0."""
+    scale = max(float(np.abs(b).mean()), 1e-6)
+    err = np.abs(a - b) / np.maximum(np.abs(b), scale)
+    return float(err.max()) <= rel, float(err.max())
+
+
+@pytest.mark.parametrize("shape,R,scale,P,sr,side", [
+    ((2, 16, 8, 32, 32), 64, 0.125, 7, 2, (10, 50)),       # nuclei-like (config 4 geometry)
+    ((1, 8, 16, 40, 40), 40, 0.25, 7, 2, (10, 60)),        # soma tile
+    ((2, 5, 6, 9, 11), 30, 0.25, 7, 2, (2, 60)),           # odd sizes, RoIs larger than the map
+    ((1, 4, 8, 25, 25), 20, 0.125, 14, 2, (20, 120)),      # mask head P=14
+    ((1, 3, 16, 40, 40), 12, 0.25, 7, 0, (10, 160)),       # adaptive sampling (sr=0), large footprints
+    ((1, 2, 20, 64, 64), 6, 1.0, 7, 2, (30, 64)),          # footprint > 16 voxels: direct path
+    ((1, 33, 4, 8, 8), 9, 0.5, 3, 1, (2, 12)),             # P=3, sr=1, channel tail
+])
+def test_roialign_fwd_bwd_vs_oracle(b2, torch_, shape, R, scale, P, sr, side):
+    from b200seg import synth
+    from b200seg.roi_align_3d import RoIAlignFunction_3d
+    feat, rois = synth.roialign_case(hash((shape, R)) % 1000, feat_shape=shape, n_rois=R, scale=scale, side=side, frac_outside=0.1)
+    rois[0, 1:] = [-50, -50, -50, -40, -40, -40]                      # completely outside
+    rois[1, 4:] = rois[1, 1:4] - 3                                    # malformed (end < start): forced to 1x1x1
+    f = torch_.from_numpy(feat).cuda().requires_grad_(True)
+    y = RoIAlignFunction_3d(P, P, P, scale, sr)(f, torch_.from_numpy(rois).cuda())
+    ref = oracle.roialign3d_fwd(feat, rois, P, scale, sr)
+    ok, err = _close(y.detach().cpu().numpy(), ref)
+    assert ok, ("fwd", err)
+    g = np.random.default_rng(1).standard_normal(ref.shape).astype(np.float32)
+    y.backward(torch_.from_numpy(g).cuda())
+    refg = oracle.roialign3d_bwd(g, rois, feat.shape, scale, sr)
+    ok, err = _close(f.grad.cpu().numpy(), refg)
+    assert ok, ("bwd", err)
+    # determinism of the atomics-free backward: bit-identical on a second run
+    f2 = torch_.from_numpy(feat).cuda().requires_grad_(True)
+    RoIAlignFunction_3d(P, P, P, scale, sr)(f2, torch_.from_numpy(rois).cuda()).backward(torch_.from_numpy(g).cuda())
+    assert torch_.equal(f.grad, f2.grad)
+
+
+def test_roialign_vs_reference_cuda_kernels(b2, torch_):
+    """Same inputs through the reference's own .cu (compiled unmodified for sm_100a)."""
+    from b200seg import synth
+    from b200seg.roi_align_3d import roialign3d_forward, roialign3d_backward
+    feat, rois = synth.roialign_case(1004, feat_shape=(2, 32, 8, 32, 32), n_rois=128, scale=0.125)
+    g = np.random.default_rng(2).standard_normal((128, 32, 7, 7, 7)).astype(np.float32)
+    got = _ref_cuda_roialign(torch_, feat, rois, 7, 0.125, 2, grad=g)
+    if got is None:
+        pytest.skip("oracle/_ref/libref_roialign3d.so not built")
+    ref_out, ref_gi = got
+    r = torch_.from_numpy(rois).cuda()
+    y = roialign3d_forward(torch_.from_numpy(feat).cuda(), r, 7, 7, 7, 0.125, 2)
+    ok, err = _close(y.cpu().numpy(), ref_out)
+    assert ok, err
+    gi = roialign3d_backward(torch_.from_numpy(g).cuda(), r, feat.shape, 0.125, 2)
+    ok, err = _close(gi.cpu().numpy(), ref_gi, rel=5e-5)          # the reference sums with atomics (order varies)
+    assert ok, err
+    # and the oracle agrees with the reference kernels too (pins the RoIAlign restatement)
+    ok, err = _close(oracle.roialign3d_fwd(feat, rois, 7, 0.125, 2), ref_out)
+    assert ok, err
+
+
+def test_roialign_layout_shw_is_adjoint_and_bf16(b2, torch_):
+    from b200seg import synth
+    from b200seg.roi_align_3d import RoIAlignFunction_3d, roialign3d_forward
+    feat, rois = synth.roialign_case(5, feat_shape=(1, 6, 6, 12, 12), n_rois=10, scale=0.25, side=(8, 30), frac_outside=0.0)
+    f = torch_.from_numpy(feat).cuda()
+    r = torch_.from_numpy(rois).cuda()
+    ref = roialign3d_forward(f, r, 7, 7, 7, 0.25, 2, layout=0)
+    shw = roialign3d_forward(f, r, 7, 7, 7, 0.25, 2, layout=1)
+    assert torch_.equal(shw, ref.permute(0, 1, 4, 2, 3).contiguous())      # (H,W,S) storage vs (S,H,W)
+    # <A x, g> == <x, A^T g> for the self-consistent layout
+    fx = f.clone().double().float().requires_grad_(True)
+    y = RoIAlignFunction_3d(7, 7, 7, 0.25, 2, layout="shw")(fx, r)
+    g = torch_.randn_like(y)
+    y.backward(g)
+    lhs = float((y.detach().double() * g.double()).sum()); rhs = float((fx.grad.double() * f.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+    # bf16 features: fp32 accumulation, result rounded once to bf16
+    yb = roialign3d_forward(f.bfloat16(), r, 7, 7, 7, 0.25, 2)
+    want = roialign3d_forward(f.bfloat16().float(), r, 7, 7, 7, 0.25, 2).bfloat16()
+    assert yb.dtype == torch_.bfloat16 and torch_.equal(yb, want)
+
+
+def test_roialign_config4_full_size(b2, torch_):
+    """BASELINE config 4: 512 RoIs x 256 ch x 7^3 on (2,256,8,32,32): sampled RoIs vs the oracle, full
+    tensor vs the reference CUDA kernel when available, backward linearity."""
+    from b200seg import synth
+    from b200seg.roi_align_3d import roialign3d_forward, roialign3d_backward
+    feat, rois = synth.roialign_case(1004)
+    f, r = torch_.from_numpy(feat).cuda(), torch_.from_numpy(rois).cuda()
+    y = roialign3d_forward(f, r, 7, 7, 7, 0.125, 2)
+    sel = np.arange(0, 512, 37)
+    ok, err = _close(y[torch_.from_numpy(sel).cuda()].cpu().numpy(), oracle.roialign3d_fwd(feat, rois[sel], 7, 0.125, 2))
+    assert ok, err
+    got = _ref_cuda_roialign(torch_, feat, rois, 7, 0.125, 2)
+    if got is not None:
+        ok, err = _close(y.cpu().numpy(), got[0])
+        assert ok, err
+    g1, g2 = torch_.randn_like(y), torch_.randn_like(y)
+    a = roialign3d_backward(g1, r, feat.shape, 0.125, 2); b = roialign3d_backward(g2, r, feat.shape, 0.125, 2)
+    c = roialign3d_backward(g1 + g2, r, feat.shape, 0.125, 2)
+    assert float((a + b - c).abs().max()) <= 1e-4 * float(c.abs().max())

@@ -1,0 +1,114 @@
+"""CPU: the oracle (oracle/oracle.c) against golden vectors produced by the reference's own code
+(tests/golden/make_golden.py) and, when present, against the reference Cython built in oracle/_ref."""
+import numpy as np
+import pytest
+
+import oracle
+from b200seg import synth
+
+
+def test_nms_golden(golden):
+    g = golden("nms_iou.npz")
+    ids = sorted({int(k[3:].split("_")[0]) for k in g.files if k.startswith("nms")})
+    assert len(ids) >= 8
+    for i in ids:
+        d, thr = g["nms%d_dets" % i], float(g["nms%d_thr" % i])
+        assert np.array_equal(oracle.nms_3d(d, thr), g["nms%d_keep" % i]), i
+        if "nms%d_keepvol" % i in g.files:
+            assert np.array_equal(oracle.nms_3d_volume(d, thr), g["nms%d_keepvol" % i]), i
+
+
+def test_iou_golden(golden):
+    g = golden("nms_iou.npz")
+    for i in range(4):
+        out = oracle.bbox_overlaps_3d(g["iou%d_boxes" % i], g["iou%d_query" % i])
+        assert np.array_equal(out.view(np.uint32), g["iou%d_out" % i].view(np.uint32)), i
+    # the reference's self-overlap is 0.9999999, not 1.0 (mixed precision); golden case 1 has identical boxes
+    assert g["iou1_out"][0, 0] < 1.0
+
+
+def test_otsu_golden(golden):
+    g = golden("otsu.npz")
+    n = int(g["count"])
+    assert n >= 10
+    for i in range(n):
+        img, prm = g["otsu%d_img" % i], g["otsu%d_prm" % i]
+        mask, k, b, hist = oracle.otsu_py_2d_fast(img, prm, want_hist=True)
+        assert k == int(g["otsu%d_k" % i]) == -1
+        assert b == int(g["otsu%d_b" % i]), i
+        assert np.array_equal(np.packbits(mask.ravel() > 0), g["otsu%d_mask" % i]), i
+        assert np.array_equal(hist.astype(np.uint32), g["otsu%d_hist" % i]), i
+        assert set(np.unique(mask)) <= {0, 255}
+
+
+def test_otsu_constant_crop_raises():
+    img = np.full((4, 5, 6), 100, np.uint16)
+    with pytest.raises(UnboundLocalError):       # the reference fails on k_max (otsu.py:277)
+        oracle.otsu_py_2d_fast(img, img)
+
+
+def test_peaks_golden(golden):
+    g = golden("peaks.npz")
+    for i in range(int(g["count"])):
+        x, win = g["pk%d_in" % i], int(g["pk%d_win" % i])
+        p, agg, _ = oracle.peak_stimulation_3d(x, win_size=win, filter_mode="median")
+        assert np.array_equal(p, g["pk%d_peaks_med" % i]), i
+        np.testing.assert_allclose(agg, g["pk%d_agg_med" % i], rtol=1e-5, atol=1e-6, equal_nan=True)
+        p0, agg0, _ = oracle.peak_stimulation_3d(x, win_size=win, filter_mode=None)
+        assert np.array_equal(p0, g["pk%d_peaks_none" % i]), i
+        np.testing.assert_allclose(agg0, g["pk%d_agg_none" % i], rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_oracle_vs_reference_cython_random():
+    """Extra pinning where the reference build is available (authoring container + GPU box)."""
+    nms = oracle.ref_module("cython_nms_3d")
+    bb = oracle.ref_module("cython_bbox_3d")
+    if nms is None or bb is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    for t in range(60):
+        n = int(rng.choice([1, 3, 50, 200, 600]))
+        d = synth.random_dets(rng, n, extent=(150, 150, 60), integer=(t % 3 == 0))
+        thr = np.float32(rng.choice([0.15, 0.23, 0.5]))
+        assert np.array_equal(nms.nms_3d(d, thr), oracle.nms_3d(d, thr))
+        q = synth.random_dets(rng, int(rng.integers(1, 40)), extent=(150, 150, 60), integer=(t % 2 == 0))[:, :6].copy()
+        a, o = bb.bbox_overlaps_3d(d[:, :6].copy(), q), oracle.bbox_overlaps_3d(d[:, :6], q)
+        assert np.array_equal(a.view(np.uint32), o.view(np.uint32))
+
+
+def test_paste_first_come_wins():
+    seg = np.zeros((4, 6, 8), np.uint16)
+    boxes = np.array([[1, 1, 0, 4, 3, 2], [3, 2, 1, 6, 5, 3]], np.int32)
+    m0 = np.ones((3, 3, 4), np.uint8)
+    m1 = np.ones((3, 4, 4), np.uint8); m1[0, 0, 0] = 0
+    surv = oracle.paste_labels(seg, boxes, np.array([1, 2], np.uint16), [m0, m1])
+    # numpy restatement of binarization_soma.py:100-102
+    ref = np.zeros_like(seg)
+    for i, (b, m) in enumerate(zip(boxes, [m0, m1])):
+        sub = ref[b[2]:b[5] + 1, b[1]:b[4] + 1, b[0]:b[3] + 1]
+        z = sub == 0
+        sub[z] = (m.astype(np.uint16) * (i + 1))[z]
+    assert np.array_equal(seg, ref)
+    assert surv.tolist() == [True, True]
+    # an instance completely covered by an earlier one does not survive
+    seg2 = np.zeros((2, 2, 2), np.uint16)
+    bx = np.array([[0, 0, 0, 1, 1, 1], [0, 0, 0, 0, 0, 0]], np.int32)
+    s2 = oracle.paste_labels(seg2, bx, np.array([1, 2], np.uint16), [np.ones((2, 2, 2), np.uint8), np.ones((1, 1, 1), np.uint8)])
+    assert s2.tolist() == [True, False] and (seg2 == 1).all()
+
+
+def test_roialign_oracle_properties():
+    """No CPU reference exists for RoIAlign3D; check invariants of the restatement:
+    constant features -> constant output inside the volume; layout quirk (H,W,S)."""
+    feat = np.full((1, 2, 6, 7, 8), 3.5, np.float32)
+    rois = np.array([[0, 4, 4, 4, 20, 20, 16]], np.float32)
+    out = oracle.roialign3d_fwd(feat, rois, 7, 0.25, 2)
+    np.testing.assert_allclose(out, 3.5, rtol=1e-6)
+    # a feature map that varies only along z: output must vary along the LAST output axis (ps fastest)
+    f2 = np.broadcast_to(np.arange(6, dtype=np.float32)[None, None, :, None, None], (1, 1, 6, 7, 8)).copy()
+    o2 = oracle.roialign3d_fwd(f2, rois, 7, 0.25, 2)[0, 0]
+    assert np.allclose(o2, o2[:1, :1, :]) and not np.allclose(o2[0, 0, 0], o2[0, 0, -1])
+    # backward of ones sums to (#bins fully inside) per channel: sum of all tap weights / count = 1 per bin
+    g = np.ones((1, 1, 7, 7, 7), np.float32)
+    gi = oracle.roialign3d_bwd(g, rois, (1, 1, 6, 7, 8), 0.25, 2)
+    np.testing.assert_allclose(gi.sum(), 343.0, rtol=1e-5)
