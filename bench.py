@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the b200seg hot path (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" = one pass of the post-processing chain (tools/binarization_soma.py:57-104: 3D NMS ->
+visit order -> per-instance crop/normalise/2D-Otsu -> label paste-back) over one batch of
+synthetic 128x512x512 uint8 volumes (BASELINE.json configs[2]/[4]; ~200 blob instances and ~800
+candidate detections per volume).  Each rank owns `--volumes-per-rank` volumes (8 by default, so
+8 GPUs process the 64-volume batch of configs[4]); scaling is weak, no data-path collective except
+the all-gather of the surviving detections at the end of each step (N > 1).
+
+One JSON line is printed by rank 0:
+  value          Gvox/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            same metric through the host-buffer C-ABI call (pinned host memory in, H2D + D2H
+                 inside the timed region)
+  roofline       dominant kernel: algorithmic bytes per launch / measured launch time vs the
+                 measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline   the oracle port of the reference chain on the host cores (bounded sample)
+  ops            per-operator numbers: RoIAlign3D fwd/bwd RoIs/s (config 4), peak stimulation,
+                 IoU matrix, NMS -- each with its own roofline fraction
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (128, 512, 512)
+NMS_THRESH = 0.23
+CASE_KW = dict(shape=SHAPE, n_blobs=200, n_dup=400, n_false=200, sigma_xy=(5, 11), sigma_z=(3, 6))
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_case(seed):
+    from b200seg import synth
+    return synth.postproc_case(seed, **CASE_KW)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the chain (oracle port), all host cores
+# ------------------------------------------------------------------------------------------------
+_CASES = {}
+
+
+def _ref_worker(seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_chain
+    if seed not in _CASES:
+        _CASES[seed] = make_case(seed)
+    t = time.perf_counter()
+    r = oracle_chain(_CASES[seed], NMS_THRESH)
+    return time.perf_counter() - t, int(len(r["order"]))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = max(1, min(args.volumes_per_rank, cores))
+    seeds = [2000 + i for i in range(per_step)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(per_step) as pool:
+        pool.map(_ref_worker, seeds)                      # builds the cases inside the workers + 1 warm run
+        for _ in range(max(0, args.warmup - 1)):
+            pool.map(_ref_worker, seeds)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, seeds)
+        dt = time.perf_counter() - t0
+    vox = per_step * np.prod(SHAPE) * args.steps
+    val = vox / dt / 1e9
+    line = {"impl": "reference", "metric": "postproc_gvox_per_s", "value": val, "unit": "Gvox/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world, per_step),
+            "cpu_baseline": {"value": val, "unit": "Gvox/s", "cores": per_step, "kind": "port",
+                             "sample": "%d volumes of 128x512x512 per step, one per worker process (oracle C port of "
+                                       "cython NMS + otsu_py_2d_fast + numpy paste), host has %d cores" % (per_step, cores)},
+            "e2e": {"value": val, "unit": "Gvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, world, vpr):
+    return {"workload": "postproc_soma_chain: 3D NMS(0.23) + per-instance 2D-Otsu + label paste-back on synthetic uint8 "
+                        "128x512x512 volumes, ~200 blobs, 800 candidate detections each (BASELINE configs[2]/[4])",
+            "volumes_per_rank": vpr, "global_volumes_per_step": vpr * world, "volume_shape": list(SHAPE),
+            "dets_per_volume": CASE_KW["n_blobs"] + CASE_KW["n_dup"] + CASE_KW["n_false"], "nms_thresh": NMS_THRESH,
+            "l2": "per-step inputs+outputs (%.0f MB per rank) exceed the 126 MB L2; no explicit flush in the chain loop, "
+                  "explicit 256 MB flush between iterations of the per-operator timings" % (vpr * 3 * np.prod(SHAPE) / 1e6),
+            "parallelism": "volumes sharded by rank (np.array_split), dp%d" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_op(torch, fn, iters, flush):
+    """CUDA-event time of fn() per call, L2 flushed (256 MB write) before each timed call."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def bench_ops(torch, peak):
+    """Per-operator timings on the BASELINE shapes (rank-local)."""
+    import b200seg
+    from b200seg import synth
+    from b200seg.roi_align_3d import roialign3d_forward, roialign3d_backward
+    from b200seg.peak_stimulation_3d import peaks_forward
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ops = {}
+
+    def entry(ms, bytes_alg, extra):
+        gbs = bytes_alg / (ms * 1e-3) / 1e9
+        d = {"ms": ms, "alg_bytes": bytes_alg, "achieved_gbs": gbs, "roofline_frac": gbs / peak}
+        d.update(extra)
+        return d
+
+    # RoIAlign3D, config 4: 512 RoIs x 256 ch x 7^3 on (2,256,8,32,32), scale 1/8, sr 2
+    feat, rois = synth.roialign_case(1004)
+    f, r = torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev)
+    R, C, P = rois.shape[0], feat.shape[1], 7
+    out_b, feat_b = R * C * P ** 3 * 4, feat.size * 4
+    ms = time_op(torch, lambda: roialign3d_forward(f, r, P, P, P, 0.125, 2), 20, flush)
+    ops["roialign3d_fwd_f32"] = entry(ms, out_b + feat_b + 28 * R, {"rois_per_s": R / (ms * 1e-3)})
+    g = torch.randn((R, C, P, P, P), device=dev)
+    ms = time_op(torch, lambda: roialign3d_backward(g, r, feat.shape, 0.125, 2), 20, flush)
+    ops["roialign3d_bwd_f32"] = entry(ms, out_b + feat_b + 28 * R, {"rois_per_s": R / (ms * 1e-3)})
+    fb = f.bfloat16()
+    ms = time_op(torch, lambda: roialign3d_forward(fb, r, P, P, P, 0.125, 2), 20, flush)
+    ops["roialign3d_fwd_bf16"] = entry(ms, (out_b + feat_b) // 2 + 28 * R, {"rois_per_s": R / (ms * 1e-3)})
+    # peak stimulation, config 3: fp32 (1,14,32,128,128), win 3, median filter
+    x = torch.from_numpy(synth.response_map(np.random.default_rng(1003), (32, 128, 128), n_peaks=60, channels=14)).to(dev)
+    ms = time_op(torch, lambda: peaks_forward(x, 3, 1), 10, flush)
+    ops["peaks3d_f32_14x32x128x128"] = entry(ms, 8 * x.numel(), {"gvox_per_s": x.numel() / (ms * 1e-3) / 1e9,
+                                                                  "note": "includes the D2H read of the peak count"})
+    # IoU matrix: anchors x gt (917504 x 50)
+    rng = np.random.default_rng(10)
+    bx = torch.from_numpy(synth.random_dets(rng, 917504, extent=(256, 256, 64), side=(8, 64))[:, :6].copy()).to(dev)
+    q = torch.from_numpy(synth.random_dets(rng, 50, extent=(256, 256, 64), side=(10, 40))[:, :6].copy()).to(dev)
+    ms = time_op(torch, lambda: b200seg.bbox_overlaps_3d(bx, q), 20, flush)
+    ops["iou3d_917504x50"] = entry(ms, 24 * (917504 + 50) + 4 * 917504 * 50, {"pairs_per_s": 917504 * 50 / (ms * 1e-3)})
+    # NMS (latency bound: report microseconds)
+    for n in (50, 1000):
+        d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)
+        off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        ms = time_op(torch, lambda: b200seg.nms_3d_batched(d, off, n, NMS_THRESH), 20, flush)
+        ops["nms3d_n%d" % n] = {"us": ms * 1e3, "pairs_per_s": n * (n - 1) / 2 / (ms * 1e-3), "note": "latency bound, 3 launches"}
+    return ops
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import b200seg
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peak, peak_src = hbm_peak()
+    vpr = args.volumes_per_rank
+    V = int(np.prod(SHAPE))
+
+    cases = [make_case(2000 + rank * vpr + i) for i in range(vpr)]
+    counts = [c["dets"].shape[0] for c in cases]
+    prm_np = np.concatenate([c["prm"] for c in cases])
+    offs, base = [], 0
+    for c in cases:
+        offs.append(c["crop_off"][:-1] + base); base += int(c["crop_off"][-1])
+    crop_off_np = np.concatenate(offs + [np.array([base], np.int64)])
+    vols = torch.from_numpy(np.stack([c["volume"] for c in cases])).to(dev)
+    dets = torch.from_numpy(np.concatenate([c["dets"] for c in cases])).to(dev)
+    boxes = torch.from_numpy(np.concatenate([c["boxes"] for c in cases])).to(dev)
+    prm = torch.from_numpy(prm_np).to(dev)
+    crop_off = torch.from_numpy(crop_off_np).to(dev)
+    pp = b200seg.SomaPostproc(vpr, SHAPE, counts, prm_np.size, device=dev)
+    n_max = max(counts)
+    gather_in = torch.zeros((vpr, n_max, 8), dtype=torch.float32, device=dev)
+    gather_out = torch.zeros((world, vpr, n_max, 8), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        pp.run(vols, dets, boxes, prm, crop_off, NMS_THRESH)
+        if world > 1:
+            # the only exchange step: surviving detections of every volume (padded block, device resident)
+            gather_in[:, :, 1:].copy_(torch.nn.utils.rnn.pad_sequence(
+                [dets[pp.det_off_host[v]:pp.det_off_host[v + 1]] for v in range(vpr)], batch_first=True)[:, :n_max])
+            dist.all_gather_into_tensor(gather_out.view(world * vpr, n_max, 8), gather_in)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = b200seg.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = b200seg.launch_count() - l0
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_step = float(ms_total.item()) / args.steps
+    value = vpr * world * V / (ms_step * 1e-3) / 1e9
+    keep_counts = pp.keep_count.cpu().numpy()
+    kept_crop_bytes = 0
+    for v in range(vpr):
+        order = pp.rank_order.cpu().numpy()[pp.det_off_host[v]:pp.det_off_host[v] + keep_counts[v]]
+        kept_crop_bytes += int(np.diff(cases[v]["crop_off"])[order].sum())
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (same inputs, same launches) -------
+    prof = {"nms": 0.0, "otsu": 0.0, "paste": 0.0}
+    reps = max(3, min(10, args.steps))
+    pp.run_profiled(vols, dets, boxes, prm, crop_off, NMS_THRESH)
+    for _ in range(reps):
+        r = pp.run_profiled(vols, dets, boxes, prm, crop_off, NMS_THRESH)
+        for k in prof:
+            prof[k] += r[k] / reps
+    alg = {"paste": (2 * V * vpr + kept_crop_bytes) / vpr,           # per launch: label volume written once + mask bytes read
+           "otsu": 3 * kept_crop_bytes / vpr,                        # image + prm read, mask written (uint8)
+           "nms": sum(28 * c + 16 * c * ((c + 63) // 64) + 8 * c for c in counts)}
+    per_launch_ms = {"paste": prof["paste"] / vpr, "otsu": prof["otsu"] / vpr, "nms": prof["nms"]}
+    kernels = {k: {"ms_per_step": prof[k], "share": prof[k] / max(sum(prof.values()), 1e-9),
+                   "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (per_launch_ms[k] * 1e-3) / 1e9 if per_launch_ms[k] > 0 else None}
+               for k in prof}
+    dom = max(prof, key=lambda k: prof[k])
+    roof = {"bound": "hbm", "kernel": {"paste": "paste_labels_kernel", "otsu": "otsu2d_kernel<1>", "nms": "nms3d (3 kernels)"}[dom],
+            "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "launch_ms": per_launch_ms[dom], "alg_bytes_per_launch": alg[dom]}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(roof["kernel"])
+        except Exception:
+            pass
+
+    # ---- e2e: host-buffer C-ABI call, pinned memory, H2D + D2H inside the timed region --------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_in = [dict(volume=pin(c["volume"]), dets=pin(c["dets"]), boxes=pin(c["boxes"]), prm=pin(c["prm"]),
+                 crop_off=pin(c["crop_off"])) for c in cases]
+    h_seg = [torch.empty(SHAPE, dtype=torch.uint16).pin_memory() for _ in range(vpr)]
+
+    def e2e_step():
+        for v in range(vpr):
+            h = h_in[v]
+            b200seg.postproc_soma_host(h["volume"].numpy(), h["dets"].numpy(), h["boxes"].numpy(), h["prm"].numpy(),
+                                       h["crop_off"].numpy(), NMS_THRESH, seg_out=h_seg[v].numpy())
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    l1 = b200seg.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = vpr * world * V * args.steps / float(dt.item()) / 1e9
+    e2e_launches = b200seg.launch_count() - l1
+    h2d = sum(c["volume"].nbytes + c["dets"].nbytes + c["boxes"].nbytes + c["prm"].nbytes + c["crop_off"].nbytes + 8 for c in cases)
+    d2h = sum(2 * V + 4 + c["dets"].shape[0] * 13 for c in cases)
+    clocks = sampler.stop() if rank == 0 else None
+    # correctness guard on the e2e output (cheap): labels present == survivors of volume 0
+    assert np.array_equal(h_seg[0].numpy(), pp.seg[0].cpu().numpy()), "e2e and device-resident chains disagree"
+
+    ops = bench_ops(torch, peak) if rank == 0 or world > 1 else {}
+    if world > 1:                                           # replicas: aggregate RoIs/s over ranks
+        for k in ("roialign3d_fwd_f32", "roialign3d_bwd_f32", "roialign3d_fwd_bf16"):
+            t = torch.tensor([ops[k]["ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ops[k]["rois_per_s_all_ranks"] = 512 * world / (float(t.item()) * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle_chain
+        t0, n_done = time.perf_counter(), 0
+        for c in cases:
+            oracle_chain(c, NMS_THRESH)
+            n_done += 1
+            if time.perf_counter() - t0 > 12.0:
+                break
+        dtc = time.perf_counter() - t0
+        cpu = {"value": n_done * V / dtc / 1e9, "unit": "Gvox/s", "cores": 1, "kind": "port",
+               "sample": "%d of the %d volumes of this step, oracle C port of the reference chain (cython NMS, otsu_py_2d_fast, "
+                         "numpy paste) on 1 of %d host cores, %.1f s" % (n_done, vpr, os.cpu_count() or 1, dtc)}
+    if rank == 0:
+        line = {"metric": "postproc_gvox_per_s", "value": value, "unit": "Gvox/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world, vpr),
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "Gvox/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "gpu_launches": int(e2e_launches)},
+                "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,
+                "kept_instances_per_volume": float(np.mean(keep_counts)),
+                "chain_roofline": {"alg_bytes_per_volume": (3 * kept_crop_bytes / vpr) + 2 * V + alg["nms"] / vpr,
+                                   "frac": ((3 * kept_crop_bytes / vpr) + 2 * V) / (ms_step / vpr * 1e-3) / 1e9 / peak}}
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--volumes-per-rank", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,52 @@ class SomaPostproc(object):
         return self.seg
 
 
+def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
+    """Same launch sequence as run(), issued step by step from Python with CUDA events around each
+    kernel class.  Returns {"nms": ms, "otsu": ms, "paste": ms, "n_paste": launches, ...} (bench.py)."""
+    torch = self.torch
+    L = _lib.lib()
+    st = _lib.current_stream()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    spans = {"nms": [], "otsu": [], "paste": []}
+    if not hasattr(self, "_ids"):
+        self._ids = torch.arange(1, max(self.n_max, 1) + 1, dtype=torch.int32, device=self.seg.device).to(torch.uint16)
+        self._nms_ws = torch.empty(L.b200seg_nms3d_workspace_bytes(self.nv, self.n_max), dtype=torch.uint8, device=self.seg.device)
+    a, b = ev(), ev()
+    a.record()
+    _lib.check(L.b200seg_nms3d_dev(_lib.ptr(dets), _lib.ptr(self.det_off_dev), self.nv, self.n_max, float(np.float32(nms_thresh)), 0,
+                                   _lib.ptr(self.keep), _lib.ptr(self.keep_count), _lib.ptr(self.rank_order),
+                                   _lib.ptr(self._nms_ws), self._nms_ws.numel(), st), "nms3d_dev")
+    b.record()
+    spans["nms"].append((a, b))
+    V = self.S * self.H * self.W
+    for v in range(self.nv):
+        base = int(self.det_off_host[v]); n = int(self.det_off_host[v + 1]) - base
+        vol = volumes[v]
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        if n > 0:
+            _lib.check(L.b200seg_soma_binarize_dev(
+                _lib.ptr(vol), self.S, self.H, self.W, _lib.ptr(boxes[base:]), _lib.ptr(prm), _lib.ptr(crop_off[base:]), n,
+                _lib.ptr(self.rank_order[base:]), _lib.ptr(self.keep_count[v:]), _lib.ptr(self.masks),
+                _lib.ptr(self.b_max[base:]), _lib.ptr(self.status[base:]), st), "soma_binarize")
+        b.record()
+        _lib.check(L.b200seg_paste_labels_dev(
+            _lib.ptr(self.seg[v]), self.S, self.H, self.W, n, _lib.ptr(boxes[base:]), _lib.ptr(self._ids), _lib.ptr(self.masks),
+            _lib.ptr(crop_off[base:]), _lib.ptr(self.rank_order[base:]), _lib.ptr(self.keep_count[v:]),
+            _lib.ptr(self.survive[base:]), st), "paste_labels")
+        c.record()
+        spans["otsu"].append((a, b)); spans["paste"].append((b, c))
+    torch.cuda.synchronize()
+    out = {k: sum(x.elapsed_time(y) for x, y in v) for k, v in spans.items()}
+    out["n_paste"] = self.nv
+    out["n_otsu"] = self.nv
+    return out
+
+
+SomaPostproc.run_profiled = _run_profiled
+
+
 def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=None):
     """numpy in / numpy out for ONE volume (H2D and D2H happen inside the C call).
     Returns dict(seg uint16 [S,H,W], n_keep, rank_order, b_max, status, survive, scores [[id, score]])."""

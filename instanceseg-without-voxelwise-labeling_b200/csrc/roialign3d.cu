@@ -41,7 +41,8 @@ struct Tap { int low, high; float l, h; bool valid; };
 // one sample of roi_align_kernel_3d.cu:130-138 + :19-58 (forward) / :187-224 (backward)
 __device__ __forceinline__ Tap axis_sample(const AxisP& a, int p, int i) {
     Tap t;
-    float c = a.start + p * a.bin + (i + .5f) * a.bin / a.g;
+    // fma(p, bin, start) + ((i+.5)*bin)/g : the contraction nvcc applies to the reference kernel
+    float c = __fadd_rn(__fmaf_rn((float)p, a.bin, a.start), __fdiv_rn(__fmul_rn(i + .5f, a.bin), (float)a.g));
     t.valid = !((double)c < a.guard || c > (float)a.dim);
     if (c <= 0) c = 0;
     int low = (int)c;
@@ -407,6 +408,8 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiMeta* __restrict__ me
                     const float4 v = reinterpret_cast<const float4*>(src)[q];
                     g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
                 }
+#pragma unroll
+                for (int p = 0; p < PT; ++p) if (p >= Pw) g[p] = 0.f;     // columns >= Pw of s_T1 are never written
 #pragma unroll
                 for (int x = 0; x < RB_T; ++x) {
                     const float4* wv = reinterpret_cast<const float4*>(&s_w[2][x][0]);

@@ -52,13 +52,13 @@ def prm_crop(blob, box_int, scale=0.8):
     return (255.0 * np.exp(-0.5 * r2)).astype(np.uint8)
 
 
-def postproc_case(seed, shape=(64, 256, 256), n_blobs=35, n_dup=10, n_false=5):
+def postproc_case(seed, shape=(64, 256, 256), n_blobs=35, n_dup=10, n_false=5, sigma_xy=(4, 9), sigma_z=(2, 5)):
     """A full binarization_soma-style input: volume, detections (tight blob boxes + jittered
     duplicates + false boxes, distinct scores), int boxes, packed PRM crops and offsets."""
     from .binarization import dets_to_boxes, crop_offsets
     rng = np.random.default_rng(seed)
     S, H, W = shape
-    vol, bx, blobs = blob_volume(rng, shape, n_blobs)
+    vol, bx, blobs = blob_volume(rng, shape, n_blobs, sigma_xy=sigma_xy, sigma_z=sigma_z)
     owners = list(range(n_blobs))
     allb = [bx]
     if n_dup:

@@ -160,6 +160,13 @@ void oracle_bbox_overlaps_3d(const float* boxes, long N, const float* query, lon
  * z guard "z < -0.1" (:187).  The adds are performed in output-index order (the reference uses
  * atomicAdd, i.e. an unspecified order).
  * ------------------------------------------------------------------------------------------ */
+/* Sample coordinate  start + p*bin + (i+.5f)*bin/grid  (.cu:130-138).  The reference is CUDA built
+ * with nvcc's default -fmad=true: the sm_100a PTX of the unmodified .cu contracts start + p*bin into
+ * ONE fma and keeps the rest as mul, div.rn, add (checked with `nvcc -ptx`).  The coordinate is
+ * evaluated the same way here, because on white-noise features a 1-ulp coordinate difference moves
+ * the interpolated value by ~1e-5 -- more than the parity tolerance. */
+#define SAMPLE_COORD(start, p, bin, i, g) (fmaf((float)(p), (bin), (start)) + (((i) + .5f) * (bin)) / (float)(g))
+
 static float trilinear(const float* data, int S, int H, int W, float z, float y, float x) {
     if (z < -1.0 || z > S || y < -1.0 || y > H || x < -1.0 || x > W) return 0;
     if (z <= 0) z = 0;
@@ -204,11 +211,11 @@ void oracle_roialign3d_fwd(const float* feat, int B, int C, int S, int H, int W,
         const float count = (float)(gs * gh * gw);
         float acc = 0.f;
         for (int iz = 0; iz < gs; ++iz) {
-            const float z = ss + ps * bs + (iz + .5f) * bs / gs;
+            const float z = SAMPLE_COORD(ss, ps, bs, iz, gs);
             for (int iy = 0; iy < gh; ++iy) {
-                const float y = sh + ph * bh + (iy + .5f) * bh / gh;
+                const float y = SAMPLE_COORD(sh, ph, bh, iy, gh);
                 for (int ix = 0; ix < gw; ++ix) {
-                    const float x = sw + pw * bw + (ix + .5f) * bw / gw;
+                    const float x = SAMPLE_COORD(sw, pw, bw, ix, gw);
                     acc += trilinear(data, S, H, W, z, y, x);
                 }
             }
@@ -241,11 +248,11 @@ void oracle_roialign3d_bwd(const float* top, int B, int C, int S, int H, int W,
         int gw = sr > 0 ? sr : (int)ceil(rw / Pw);
         const float count = (float)(gs * gh * gw);
         for (int iz = 0; iz < gs; ++iz) {
-            float z = ss + ps * bs + (iz + .5f) * bs / gs;
+            float z = SAMPLE_COORD(ss, ps, bs, iz, gs);
             for (int iy = 0; iy < gh; ++iy) {
-                float y = sh + ph * bh + (iy + .5f) * bh / gh;
+                float y = SAMPLE_COORD(sh, ph, bh, iy, gh);
                 for (int ix = 0; ix < gw; ++ix) {
-                    float x = sw + pw * bw + (ix + .5f) * bw / gw;
+                    float x = SAMPLE_COORD(sw, pw, bw, ix, gw);
                     float zz = z, yy = y, xx = x;
                     if (zz < -0.1 || zz > S || yy < -1.0 || yy > H || xx < -1.0 || xx > W) continue;
                     if (zz <= 0) zz = 0;

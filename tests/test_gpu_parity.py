@@ -373,11 +373,15 @@ def _ref_cuda_roialign(torch_, feat, rois, P, scale, sr, grad=None):
     return out.cpu().numpy(), (gi.cpu().numpy() if gi is not None else None)
 
 
-def _close(a, b, rel=1e-5):
-    """|a-b| <= rel * max(|b|, typical magnitude): 1e-5 relative in fp32, robust to cancellation to ~0."""
-    scale = max(float(np.abs(b).mean()), 1e-6)
+def _close(a, b, rel=1e-5, floor="mean"):
+    """fp32 tolerance of BASELINE.json: |a-b| <= 1e-5 * max(|b|, floor).
+    floor="mean" (forward): mean |b|, i.e. elementwise-relative except where the result cancels to ~0.
+    floor="max"  (backward): max |b| (norm-wise).  A grad_in voxel sums hundreds of signed taps from
+    several RoIs; its fp32 value depends on the summation order at the 1e-5*|b| level -- the reference
+    itself accumulates with atomicAdd in an unspecified order (roi_align_kernel_3d.cu:325-332)."""
+    scale = max(float(np.abs(b).mean() if floor == "mean" else np.abs(b).max()), 1e-6)
     err = np.abs(a - b) / np.maximum(np.abs(b), scale)
-    return float(err.max()) <= rel, float(err.max())
+    return bool(np.isfinite(a).all()) and float(err.max()) <= rel, float(err.max())
 
 
 @pytest.mark.parametrize("shape,R,scale,P,sr,side", [
@@ -403,7 +407,7 @@ def test_roialign_fwd_bwd_vs_oracle(b2, torch_, shape, R, scale, P, sr, side):
     g = np.random.default_rng(1).standard_normal(ref.shape).astype(np.float32)
     y.backward(torch_.from_numpy(g).cuda())
     refg = oracle.roialign3d_bwd(g, rois, feat.shape, scale, sr)
-    ok, err = _close(f.grad.cpu().numpy(), refg)
+    ok, err = _close(f.grad.cpu().numpy(), refg, floor="max")
     assert ok, ("bwd", err)
     # determinism of the atomics-free backward: bit-identical on a second run
     f2 = torch_.from_numpy(feat).cuda().requires_grad_(True)
@@ -426,7 +430,7 @@ def test_roialign_vs_reference_cuda_kernels(b2, torch_):
     ok, err = _close(y.cpu().numpy(), ref_out)
     assert ok, err
     gi = roialign3d_backward(torch_.from_numpy(g).cuda(), r, feat.shape, 0.125, 2)
-    ok, err = _close(gi.cpu().numpy(), ref_gi, rel=5e-5)          # the reference sums with atomics (order varies)
+    ok, err = _close(gi.cpu().numpy(), ref_gi, floor="max")      # the reference sums with atomics (order varies)
     assert ok, err
     # and the oracle agrees with the reference kernels too (pins the RoIAlign restatement)
     ok, err = _close(oracle.roialign3d_fwd(feat, rois, 7, 0.125, 2), ref_out)
