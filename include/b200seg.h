@@ -141,34 +141,46 @@ int b200seg_otsu2d_host(const uint16_t* image, const uint16_t* prm, long long n,
 
 /* ----------------------------------------------------------------------------------------------
  * Per-instance binarization straight from the raw volume (tools/binarization_soma.py:78-94):
- * crop by the int()-truncated box, normalise image and PRM (:85-91), 2D-Otsu (:94).
- *   volume [S,H,W] uint8; boxes [n,6] int32 inclusive voxel coords inside the volume;
- *   prm: raw uint8 PRM crops (box-shaped, [sz,sy,sx]) packed at crop_off[i];
- *   order [n] int32 or NULL: process instance order[i] as i-th (visit order from NMS);
- *   n_valid (device int32) or NULL: only the first *n_valid instances are processed.
+ * crop by the int()-truncated box, normalise image and PRM (:85-91), 2D-Otsu (:94); one launch for
+ * every instance of a batch of equally shaped volumes.
+ *   volumes [n_volumes,S,H,W] uint8; det_off [n_volumes+1] int32 (device): volume v owns instances
+ *   [det_off[v], det_off[v+1]) of boxes / crop_off / order / b_max / status (may be NULL when
+ *   n_volumes == 1: the single volume then owns instances [0, n_max)); n_max = upper bound of the
+ *   per-volume instance count (host-known, sizes the grid);
+ *   boxes [total,6] int32 inclusive voxel coords inside the volume;
+ *   prm: raw uint8 PRM crops (box-shaped, [sz,sy,sx]), instance i at crop_off[i] (int64 [total+1]);
+ *   order [total] int32 or NULL: volume v visits instance det_off[v] + order[det_off[v] + r] r-th
+ *   (visit order from NMS); n_valid [n_volumes] int32 (device) or NULL: only the first n_valid[v]
+ *   visits of volume v are processed.
  * Outputs as b200seg_otsu2d_dev, plus status 3 = PRM crop has no positive voxel (skipped,
  * binarization_soma.py:74-76, mask all 0).  Masks are written in the packing of `prm`.
  * ---------------------------------------------------------------------------------------------- */
-int b200seg_soma_binarize_dev(const uint8_t* volume, int S, int H, int W,
+int b200seg_soma_binarize_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
+                              const int32_t* det_off, int n_max,
                               const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,
-                              int n, const int32_t* order, const int32_t* n_valid,
+                              const int32_t* order, const int32_t* n_valid,
                               uint8_t* mask, int32_t* b_max, int32_t* status,
                               b200seg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Label paste-back -- replaces the inline numpy of tools/binarization_soma.py:100-104 (and
  * binarization_nuclei.py:141-149): instances are visited in order, instance i writes label
- * ids[i] where its mask is set and the label volume is still 0.  seg [S,H,W] uint16 is written
- * exactly once per voxel (zero-fill folded in; no pre-clear needed).
- *   order / n_valid as above (instance order[i] is visited i-th); ids [n] indexed by visit rank.
- *   survive [n] uint8 (by visit rank): 1 when the label is present in the volume
- *   (`mask_id in np.unique(seg)`, :103).
+ * ids[i] where its mask is set and the label volume is still 0.  seg [n_volumes,S,H,W] uint16 is
+ * written exactly once per voxel (zero-fill folded in; no pre-clear needed).  Batched over volumes
+ * like b200seg_soma_binarize_dev (det_off / n_max / order / n_valid have the same meaning).
+ *   ids [n_max] uint16 indexed by visit rank (shared by all volumes);
+ *   survive (by visit rank, volume v at det_off[v]): 1 when the label is present in the volume
+ *   (`mask_id in np.unique(seg)`, :103).  With det_off == NULL survive[n_max] is cleared by the
+ *   call; with det_off given the caller clears survive[total] beforehand.
  * ---------------------------------------------------------------------------------------------- */
-int b200seg_paste_labels_dev(uint16_t* seg, int S, int H, int W, int n,
+size_t b200seg_paste_labels_workspace_bytes(int n_volumes, int S, int H, int W, int n_max);
+int b200seg_paste_labels_dev(uint16_t* seg, int n_volumes, int S, int H, int W,
+                             const int32_t* det_off, int n_max,
                              const int32_t* boxes, const uint16_t* ids,
                              const uint8_t* masks, const int64_t* mask_off,
                              const int32_t* order, const int32_t* n_valid,
-                             uint8_t* survive, b200seg_stream_t stream);
+                             uint8_t* survive, void* workspace, size_t workspace_bytes,
+                             b200seg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Post-processing chain of tools/binarization_soma.py:57-104 for a batch of volumes, device
@@ -183,7 +195,7 @@ int b200seg_paste_labels_dev(uint16_t* seg, int S, int H, int W, int n,
  * else as b200seg_soma_binarize_dev), survive[total] (set b, visit rank r at det_off[b] + r).
  * The largest-connected-component step (:97-99) is not part of the chain.
  * ---------------------------------------------------------------------------------------------- */
-size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max);
+size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W);
 int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
                               const float* dets, const int32_t* det_off_dev, const int32_t* det_off_host,
                               const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,

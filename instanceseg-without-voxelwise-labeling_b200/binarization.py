@@ -41,7 +41,7 @@ def soma_binarize(volume, boxes, prm, crop_off, order=None, n_valid=None):
     b_max = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
     status = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().b200seg_soma_binarize_dev(
-        _lib.ptr(volume), S, H, W, _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off), n, _lib.ptr(order),
+        _lib.ptr(volume), 1, S, H, W, None, n, _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off), _lib.ptr(order),
         _lib.ptr(n_valid), _lib.ptr(mask), _lib.ptr(b_max), _lib.ptr(status), _lib.current_stream()), "soma_binarize")
     return mask, b_max[:n], status[:n]
 
@@ -52,9 +52,12 @@ def paste_labels(seg, boxes, ids, masks, mask_off, order=None, n_valid=None):
     S, H, W = seg.shape
     n = boxes.shape[0]
     survive = torch.zeros(max(n, 1), dtype=torch.uint8, device=seg.device)
-    _lib.check(_lib.lib().b200seg_paste_labels_dev(
-        _lib.ptr(seg), S, H, W, n, _lib.ptr(boxes), _lib.ptr(ids), _lib.ptr(masks), _lib.ptr(mask_off),
-        _lib.ptr(order), _lib.ptr(n_valid), _lib.ptr(survive), _lib.current_stream()), "paste_labels")
+    L = _lib.lib()
+    ws_bytes = L.b200seg_paste_labels_workspace_bytes(1, S, H, W, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=seg.device)
+    _lib.check(L.b200seg_paste_labels_dev(
+        _lib.ptr(seg), 1, S, H, W, None, n, _lib.ptr(boxes), _lib.ptr(ids), _lib.ptr(masks), _lib.ptr(mask_off),
+        _lib.ptr(order), _lib.ptr(n_valid), _lib.ptr(survive), _lib.ptr(ws), ws_bytes, _lib.current_stream()), "paste_labels")
     return survive[:n]
 
 
@@ -82,13 +85,12 @@ class SomaPostproc(object):
         self.b_max = torch.zeros(t, dtype=torch.int32, device=dev)
         self.status = torch.zeros(t, dtype=torch.int32, device=dev)
         self.survive = torch.zeros(t, dtype=torch.uint8, device=dev)
-        self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(self.nv, self.n_max)
+        self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(self.nv, self.n_max, self.S, self.H, self.W)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
     def launches_per_call(self):
-        """Kernels launched by one run(): 3 NMS + iota + per volume (binarize + paste)."""
-        nz = int(np.count_nonzero(np.diff(self.det_off_host)))
-        return (3 + 1 if self.n_max > 0 else 0) + nz + self.nv
+        """Kernels launched by one run(): 3 NMS + iota + binarize + paste bin + paste (all volumes per launch)."""
+        return (3 + 1 + 1 + 1 if self.n_max > 0 else 0) + 1
 
     def run(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
         """All arguments are cuda tensors (volumes uint8 [nv,S,H,W], dets f32 [total,7], boxes int32
@@ -113,6 +115,8 @@ def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
     if not hasattr(self, "_ids"):
         self._ids = torch.arange(1, max(self.n_max, 1) + 1, dtype=torch.int32, device=self.seg.device).to(torch.uint16)
         self._nms_ws = torch.empty(L.b200seg_nms3d_workspace_bytes(self.nv, self.n_max), dtype=torch.uint8, device=self.seg.device)
+        self._paste_ws = torch.empty(L.b200seg_paste_labels_workspace_bytes(self.nv, self.S, self.H, self.W, self.n_max), dtype=torch.uint8,
+                                     device=self.seg.device)
     a, b = ev(), ev()
     a.record()
     _lib.check(L.b200seg_nms3d_dev(_lib.ptr(dets), _lib.ptr(self.det_off_dev), self.nv, self.n_max, float(np.float32(nms_thresh)), 0,
@@ -120,28 +124,26 @@ def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
                                    _lib.ptr(self._nms_ws), self._nms_ws.numel(), st), "nms3d_dev")
     b.record()
     spans["nms"].append((a, b))
-    V = self.S * self.H * self.W
-    for v in range(self.nv):
-        base = int(self.det_off_host[v]); n = int(self.det_off_host[v + 1]) - base
-        vol = volumes[v]
-        a, b, c = ev(), ev(), ev()
-        a.record()
-        if n > 0:
-            _lib.check(L.b200seg_soma_binarize_dev(
-                _lib.ptr(vol), self.S, self.H, self.W, _lib.ptr(boxes[base:]), _lib.ptr(prm), _lib.ptr(crop_off[base:]), n,
-                _lib.ptr(self.rank_order[base:]), _lib.ptr(self.keep_count[v:]), _lib.ptr(self.masks),
-                _lib.ptr(self.b_max[base:]), _lib.ptr(self.status[base:]), st), "soma_binarize")
-        b.record()
-        _lib.check(L.b200seg_paste_labels_dev(
-            _lib.ptr(self.seg[v]), self.S, self.H, self.W, n, _lib.ptr(boxes[base:]), _lib.ptr(self._ids), _lib.ptr(self.masks),
-            _lib.ptr(crop_off[base:]), _lib.ptr(self.rank_order[base:]), _lib.ptr(self.keep_count[v:]),
-            _lib.ptr(self.survive[base:]), st), "paste_labels")
-        c.record()
-        spans["otsu"].append((a, b)); spans["paste"].append((b, c))
+    a, b, c = ev(), ev(), ev()
+    a.record()
+    if self.n_max > 0:
+        self.status.fill_(-1)
+        self.survive.zero_()
+        _lib.check(L.b200seg_soma_binarize_dev(
+            _lib.ptr(volumes), self.nv, self.S, self.H, self.W, _lib.ptr(self.det_off_dev), self.n_max, _lib.ptr(boxes),
+            _lib.ptr(prm), _lib.ptr(crop_off), _lib.ptr(self.rank_order), _lib.ptr(self.keep_count), _lib.ptr(self.masks),
+            _lib.ptr(self.b_max), _lib.ptr(self.status), st), "soma_binarize")
+    b.record()
+    _lib.check(L.b200seg_paste_labels_dev(
+        _lib.ptr(self.seg), self.nv, self.S, self.H, self.W, _lib.ptr(self.det_off_dev), self.n_max, _lib.ptr(boxes),
+        _lib.ptr(self._ids), _lib.ptr(self.masks), _lib.ptr(crop_off), _lib.ptr(self.rank_order), _lib.ptr(self.keep_count),
+        _lib.ptr(self.survive), _lib.ptr(self._paste_ws), self._paste_ws.numel(), st), "paste_labels")
+    c.record()
+    spans["otsu"].append((a, b)); spans["paste"].append((b, c))
     torch.cuda.synchronize()
     out = {k: sum(x.elapsed_time(y) for x, y in v) for k, v in spans.items()}
-    out["n_paste"] = self.nv
-    out["n_otsu"] = self.nv
+    out["n_paste"] = 1
+    out["n_otsu"] = 1
     return out
 
 

@@ -157,8 +157,15 @@ nms_mask_kernel(const SortedBox* __restrict__ sorted_all, const int32_t* __restr
 }
 
 constexpr int REDUCE_THREADS = 256;
+constexpr size_t NMS_PRELOAD_BYTES = 160 * 1024;     // whole suppression mask staged in shared memory when it fits
 
-// dynamic smem: removed[w64] u64 | flags[w64] u64 (bit = original index kept)
+// One CTA per detection set.  dynamic smem: removed[w64] u64 | flags[w64] u64 | mask copy (PRELOAD) or diag words.
+// PRELOAD: the set's whole bitmask (n x w64 words) is copied to shared memory first with coalesced loads, so the
+// 64-row chunk walk never waits on L2.  Otherwise only the diagonal words are staged and the kept rows' words are
+// read from global memory chunk by chunk.
+// Per chunk, warp 0 resolves the diagonal tile: only ALIVE rows with a NON-ZERO diagonal word form the serial
+// chain (a row with an empty diagonal word suppresses nobody inside the chunk), everything else is bit arithmetic.
+template <bool PRELOAD>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long long* __restrict__ mask_all,
                   const int32_t* __restrict__ offsets, int n_max, int w64,
@@ -167,6 +174,7 @@ nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long 
     extern __shared__ unsigned long long s_dyn[];
     unsigned long long* removed = s_dyn;
     unsigned long long* flags = s_dyn + w64;
+    unsigned long long* s_mask = s_dyn + 2 * w64;         // PRELOAD: [n][w64]; else diag[n]
     __shared__ int s_rows[64];
     __shared__ int s_nk;
     __shared__ int s_scan[REDUCE_THREADS];
@@ -180,40 +188,57 @@ nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long 
     const int tid = threadIdx.x;
 
     for (int w = tid; w < nw; w += REDUCE_THREADS) { removed[w] = 0ull; flags[w] = 0ull; }
+    int* s_orig = reinterpret_cast<int*>(s_mask + (PRELOAD ? (size_t)n_max * w64 : (size_t)n_max));   // original index per row
+    for (int r = tid; r < n; r += REDUCE_THREADS) s_orig[r] = sorted[r].orig;
+    if (PRELOAD) {
+        // stage the set's bitmask rows (words at or right of the diagonal; the rest is never written/read):
+        // one warp per row, 8 rows in flight per warp pass -> independent coalesced loads
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < n; r += REDUCE_THREADS / 32) {
+            const int wd = r >> 6;
+            for (int w = wd + lane; w < nw; w += 32) s_mask[(size_t)r * w64 + w] = mask[(size_t)r * w64 + w];
+        }
+    } else {
+        for (int r = tid; r < n; r += REDUCE_THREADS) s_mask[r] = mask[(size_t)r * w64 + (r >> 6)];
+    }
     __syncthreads();
 
     int n_kept = 0;    // uniform across the CTA
     for (int c = 0; c < nw; ++c) {
         if (tid < 32) {
             const int r0 = c * 64 + tid, r1 = r0 + 32;
-            const unsigned long long d0 = r0 < n ? mask[(size_t)r0 * w64 + c] : 0ull;
-            const unsigned long long d1 = r1 < n ? mask[(size_t)r1 * w64 + c] : 0ull;
+            const unsigned long long d0 = r0 < n ? (PRELOAD ? s_mask[(size_t)r0 * w64 + c] : s_mask[r0]) : 0ull;
+            const unsigned long long d1 = r1 < n ? (PRELOAD ? s_mask[(size_t)r1 * w64 + c] : s_mask[r1]) : 0ull;
+            const unsigned long long nz = (unsigned long long)__ballot_sync(0xffffffffu, d0 != 0ull) |
+                                          ((unsigned long long)__ballot_sync(0xffffffffu, d1 != 0ull) << 32);
             const int rows = min(64, n - c * 64);
             unsigned long long alive = ~removed[c];
             if (rows < 64) alive &= ((1ull << rows) - 1ull);
-            int nk = 0;
-            while (alive) {                                    // warp-uniform loop
-                const int r = __ffsll((long long)alive) - 1;
+            unsigned long long cand = alive & nz;
+            while (cand) {                                     // warp-uniform serial chain: suppressing rows only
+                const int r = __ffsll((long long)cand) - 1;
                 const unsigned long long lo = __shfl_sync(0xffffffffu, d0, r & 31);
                 const unsigned long long hi = __shfl_sync(0xffffffffu, d1, r & 31);
-                const unsigned long long d = (r < 32) ? lo : hi;
-                alive &= ~d;
-                alive &= ~(1ull << r);
-                if (tid == 0) s_rows[nk] = c * 64 + r;
-                ++nk;
+                alive &= ~((r < 32) ? lo : hi);
+                cand = alive & nz & ~((2ull << r) - 1ull);     // candidates strictly after r (2<<63 wraps to 0: all cleared)
+                if (r == 63) cand = 0ull;
             }
-            if (tid == 0) s_nk = nk;
+            // kept rows of this chunk, in order: lane l owns rows l and l+32, position = popcount of lower kept bits
+            if (tid == 0) s_nk = __popcll(alive);
+            if ((alive >> tid) & 1ull) s_rows[__popcll(alive & ((1ull << tid) - 1ull))] = c * 64 + tid;
+            if ((alive >> (tid + 32)) & 1ull) s_rows[__popcll(alive & ((1ull << (tid + 32)) - 1ull))] = c * 64 + tid + 32;
         }
         __syncthreads();
         const int nk = s_nk;
         const int rest = nw - c - 1;
         for (int item = tid; item < nk * rest; item += REDUCE_THREADS) {
             const int k = item / rest, w = c + 1 + item % rest;
-            const unsigned long long m = mask[(size_t)s_rows[k] * w64 + w];
+            const size_t idx = (size_t)s_rows[k] * w64 + w;
+            const unsigned long long m = PRELOAD ? s_mask[idx] : mask[idx];
             if (m) atomicOr(&removed[w], m);
         }
         for (int k = tid; k < nk; k += REDUCE_THREADS) {
-            const int orig = sorted[s_rows[k]].orig;
+            const int orig = s_orig[s_rows[k]];
             atomicOr(&flags[orig >> 6], 1ull << (orig & 63));
             if (rank_order) rank_order[off + n_kept + k] = orig;
         }
@@ -278,7 +303,6 @@ extern "C" int b200seg_nms3d_dev(const float* dets, const int32_t* offsets, int 
         return B200SEG_EWORKSPACE;
     }
     const int w64 = (n_max + 63) / 64;
-    B200_CHECK_ARG(2 * (size_t)w64 * 8 <= 200 * 1024, "nms3d: n_max=%d too large", n_max);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     SortedBox* sorted = (SortedBox*)ws;
     unsigned long long* mask = (unsigned long long*)(ws + align_up((size_t)n_max * sizeof(SortedBox), 256) * batch);
@@ -289,11 +313,19 @@ extern "C" int b200seg_nms3d_dev(const float* dets, const int32_t* offsets, int 
     dim3 g2(w64, w64, batch);
     nms_mask_kernel<<<g2, 64, 0, stream>>>(sorted, offsets, n_max, w64, thresh, mask);
     B200_LAUNCH_CHECK("nms_mask_kernel");
-    const size_t smem = 2 * (size_t)w64 * 8;
-    if (smem > 48 * 1024)
-        B200_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_reduce_kernel<<<batch, REDUCE_THREADS, smem, stream>>>(sorted, mask, offsets, n_max, w64, keep,
-                                                              keep_count, rank_order);
+    const size_t pre_bytes = (size_t)n_max * w64 * 8;
+    const bool preload = pre_bytes <= NMS_PRELOAD_BYTES;
+    const size_t smem = 2 * (size_t)w64 * 8 + (preload ? pre_bytes : (size_t)n_max * 8) + (size_t)n_max * 4;
+    B200_CHECK_ARG(smem <= 220 * 1024, "nms3d: n_max=%d too large for the reduce kernel", n_max);
+    if (preload) {
+        if (smem > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_reduce_kernel<true><<<batch, REDUCE_THREADS, smem, stream>>>(sorted, mask, offsets, n_max, w64, keep, keep_count, rank_order);
+    } else {
+        if (smem > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_reduce_kernel<false><<<batch, REDUCE_THREADS, smem, stream>>>(sorted, mask, offsets, n_max, w64, keep, keep_count, rank_order);
+    }
     B200_LAUNCH_CHECK("nms_reduce_kernel");
     return 0;
 }

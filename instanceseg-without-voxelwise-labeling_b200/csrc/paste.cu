@@ -5,140 +5,245 @@
 // is set AND the label volume is still 0 ("first come wins"); afterwards `mask_id in np.unique(seg)`
 // decides whether the instance survives.  The serial loop is replaced by an owner-computes gather:
 // every voxel of the label volume is produced exactly once as "label of the first instance, in
-// visit order, whose box covers the voxel and whose mask is set there" -- no atomics, no pre-clear,
-// the zero fill is folded into the single 128-bit streaming store per 8 voxels.
+// visit order, whose box covers the voxel and whose mask is set there" -- no atomics on the volume,
+// no pre-clear, the zero fill is folded into the single 128-bit streaming store per 8 voxels.
 //
+// Two launches for a whole batch of volumes:
+//   paste_bin_kernel     one CTA per (visited instance, volume): writes its box record in visit order
+//                        and ORs its visit rank into the bitmap of every 4x16x64-voxel tile its box
+//                        touches (bitmap = ceil(n/32) words per tile; OR is order independent).
+//   paste_labels_kernel  persistent CTAs walk the tiles of all volumes; each warp fetches the tile's
+//                        bitmap with ONE coalesced load (lane = word, prefetched one tile ahead), ballots
+//                        the non-empty words and visits the set bits in increasing rank = visit order.
+//                        No __syncthreads, no shared memory.  A thread owns 8 x-voxels on the 4 planes of
+//                        the tile: an empty tile costs four 16-byte stores per thread; a covering
+//                        instance costs four 8-byte mask-row reads (two aligned 64-bit loads + funnel
+//                        shift) that are independent of each other.
 // HBM traffic = 2 B/voxel written + the mask bytes of covered voxels read (L2-resident crops).
-// Each CTA owns a 4 x 8 x 128 voxel tile: it first compacts, in visit order, the instances whose
-// box intersects the tile (warp ballot), then its 512 threads resolve 8 consecutive voxels each.
 #include "common.cuh"
 
 namespace b200seg {
 
-constexpr int PT_X = 128, PT_Y = 8, PT_Z = 4;
-constexpr int PASTE_THREADS = (PT_X / 8) * PT_Y * PT_Z;   // 512
-constexpr int PASTE_MAXL = 96;
+constexpr int PT_X = 64, PT_Y = 16, PT_Z = 4;
+constexpr int PASTE_THREADS = (PT_X / 8) * PT_Y;          // 128: one thread = 8 consecutive x voxels on PT_Z planes
 
-struct PasteItem {
+struct __align__(8) VBox {          // box record in visit order
     int x1, y1, z1, x2, y2, z2;
     int sx, sy;
-    long long moff;
-    int rank;
-    int pad;
+    long long moff;                 // offset of the mask crop
+    long long mend;                 // one past its last byte
 };
 
+struct PasteGeom {
+    int S, H, W;
+    int tiles_x, tiles_y, tiles_z;
+    int words;                      // bitmap words per tile
+    int n_max;                      // slots per volume (vbox stride)
+};
+
+// grid (n_max, n_volumes)
+__global__ void __launch_bounds__(128)
+paste_bin_kernel(PasteGeom g, const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
+                 const int64_t* __restrict__ mask_off, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ n_valid, VBox* __restrict__ vbox_all, uint32_t* __restrict__ tile_bits_all) {
+    const int slot = blockIdx.x, vol = blockIdx.y;
+    const int base = det_off ? det_off[vol] : 0;
+    const int n_here = det_off ? det_off[vol + 1] - base : g.n_max;
+    const int nv = n_valid ? min(n_here, n_valid[vol]) : n_here;
+    if (slot >= nv) return;
+    const int inst = base + (order ? order[base + slot] : slot);
+    const int32_t* b = boxes + 6 * (size_t)inst;
+    const int x1 = b[0], y1 = b[1], z1 = b[2], x2 = b[3], y2 = b[4], z2 = b[5];
+    if (threadIdx.x == 0) {
+        VBox v;
+        v.x1 = x1; v.y1 = y1; v.z1 = z1; v.x2 = x2; v.y2 = y2; v.z2 = z2;
+        v.sx = x2 - x1 + 1; v.sy = y2 - y1 + 1; v.moff = mask_off[inst];
+        v.mend = v.moff + (long long)v.sx * v.sy * (z2 - z1 + 1);
+        vbox_all[(size_t)vol * g.n_max + slot] = v;
+    }
+    // tiles touched by the (volume-clipped) box
+    const int cx1 = max(x1, 0), cy1 = max(y1, 0), cz1 = max(z1, 0);
+    const int cx2 = min(x2, g.W - 1), cy2 = min(y2, g.H - 1), cz2 = min(z2, g.S - 1);
+    if (cx2 < cx1 || cy2 < cy1 || cz2 < cz1) return;
+    const int tx1 = cx1 / PT_X, tx2 = cx2 / PT_X, ty1 = cy1 / PT_Y, ty2 = cy2 / PT_Y, tz1 = cz1 / PT_Z, tz2 = cz2 / PT_Z;
+    const int nx = tx2 - tx1 + 1, ny = ty2 - ty1 + 1, nz = tz2 - tz1 + 1;
+    const uint32_t bit = 1u << (slot & 31);
+    const int w = slot >> 5;
+    const size_t ntiles = (size_t)g.tiles_x * g.tiles_y * g.tiles_z;
+    uint32_t* tile_bits = tile_bits_all + (size_t)vol * ntiles * g.words;
+    for (int t = threadIdx.x; t < nx * ny * nz; t += blockDim.x) {
+        const int tx = tx1 + t % nx, ty = ty1 + (t / nx) % ny, tz = tz1 + t / (nx * ny);
+        const size_t tile = ((size_t)tz * g.tiles_y + ty) * g.tiles_x + tx;
+        atomicOr(&tile_bits[tile * g.words + w], bit);
+    }
+}
+
+// 8 mask bytes starting at p (any alignment), as a little-endian 64-bit value
+__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(a & 7) * 8;
+    const unsigned long long lo = __ldg(q);
+    if (sh == 0) return lo;
+    const unsigned long long hi = __ldg(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
 __global__ void __launch_bounds__(PASTE_THREADS)
-paste_labels_kernel(uint16_t* __restrict__ seg, int S, int H, int W, int n,
-                    const int32_t* __restrict__ boxes, const uint16_t* __restrict__ ids,
-                    const uint8_t* __restrict__ masks, const int64_t* __restrict__ mask_off,
-                    const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid,
-                    uint8_t* __restrict__ survive, int vec_ok) {
-    __shared__ PasteItem s_list[PASTE_MAXL];
-    __shared__ int s_count;
-
-    const int tx0 = blockIdx.x * PT_X, ty0 = blockIdx.y * PT_Y, tz0 = blockIdx.z * PT_Z;
-    const int tid = threadIdx.x;
-    const int nv = n_valid ? min(n, *n_valid) : n;
-
-    // ---- ordered compaction of the instances that intersect this tile (warp 0) ------------------
-    if (tid < 32) {
-        int count = 0;
-        for (int base = 0; base < nv; base += 32) {
-            const int slot = base + tid;
-            bool hit = false;
-            int inst = 0;
-            int b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
-            if (slot < nv) {
-                inst = order ? order[slot] : slot;
-                const int32_t* b = boxes + 6 * inst;
-                b0 = b[0]; b1 = b[1]; b2 = b[2]; b3 = b[3]; b4 = b[4]; b5 = b[5];
-                hit = b0 < tx0 + PT_X && b3 >= tx0 && b1 < ty0 + PT_Y && b4 >= ty0 && b2 < tz0 + PT_Z && b5 >= tz0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int pos = count + __popc(m & ((1u << tid) - 1u));
-                if (pos < PASTE_MAXL) {
-                    PasteItem it;
-                    it.x1 = b0; it.y1 = b1; it.z1 = b2; it.x2 = b3; it.y2 = b4; it.z2 = b5;
-                    it.sx = b3 - b0 + 1; it.sy = b4 - b1 + 1;
-                    it.moff = mask_off[inst];
-                    it.rank = slot; it.pad = 0;
-                    s_list[pos] = it;
+paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, const uint16_t* __restrict__ ids,
+                    const uint8_t* __restrict__ masks, const VBox* __restrict__ vbox_all,
+                    const uint32_t* __restrict__ tile_bits_all, uint8_t* __restrict__ survive_all,
+                    const int32_t* __restrict__ det_off, int vec_ok, int vec_mask_ok) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int lx = tid % (PT_X / 8), ly = tid / (PT_X / 8);
+    const int ntiles = g.tiles_x * g.tiles_y * g.tiles_z;
+    const int total_tiles = ntiles * n_volumes;
+    const int txy = g.tiles_x * g.tiles_y;
+    const size_t V = (size_t)g.S * g.H * g.W;
+    int gt = blockIdx.x;
+    // software prefetch of the next tile's first 32 bitmap words (takes the load off the per-tile chain)
+    uint32_t next_word = (gt < total_tiles && lane < g.words) ? __ldg(tile_bits_all + (size_t)gt * g.words + lane) : 0u;
+    for (; gt < total_tiles; gt += gridDim.x) {
+        const uint32_t first_word = next_word;
+        const int ngt = gt + gridDim.x;
+        next_word = (ngt < total_tiles && lane < g.words) ? __ldg(tile_bits_all + (size_t)ngt * g.words + lane) : 0u;
+        const int vol = gt / ntiles, tile = gt - vol * ntiles;
+        const int tz = tile / txy, trem = tile - tz * txy, ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
+        const int x = tx * PT_X + lx * 8, y = ty * PT_Y + ly, z0 = tz * PT_Z;
+        const bool inside = x < g.W && y < g.H;
+        uint16_t lab[PT_Z][8];
+#pragma unroll
+        for (int p = 0; p < PT_Z; ++p)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) lab[p][k] = 0;
+        const uint32_t* bits = tile_bits_all + (size_t)gt * g.words;
+        const VBox* vbox = vbox_all + (size_t)vol * g.n_max;
+        uint8_t* survive = survive_all + (det_off ? det_off[vol] : 0);
+        for (int w0 = 0; w0 < g.words; w0 += 32) {
+            const uint32_t myword = w0 == 0 ? first_word : ((w0 + lane < g.words) ? __ldg(bits + w0 + lane) : 0u);
+            unsigned nzw = __ballot_sync(0xffffffffu, myword != 0u);
+            while (nzw) {                                           // warp-uniform
+                const int wl = __ffs(nzw) - 1;
+                nzw &= nzw - 1;
+                uint32_t m = __shfl_sync(0xffffffffu, myword, wl);
+                while (m) {
+                    const int rank = (w0 + wl) * 32 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const VBox vb = vbox[rank];                    // uniform address: one broadcast transaction
+                    if (!inside || y < vb.y1 || y > vb.y2 || x + 7 < vb.x1 || x > vb.x2) continue;
+                    const uint16_t id = ids[rank];
+                    // bytes k in [klo,khi] of my 8-voxel group lie inside the box
+                    const int klo = max(0, vb.x1 - x), khi = min(7, vb.x2 - x);
+                    const unsigned long long range = (~0ull >> (8 * (7 - khi))) & (~0ull << (8 * klo));
+                    const long long row0 = vb.moff + (long long)(y - vb.y1) * vb.sx + (x - vb.x1);   // may start before the row
+                    const long long zstride = (long long)vb.sy * vb.sx;
+                    bool wrote = false;
+#pragma unroll
+                    for (int p = 0; p < PT_Z; ++p) {
+                        const int z = z0 + p;
+                        if (z < vb.z1 || z > vb.z2) continue;
+                        const long long o = row0 + (long long)(z - vb.z1) * zstride;
+                        unsigned long long mb;
+                        if (vec_mask_ok && o >= vb.moff && o + 16 <= vb.mend) {
+                            mb = load8_unaligned(masks + o);           // both aligned words stay inside this crop
+                        } else {                                       // crop edge: byte reads inside [moff, mend)
+                            mb = 0ull;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (k >= klo && k <= khi) mb |= (unsigned long long)masks[o + k] << (8 * k);
+                        }
+                        mb &= range;
+                        if (mb == 0ull) continue;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (lab[p][k] == 0 && ((mb >> (8 * k)) & 0xFFull)) { lab[p][k] = id; wrote = true; }
+                    }
+                    if (wrote) survive[rank] = 1;                  // benign race: every writer stores the same value
                 }
             }
-            count += __popc(m);
         }
-        if (tid == 0) s_count = count;
-    }
-    __syncthreads();
-    const int count = s_count;
-
-    const int lx = tid % (PT_X / 8), ly = (tid / (PT_X / 8)) % PT_Y, lz = tid / ((PT_X / 8) * PT_Y);
-    const int x = tx0 + lx * 8, y = ty0 + ly, z = tz0 + lz;
-    if (x >= W || y >= H || z >= S) return;
-
-    uint16_t lab[8];
+        if (inside) {
+            uint16_t* seg = seg_all + (size_t)vol * V;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) lab[k] = 0;
-
-    if (count > 0) {
-        const int nl = min(count, PASTE_MAXL);
-        auto apply = [&](int x1, int y1, int z1, int x2, int y2, int z2, int sx, int sy, long long moff, int rank) {
-            if (y < y1 || y > y2 || z < z1 || z > z2 || x + 7 < x1 || x > x2) return;
-            const uint8_t* m = masks + moff + ((long long)(z - z1) * sy + (y - y1)) * sx;
-            const uint16_t id = ids[rank];
-            bool wrote = false;
+            for (int p = 0; p < PT_Z; ++p) {
+                const int z = z0 + p;
+                if (z >= g.S) break;
+                uint16_t* dst = seg + ((size_t)z * g.H + y) * g.W + x;
+                if (vec_ok && x + 7 < g.W) {
+                    uint4 v;
+                    v.x = lab[p][0] | ((uint32_t)lab[p][1] << 16); v.y = lab[p][2] | ((uint32_t)lab[p][3] << 16);
+                    v.z = lab[p][4] | ((uint32_t)lab[p][5] << 16); v.w = lab[p][6] | ((uint32_t)lab[p][7] << 16);
+                    st_stream_u4(dst, v);
+                } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int xx = x + k;
-                if (lab[k] == 0 && xx >= x1 && xx <= x2 && m[xx - x1]) { lab[k] = id; wrote = true; }
-            }
-            if (wrote) survive[rank] = 1;     // benign race: every writer stores the same value
-        };
-        for (int i = 0; i < nl; ++i) {
-            const PasteItem& it = s_list[i];
-            apply(it.x1, it.y1, it.z1, it.x2, it.y2, it.z2, it.sx, it.sy, it.moff, it.rank);
-        }
-        if (count > PASTE_MAXL) {
-            // rare overflow: continue over the remaining instances straight from global memory
-            for (int slot = s_list[PASTE_MAXL - 1].rank + 1; slot < nv; ++slot) {
-                const int inst = order ? order[slot] : slot;
-                const int32_t* b = boxes + 6 * inst;
-                apply(b[0], b[1], b[2], b[3], b[4], b[5], b[3] - b[0] + 1, b[4] - b[1] + 1, mask_off[inst], slot);
+                    for (int k = 0; k < 8; ++k) if (x + k < g.W) dst[k] = lab[p][k];
+                }
             }
         }
     }
+}
 
-    uint16_t* dst = seg + ((size_t)z * H + y) * W + x;
-    if (vec_ok && x + 7 < W) {
-        uint4 v;
-        v.x = lab[0] | ((uint32_t)lab[1] << 16); v.y = lab[2] | ((uint32_t)lab[3] << 16);
-        v.z = lab[4] | ((uint32_t)lab[5] << 16); v.w = lab[6] | ((uint32_t)lab[7] << 16);
-        st_stream_u4(dst, v);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (x + k < W) dst[k] = lab[k];
-    }
+static PasteGeom paste_geom(int S, int H, int W, int n_max) {
+    PasteGeom g;
+    g.S = S; g.H = H; g.W = W;
+    g.tiles_x = (W + PT_X - 1) / PT_X; g.tiles_y = (H + PT_Y - 1) / PT_Y; g.tiles_z = (S + PT_Z - 1) / PT_Z;
+    g.words = (n_max + 31) / 32;
+    if (g.words < 1) g.words = 1;
+    g.n_max = n_max > 0 ? n_max : 1;
+    return g;
 }
 
 }  // namespace b200seg
 
 using namespace b200seg;
 
-extern "C" int b200seg_paste_labels_dev(uint16_t* seg, int S, int H, int W, int n, const int32_t* boxes,
+extern "C" size_t b200seg_paste_labels_workspace_bytes(int n_volumes, int S, int H, int W, int n_max) {
+    if (S <= 0 || H <= 0 || W <= 0 || n_max < 0 || n_volumes <= 0) return 256;
+    const PasteGeom g = paste_geom(S, H, W, n_max);
+    const size_t ntiles = (size_t)g.tiles_x * g.tiles_y * g.tiles_z;
+    return align_up((size_t)n_volumes * ntiles * g.words * 4, 256) + align_up((size_t)n_volumes * g.n_max * sizeof(VBox), 256) + 256;
+}
+
+extern "C" int b200seg_paste_labels_dev(uint16_t* seg, int n_volumes, int S, int H, int W,
+                                        const int32_t* det_off, int n_max, const int32_t* boxes,
                                         const uint16_t* ids, const uint8_t* masks, const int64_t* mask_off,
                                         const int32_t* order, const int32_t* n_valid, uint8_t* survive,
-                                        b200seg_stream_t stream_) {
+                                        void* workspace, size_t workspace_bytes, b200seg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B200_CHECK_ARG(S > 0 && H > 0 && W > 0 && n >= 0, "paste_labels: bad sizes");
-    B200_CHECK_ARG(seg, "paste_labels: null seg");
-    B200_CHECK_ARG(n == 0 || (boxes && ids && masks && mask_off && survive), "paste_labels: null pointer");
-    if (n > 0) B200_CUDA(cudaMemsetAsync(survive, 0, (size_t)n, stream));
-    dim3 grid((W + PT_X - 1) / PT_X, (H + PT_Y - 1) / PT_Y, (S + PT_Z - 1) / PT_Z);
-    B200_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "paste_labels: volume too large for the grid");
-    const int vec_ok = (W % 8 == 0) && ((((uintptr_t)seg) & 15) == 0);
-    paste_labels_kernel<<<grid, PASTE_THREADS, 0, stream>>>(seg, S, H, W, n, boxes, ids, masks, mask_off, order,
-                                                           n_valid, survive, vec_ok);
+    B200_CHECK_ARG(S > 0 && H > 0 && W > 0 && n_max >= 0 && n_volumes >= 0, "paste_labels: bad sizes");
+    if (n_volumes == 0) return 0;
+    B200_CHECK_ARG(seg && workspace, "paste_labels: null seg/workspace");
+    B200_CHECK_ARG(n_volumes == 1 || det_off, "paste_labels: det_off is required for more than one volume");
+    B200_CHECK_ARG(n_volumes <= 65535, "paste_labels: too many volumes in one call");
+    B200_CHECK_ARG(n_max == 0 || (boxes && ids && masks && mask_off && survive), "paste_labels: null pointer");
+    if (workspace_bytes < b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max)) {
+        set_error("paste_labels: workspace too small");
+        return B200SEG_EWORKSPACE;
+    }
+    const PasteGeom g = paste_geom(S, H, W, n_max);
+    const size_t ntiles = (size_t)g.tiles_x * g.tiles_y * g.tiles_z;
+    B200_CHECK_ARG(ntiles * n_volumes < (1ull << 31), "paste_labels: too many tiles");
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint32_t* tile_bits = (uint32_t*)ws;
+    const size_t bits_bytes = (size_t)n_volumes * ntiles * g.words * 4;
+    VBox* vbox = (VBox*)(ws + align_up(bits_bytes, 256));
+    B200_CUDA(cudaMemsetAsync(tile_bits, 0, bits_bytes, stream));
+    if (n_max > 0) {
+        // single volume: survive[n_max] is cleared here; batched (det_off given): the caller clears survive[total]
+        if (!det_off) B200_CUDA(cudaMemsetAsync(survive, 0, (size_t)n_max, stream));
+        dim3 gb(n_max, n_volumes);
+        paste_bin_kernel<<<gb, 128, 0, stream>>>(g, det_off, boxes, mask_off, order, n_valid, vbox, tile_bits);
+        B200_LAUNCH_CHECK("paste_bin_kernel");
+    }
+    const int vec_ok = (W % 8 == 0) && ((((uintptr_t)seg) & 15) == 0) && (((size_t)S * H * W) % 8 == 0);
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_labels_kernel, PASTE_THREADS, 0) != cudaSuccess || occ < 1) occ = 4;
+    }
+    long long grid = (long long)num_sms() * occ;
+    if (grid > (long long)(ntiles * n_volumes)) grid = (long long)(ntiles * n_volumes);
+    paste_labels_kernel<<<(unsigned)grid, PASTE_THREADS, 0, stream>>>(seg, g, n_volumes, ids, masks, vbox, tile_bits, survive,
+                                                                     det_off, vec_ok, (int)((((uintptr_t)masks) & 7) == 0));
     B200_LAUNCH_CHECK("paste_labels_kernel");
     return 0;
 }

@@ -147,8 +147,10 @@ peaks_scan_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x
             if (do_hist) {                                   // warp-uniform: every lane reaches the match
                 const uint32_t bin = inb ? (ordered_key(v) >> 20) : 0xFFFFFFFFu;
                 if (inb && v != v) ++nan_local;
-                const unsigned peers = __match_any_sync(0xffffffffu, bin);
-                if (inb && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+                // warp aggregation for the contended case (all lanes in one bin); otherwise plain atomics
+                const uint32_t b0 = __shfl_sync(0xffffffffu, bin, 0);
+                if (__all_sync(0xffffffffu, bin == b0)) { if (lane == 0 && b0 != 0xFFFFFFFFu) atomicAdd(&s_hist[b0], 32u); }
+                else if (inb) atomicAdd(&s_hist[bin], 1u);
             }
             if (peak) {
                 const long long flat = ((long long)gz * H + gy) * W + gx;

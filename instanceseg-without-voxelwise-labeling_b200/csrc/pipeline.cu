@@ -22,8 +22,9 @@ __global__ void iota_u16_kernel(uint16_t* p, int n) {
 
 using namespace b200seg;
 
-extern "C" size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max) {
-    return b200seg_nms3d_workspace_bytes(n_volumes, n_max) + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256) + 512;
+extern "C" size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W) {
+    return align_up(b200seg_nms3d_workspace_bytes(n_volumes, n_max), 256) + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256) +
+           align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256) + 512;
 }
 
 extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
@@ -47,13 +48,15 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
     const int total = det_off_host[n_volumes];
     B200_CHECK_ARG(total == 0 || (dets && boxes && prm && crop_off && keep && rank_order && masks && b_max && status && survive),
                    "postproc_soma: null pointer");
-    if (workspace_bytes < b200seg_postproc_soma_workspace_bytes(n_volumes, n_max)) {
+    if (workspace_bytes < b200seg_postproc_soma_workspace_bytes(n_volumes, n_max, S, H, W)) {
         set_error("postproc_soma: workspace too small");
         return B200SEG_EWORKSPACE;
     }
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     uint16_t* ids = (uint16_t*)ws;
-    char* nms_ws = ws + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256);
+    char* paste_ws = ws + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256);
+    const size_t paste_ws_bytes = align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256);
+    char* nms_ws = paste_ws + paste_ws_bytes;
     const size_t nms_ws_bytes = workspace_bytes - (size_t)(nms_ws - (char*)workspace);
 
     int e = b200seg_nms3d_dev(dets, det_off_dev, n_volumes, n_max, nms_thresh, 0, keep, keep_count, rank_order,
@@ -63,21 +66,14 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
         iota_u16_kernel<<<(n_max + 255) / 256, 256, 0, stream>>>(ids, n_max);
         B200_LAUNCH_CHECK("iota_u16_kernel");
         B200_CUDA(cudaMemsetAsync(status, 0xFF, sizeof(int32_t) * (size_t)total, stream));   // -1 = not visited (suppressed)
-    }
-    const size_t V = (size_t)S * H * W;
-    for (int b = 0; b < n_volumes; ++b) {
-        const int base = det_off_host[b];
-        const int n = det_off_host[b + 1] - base;
-        if (n > 0) {
-            e = b200seg_soma_binarize_dev(volumes + b * V, S, H, W, boxes + 6 * (size_t)base, prm, crop_off + base, n,
-                                          rank_order + base, keep_count + b, masks, b_max + base, status + base, stream);
-            if (e) return e;
-        }
-        e = b200seg_paste_labels_dev(seg + b * V, S, H, W, n, boxes + 6 * (size_t)base, ids, masks, crop_off + base,
-                                     rank_order + base, keep_count + b, survive + base, stream);
+        B200_CUDA(cudaMemsetAsync(survive, 0, (size_t)total, stream));
+        // one launch for the instances of every volume: grid (n_max, n_volumes)
+        e = b200seg_soma_binarize_dev(volumes, n_volumes, S, H, W, det_off_dev, n_max, boxes, prm, crop_off,
+                                      rank_order, keep_count, masks, b_max, status, stream);
         if (e) return e;
     }
-    return 0;
+    return b200seg_paste_labels_dev(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
+                                    rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream);
 }
 
 // HOST-buffer entry point for ONE volume: what a drop-in binarization call site binds to.
@@ -96,7 +92,7 @@ extern "C" int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, i
     const size_t V = (size_t)S * H * W;
     const size_t nn = n > 0 ? n : 1;
     const size_t prm_bytes = n > 0 ? (size_t)crop_off[n] : 0;
-    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n);
+    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n, S, H, W);
     size_t total = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
                    2 * Carver::need(prm_bytes + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(4) +
                    3 * Carver::need(nn * 4) + Carver::need(nn) + ws_bytes;
