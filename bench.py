@@ -400,12 +400,18 @@ def main():
     ap.add_argument("--volumes-per-rank", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chain-only", action="store_true", help="profiling aid: time only the device-resident chain")
+    ap.add_argument("--ops-only", action="store_true", help="profiling aid: only the per-operator timings (RoIAlign3D, peaks, IoU, NMS)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.ops_only:
+        import torch
+        torch.cuda.set_device(local_rank)
+        print(json.dumps({"ops": bench_ops(torch, hbm_peak()[0]), "note": "ops-only profiling run"}))
         return
     if world > 1:
         import torch.distributed as dist

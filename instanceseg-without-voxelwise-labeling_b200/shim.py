@@ -10,7 +10,7 @@ registers these modules in sys.modules:
     modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d -> RoIAlignFunction_3d
     modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d   -> RoIAlign_3d, RoIAlignAvg_3d, RoIAlignMax_3d
     prm.peak_stimulation_3d      -> peak_stimulation_3d, PeakStimulation
-    otsu                         -> otsu_py_2d_fast
+    otsu                         -> otsu_py_2d_fast, otsu_py_2d (+ import-compat stubs otsu_py, otsu_mat)
 """
 import sys
 import types
@@ -40,7 +40,8 @@ def install(overwrite=True):
         "prm.peak_stimulation_3d": _module("prm.peak_stimulation_3d",
                                            peak_stimulation_3d=peak_stimulation_3d.peak_stimulation_3d,
                                            PeakStimulation=peak_stimulation_3d.PeakStimulation),
-        "otsu": _module("otsu", otsu_py_2d_fast=otsu.otsu_py_2d_fast),
+        "otsu": _module("otsu", otsu_py_2d_fast=otsu.otsu_py_2d_fast, otsu_py_2d=otsu.otsu_py_2d,
+                        otsu_py=otsu.otsu_py, otsu_mat=otsu.otsu_mat),
     }
     installed = []
     for name, mod in mods.items():

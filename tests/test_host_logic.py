@@ -37,7 +37,11 @@ def test_shim_installs_reference_names():
     from modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d import RoIAlignFunction_3d
     from modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d import RoIAlign_3d, RoIAlignAvg_3d, RoIAlignMax_3d
     from prm.peak_stimulation_3d import peak_stimulation_3d
-    from otsu import otsu_py_2d_fast
+    from otsu import otsu_py, otsu_py_2d, otsu_py_2d_fast      # binarization_soma.py:19, binarization_nuclei.py:12
+    import pytest
+    with pytest.raises(NotImplementedError):
+        otsu_py(None)
+    assert callable(otsu_py_2d)
     assert callable(m1.nms_3d) and callable(m1.nms_3d_volume) and callable(m2.bbox_overlaps_3d)
     f = RoIAlignFunction_3d(7, 7, 7, 0.25, 2)
     assert (f.aligned_slices, f.spatial_scale, f.sampling_ratio) == (7, 0.25, 2)
