@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200seg.so")
-SOURCES = ["api.cu", "nms3d.cu", "iou3d.cu", "roialign3d.cu", "peaks3d.cu", "otsu2d.cu", "paste.cu", "pipeline.cu"]
+SOURCES = ["api.cu", "nms3d.cu", "iou3d.cu", "roialign3d.cu", "peaks3d.cu", "otsu2d.cu", "soma_binarize.cu", "paste.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -27,7 +27,7 @@ def _newer(a, deps):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    common = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b200seg.h")]
+    common = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "otsu_common.cuh"), os.path.join(HERE, "..", "include", "b200seg.h")]
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)

@@ -89,4 +89,24 @@ __device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 8 bytes starting at p (any alignment) as a little-endian 64-bit value, fetched with one or two ALIGNED
+// 64-bit loads.  Only the first `nbytes` (1..8) bytes are meaningful: the second word is read only when
+// one of them lives there.  `safe_end` = end of the underlying buffer rounded DOWN to 8 bytes; windows
+// that would touch an aligned word crossing it fall back to byte loads (never reads out of bounds).
+__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t* p, int nbytes, const uint8_t* safe_end) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned mis = (unsigned)(a & 7);
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a - mis);
+    const bool need_hi = mis + (unsigned)nbytes > 8u;
+    if (reinterpret_cast<const uint8_t*>(q) + (need_hi ? 16 : 8) <= safe_end) {
+        const unsigned long long lo = __ldg(q);
+        if (!need_hi) return lo >> (mis * 8);
+        const unsigned long long hi = __ldg(q + 1);
+        return (lo >> (mis * 8)) | (hi << (64 - mis * 8));       // mis >= 1 here
+    }
+    unsigned long long v = 0ull;
+    for (int k = 0; k < nbytes; ++k) v |= (unsigned long long)__ldg(p + k) << (8 * k);
+    return v;
+}
+
 }  // namespace b200seg
