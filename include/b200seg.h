@@ -88,7 +88,8 @@ int b200seg_iou3d_host(const float* boxes, long long N, const float* query, long
  *         1 = "shw": forward emits (S,H,W) order and backward is its exact adjoint.
  * The backward is deterministic and atomics-free: every grad_in element is written exactly once.
  * ---------------------------------------------------------------------------------------------- */
-size_t b200seg_roialign3d_workspace_bytes(int R);
+/* workspace of the backward: per-RoI footprint boxes + per-axis adjoint tables (R x (S+H+W) x 8|16 floats) */
+size_t b200seg_roialign3d_workspace_bytes(int R, int S, int H, int W, int P_max);
 int b200seg_roialign3d_fwd_dev(const void* features, int dtype, const float* rois, void* output,
                                int B, int C, int S, int H, int W, int R,
                                int Ps, int Ph, int Pw, float spatial_scale, int sampling_ratio,

@@ -254,186 +254,222 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// "Owner computes": a CTA owns an 8x8x8 feature tile of one batch element and 8 channels (one channel per
+// warp).  roialign3d_prep_kernel turns every RoI into (a) its footprint box and (b) dense per-axis adjoint
+// tables W[axis][voxel coordinate][bin] over the whole feature extent, so a tile's slice of a table is one
+// contiguous 8 x PT block.  The CTA compacts the RoIs that hit its tile into an ordered list once; then every
+// warp walks that list on its own (no block barrier inside the loop): three small contractions per
+// (RoI, channel) restricted to the tile,
+//     T2[z][ph][pw] = sum_ps Wz[z][ps] G[ps][ph][pw],   T1[z][y][pw] = sum_ph Wy[y][ph] T2[z][ph][pw],
+//     acc[z][y][x] += (sum_pw Wx[x][pw] T1[z][y][pw]) / count,
+// with the tile gradient held in registers (a lane owns two (z,y) rows of 8 voxels).  RoIs are visited in index
+// order, so the result is deterministic, and every grad_in element is written exactly once (zero fill folded in).
 constexpr int RB_T = 8;            // feature tile edge (z,y,x)
+constexpr int RB_WARPS = 8;        // channels per CTA
+constexpr int RB_LIST = 1024;      // RoIs compacted per round
 
-struct RoiMeta {                   // one per RoI, built by roialign3d_prep_kernel
-    float start[3], bin[3];
-    int g[3];
+struct __align__(16) RoiBox {      // one per RoI, built by roialign3d_prep_kernel
     int lo[3], hi[3];              // footprint (inclusive), hi < lo when no valid sample on that axis
     int batch;
-    float count;
-    int pad[3];
+    float inv_count;
 };
 
-__global__ void roialign3d_prep_kernel(const float* __restrict__ rois, int R, RoiMeta* __restrict__ meta,
-                                       int S, int H, int W, int Ps, int Ph, int Pw, float scale, int sr, double zguard) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
+// grid = R, block = 64.  tables [R][S+H+W][PT] are cleared by the launcher beforehand.
+template <int PT>
+__global__ void __launch_bounds__(64)
+roialign3d_prep_kernel(const float* __restrict__ rois, int R, RoiBox* __restrict__ boxes, float* __restrict__ tables,
+                       int S, int H, int W, int Ps, int Ph, int Pw, float scale, int sr, double zguard) {
+    const int r = blockIdx.x;
+    __shared__ int s_lo[3], s_hi[3];
     AxisP ax[3];
     int batch; float count;
     roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, zguard, ax[0], ax[1], ax[2], batch, count);
     const int Pa[3] = {Ps, Ph, Pw};
-    RoiMeta m;
-    for (int a = 0; a < 3; ++a) {
-        int lo = 0x7fffffff, hi = -1;
-        for (int p = 0; p < Pa[a]; ++p)
-            for (int i = 0; i < ax[a].g; ++i) {
+    const int seg[3] = {0, S, S + H};
+    if (threadIdx.x < 3) { s_lo[threadIdx.x] = 0x7fffffff; s_hi[threadIdx.x] = -1; }
+    __syncthreads();
+    if (threadIdx.x < 3 * PT) {
+        const int a = threadIdx.x / PT, p = threadIdx.x % PT;
+        if (p < Pa[a]) {
+            float* col = tables + ((size_t)r * (S + H + W) + seg[a]) * PT + p;     // column p of axis a: stride PT
+            int lo = 0x7fffffff, hi = -1;
+            for (int i = 0; i < ax[a].g; ++i) {                                    // one thread per column: no races
                 const Tap t = axis_sample(ax[a], p, i);
-                if (t.valid) { lo = min(lo, t.low); hi = max(hi, t.high); }
+                if (!t.valid) continue;
+                col[(size_t)t.low * PT] += t.h;
+                col[(size_t)t.high * PT] += t.l;
+                lo = min(lo, t.low); hi = max(hi, t.high);
             }
-        m.start[a] = ax[a].start; m.bin[a] = ax[a].bin; m.g[a] = ax[a].g; m.lo[a] = lo; m.hi[a] = hi;
+            if (hi >= 0) { atomicMin(&s_lo[a], lo); atomicMax(&s_hi[a], hi); }
+        }
     }
-    m.batch = batch; m.count = count; m.pad[0] = m.pad[1] = m.pad[2] = 0;
-    meta[r] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RoiBox b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = s_lo[a]; b.hi[a] = s_hi[a]; }
+        b.batch = batch; b.inv_count = 1.0f / count;
+        boxes[r] = b;
+    }
 }
 
-template <int PT> struct BwdCfg { static constexpr int CC = PT == 8 ? 16 : 4; };
-
 template <typename T, int PT>
-__global__ void __launch_bounds__(RA_THREADS)
-roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiMeta* __restrict__ meta, T* __restrict__ gin,
-                      int C, int S, int H, int W, int R, int Ps, int Ph, int Pw, int layout, double zguard,
+__global__ void __launch_bounds__(RB_WARPS * 32)
+roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ boxes, const float* __restrict__ tables,
+                      T* __restrict__ gin, int C, int S, int H, int W, int R, int Ps, int Ph, int Pw,
                       int tiles_x, int tiles_y) {
-    constexpr int CC = BwdCfg<PT>::CC;
-    constexpr int ROWS = CC * RB_T * RB_T / RA_THREADS;        // feature rows (8 voxels) owned per thread
-    static_assert(CC * RB_T * RB_T % RA_THREADS == 0, "row ownership must be exact");
+    constexpr int V4 = PT / 4;
+    constexpr int WARP_FLOATS = 3 * RB_T * PT + RB_T * PT * PT + RB_T * RB_T * PT;
     extern __shared__ __align__(16) float s_dynb[];
-    __shared__ __align__(16) float s_w[3][RB_T][16];            // tile-local adjoint tables W[t][p]
-    float* s_T2 = s_dynb;                                       // [c][tz][ph][pw]   CC*RB_T*PT*PT
-    float* s_T1 = s_dynb + CC * RB_T * PT * PT;                 // [c][tz][ty][pw]   CC*RB_T*RB_T*PT
+    __shared__ int s_list[RB_LIST];
+    __shared__ int s_wcnt[RB_WARPS];
+    __shared__ int s_n;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* sW = s_dynb + (size_t)warp * WARP_FLOATS;              // [3][RB_T][PT]   tile slice of the adjoint tables
+    float* sT2 = sW + 3 * RB_T * PT;                              // [RB_T][PT(ph)][PT(pw)]
+    float* sT1 = sT2 + RB_T * PT * PT;                            // [RB_T][RB_T][PT(pw)]
 
     const int tile = blockIdx.x;
-    const int tx0 = (tile % tiles_x) * RB_T, ty0 = ((tile / tiles_x) % tiles_y) * RB_T, tz0 = (tile / (tiles_x * tiles_y)) * RB_T;
-    const int c0 = blockIdx.y * CC;
-    const int nc = min(CC, C - c0);
-    const int b = blockIdx.z;
-    const int tid = threadIdx.x;
-    const int t0[3] = {tz0, ty0, tx0};
+    const int t0[3] = {(tile / (tiles_x * tiles_y)) * RB_T, ((tile / tiles_x) % tiles_y) * RB_T, (tile % tiles_x) * RB_T};
     const int dims[3] = {S, H, W};
-    const int Pa[3] = {Ps, Ph, Pw};
+    const int seg[3] = {0, S, S + H};
+    const int c = blockIdx.y * RB_WARPS + warp;
+    const bool c_ok = c < C;
+    const int b = blockIdx.z;
     const size_t P3 = (size_t)Ps * Ph * Pw;
+    const int t1[3] = {min(t0[0] + RB_T, S) - 1, min(t0[1] + RB_T, H) - 1, min(t0[2] + RB_T, W) - 1};   // last voxel of the tile
 
-    float acc[ROWS][RB_T];
+    // lane owns rows (z = lane / 8 + 4 i, y = lane % 8), i = 0, 1
+    const int my_y = lane & 7, my_z = lane >> 3;
+    float acc[2][RB_T];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int x = 0; x < RB_T; ++x) acc[i][x] = 0.f;
 
-    for (int r = 0; r < R; ++r) {
-        const RoiMeta m = meta[r];                              // uniform broadcast load
-        if (m.batch != b) continue;
-        bool hit = true;
-        int rlo[3], rhi[3];                                     // tile-local index ranges touched by this RoI
+    for (int r0 = 0; r0 < R; r0 += RB_LIST) {
+        // ---- ordered list of the RoIs of this round that hit the tile ------------------------------
+        __syncthreads();                                          // every warp is done with the previous list
+        const int rn = min(RB_LIST, R - r0);
+        int n_list = 0;
+        for (int q0 = 0; q0 < rn; q0 += RB_WARPS * 32) {
+            const int q = q0 + tid;
+            bool hit = false;
+            if (q < rn) {
+                const RoiBox bx = boxes[r0 + q];
+                hit = bx.batch == b;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            rlo[a] = max(m.lo[a], t0[a]) - t0[a];
-            rhi[a] = min(m.hi[a], min(t0[a] + RB_T, dims[a]) - 1) - t0[a];
-            hit = hit && (m.hi[a] >= m.lo[a]) && rhi[a] >= rlo[a];
+                for (int a = 0; a < 3; ++a) hit = hit && bx.hi[a] >= bx.lo[a] && bx.hi[a] >= t0[a] && bx.lo[a] <= t1[a];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            int before = n_list;
+            for (int w = 0; w < warp; ++w) before += s_wcnt[w];
+            if (hit) s_list[before + __popc(m & ((1u << lane) - 1u))] = r0 + q;
+            for (int w = 0; w < RB_WARPS; ++w) n_list += s_wcnt[w];
+            __syncthreads();
         }
-        if (!hit) continue;                                     // CTA-uniform
-        __syncthreads();                                        // previous RoI done with s_w / s_T*
-        for (int i = tid; i < 3 * RB_T * 16; i += RA_THREADS) (&s_w[0][0][0])[i] = 0.f;
-        __syncthreads();
-        if (tid < 3 * 16) {
-            const int a = tid >> 4, p = tid & 15;
-            if (p < Pa[a]) {
-                AxisP ap;
-                ap.start = m.start[a]; ap.bin = m.bin[a]; ap.g = m.g[a]; ap.dim = dims[a];
-                ap.guard = a == 0 ? zguard : -1.0;
-                for (int i = 0; i < ap.g; ++i) {
-                    const Tap t = axis_sample(ap, p, i);
-                    if (!t.valid) continue;
-                    const int l = t.low - t0[a], h = t.high - t0[a];
-                    if (l >= 0 && l < RB_T) s_w[a][l][p] += t.h;
-                    if (h >= 0 && h < RB_T) s_w[a][h][p] += t.l;
+        if (!c_ok) continue;                                      // (still takes part in the barriers above)
+
+        for (int k = 0; k < n_list; ++k) {
+            const int r = s_list[k];
+            const RoiBox bx = boxes[r];                           // uniform address: one broadcast transaction
+            int rlo[3], rhi[3];                                   // tile-local index ranges touched by this RoI
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { rlo[a] = max(bx.lo[a], t0[a]) - t0[a]; rhi[a] = min(bx.hi[a], t1[a]) - t0[a]; }
+            // ---- tile slice of the three tables: [RB_T][PT] contiguous per axis ------------------------
+            const float* tab = tables + (size_t)r * (S + H + W) * PT;
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                for (int e = lane; e < RB_T * PT; e += 32) {
+                    const int t = e / PT;
+                    sW[a * RB_T * PT + e] = (t0[a] + t < dims[a]) ? __ldg(tab + (size_t)(seg[a] + t0[a]) * PT + e) : 0.f;
                 }
             }
-        }
-        __syncthreads();
-        const int nz = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1;
-        const T* g_r = gout + ((size_t)r * C + c0) * P3;
-        // ---- pass Z^T: thread = (c, ph, pw): T2[c][tz][ph][pw] = sum_ps Wz[tz][ps] * G[c][ps][ph][pw]
-        for (int item = tid; item < nc * Ph * Pw; item += RA_THREADS) {
-            const int pw = item % Pw, ph = (item / Pw) % Ph, c = item / (Pw * Ph);
-            float g[PT];
-            const T* gc = g_r + (size_t)c * P3;
-#pragma unroll
-            for (int p = 0; p < PT; ++p) {
-                g[p] = 0.f;
-                // grad_out is read in (S,H,W) order in both layouts: that is what the reference does
-                // (.cu:272-275) and it is also the exact adjoint of the layout-1 forward.
-                if (p < Ps) g[p] = to_f(gc[((size_t)p * Ph + ph) * Pw + pw]);
-            }
-            for (int z = 0; z < nz; ++z) {
-                const float4* wv = reinterpret_cast<const float4*>(&s_w[0][rlo[0] + z][0]);
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 w4 = wv[q];
-                    s += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
-                }
-                s_T2[((c * RB_T + z) * PT + ph) * PT + pw] = s;
-            }
-        }
-        __syncthreads();
-        // ---- pass Y^T: thread = (c, tz, pw): T1[c][tz][ty][pw] = sum_ph Wy[ty][ph] * T2[c][tz][ph][pw]
-        for (int item = tid; item < nc * nz * Pw; item += RA_THREADS) {
-            const int pw = item % Pw, z = (item / Pw) % nz, c = item / (Pw * nz);
-            float g[PT];
-#pragma unroll
-            for (int p = 0; p < PT; ++p) g[p] = p < Ph ? s_T2[((c * RB_T + z) * PT + p) * PT + pw] : 0.f;
-            for (int y = 0; y < ny; ++y) {
-                const float4* wv = reinterpret_cast<const float4*>(&s_w[1][rlo[1] + y][0]);
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 w4 = wv[q];
-                    s += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
-                }
-                s_T1[((c * RB_T + z) * RB_T + y) * PT + pw] = s;
-            }
-        }
-        __syncthreads();
-        // ---- pass X^T: thread owns fixed feature rows (c, tz, ty); accumulate in registers ----------
-        const float count = m.count;
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-            const int row = tid + i * RA_THREADS;               // row = (c * RB_T + tz) * RB_T + ty
-            const int ty = row % RB_T, tz = (row / RB_T) % RB_T, c = row / (RB_T * RB_T);
-            if (c < nc && tz >= rlo[0] && tz <= rhi[0] && ty >= rlo[1] && ty <= rhi[1]) {
-                const float* src = s_T1 + ((c * RB_T + (tz - rlo[0])) * RB_T + (ty - rlo[1])) * PT;
+            __syncwarp();
+            const int nz = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1;
+            const T* gc = gout + ((size_t)r * C + c) * P3;
+            // ---- pass Z^T: lane = (ph, pw) ---------------------------------------------------------------
+            // grad_out is read in (S,H,W) order in both layouts: that is what the reference does (.cu:272-275)
+            // and it is also the exact adjoint of the layout-1 forward.
+            for (int item = lane; item < Ph * Pw; item += 32) {
                 float g[PT];
 #pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 v = reinterpret_cast<const float4*>(src)[q];
-                    g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
-                }
+                for (int p = 0; p < PT; ++p) g[p] = p < Ps ? to_f(gc[(size_t)p * Ph * Pw + item]) : 0.f;
+                const int ph = item / Pw, pw = item - ph * Pw;
+                for (int z = 0; z < nz; ++z) {
+                    const float4* wv = reinterpret_cast<const float4*>(sW + (rlo[0] + z) * PT);
+                    float sum = 0.f;
 #pragma unroll
-                for (int p = 0; p < PT; ++p) if (p >= Pw) g[p] = 0.f;     // columns >= Pw of s_T1 are never written
-#pragma unroll
-                for (int x = 0; x < RB_T; ++x) {
-                    const float4* wv = reinterpret_cast<const float4*>(&s_w[2][x][0]);
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < PT / 4; ++q) {
+                    for (int q = 0; q < V4; ++q) {
                         const float4 w4 = wv[q];
-                        s += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
+                        sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
                     }
-                    acc[i][x] += s / count;
+                    sT2[(z * PT + ph) * PT + pw] = sum;
+                }
+            }
+            __syncwarp();
+            // ---- pass Y^T: lane = (z, pw) ----------------------------------------------------------------
+            for (int item = lane; item < nz * Pw; item += 32) {
+                const int z = item / Pw, pw = item - z * Pw;
+                float g[PT];
+#pragma unroll
+                for (int p = 0; p < PT; ++p) g[p] = p < Ph ? sT2[(z * PT + p) * PT + pw] : 0.f;
+                for (int y = 0; y < ny; ++y) {
+                    const float4* wv = reinterpret_cast<const float4*>(sW + (RB_T + rlo[1] + y) * PT);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < V4; ++q) {
+                        const float4 w4 = wv[q];
+                        sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
+                    }
+                    sT1[((z * RB_T + y) * PT) + pw] = sum;
+                }
+            }
+            __syncwarp();
+            // ---- pass X^T: lane owns fixed feature rows; accumulate in registers ------------------------
+            const float inv_count = bx.inv_count;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int tz = my_z + 4 * i;
+                if (tz >= rlo[0] && tz <= rhi[0] && my_y >= rlo[1] && my_y <= rhi[1]) {
+                    const float* src = sT1 + ((tz - rlo[0]) * RB_T + (my_y - rlo[1])) * PT;
+                    float g[PT];
+#pragma unroll
+                    for (int q = 0; q < V4; ++q) {
+                        const float4 v = reinterpret_cast<const float4*>(src)[q];
+                        g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int p = 0; p < PT; ++p) if (p >= Pw) g[p] = 0.f;     // columns >= Pw of sT1 are never written
+#pragma unroll
+                    for (int x = 0; x < RB_T; ++x) {
+                        if (x < rlo[2] || x > rhi[2]) continue;              // warp-uniform
+                        const float4* wv = reinterpret_cast<const float4*>(sW + (2 * RB_T + x) * PT);
+                        float sum = 0.f;
+#pragma unroll
+                        for (int q = 0; q < V4; ++q) {
+                            const float4 w4 = wv[q];
+                            sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
+                        }
+                        acc[i][x] += sum * inv_count;
+                    }
                 }
             }
         }
     }
     // ---- every grad_in element of the tile is written exactly once --------------------------------
+    if (c_ok) {
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) {
-        const int row = tid + i * RA_THREADS;
-        const int ty = row % RB_T, tz = (row / RB_T) % RB_T, c = row / (RB_T * RB_T);
-        const int z = tz0 + tz, y = ty0 + ty;
-        if (c < nc && z < S && y < H) {
-            T* dst = gin + ((((size_t)b * C + c0 + c) * S + z) * H + y) * W + tx0;
+        for (int i = 0; i < 2; ++i) {
+            const int z = t0[0] + my_z + 4 * i, y = t0[1] + my_y;
+            if (z < S && y < H) {
+                T* dst = gin + ((((size_t)b * C + c) * S + z) * H + y) * W + t0[2];
 #pragma unroll
-            for (int x = 0; x < RB_T; ++x) if (tx0 + x < W) dst[x] = from_f<T>(acc[i][x]);
+                for (int x = 0; x < RB_T; ++x) if (t0[2] + x < W) dst[x] = from_f<T>(acc[i][x]);
+            }
         }
     }
 }
@@ -442,8 +478,13 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiMeta* __restrict__ me
 
 using namespace b200seg;
 
-extern "C" size_t b200seg_roialign3d_workspace_bytes(int R) {
-    return align_up((size_t)(R > 0 ? R : 1) * sizeof(RoiMeta), 256) + 256;
+static size_t bwd_table_floats(int R, int S, int H, int W, int PT) { return (size_t)R * (size_t)(S + H + W) * PT; }
+
+extern "C" size_t b200seg_roialign3d_workspace_bytes(int R, int S, int H, int W, int P_max) {
+    const int PT = P_max <= 8 ? 8 : 16;
+    const size_t r = R > 0 ? R : 1;
+    if (S <= 0 || H <= 0 || W <= 0) return 256;
+    return align_up(r * sizeof(RoiBox), 256) + align_up(bwd_table_floats((int)r, S, H, W, PT) * sizeof(float), 256) + 256;
 }
 
 template <typename T>
@@ -483,24 +524,21 @@ extern "C" int b200seg_roialign3d_fwd_dev(const void* features, int dtype, const
     return launch_fwd<__nv_bfloat16>(features, rois, output, C, S, H, W, R, Ps, Ph, Pw, spatial_scale, sampling_ratio, layout, stream);
 }
 
-template <typename T>
-static int launch_bwd(const void* grad_out, const RoiMeta* meta, void* grad_in, int B, int C, int S, int H, int W, int R,
-                      int Ps, int Ph, int Pw, int layout, double zguard, cudaStream_t stream) {
-    const int pmax = Ps > Ph ? (Ps > Pw ? Ps : Pw) : (Ph > Pw ? Ph : Pw);
-    const int tiles_x = (W + RB_T - 1) / RB_T, tiles_y = (H + RB_T - 1) / RB_T, tiles_z = (S + RB_T - 1) / RB_T;
-    if (pmax <= 8) {
-        dim3 grid(tiles_x * tiles_y * tiles_z, (C + BwdCfg<8>::CC - 1) / BwdCfg<8>::CC, B);
-        const size_t smem = (size_t)BwdCfg<8>::CC * RB_T * (8 * 8 + RB_T * 8) * sizeof(float);
-        B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roialign3d_bwd_kernel<T, 8><<<grid, RA_THREADS, smem, stream>>>((const T*)grad_out, meta, (T*)grad_in, C, S, H, W, R,
-                                                                     Ps, Ph, Pw, layout, zguard, tiles_x, tiles_y);
-    } else {
-        dim3 grid(tiles_x * tiles_y * tiles_z, (C + BwdCfg<16>::CC - 1) / BwdCfg<16>::CC, B);
-        const size_t smem = (size_t)BwdCfg<16>::CC * RB_T * (16 * 16 + RB_T * 16) * sizeof(float);
-        B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roialign3d_bwd_kernel<T, 16><<<grid, RA_THREADS, smem, stream>>>((const T*)grad_out, meta, (T*)grad_in, C, S, H, W, R,
-                                                                      Ps, Ph, Pw, layout, zguard, tiles_x, tiles_y);
+template <typename T, int PT>
+static int launch_bwd_pt(const void* grad_out, const float* rois, void* grad_in, int B, int C, int S, int H, int W, int R,
+                         int Ps, int Ph, int Pw, float scale, int sr, double zguard, RoiBox* boxes, float* tables,
+                         cudaStream_t stream) {
+    if (R > 0) {
+        B200_CUDA(cudaMemsetAsync(tables, 0, bwd_table_floats(R, S, H, W, PT) * sizeof(float), stream));
+        roialign3d_prep_kernel<PT><<<R, 64, 0, stream>>>(rois, R, boxes, tables, S, H, W, Ps, Ph, Pw, scale, sr, zguard);
+        B200_LAUNCH_CHECK("roialign3d_prep_kernel");
     }
+    const int tiles_x = (W + RB_T - 1) / RB_T, tiles_y = (H + RB_T - 1) / RB_T, tiles_z = (S + RB_T - 1) / RB_T;
+    dim3 grid(tiles_x * tiles_y * tiles_z, (C + RB_WARPS - 1) / RB_WARPS, B);
+    const size_t smem = (size_t)RB_WARPS * (3 * RB_T * PT + RB_T * PT * PT + RB_T * RB_T * PT) * sizeof(float);
+    B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roialign3d_bwd_kernel<T, PT><<<grid, RB_WARPS * 32, smem, stream>>>((const T*)grad_out, boxes, tables, (T*)grad_in, C, S, H, W, R,
+                                                                       Ps, Ph, Pw, tiles_x, tiles_y);
     B200_LAUNCH_CHECK("roialign3d_bwd_kernel");
     return 0;
 }
@@ -516,20 +554,23 @@ extern "C" int b200seg_roialign3d_bwd_dev(const void* grad_out, int dtype, const
     B200_CHECK_ARG(layout == 0 || layout == 1, "roialign3d_bwd: bad layout");
     B200_CHECK_ARG(dtype == B200SEG_F32 || dtype == B200SEG_BF16, "roialign3d_bwd: bad dtype");
     B200_CHECK_ARG(grad_in && (R == 0 || (grad_out && rois && workspace)), "roialign3d_bwd: null pointer");
-    B200_CHECK_ARG(B <= 65535, "roialign3d_bwd: batch too large");
-    if (workspace_bytes < b200seg_roialign3d_workspace_bytes(R)) {
+    B200_CHECK_ARG(B <= 65535 && (C + RB_WARPS - 1) / RB_WARPS <= 65535, "roialign3d_bwd: batch / channel count too large");
+    const int pmax = Ps > Ph ? (Ps > Pw ? Ps : Pw) : (Ph > Pw ? Ph : Pw);
+    if (workspace_bytes < b200seg_roialign3d_workspace_bytes(R, S, H, W, pmax)) {
         set_error("roialign3d_bwd: workspace too small");
         return B200SEG_EWORKSPACE;
     }
-    RoiMeta* meta = (RoiMeta*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    RoiBox* boxes = (RoiBox*)ws;
+    float* tables = (float*)(ws + align_up((size_t)(R > 0 ? R : 1) * sizeof(RoiBox), 256));
     // layout 0 keeps the reference's backward z guard (-0.1); layout 1 is the exact adjoint (-1.0)
     const double zguard = layout == 0 ? -0.1 : -1.0;
-    if (R > 0) {
-        roialign3d_prep_kernel<<<(R + 127) / 128, 128, 0, stream>>>(rois, R, meta, S, H, W, Ps, Ph, Pw, spatial_scale,
-                                                                   sampling_ratio, zguard);
-        B200_LAUNCH_CHECK("roialign3d_prep_kernel");
+    if (pmax <= 8) {
+        if (dtype == B200SEG_F32)
+            return launch_bwd_pt<float, 8>(grad_out, rois, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, spatial_scale, sampling_ratio, zguard, boxes, tables, stream);
+        return launch_bwd_pt<__nv_bfloat16, 8>(grad_out, rois, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, spatial_scale, sampling_ratio, zguard, boxes, tables, stream);
     }
     if (dtype == B200SEG_F32)
-        return launch_bwd<float>(grad_out, meta, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, layout, zguard, stream);
-    return launch_bwd<__nv_bfloat16>(grad_out, meta, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, layout, zguard, stream);
+        return launch_bwd_pt<float, 16>(grad_out, rois, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, spatial_scale, sampling_ratio, zguard, boxes, tables, stream);
+    return launch_bwd_pt<__nv_bfloat16, 16>(grad_out, rois, grad_in, B, C, S, H, W, R, Ps, Ph, Pw, spatial_scale, sampling_ratio, zguard, boxes, tables, stream);
 }

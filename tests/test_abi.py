@@ -40,7 +40,7 @@ def test_argument_validation_without_gpu(built_lib):
     assert L.b200seg_peaks3d_dev(None, 1, 1, 4, 4, 4, 4, 0, None, None, 0, None, None, None, None, 0, None) == -1
     assert L.b200seg_roialign3d_fwd_dev(None, 0, None, None, 1, 1, 4, 4, 4, 1, 32, 7, 7, 0.25, 2, 0, None) == -1
     assert L.b200seg_nms3d_workspace_bytes(2, 1000) > 2 * 1000 * 16 * 8
-    assert L.b200seg_roialign3d_workspace_bytes(512) >= 512 * 64
+    assert L.b200seg_roialign3d_workspace_bytes(512, 8, 32, 32, 7) >= 512 * (32 + 72 * 8 * 4)
     assert L.b200seg_paste_labels_workspace_bytes(2, 128, 512, 512, 800) >= 2 * 8192 * 25 * 4
 
 
