@@ -27,7 +27,7 @@ namespace b200seg {
 constexpr int RA_THREADS = 256;
 constexpr int RA_FMAX = 16;        // max footprint voxels per axis handled by the separable forward path
 constexpr int RA_CC = 32;          // channels per forward CTA
-constexpr int RA_FWD_SMEM_FLOATS = 16384;   // 64 KB of intermediates
+template <int PT> struct FwdCfg { static constexpr int SMEM_FLOATS = PT == 8 ? 10240 : 24576; };   // 40 KB / 96 KB of per-warp buffers
 
 struct AxisP {
     float start, bin;
@@ -78,6 +78,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) FwdShared {
     float w[3][RA_FMAX][16];     // [axis z,y,x][footprint voxel][bin]
+    int row_off[RA_FMAX * RA_FMAX];   // offset of footprint row (z, y) inside one channel volume
     int lo[3], hi[3];
 };
 
@@ -123,8 +124,13 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
         return;
     }
     const T* feat_b = feat + ((size_t)batch * C + c0) * S * H * W;
-    const bool separable = Fz <= RA_FMAX && Fy <= RA_FMAX && Fx <= RA_FMAX &&
-                           (Fz * Fy * PT + Fz * PT * PT) <= RA_FWD_SMEM_FLOATS;
+    // per-warp buffers of the separable path (floats): A = stage [rows][RSx] + T1 [rows][PT] (reused as the output
+    // staging area [P3]), B = T2 [Fz][PT][PT]
+    const int rows = Fz * Fy;
+    const int RSx = Fx | 1;                               // odd row stride: conflict-free column walks
+    const int sizeA = max(rows * (RSx + PT), (int)((P3 + 3) & ~(size_t)3));
+    const int need = sizeA + Fz * PT * PT;
+    const bool separable = Fz <= RA_FMAX && Fy <= RA_FMAX && Fx <= RA_FMAX && need <= FwdCfg<PT>::SMEM_FLOATS;
     if (!separable) {
         // direct evaluation (reference arithmetic), coalesced over the output span of this CTA
         for (size_t idx = tid; idx < (size_t)nc * P3; idx += RA_THREADS) {
@@ -167,87 +173,114 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
             }
         }
     }
+    // offset of every footprint row (z, y) inside one channel volume
+    for (int row = tid; row < rows; row += RA_THREADS) {
+        const int z = row / Fy, y = row - z * Fy;
+        sh.row_off[row] = ((zlo + z) * H + (ylo + y)) * W + xlo;
+    }
     __syncthreads();
 
-    const int per_c = Fz * Fy * PT + Fz * PT * PT;
-    const int cc_fit = min(nc, RA_FWD_SMEM_FLOATS / per_c);
-    for (int cs = 0; cs < nc; cs += cc_fit) {
-        const int cc = min(cc_fit, nc - cs);
-        float* T1 = s_buf;                              // [cc][Fz][Fy][PT]
-        float* T2 = s_buf + (size_t)cc * Fz * Fy * PT;  // [cc][Fz][PT(ph)][PT(pw)]
-        // ---- pass X: thread = (c, z, y) row; PT-vector over pw ------------------------------------
-        for (int item = tid; item < cc * Fz * Fy; item += RA_THREADS) {
-            const int y = item % Fy, z = (item / Fy) % Fz, c = item / (Fy * Fz);
-            const T* row = feat_b + (((size_t)(cs + c) * S + (zlo + z)) * H + (ylo + y)) * W + xlo;
+    // ---- from here on every warp works on its own channels; no block barrier ------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_active = min(RA_THREADS / 32, FwdCfg<PT>::SMEM_FLOATS / need);
+    if (warp >= n_active) return;
+    float* bufA = s_buf + (size_t)warp * need;            // stage [rows][RSx], then T1 [rows][PT] behind it; later out [P3]
+    float* sT1 = bufA + rows * RSx;
+    float* sT2 = bufA + sizeA;                            // [Fz][PT(ph)][PT(pw)]
+    const int XS = Fx <= 8 ? 8 : 16;                      // lanes per footprint row while staging
+    const int lx = lane & (XS - 1), lr = lane / XS, rpi = 32 / XS;
+    constexpr int ZP_ITERS = (PT * PT + 31) / 32;
+    int zp_src[ZP_ITERS], zp_dst[ZP_ITERS];               // pass Z items of this lane: (ph, pw) = item / Pw, item % Pw
+#pragma unroll
+    for (int k = 0; k < ZP_ITERS; ++k) {
+        const int item = lane + 32 * k;
+        const int ph = item / Pw, pw = item - ph * Pw;
+        zp_src[k] = item < Ph * Pw ? ph * PT + pw : -1;
+        zp_dst[k] = layout == 0 ? item * Ps : item;       // layout 0: (H,W,S) order, bins of one (ph,pw) contiguous
+    }
+    const int ps_stride = layout == 0 ? 1 : Ph * Pw;
+    const int icount = ax[0].g * ax[1].g * ax[2].g;
+    const bool pow2 = (icount & (icount - 1)) == 0;
+    const float inv_count = 1.0f / count;                 // exact when count is a power of two (sr = 2: count = 8)
+    const size_t SHW = (size_t)S * H * W;
+
+    for (int c = warp; c < nc; c += n_active) {
+        const T* fc = feat_b + (size_t)c * SHW;
+        // ---- stage the footprint: XS lanes per row, coalesced within a row ---------------------------
+        __syncwarp();
+        for (int row = lr; row < rows; row += rpi)
+            if (lx < Fx) bufA[row * RSx + lx] = to_f(fc[sh.row_off[row] + lx]);
+        __syncwarp();
+        // ---- pass X: lane = footprint row; PT-vector over pw -------------------------------------------
+        for (int row = lane; row < rows; row += 32) {
             float acc[PT];
 #pragma unroll
             for (int p = 0; p < PT; ++p) acc[p] = 0.f;
+            const float* src = bufA + row * RSx;
             for (int x = 0; x < Fx; ++x) {
-                const float v = to_f(row[x]);
+                const float v = src[x];
                 const float4* wv = reinterpret_cast<const float4*>(&sh.w[2][x][0]);
 #pragma unroll
                 for (int q = 0; q < PT / 4; ++q) {
                     const float4 w4 = wv[q];
-                    acc[4 * q + 0] += w4.x * v; acc[4 * q + 1] += w4.y * v;
-                    acc[4 * q + 2] += w4.z * v; acc[4 * q + 3] += w4.w * v;
+                    acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
                 }
             }
-            float4* dst = reinterpret_cast<float4*>(T1 + (size_t)item * PT);
 #pragma unroll
-            for (int q = 0; q < PT / 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int p = 0; p < PT; ++p) sT1[row * PT + p] = acc[p];
         }
-        __syncthreads();
-        // ---- pass Y: thread = (c, z, pw); PT-vector over ph ----------------------------------------
-        for (int item = tid; item < cc * Fz * PT; item += RA_THREADS) {
-            const int pw = item % PT, cz = item / PT;
-            if (pw >= Pw) continue;
+        __syncwarp();
+        // ---- pass Y: lane = (z, pw); PT-vector over ph -------------------------------------------------
+        {
+            const int pw = lane % PT;
+            for (int z = lane / PT; z < Fz; z += 32 / PT) {
+                float acc[PT];
+#pragma unroll
+                for (int p = 0; p < PT; ++p) acc[p] = 0.f;
+                const float* src = sT1 + z * Fy * PT + pw;
+                for (int y = 0; y < Fy; ++y) {
+                    const float v = src[y * PT];
+                    const float4* wv = reinterpret_cast<const float4*>(&sh.w[1][y][0]);
+#pragma unroll
+                    for (int q = 0; q < PT / 4; ++q) {
+                        const float4 w4 = wv[q];
+                        acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
+                    }
+                }
+                float* dst = sT2 + z * PT * PT + pw;
+#pragma unroll
+                for (int p = 0; p < PT; ++p) dst[p * PT] = acc[p];
+            }
+        }
+        __syncwarp();
+        // ---- pass Z: lane = (ph, pw); PT-vector over ps, staged in bufA in the output order -----------
+#pragma unroll
+        for (int k = 0; k < ZP_ITERS; ++k) {
+            if (zp_src[k] < 0) continue;
             float acc[PT];
 #pragma unroll
             for (int p = 0; p < PT; ++p) acc[p] = 0.f;
-            const float* src = T1 + (size_t)cz * Fy * PT + pw;
-            for (int y = 0; y < Fy; ++y) {
-                const float v = src[y * PT];
-                const float4* wv = reinterpret_cast<const float4*>(&sh.w[1][y][0]);
-#pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 w4 = wv[q];
-                    acc[4 * q + 0] += w4.x * v; acc[4 * q + 1] += w4.y * v;
-                    acc[4 * q + 2] += w4.z * v; acc[4 * q + 3] += w4.w * v;
-                }
-            }
-            float* dst = T2 + (size_t)cz * PT * PT + pw;
-#pragma unroll
-            for (int p = 0; p < PT; ++p) dst[p * PT] = acc[p];
-        }
-        __syncthreads();
-        // ---- pass Z: thread = (c, ph, pw); PT-vector over ps, written contiguously -----------------
-        for (int item = tid; item < cc * Ph * Pw; item += RA_THREADS) {
-            const int pw = item % Pw, ph = (item / Pw) % Ph, c = item / (Pw * Ph);
-            float acc[PT];
-#pragma unroll
-            for (int p = 0; p < PT; ++p) acc[p] = 0.f;
-            const float* src = T2 + (size_t)c * Fz * PT * PT + ph * PT + pw;
+            const float* src = sT2 + zp_src[k];
             for (int z = 0; z < Fz; ++z) {
-                const float v = src[(size_t)z * PT * PT];
+                const float v = src[z * PT * PT];
                 const float4* wv = reinterpret_cast<const float4*>(&sh.w[0][z][0]);
 #pragma unroll
                 for (int q = 0; q < PT / 4; ++q) {
                     const float4 w4 = wv[q];
-                    acc[4 * q + 0] += w4.x * v; acc[4 * q + 1] += w4.y * v;
-                    acc[4 * q + 2] += w4.z * v; acc[4 * q + 3] += w4.w * v;
+                    acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
                 }
             }
-            T* o = out_r + (size_t)(cs + c) * P3;
-            if (layout == 0) {
-                T* o2 = o + ((size_t)ph * Pw + pw) * Ps;
+            float* dst = bufA + zp_dst[k];
 #pragma unroll
-                for (int p = 0; p < PT; ++p) if (p < Ps) o2[p] = from_f<T>(acc[p] / count);
-            } else {
-#pragma unroll
-                for (int p = 0; p < PT; ++p) if (p < Ps) o[((size_t)p * Ph + ph) * Pw + pw] = from_f<T>(acc[p] / count);
-            }
+            for (int p = 0; p < PT; ++p) if (p < Ps) dst[p * ps_stride] = pow2 ? acc[p] * inv_count : acc[p] / count;
         }
-        __syncthreads();
+        __syncwarp();
+        // ---- coalesced copy-out of the P3 bins of this (roi, channel) ----------------------------------
+        T* o = out_r + (size_t)c * P3;
+        for (int i = lane; i < (int)P3; i += 32) o[i] = from_f<T>(bufA[i]);
     }
 }
 
@@ -312,18 +345,34 @@ roialign3d_prep_kernel(const float* __restrict__ rois, int R, RoiBox* __restrict
     }
 }
 
-template <typename T, int PT>
+// dot product of PT table weights (shared memory, 16-byte aligned row) with PT register values
+template <int PT>
+__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float (&g)[PT]) {
+    float s0 = 0.f, s1 = 0.f;                                  // two chains: halves the dependent-FMA latency
+#pragma unroll
+    for (int q = 0; q < PT / 4; ++q) {
+        const float4 w4 = reinterpret_cast<const float4*>(wrow)[q];
+        s0 = fmaf(w4.x, g[4 * q], s0); s1 = fmaf(w4.y, g[4 * q + 1], s1);
+        s0 = fmaf(w4.z, g[4 * q + 2], s0); s1 = fmaf(w4.w, g[4 * q + 3], s1);
+    }
+    return s0 + s1;
+}
+
+// PC > 0: cubic pooled size known at compile time (Ps == Ph == Pw == PC): constant strides, no divisions.
+template <typename T, int PT, int PC>
 __global__ void __launch_bounds__(RB_WARPS * 32)
 roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ boxes, const float* __restrict__ tables,
-                      T* __restrict__ gin, int C, int S, int H, int W, int R, int Ps, int Ph, int Pw,
+                      T* __restrict__ gin, int C, int S, int H, int W, int R, int Ps_, int Ph_, int Pw_,
                       int tiles_x, int tiles_y) {
-    constexpr int V4 = PT / 4;
     constexpr int WARP_FLOATS = 3 * RB_T * PT + RB_T * PT * PT + RB_T * RB_T * PT;
+    constexpr int ZT_ITERS = (PT * PT + 31) / 32;                 // (ph,pw) items per lane in pass Z^T
+    constexpr int ZPI = 32 / PT;                                  // z slices per iteration in pass Y^T (lane = z * PT + pw)
     extern __shared__ __align__(16) float s_dynb[];
     __shared__ int s_list[RB_LIST];
     __shared__ int s_wcnt[RB_WARPS];
-    __shared__ int s_n;
 
+    const int Ps = PC > 0 ? PC : Ps_, Ph = PC > 0 ? PC : Ph_, Pw = PC > 0 ? PC : Pw_;
+    const int PP = Ph * Pw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* sW = s_dynb + (size_t)warp * WARP_FLOATS;              // [3][RB_T][PT]   tile slice of the adjoint tables
     float* sT2 = sW + 3 * RB_T * PT;                              // [RB_T][PT(ph)][PT(pw)]
@@ -336,9 +385,17 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ box
     const int c = blockIdx.y * RB_WARPS + warp;
     const bool c_ok = c < C;
     const int b = blockIdx.z;
-    const size_t P3 = (size_t)Ps * Ph * Pw;
+    const size_t P3 = (size_t)Ps * PP;
     const int t1[3] = {min(t0[0] + RB_T, S) - 1, min(t0[1] + RB_T, H) - 1, min(t0[2] + RB_T, W) - 1};   // last voxel of the tile
 
+    // pass Z^T items of this lane: item = lane + 32 k -> (ph, pw), fixed for the whole kernel
+    int zt_off[ZT_ITERS];                                         // offset of (ph, pw) inside a [PT][PT] plane of sT2
+#pragma unroll
+    for (int k = 0; k < ZT_ITERS; ++k) {
+        const int item = lane + 32 * k;
+        const int ph = item / Pw, pw = item - ph * Pw;
+        zt_off[k] = item < PP ? ph * PT + pw : -1;
+    }
     // lane owns rows (z = lane / 8 + 4 i, y = lane % 8), i = 0, 1
     const int my_y = lane & 7, my_z = lane >> 3;
     float acc[2][RB_T];
@@ -383,49 +440,46 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ box
             __syncwarp();
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                for (int e = lane; e < RB_T * PT; e += 32) {
-                    const int t = e / PT;
-                    sW[a * RB_T * PT + e] = (t0[a] + t < dims[a]) ? __ldg(tab + (size_t)(seg[a] + t0[a]) * PT + e) : 0.f;
+                const float2* src = reinterpret_cast<const float2*>(tab + (size_t)(seg[a] + t0[a]) * PT);
+#pragma unroll
+                for (int e = 0; e < RB_T * PT / 64; ++e) {
+                    const int f2 = lane + 32 * e;                 // float2 index inside the [RB_T][PT] slice
+                    const int t = (2 * f2) / PT;
+                    const float2 v = (t0[a] + t < dims[a]) ? __ldg(src + f2) : make_float2(0.f, 0.f);
+                    reinterpret_cast<float2*>(sW + a * RB_T * PT)[f2] = v;
                 }
             }
             __syncwarp();
             const int nz = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1;
-            const T* gc = gout + ((size_t)r * C + c) * P3;
+            const T* gc = gout + ((size_t)r * C + c) * P3 + lane;
             // ---- pass Z^T: lane = (ph, pw) ---------------------------------------------------------------
             // grad_out is read in (S,H,W) order in both layouts: that is what the reference does (.cu:272-275)
             // and it is also the exact adjoint of the layout-1 forward.
-            for (int item = lane; item < Ph * Pw; item += 32) {
+#pragma unroll
+            for (int it = 0; it < ZT_ITERS; ++it) {
+                if (zt_off[it] < 0) continue;
                 float g[PT];
 #pragma unroll
-                for (int p = 0; p < PT; ++p) g[p] = p < Ps ? to_f(gc[(size_t)p * Ph * Pw + item]) : 0.f;
-                const int ph = item / Pw, pw = item - ph * Pw;
-                for (int z = 0; z < nz; ++z) {
-                    const float4* wv = reinterpret_cast<const float4*>(sW + (rlo[0] + z) * PT);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int q = 0; q < V4; ++q) {
-                        const float4 w4 = wv[q];
-                        sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
-                    }
-                    sT2[(z * PT + ph) * PT + pw] = sum;
-                }
+                for (int p = 0; p < PT; ++p) g[p] = p < Ps ? to_f(gc[p * PP + 32 * it]) : 0.f;
+                float* dst = sT2 + zt_off[it];
+#pragma unroll 2
+                for (int z = 0; z < nz; ++z) dst[z * PT * PT] = dot_row<PT>(sW + (rlo[0] + z) * PT, g);
             }
             __syncwarp();
             // ---- pass Y^T: lane = (z, pw) ----------------------------------------------------------------
-            for (int item = lane; item < nz * Pw; item += 32) {
-                const int z = item / Pw, pw = item - z * Pw;
-                float g[PT];
+            {
+                const int pw = lane % PT;
 #pragma unroll
-                for (int p = 0; p < PT; ++p) g[p] = p < Ph ? sT2[(z * PT + p) * PT + pw] : 0.f;
-                for (int y = 0; y < ny; ++y) {
-                    const float4* wv = reinterpret_cast<const float4*>(sW + (RB_T + rlo[1] + y) * PT);
-                    float sum = 0.f;
+                for (int it = 0; it < RB_T / ZPI; ++it) {
+                    const int z = lane / PT + it * ZPI;
+                    if (z < nz && pw < Pw) {
+                        float g[PT];
 #pragma unroll
-                    for (int q = 0; q < V4; ++q) {
-                        const float4 w4 = wv[q];
-                        sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
+                        for (int p = 0; p < PT; ++p) g[p] = p < Ph ? sT2[(z * PT + p) * PT + pw] : 0.f;
+                        float* dst = sT1 + z * RB_T * PT + pw;
+#pragma unroll 2
+                        for (int y = 0; y < ny; ++y) dst[y * PT] = dot_row<PT>(sW + (RB_T + rlo[1] + y) * PT, g);
                     }
-                    sT1[((z * RB_T + y) * PT) + pw] = sum;
                 }
             }
             __syncwarp();
@@ -438,24 +492,15 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ box
                     const float* src = sT1 + ((tz - rlo[0]) * RB_T + (my_y - rlo[1])) * PT;
                     float g[PT];
 #pragma unroll
-                    for (int q = 0; q < V4; ++q) {
+                    for (int q = 0; q < PT / 4; ++q) {
                         const float4 v = reinterpret_cast<const float4*>(src)[q];
                         g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
                     }
 #pragma unroll
                     for (int p = 0; p < PT; ++p) if (p >= Pw) g[p] = 0.f;     // columns >= Pw of sT1 are never written
+                    // rows of the Wx slice outside the footprint are zero, so all 8 voxels can be updated blindly
 #pragma unroll
-                    for (int x = 0; x < RB_T; ++x) {
-                        if (x < rlo[2] || x > rhi[2]) continue;              // warp-uniform
-                        const float4* wv = reinterpret_cast<const float4*>(sW + (2 * RB_T + x) * PT);
-                        float sum = 0.f;
-#pragma unroll
-                        for (int q = 0; q < V4; ++q) {
-                            const float4 w4 = wv[q];
-                            sum += w4.x * g[4 * q] + w4.y * g[4 * q + 1] + w4.z * g[4 * q + 2] + w4.w * g[4 * q + 3];
-                        }
-                        acc[i][x] += sum * inv_count;
-                    }
+                    for (int x = 0; x < RB_T; ++x) acc[i][x] = fmaf(dot_row<PT>(sW + (2 * RB_T + x) * PT, g), inv_count, acc[i][x]);
                 }
             }
         }
@@ -492,12 +537,13 @@ static int launch_fwd(const void* features, const float* rois, void* output, int
                       int Ps, int Ph, int Pw, float scale, int sr, int layout, cudaStream_t stream) {
     const int pmax = Ps > Ph ? (Ps > Pw ? Ps : Pw) : (Ph > Pw ? Ph : Pw);
     dim3 grid(R, (C + RA_CC - 1) / RA_CC);
-    const size_t smem = RA_FWD_SMEM_FLOATS * sizeof(float);
     if (pmax <= 8) {
+        const size_t smem = FwdCfg<8>::SMEM_FLOATS * sizeof(float);
         B200_CUDA(cudaFuncSetAttribute(roialign3d_fwd_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         roialign3d_fwd_kernel<T, 8><<<grid, RA_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W,
                                                                         Ps, Ph, Pw, scale, sr, layout);
     } else {
+        const size_t smem = FwdCfg<16>::SMEM_FLOATS * sizeof(float);
         B200_CUDA(cudaFuncSetAttribute(roialign3d_fwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         roialign3d_fwd_kernel<T, 16><<<grid, RA_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W,
                                                                          Ps, Ph, Pw, scale, sr, layout);
@@ -536,9 +582,16 @@ static int launch_bwd_pt(const void* grad_out, const float* rois, void* grad_in,
     const int tiles_x = (W + RB_T - 1) / RB_T, tiles_y = (H + RB_T - 1) / RB_T, tiles_z = (S + RB_T - 1) / RB_T;
     dim3 grid(tiles_x * tiles_y * tiles_z, (C + RB_WARPS - 1) / RB_WARPS, B);
     const size_t smem = (size_t)RB_WARPS * (3 * RB_T * PT + RB_T * PT * PT + RB_T * RB_T * PT) * sizeof(float);
-    B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roialign3d_bwd_kernel<T, PT><<<grid, RB_WARPS * 32, smem, stream>>>((const T*)grad_out, boxes, tables, (T*)grad_in, C, S, H, W, R,
-                                                                       Ps, Ph, Pw, tiles_x, tiles_y);
+    constexpr int PC = PT == 8 ? 7 : 14;                           // the pooled sizes the model uses (box head 7, mask head 14)
+    if (Ps == PC && Ph == PC && Pw == PC) {
+        B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, PT, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roialign3d_bwd_kernel<T, PT, PC><<<grid, RB_WARPS * 32, smem, stream>>>((const T*)grad_out, boxes, tables, (T*)grad_in, C, S, H, W, R,
+                                                                               Ps, Ph, Pw, tiles_x, tiles_y);
+    } else {
+        B200_CUDA(cudaFuncSetAttribute(roialign3d_bwd_kernel<T, PT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roialign3d_bwd_kernel<T, PT, 0><<<grid, RB_WARPS * 32, smem, stream>>>((const T*)grad_out, boxes, tables, (T*)grad_in, C, S, H, W, R,
+                                                                              Ps, Ph, Pw, tiles_x, tiles_y);
+    }
     B200_LAUNCH_CHECK("roialign3d_bwd_kernel");
     return 0;
 }
