@@ -173,6 +173,10 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
             }
         }
     }
+    const int icount = ax[0].g * ax[1].g * ax[2].g;
+    const bool pow2 = (icount & (icount - 1)) == 0;       // sr = 2: count = 8 -> scaling by 1/count is exact
+    __syncthreads();
+    if (pow2) for (int i = tid; i < RA_FMAX * 16; i += RA_THREADS) (&sh.w[0][0][0])[i] *= 1.0f / count;
     // offset of every footprint row (z, y) inside one channel volume
     for (int row = tid; row < rows; row += RA_THREADS) {
         const int z = row / Fy, y = row - z * Fy;
@@ -199,17 +203,18 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
         zp_dst[k] = layout == 0 ? item * Ps : item;       // layout 0: (H,W,S) order, bins of one (ph,pw) contiguous
     }
     const int ps_stride = layout == 0 ? 1 : Ph * Pw;
-    const int icount = ax[0].g * ax[1].g * ax[2].g;
-    const bool pow2 = (icount & (icount - 1)) == 0;
-    const float inv_count = 1.0f / count;                 // exact when count is a power of two (sr = 2: count = 8)
     const size_t SHW = (size_t)S * H * W;
 
     for (int c = warp; c < nc; c += n_active) {
         const T* fc = feat_b + (size_t)c * SHW;
         // ---- stage the footprint: XS lanes per row, coalesced within a row ---------------------------
         __syncwarp();
-        for (int row = lr; row < rows; row += rpi)
-            if (lx < Fx) bufA[row * RSx + lx] = to_f(fc[sh.row_off[row] + lx]);
+        if (lx < Fx) {
+            const T* fcl = fc + lx;
+            float* dst = bufA + lr * RSx + lx;
+            const int dstep = rpi * RSx;
+            for (int row = lr; row < rows; row += rpi, dst += dstep) *dst = to_f(fcl[sh.row_off[row]]);
+        }
         __syncwarp();
         // ---- pass X: lane = footprint row; PT-vector over pw -------------------------------------------
         for (int row = lane; row < rows; row += 32) {
@@ -275,12 +280,26 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
             }
             float* dst = bufA + zp_dst[k];
 #pragma unroll
-            for (int p = 0; p < PT; ++p) if (p < Ps) dst[p * ps_stride] = pow2 ? acc[p] * inv_count : acc[p] / count;
+            if (pow2) {                                    // 1/count already folded into the z table
+#pragma unroll
+                for (int p = 0; p < PT; ++p) if (p < Ps) dst[p * ps_stride] = acc[p];
+            } else {
+#pragma unroll
+                for (int p = 0; p < PT; ++p) if (p < Ps) dst[p * ps_stride] = acc[p] / count;
+            }
         }
         __syncwarp();
         // ---- coalesced copy-out of the P3 bins of this (roi, channel) ----------------------------------
         T* o = out_r + (size_t)c * P3;
-        for (int i = lane; i < (int)P3; i += 32) o[i] = from_f<T>(bufA[i]);
+        {
+            const int n3 = (int)P3;
+            int i = lane;
+            for (; i + 96 < n3; i += 128) {
+                const float v0 = bufA[i], v1 = bufA[i + 32], v2 = bufA[i + 64], v3 = bufA[i + 96];
+                o[i] = from_f<T>(v0); o[i + 32] = from_f<T>(v1); o[i + 64] = from_f<T>(v2); o[i + 96] = from_f<T>(v3);
+            }
+            for (; i < n3; i += 32) o[i] = from_f<T>(bufA[i]);
+        }
     }
 }
 
