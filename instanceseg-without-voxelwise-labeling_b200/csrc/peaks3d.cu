@@ -64,31 +64,38 @@ static PeakWs peak_layout(void* base, int BA, long long V) {
 }
 
 // Finds the bin holding ascending rank k in hist[nbins]; returns bin and the rank inside it.
-// Must be called by all PK_THREADS threads; s_tmp has PK_THREADS+2 entries.
+// Must be called by all PK_THREADS threads; s_tmp has PK_THREADS+2 entries.  Block-wide prefix sum of per-thread
+// bin groups (warp shuffles + one shared-memory hop); the single thread whose group contains rank k resolves it.
 __device__ void select_bin(const uint32_t* __restrict__ hist, int nbins, unsigned long long k,
                            unsigned long long* s_tmp, int* out_bin, unsigned long long* out_k) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PK_THREADS / 32;
     const int per = (nbins + PK_THREADS - 1) / PK_THREADS;
     const int b0 = min(nbins, tid * per), b1 = min(nbins, b0 + per);
     unsigned long long local = 0;
     for (int b = b0; b < b1; ++b) local += hist[b];
-    s_tmp[tid] = local;
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    if (tid == 0) { s_tmp[NW] = (unsigned long long)(nbins - 1); s_tmp[NW + 1] = 0ull; }   // fallback: rank beyond the total
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long acc = 0;
-        int t = 0;
-        for (; t < PK_THREADS; ++t) { if (acc + s_tmp[t] > k) break; acc += s_tmp[t]; }
-        if (t >= PK_THREADS) t = PK_THREADS - 1;
-        const int c0 = min(nbins, t * per), c1 = min(nbins, c0 + per);
-        int b = c0;
-        for (; b < c1; ++b) { const unsigned long long h = hist[b]; if (acc + h > k) break; acc += h; }
-        if (b >= nbins) b = nbins - 1;
-        s_tmp[PK_THREADS] = (unsigned long long)b;
-        s_tmp[PK_THREADS + 1] = k - acc;
+    unsigned long long before = 0;
+    for (int w = 0; w < warp; ++w) before += s_tmp[w];
+    const unsigned long long excl = before + incl - local;
+    if (k >= excl && k < excl + local) {                   // exactly one thread (groups are disjoint, local > 0 here)
+        unsigned long long acc = excl;
+        int b = b0;
+        for (; b < b1; ++b) { const unsigned long long h = hist[b]; if (acc + h > k) break; acc += h; }
+        s_tmp[NW] = (unsigned long long)b;
+        s_tmp[NW + 1] = k - acc;
     }
     __syncthreads();
-    *out_bin = (int)s_tmp[PK_THREADS];
-    *out_k = s_tmp[PK_THREADS + 1];
+    *out_bin = (int)s_tmp[NW];
+    *out_k = s_tmp[NW + 1];
     __syncthreads();
 }
 
@@ -166,6 +173,99 @@ peaks_scan_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x
     }
 }
 
+// ---- window 3 (the reference default, peak_response_mapping_3d.py:29): register sliding window ----------
+// The tile is stored as ORDERED KEYS (monotone uint32 image of the float, every NaN = 0xFFFFFFFF), so the ATen
+// arg-max rule becomes integer arithmetic: with Kb / Ka the unsigned maxima over the 13 neighbours that come
+// earlier / later in the (z,y,x) window scan,
+//     v not NaN:  peak <=> v != -inf  and  Kb < key(v)  and  Ka <= key(v)      (a NaN neighbour has the largest key)
+//     v NaN:      peak <=> Ka != key(NaN)                                       (the LAST NaN of a window wins)
+// A thread owns one (x,y) column of the tile and marches along z keeping three plane summaries in registers
+// (max of the 9, max of the upper row, max of the lower row, left, centre, right): 9 shared loads, 6 three-input
+// integer maxima and two compares per voxel, no branches.  The level-1 radix histogram of the exact median
+// uses the key's top 12 bits directly.
+constexpr int P3_TX = 32, P3_TY = 8, P3_TZ = 16;
+constexpr int P3_HX = P3_TX + 2, P3_HY = P3_TY + 2, P3_HZ = P3_TZ + 2;
+
+struct PlaneStat { uint32_t m9, top3, bot3, l, c, r; };
+
+__device__ __forceinline__ PlaneStat plane_stat(const uint32_t* __restrict__ p) {   // p -> key (dy=0, dx=0) of the 3x3 patch
+    PlaneStat s;
+    s.top3 = __vimax3_u32(p[0], p[1], p[2]);
+    s.l = p[P3_HX]; s.c = p[P3_HX + 1]; s.r = p[P3_HX + 2];
+    s.bot3 = __vimax3_u32(p[2 * P3_HX], p[2 * P3_HX + 1], p[2 * P3_HX + 2]);
+    s.m9 = __vimax3_u32(s.top3, s.bot3, __vimax3_u32(s.l, s.c, s.r));
+    return s;
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+peaks_scan3_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x, int tiles_y, int tiles_z,
+                   int do_hist, PeakWs ws) {
+    __shared__ uint32_t s_key[P3_HZ * P3_HY * P3_HX];
+    __shared__ uint32_t s_hist[PK_BINS1];
+    const int ba = blockIdx.y;
+    const long long V = (long long)S * H * W;
+    const float* vol = in + (size_t)ba * V;
+    uint32_t* bits = ws.bits + (size_t)ba * ws.words;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t KEY_NAN = 0xFFFFFFFFu, KEY_NINF = 0x007FFFFFu;          // ordered_key(-inf) = ~0xFF800000
+    if (do_hist) for (int i = tid; i < PK_BINS1; i += PK_THREADS) s_hist[i] = 0u;
+    unsigned nan_local = 0;
+    const int ntiles = tiles_x * tiles_y * tiles_z;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, tz = tile / (tiles_x * tiles_y);
+        const int x0 = tx * P3_TX, y0 = ty * P3_TY, z0 = tz * P3_TZ;
+        __syncthreads();
+        // ---- load: one warp per halo row; lanes 0,1 also fetch the two halo columns --------------------
+        for (int rr = warp; rr < P3_HY * P3_HZ; rr += PK_THREADS / 32) {
+            const int hz = rr / P3_HY, hy = rr - hz * P3_HY;
+            const int gy = y0 + hy - 1, gz = z0 + hz - 1;
+            const bool row_ok = gy >= 0 && gy < H && gz >= 0 && gz < S;     // warp-uniform
+            uint32_t* dst = s_key + rr * P3_HX;
+            uint32_t k = KEY_NINF, kh = KEY_NINF;
+            if (row_ok) {
+                const float* row = vol + ((size_t)gz * H + gy) * W;
+                const int gx = x0 + lane;
+                if (gx < W) k = ordered_key(row[gx]);
+                if (lane < 2) { const int hxg = lane == 0 ? x0 - 1 : x0 + P3_TX; if (hxg >= 0 && hxg < W) kh = ordered_key(row[hxg]); }
+            }
+            dst[1 + lane] = k;
+            if (lane < 2) dst[lane == 0 ? 0 : P3_HX - 1] = kh;
+        }
+        __syncthreads();
+        // ---- compute: thread = (x, y) column, march along z -------------------------------------------
+        const int lx = lane, ly = warp;                   // 32 x 8 threads
+        const int gx = x0 + lx, gy = y0 + ly;
+        const bool col_ok = gx < W && gy < H;
+        const uint32_t* colp = s_key + ly * P3_HX + lx;   // (dy = 0, dx = 0) of the patch in halo plane 0
+        PlaneStat prev = plane_stat(colp), cur = plane_stat(colp + P3_HY * P3_HX);
+#pragma unroll 4
+        for (int lz = 0; lz < P3_TZ; ++lz) {
+            const PlaneStat next = plane_stat(colp + (lz + 2) * P3_HY * P3_HX);
+            const uint32_t kb = __vimax3_u32(prev.m9, cur.top3, cur.l);
+            const uint32_t ka = __vimax3_u32(next.m9, cur.bot3, cur.r);
+            const uint32_t kv = cur.c;
+            const int gz = z0 + lz;
+            const bool inb = col_ok && gz < S;
+            const bool peak = inb && (kv == KEY_NAN ? ka != KEY_NAN : (kv != KEY_NINF && kb < kv && ka <= kv));
+            if (do_hist && inb) {
+                if (kv == KEY_NAN) ++nan_local;
+                atomicAdd(&s_hist[kv >> 20], 1u);
+            }
+            if (peak) {
+                const long long flat = ((long long)gz * H + gy) * W + gx;
+                atomicOr(&bits[flat >> 5], 1u << (flat & 31));
+            }
+            prev = cur; cur = next;
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        uint32_t* gh = ws.hist1 + (size_t)ba * PK_BINS1;
+        for (int i = tid; i < PK_BINS1; i += PK_THREADS) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&gh[i], c); }
+        if (nan_local) atomicAdd(&ws.nan_cnt[ba], nan_local);
+    }
+}
+
 // LEVEL 2: bins = key bits 19..8 of elements whose top 12 bits match the level-1 bin.
 // LEVEL 3: bins = key bits 7..0 of elements whose top 24 bits match.
 template <int LEVEL>
@@ -199,9 +299,22 @@ peaks_refine_kernel(const float* __restrict__ in, long long V, PeakWs ws) {
             atomicAdd(&s_hist[bin], 1u);
         }
     };
-    for (long long i = (long long)blockIdx.x * PK_THREADS + tid; i < nvec; i += (long long)gridDim.x * PK_THREADS) {
-        const uint4 u = ld_stream_u4(vol + (i << 2));
-        add(__uint_as_float(u.x)); add(__uint_as_float(u.y)); add(__uint_as_float(u.z)); add(__uint_as_float(u.w));
+    {
+        const long long stride = (long long)gridDim.x * PK_THREADS;
+        long long i = (long long)blockIdx.x * PK_THREADS + tid;
+        for (; i + 3 * stride < nvec; i += 4 * stride) {           // 4 independent 128-bit loads in flight
+            uint4 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = ld_stream_u4(vol + ((i + j * stride) << 2));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                add(__uint_as_float(u[j].x)); add(__uint_as_float(u[j].y)); add(__uint_as_float(u[j].z)); add(__uint_as_float(u[j].w));
+            }
+        }
+        for (; i < nvec; i += stride) {
+            const uint4 u = ld_stream_u4(vol + (i << 2));
+            add(__uint_as_float(u.x)); add(__uint_as_float(u.y)); add(__uint_as_float(u.z)); add(__uint_as_float(u.w));
+        }
     }
     for (long long i = (nvec << 2) + (long long)blockIdx.x * PK_THREADS + tid; i < V; i += (long long)gridDim.x * PK_THREADS)
         add(vol[i]);
@@ -402,20 +515,23 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         return B200SEG_EWORKSPACE;
     }
     B200_CUDA(cudaMemsetAsync(base, 0, ws.zero_bytes, stream));
-    const int tiles_x = (W + PK_TX - 1) / PK_TX, tiles_y = (H + PK_TY - 1) / PK_TY, tiles_z = (S + PK_TZ - 1) / PK_TZ;
-    const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
-    B200_CHECK_ARG(ntiles < (1ll << 31), "peaks3d: too many tiles");
     const int sms = num_sms();
-    int gx = (int)(ntiles < (long long)sms * 8 ? ntiles : (long long)sms * 8);
-    gx = (gx + BA - 1) / BA;           // spread the resident CTAs over the B*A maps
-    if (gx < 1) gx = 1;
-    if ((long long)gx > ntiles) gx = (int)ntiles;
     const int do_hist = filter_mode == 1;
-    dim3 g1(gx, BA);
-    if (win == 3) peaks_scan_kernel<3><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
-    else if (win == 5) peaks_scan_kernel<5><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
-    else peaks_scan_kernel<7><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
-    B200_LAUNCH_CHECK("peaks_scan_kernel");
+    {
+        const int TX = win == 3 ? P3_TX : PK_TX, TY = win == 3 ? P3_TY : PK_TY, TZ = win == 3 ? P3_TZ : PK_TZ;
+        const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, tiles_z = (S + TZ - 1) / TZ;
+        const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
+        B200_CHECK_ARG(ntiles < (1ll << 31), "peaks3d: too many tiles");
+        // persistent CTAs: about 5 resident CTAs per SM in total, spread over the B*A maps
+        long long per_map = ((long long)sms * 5 + BA - 1) / BA;
+        if (per_map > ntiles) per_map = ntiles;
+        if (per_map < 1) per_map = 1;
+        dim3 g1((unsigned)per_map, BA);
+        if (win == 3) peaks_scan3_kernel<<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
+        else if (win == 5) peaks_scan_kernel<5><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
+        else peaks_scan_kernel<7><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
+        B200_LAUNCH_CHECK("peaks_scan_kernel");
+    }
     if (filter_mode == 1) {
         long long want = (V / 4 + PK_THREADS - 1) / PK_THREADS;
         int gr = (int)(want < 1 ? 1 : (want > (long long)sms * 8 / BA + 1 ? (long long)sms * 8 / BA + 1 : want));
