@@ -216,20 +216,33 @@ peaks_scan3_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_
         const int x0 = tx * P3_TX, y0 = ty * P3_TY, z0 = tz * P3_TZ;
         __syncthreads();
         // ---- load: one warp per halo row; lanes 0,1 also fetch the two halo columns --------------------
-        for (int rr = warp; rr < P3_HY * P3_HZ; rr += PK_THREADS / 32) {
-            const int hz = rr / P3_HY, hy = rr - hz * P3_HY;
-            const int gy = y0 + hy - 1, gz = z0 + hz - 1;
-            const bool row_ok = gy >= 0 && gy < H && gz >= 0 && gz < S;     // warp-uniform
-            uint32_t* dst = s_key + rr * P3_HX;
-            uint32_t k = KEY_NINF, kh = KEY_NINF;
-            if (row_ok) {
-                const float* row = vol + ((size_t)gz * H + gy) * W;
+        constexpr int NWARP = PK_THREADS / 32, RU = 4;    // RU rows per warp in flight: the loads of a batch are independent
+        for (int rb = warp; rb < P3_HY * P3_HZ; rb += NWARP * RU) {
+            float v[RU], vh[RU];
+            bool ok[RU], okh[RU];
+#pragma unroll
+            for (int j = 0; j < RU; ++j) {
+                const int rr = rb + j * NWARP;
+                const int hz = rr / P3_HY, hy = rr - hz * P3_HY;
+                const int gy = y0 + hy - 1, gz = z0 + hz - 1;
+                const bool row_ok = rr < P3_HY * P3_HZ && gy >= 0 && gy < H && gz >= 0 && gz < S;   // warp-uniform
+                const float* row = vol + ((size_t)(row_ok ? gz : 0) * H + (row_ok ? gy : 0)) * W;
                 const int gx = x0 + lane;
-                if (gx < W) k = ordered_key(row[gx]);
-                if (lane < 2) { const int hxg = lane == 0 ? x0 - 1 : x0 + P3_TX; if (hxg >= 0 && hxg < W) kh = ordered_key(row[hxg]); }
+                const int hxg = lane == 0 ? x0 - 1 : x0 + P3_TX;
+                ok[j] = row_ok && gx < W;
+                okh[j] = row_ok && lane < 2 && hxg >= 0 && hxg < W;
+                v[j] = ok[j] ? row[gx] : 0.f;
+                vh[j] = okh[j] ? row[hxg] : 0.f;
             }
-            dst[1 + lane] = k;
-            if (lane < 2) dst[lane == 0 ? 0 : P3_HX - 1] = kh;
+#pragma unroll
+            for (int j = 0; j < RU; ++j) {
+                const int rr = rb + j * NWARP;
+                if (rr < P3_HY * P3_HZ) {
+                    uint32_t* dst = s_key + rr * P3_HX;
+                    dst[1 + lane] = ok[j] ? ordered_key(v[j]) : KEY_NINF;
+                    if (lane < 2) dst[lane == 0 ? 0 : P3_HX - 1] = okh[j] ? ordered_key(vh[j]) : KEY_NINF;
+                }
+            }
         }
         __syncthreads();
         // ---- compute: thread = (x, y) column, march along z -------------------------------------------
