@@ -332,11 +332,13 @@ def run_ours(args, rank, world, local_rank):
                  crop_off=pin(c["crop_off"])) for c in cases]
     h_seg = [torch.empty(SHAPE, dtype=torch.uint16).pin_memory() for _ in range(vpr)]
 
+    e2e_cases = [dict(volume=h["volume"].numpy(), dets=h["dets"].numpy(), boxes=h["boxes"].numpy(), prm=h["prm"].numpy(),
+                      crop_off=h["crop_off"].numpy()) for h in h_in]
+    e2e_segs = [t.numpy() for t in h_seg]
+
     def e2e_step():
-        for v in range(vpr):
-            h = h_in[v]
-            b200seg.postproc_soma_host(h["volume"].numpy(), h["dets"].numpy(), h["boxes"].numpy(), h["prm"].numpy(),
-                                       h["crop_off"].numpy(), NMS_THRESH, seg_out=h_seg[v].numpy())
+        # one C call for the rank's batch: uploads, kernels and downloads of consecutive volumes overlap
+        b200seg.postproc_soma_host_batch(e2e_cases, NMS_THRESH, seg_out=e2e_segs)
     for _ in range(2):
         e2e_step()
     barrier()

@@ -211,6 +211,16 @@ int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
                                uint16_t* seg, int* n_keep, int32_t* rank_order,
                                int32_t* b_max, int32_t* status, uint8_t* survive);
 
+/* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
+ * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
+ * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */
+int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
+                                     const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
+                                     const int32_t* const* boxes, const uint8_t* const* prm,
+                                     const int64_t* const* crop_off, float nms_thresh,
+                                     uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
+                                     int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200seg_postproc_soma_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200seg_postproc_soma_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200seg_postproc_soma_host_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200seg_postproc_soma_host": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, C.POINTER(C.c_int),
                                         _vp, _vp, _vp, _vp]),
 }

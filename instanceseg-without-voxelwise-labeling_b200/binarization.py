@@ -178,3 +178,46 @@ def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=N
         np.zeros((0, 2), dtype=np.float32)
     return dict(seg=seg, n_keep=k, rank_order=order.copy(), b_max=b_max[:n], status=status[:n],
                 survive=alive, scores=scores.astype(np.float32))
+
+
+def postproc_soma_host_batch(cases, nms_thresh, seg_out=None):
+    """numpy in / numpy out for a BATCH of equally shaped volumes (one C call; uploads, kernels and downloads of
+    consecutive volumes overlap on three streams -- pass pinned arrays for real overlap).
+    cases: list of dict(volume, dets, boxes, prm, crop_off).  Returns a list of dicts like postproc_soma_host."""
+    nv = len(cases)
+    if nv == 0:
+        return []
+    vols = [np.ascontiguousarray(c["volume"], dtype=np.uint8) for c in cases]
+    dets = [np.ascontiguousarray(c["dets"], dtype=np.float32) for c in cases]
+    boxes = [np.ascontiguousarray(c["boxes"], dtype=np.int32) for c in cases]
+    prm = [np.ascontiguousarray(c["prm"], dtype=np.uint8) for c in cases]
+    coff = [np.ascontiguousarray(c["crop_off"], dtype=np.int64) for c in cases]
+    S, H, W = vols[0].shape
+    for v in vols:
+        if v.shape != (S, H, W):
+            raise ValueError("all volumes of a batch must have the same shape")
+    n = np.array([d.shape[0] for d in dets], dtype=np.int32)
+    segs = list(seg_out) if seg_out is not None else [np.empty((S, H, W), dtype=np.uint16) for _ in range(nv)]
+    rank = [np.zeros(max(int(k), 1), dtype=np.int32) for k in n]
+    b_max = [np.zeros(max(int(k), 1), dtype=np.int32) for k in n]
+    status = [np.zeros(max(int(k), 1), dtype=np.int32) for k in n]
+    survive = [np.zeros(max(int(k), 1), dtype=np.uint8) for k in n]
+    n_keep = np.zeros(nv, dtype=np.int32)
+
+    def parr(arrs):
+        return (C.c_void_p * nv)(*[a.ctypes.data for a in arrs])
+    keepalive = [parr(a) for a in (vols, dets, boxes, prm, coff, segs, rank, b_max, status, survive)]
+    pv, pd, pb, pp, pc, ps, pr, pm, pst, psv = keepalive
+    _lib.check(_lib.lib().b200seg_postproc_soma_host_batch(
+        nv, S, H, W, pv, pd, _lib.ptr(n), pb, pp, pc, float(np.float32(nms_thresh)), ps, _lib.ptr(n_keep), pr, pm, pst, psv),
+        "postproc_soma_host_batch")
+    out = []
+    for v in range(nv):
+        k = int(n_keep[v]); nd = int(n[v])
+        order = rank[v][:k]
+        alive = survive[v][:k].astype(bool)
+        scores = np.stack([np.arange(1, k + 1, dtype=np.float32)[alive], dets[v][order, 6][alive]], axis=1) if k else \
+            np.zeros((0, 2), dtype=np.float32)
+        out.append(dict(seg=segs[v], n_keep=k, rank_order=order.copy(), b_max=b_max[v][:nd], status=status[v][:nd],
+                        survive=alive, scores=scores.astype(np.float32)))
+    return out

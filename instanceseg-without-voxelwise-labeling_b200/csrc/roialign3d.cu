@@ -279,7 +279,6 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
                 }
             }
             float* dst = bufA + zp_dst[k];
-#pragma unroll
             if (pow2) {                                    // 1/count already folded into the z table
 #pragma unroll
                 for (int p = 0; p < PT; ++p) if (p < Ps) dst[p * ps_stride] = acc[p];

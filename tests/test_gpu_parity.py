@@ -240,6 +240,22 @@ def test_postproc_chain_host_vs_oracle(b2, seed, shape, nb):
     assert (out["status"][np.setdiff1d(np.arange(len(case["dets"])), ref["order"])] == -1).all()
 
 
+def test_postproc_host_batch_matches_single_volume_calls(b2):
+    from b200seg import synth
+    cases = [synth.postproc_case(500 + i, shape=(24, 80, 96), n_blobs=6 + 3 * i, n_dup=3, n_false=2) for i in range(5)]
+    cases.append(dict(cases[0], dets=np.zeros((0, 7), np.float32), boxes=np.zeros((0, 6), np.int32),
+                      prm=np.zeros(0, np.uint8), crop_off=np.zeros(1, np.int64)))          # a volume without detections
+    outs = b2.postproc_soma_host_batch(cases, 0.23)
+    assert len(outs) == len(cases)
+    for c, o in zip(cases, outs):
+        ref = b2.postproc_soma_host(c["volume"], c["dets"], c["boxes"], c["prm"], c["crop_off"], 0.23)
+        assert o["n_keep"] == ref["n_keep"]
+        assert np.array_equal(o["seg"], ref["seg"])
+        for k in ("rank_order", "b_max", "status", "survive", "scores"):
+            assert np.array_equal(o[k], ref[k]), k
+    assert outs[-1]["n_keep"] == 0 and not outs[-1]["seg"].any()
+
+
 def test_postproc_batched_device_and_fullsize_properties(b2, torch_):
     """Two 128x512x512 volumes (BASELINE config 3/5 size) through the device chain:
     volume 0 is checked voxel-exact against the oracle, both against size-independent properties."""
