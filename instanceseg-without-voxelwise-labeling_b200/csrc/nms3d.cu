@@ -191,13 +191,18 @@ nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long 
     int* s_orig = reinterpret_cast<int*>(s_mask + (PRELOAD ? (size_t)n_max * w64 : (size_t)n_max));   // original index per row
     for (int r = tid; r < n; r += REDUCE_THREADS) s_orig[r] = sorted[r].orig;
     if (PRELOAD) {
-        // stage the set's bitmask rows (words at or right of the diagonal; the rest is never written/read):
-        // one warp per row, 8 rows in flight per warp pass -> independent coalesced loads
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < n; r += REDUCE_THREADS / 32) {
-            const int wd = r >> 6;
-            for (int w = wd + lane; w < nw; w += 32) s_mask[(size_t)r * w64 + w] = mask[(size_t)r * w64 + w];
+        // stage the set's whole bitmask with flat coalesced loads, 8 independent words in flight per thread.
+        // Words left of the diagonal were never written by nms_mask_kernel and are never read here either.
+        const int total = n * w64;
+        int i = tid;
+        for (; i + 7 * REDUCE_THREADS < total; i += 8 * REDUCE_THREADS) {
+            unsigned long long v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = mask[i + j * REDUCE_THREADS];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_mask[i + j * REDUCE_THREADS] = v[j];
         }
+        for (; i < total; i += REDUCE_THREADS) s_mask[i] = mask[i];
     } else {
         for (int r = tid; r < n; r += REDUCE_THREADS) s_mask[r] = mask[(size_t)r * w64 + (r >> 6)];
     }

@@ -78,18 +78,26 @@ paste_bin_kernel(PasteGeom g, const int32_t* __restrict__ det_off, const int32_t
     }
 }
 
-// 8 mask bytes starting at p (any alignment), as a little-endian 64-bit value
-__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
-    const unsigned sh = (unsigned)(a & 7) * 8;
-    const unsigned long long lo = __ldg(q);
-    if (sh == 0) return lo;
-    const unsigned long long hi = __ldg(q + 1);
-    return (lo >> sh) | (hi << (64 - sh));
+// 8 mask bytes starting at p (any alignment) as two little-endian 32-bit words: three aligned 32-bit loads and
+// two funnel shifts (the caller guarantees that the three words lie inside the mask buffer)
+__device__ __forceinline__ uint2 load8_fs(const uint8_t* p) {
+    const unsigned int mis = (unsigned int)(reinterpret_cast<uintptr_t>(p) & 3);
+    const unsigned int* q = reinterpret_cast<const unsigned int*>(p - mis);
+    const unsigned int w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    return make_uint2(__funnelshift_r(w0, w1, mis * 8), __funnelshift_r(w1, w2, mis * 8));
 }
+// 0xFF in every byte of x that is non-zero, 0x00 elsewhere
+__device__ __forceinline__ unsigned int nonzero_bytes(unsigned int x) {
+    unsigned int t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;       // bit 7 of each byte = byte != 0
+    unsigned int d;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(d) : "r"(t));       // replicate each byte's sign bit over the byte
+    return d;
+}
+// bytes (lo, lo+1) of m, each 0x00 / 0xFF, widened to two 16-bit lanes 0x0000 / 0xFFFF
+__device__ __forceinline__ unsigned int widen01(unsigned int m) { return __byte_perm(m, 0u, 0x1100); }
+__device__ __forceinline__ unsigned int widen23(unsigned int m) { return __byte_perm(m, 0u, 0x3322); }
 
-__global__ void __launch_bounds__(PASTE_THREADS)
+__global__ void __launch_bounds__(PASTE_THREADS, 8)
 paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, const uint16_t* __restrict__ ids,
                     const uint8_t* __restrict__ masks, const VBox* __restrict__ vbox_all,
                     const uint32_t* __restrict__ tile_bits_all, uint8_t* __restrict__ survive_all,
@@ -101,24 +109,43 @@ paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, 
     const int txy = g.tiles_x * g.tiles_y;
     const size_t V = (size_t)g.S * g.H * g.W;
     int gt = blockIdx.x;
+    // tile coordinates (tx, ty, tz, vol) of gt, advanced by gridDim.x tiles per step in mixed radix: the
+    // divisions happen once per kernel, not once per tile
+    int tx, ty, tz, vol, dtx, dty, dtz, dvol;
+    {
+        int r = gt;
+        vol = r / ntiles; r -= vol * ntiles; tz = r / txy; r -= tz * txy; ty = r / g.tiles_x; tx = r - ty * g.tiles_x;
+        r = gridDim.x;
+        dvol = r / ntiles; r -= dvol * ntiles; dtz = r / txy; r -= dtz * txy; dty = r / g.tiles_x; dtx = r - dty * g.tiles_x;
+    }
+    int surv_off = det_off ? det_off[vol] : 0, surv_vol = vol;
     // software prefetch of the next tile's first 32 bitmap words (takes the load off the per-tile chain)
     uint32_t next_word = (gt < total_tiles && lane < g.words) ? __ldg(tile_bits_all + (size_t)gt * g.words + lane) : 0u;
     for (; gt < total_tiles; gt += gridDim.x) {
         const uint32_t first_word = next_word;
         const int ngt = gt + gridDim.x;
         next_word = (ngt < total_tiles && lane < g.words) ? __ldg(tile_bits_all + (size_t)ngt * g.words + lane) : 0u;
-        const int vol = gt / ntiles, tile = gt - vol * ntiles;
-        const int tz = tile / txy, trem = tile - tz * txy, ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int x = tx * PT_X + lx * 8, y = ty * PT_Y + ly, z0 = tz * PT_Z;
+        const int cur_vol = vol;
+        {   // advance to the tile of the next iteration
+            tx += dtx; int c = tx >= g.tiles_x; tx -= c ? g.tiles_x : 0;
+            ty += dty + c; c = ty >= g.tiles_y; ty -= c ? g.tiles_y : 0;
+            tz += dtz + c; c = tz >= g.tiles_z; tz -= c ? g.tiles_z : 0;
+            vol += dvol + c;
+        }
         const bool inside = x < g.W && y < g.H;
-        uint16_t lab[PT_Z][8];
+        // per plane: 8 labels as four packed words (two uint16 each) + a byte mask of the voxels already labelled
+        unsigned int lab[PT_Z][4], filled[PT_Z][2];
 #pragma unroll
-        for (int p = 0; p < PT_Z; ++p)
+        for (int p = 0; p < PT_Z; ++p) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) lab[p][k] = 0;
+            for (int k = 0; k < 4; ++k) lab[p][k] = 0u;
+            filled[p][0] = filled[p][1] = 0u;
+        }
         const uint32_t* bits = tile_bits_all + (size_t)gt * g.words;
-        const VBox* vbox = vbox_all + (size_t)vol * g.n_max;
-        uint8_t* survive = survive_all + (det_off ? det_off[vol] : 0);
+        const VBox* vbox = vbox_all + (size_t)cur_vol * g.n_max;
+        if (cur_vol != surv_vol) { surv_vol = cur_vol; surv_off = det_off ? det_off[cur_vol] : 0; }
+        uint8_t* survive = survive_all + surv_off;
         for (int w0 = 0; w0 < g.words; w0 += 32) {
             const uint32_t myword = w0 == 0 ? first_word : ((w0 + lane < g.words) ? __ldg(bits + w0 + lane) : 0u);
             unsigned nzw = __ballot_sync(0xffffffffu, myword != 0u);
@@ -131,52 +158,54 @@ paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, 
                     m &= m - 1;
                     const VBox vb = vbox[rank];                    // uniform address: one broadcast transaction
                     if (!inside || y < vb.y1 || y > vb.y2 || x + 7 < vb.x1 || x > vb.x2) continue;
-                    const uint16_t id = ids[rank];
+                    const unsigned int id = ids[rank];
+                    const unsigned int id2 = id | (id << 16);
                     // bytes k in [klo,khi] of my 8-voxel group lie inside the box
                     const int klo = max(0, vb.x1 - x), khi = min(7, vb.x2 - x);
                     const unsigned long long range = (~0ull >> (8 * (7 - khi))) & (~0ull << (8 * klo));
+                    const unsigned int range_lo = (unsigned int)range, range_hi = (unsigned int)(range >> 32);
                     const long long row0 = vb.moff + (long long)(y - vb.y1) * vb.sx + (x - vb.x1);   // may start before the row
                     const long long zstride = (long long)vb.sy * vb.sx;
-                    bool wrote = false;
+                    unsigned int wrote = 0u;
 #pragma unroll
                     for (int p = 0; p < PT_Z; ++p) {
                         const int z = z0 + p;
                         if (z < vb.z1 || z > vb.z2) continue;
                         const long long o = row0 + (long long)(z - vb.z1) * zstride;
-                        unsigned long long mb;
-                        if (vec_mask_ok && o >= vb.moff && o + 16 <= vb.mend) {
-                            mb = load8_unaligned(masks + o);           // both aligned words stay inside this crop
+                        uint2 mb;
+                        if (vec_mask_ok && o >= vb.moff + 3 && o + 12 <= vb.mend) {
+                            mb = load8_fs(masks + o);                  // the three aligned words stay inside this crop
                         } else {                                       // crop edge: byte reads inside [moff, mend)
-                            mb = 0ull;
+                            unsigned int b[2] = {0u, 0u};
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
-                                if (k >= klo && k <= khi) mb |= (unsigned long long)masks[o + k] << (8 * k);
+                                if (k >= klo && k <= khi) b[k >> 2] |= (unsigned int)masks[o + k] << (8 * (k & 3));
+                            mb = make_uint2(b[0], b[1]);
                         }
-                        mb &= range;
-                        if (mb == 0ull) continue;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (lab[p][k] == 0 && ((mb >> (8 * k)) & 0xFFull)) { lab[p][k] = id; wrote = true; }
+                        // voxels this instance takes: mask set, inside the box, not labelled yet ("first come wins")
+                        const unsigned int set_lo = nonzero_bytes(mb.x) & range_lo, set_hi = nonzero_bytes(mb.y) & range_hi;
+                        const unsigned int take_lo = set_lo & ~filled[p][0], take_hi = set_hi & ~filled[p][1];
+                        if ((take_lo | take_hi) == 0u) continue;
+                        filled[p][0] |= take_lo; filled[p][1] |= take_hi;
+                        lab[p][0] |= id2 & widen01(take_lo); lab[p][1] |= id2 & widen23(take_lo);
+                        lab[p][2] |= id2 & widen01(take_hi); lab[p][3] |= id2 & widen23(take_hi);
+                        wrote = 1u;
                     }
                     if (wrote) survive[rank] = 1;                  // benign race: every writer stores the same value
                 }
             }
         }
         if (inside) {
-            uint16_t* seg = seg_all + (size_t)vol * V;
+            const size_t HW = (size_t)g.H * g.W;
+            uint16_t* dst = seg_all + (size_t)cur_vol * V + (size_t)z0 * HW + (size_t)y * g.W + x;
 #pragma unroll
-            for (int p = 0; p < PT_Z; ++p) {
-                const int z = z0 + p;
-                if (z >= g.S) break;
-                uint16_t* dst = seg + ((size_t)z * g.H + y) * g.W + x;
+            for (int p = 0; p < PT_Z; ++p, dst += HW) {
+                if (z0 + p >= g.S) break;
                 if (vec_ok && x + 7 < g.W) {
-                    uint4 v;
-                    v.x = lab[p][0] | ((uint32_t)lab[p][1] << 16); v.y = lab[p][2] | ((uint32_t)lab[p][3] << 16);
-                    v.z = lab[p][4] | ((uint32_t)lab[p][5] << 16); v.w = lab[p][6] | ((uint32_t)lab[p][7] << 16);
-                    st_stream_u4(dst, v);
+                    st_stream_u4(dst, make_uint4(lab[p][0], lab[p][1], lab[p][2], lab[p][3]));
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) if (x + k < g.W) dst[k] = lab[p][k];
+                    for (int k = 0; k < 8; ++k) if (x + k < g.W) dst[k] = (uint16_t)(lab[p][k >> 1] >> (16 * (k & 1)));
                 }
             }
         }
