@@ -235,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     vpr = args.volumes_per_rank
     V = int(np.prod(SHAPE))
 
-    cases = [make_case(2000 + rank * vpr + i) for i in range(vpr)]
+    cases = [make_case(args.seed_base + rank * vpr + i) for i in range(vpr)]
     counts = [c["dets"].shape[0] for c in cases]
     prm_np = np.concatenate([c["prm"] for c in cases])
     offs, base = [], 0
@@ -249,16 +249,34 @@ def run_ours(args, rank, world, local_rank):
     crop_off = torch.from_numpy(crop_off_np).to(dev)
     pp = b200seg.SomaPostproc(vpr, SHAPE, counts, prm_np.size, device=dev)
     n_max = max(counts)
-    gather_in = torch.zeros((vpr, n_max, 8), dtype=torch.float32, device=dev)
-    gather_out = torch.zeros((world, vpr, n_max, 8), dtype=torch.float32, device=dev) if world > 1 else None
+    # the detections live inside the chain's exchange buffer: the per-step gather needs no packing
+    pp.dets_in.copy_(dets)
+    dets = pp.dets_in
+    gather_out = torch.zeros((world, pp.exchange.numel()), dtype=torch.int32, device=dev) if world > 1 else None
+    # The exchange of step i runs on a side stream and overlaps the (latency-bound) NMS phase of step i+1: the
+    # chain's exchange buffer is snapshotted (0.2 MB device copy) so the next step may overwrite it.
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    snap = torch.empty_like(pp.exchange) if world > 1 else None
+    ev_chain, ev_gather = torch.cuda.Event(), torch.cuda.Event()
 
     def step():
         pp.run(vols, dets, boxes, prm, crop_off, NMS_THRESH)
         if world > 1:
-            # the only exchange step: surviving detections of every volume (padded block, device resident)
-            gather_in[:, :, 1:].copy_(torch.nn.utils.rnn.pad_sequence(
-                [dets[pp.det_off_host[v]:pp.det_off_host[v + 1]] for v in range(vpr)], batch_first=True)[:, :n_max])
-            dist.all_gather_into_tensor(gather_out.view(world * vpr, n_max, 8), gather_in)
+            main = torch.cuda.current_stream()
+            main.wait_event(ev_gather)                      # the previous gather has finished reading `snap`
+            snap.copy_(pp.exchange)
+            ev_chain.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_chain)
+                # the only exchange step: detections, visit order, survivor counts and flags of every volume
+                # (one all-gather of ~0.2 MB per rank over NCCL / NVLink)
+                if os.environ.get("B200SEG_BENCH_EXCHANGE", "overlap") != "none":        # diagnostic switch
+                    dist.all_gather_into_tensor(gather_out.view(-1), snap)
+                ev_gather.record(side)
+
+    def finish_steps():
+        if world > 1:
+            torch.cuda.current_stream().wait_event(ev_gather)   # the last exchange belongs to the timed region
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,15 +286,16 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                     # before the barrier: spawning nvidia-smi must not skew rank 0
+    barrier()
     l0 = b200seg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
+    finish_steps()
     e1.record()
     barrier()
     launches = b200seg.launch_count() - l0
@@ -401,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volumes-per-rank", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed-base", type=int, default=2000, help="seed of the first synthetic volume (volume i of rank r: base + r*vpr + i)")
     ap.add_argument("--chain-only", action="store_true", help="profiling aid: time only the device-resident chain")
     ap.add_argument("--ops-only", action="store_true", help="profiling aid: only the per-operator timings (RoIAlign3D, peaks, IoU, NMS)")
     args = ap.parse_args()

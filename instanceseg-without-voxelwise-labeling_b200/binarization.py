@@ -79,12 +79,19 @@ class SomaPostproc(object):
         t = max(total, 1)
         self.seg = torch.empty((self.nv, self.S, self.H, self.W), dtype=torch.uint16, device=dev)
         self.keep = torch.empty(t, dtype=torch.int64, device=dev)
-        self.keep_count = torch.zeros(max(self.nv, 1), dtype=torch.int32, device=dev)
-        self.rank_order = torch.empty(t, dtype=torch.int32, device=dev)
         self.masks = torch.empty(max(int(prm_bytes), 1) + 16, dtype=torch.uint8, device=dev)
         self.b_max = torch.zeros(t, dtype=torch.int32, device=dev)
         self.status = torch.zeros(t, dtype=torch.int32, device=dev)
-        self.survive = torch.zeros(t, dtype=torch.uint8, device=dev)
+        # Everything another rank needs to know about this rank's volumes lives in ONE flat buffer, so the
+        # exchange step of a multi-GPU run is a single all_gather with no packing kernels:
+        #   [dets total x 7 f32 | rank_order total i32 | keep_count nv i32 | survive total u8 (padded to 4)]
+        # `dets_in` is where the caller should write (or keep) the detections to avoid a copy.
+        words = 7 * t + t + max(self.nv, 1) + (t + 3) // 4
+        self.exchange = torch.zeros(words, dtype=torch.int32, device=dev)
+        self.dets_in = self.exchange[:7 * t].view(torch.float32).view(t, 7)
+        self.rank_order = self.exchange[7 * t:8 * t]
+        self.keep_count = self.exchange[8 * t:8 * t + max(self.nv, 1)]
+        self.survive = self.exchange[8 * t + max(self.nv, 1):].view(torch.uint8)[:t]
         self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(self.nv, self.n_max, self.S, self.H, self.W)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
