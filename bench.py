@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 A "step" = one pass of the post-processing chain (tools/binarization_soma.py:57-104: 3D NMS ->
-visit order -> per-instance crop/normalise/2D-Otsu -> label paste-back) over one batch of
+visit order -> per-instance crop/normalise/2D-Otsu -> largest connected component -> label paste-back) over one batch of
 synthetic 128x512x512 uint8 volumes (BASELINE.json configs[2]/[4]; ~200 blob instances and ~800
 candidate detections per volume).  Each rank owns `--volumes-per-rank` volumes (8 by default, so
 8 GPUs process the 64-volume batch of configs[4]); scaling is weak, no data-path collective except
@@ -36,7 +36,8 @@ sys.path.insert(0, ROOT)
 
 SHAPE = (128, 512, 512)
 NMS_THRESH = 0.23
-CASE_KW = dict(shape=SHAPE, n_blobs=200, n_dup=400, n_false=200, sigma_xy=(5, 11), sigma_z=(3, 6))
+CASE_KW = dict(shape=SHAPE, n_blobs=200, n_dup=400, n_false=200, sigma_xy=(5, float(os.environ.get("B200SEG_BENCH_SIGMA_MAX", "11"))),
+               sigma_z=(3, 6))
 
 
 def hbm_peak():
@@ -149,7 +150,7 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world, vpr):
-    return {"workload": "postproc_soma_chain: 3D NMS(0.23) + per-instance 2D-Otsu + label paste-back on synthetic uint8 "
+    return {"workload": "postproc_soma_chain: 3D NMS(0.23) + per-instance 2D-Otsu + largest connected component + label paste-back on synthetic uint8 "
                         "128x512x512 volumes, ~200 blobs, 800 candidate detections each (BASELINE configs[2]/[4])",
             "volumes_per_rank": vpr, "global_volumes_per_step": vpr * world, "volume_shape": list(SHAPE),
             "dets_per_volume": CASE_KW["n_blobs"] + CASE_KW["n_dup"] + CASE_KW["n_false"], "nms_thresh": NMS_THRESH,
@@ -313,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
         kept_crop_bytes += int(np.diff(cases[v]["crop_off"])[order].sum())
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (same inputs, same launches) -------
-    prof = {"nms": 0.0, "otsu": 0.0, "paste": 0.0}
+    prof = {"nms": 0.0, "otsu": 0.0, "cc": 0.0, "paste": 0.0}
     reps = max(3, min(10, args.steps))
     pp.run_profiled(vols, dets, boxes, prm, crop_off, NMS_THRESH)
     for _ in range(reps):
@@ -323,13 +324,14 @@ def run_ours(args, rank, world, local_rank):
     # one launch covers every volume of the rank's batch
     alg = {"paste": 2 * V * vpr + kept_crop_bytes,                   # label volumes written once + mask bytes read
            "otsu": 3 * kept_crop_bytes,                              # image + prm read, mask written (uint8)
+           "cc": kept_crop_bytes,                                    # masks read once (cleared runs are a few % more)
            "nms": sum(28 * c + 16 * c * ((c + 63) // 64) + 8 * c for c in counts)}
-    per_launch_ms = {"paste": prof["paste"], "otsu": prof["otsu"], "nms": prof["nms"]}
+    per_launch_ms = {"paste": prof["paste"], "otsu": prof["otsu"], "cc": prof["cc"], "nms": prof["nms"]}
     kernels = {k: {"ms_per_step": prof[k], "share": prof[k] / max(sum(prof.values()), 1e-9),
                    "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (per_launch_ms[k] * 1e-3) / 1e9 if per_launch_ms[k] > 0 else None}
                for k in prof}
     dom = max(prof, key=lambda k: prof[k])
-    roof = {"bound": "hbm", "kernel": {"paste": "paste_labels_kernel", "otsu": "otsu2d_kernel<1>", "nms": "nms3d (3 kernels)"}[dom],
+    roof = {"bound": "hbm", "kernel": {"paste": "paste_labels_kernel", "otsu": "soma_binarize_kernel", "cc": "largest_cc_kernel", "nms": "nms3d (3 kernels)"}[dom],
             "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
             "launch_ms": per_launch_ms[dom], "alg_bytes_per_launch": alg[dom]}
@@ -407,8 +409,8 @@ def run_ours(args, rank, world, local_rank):
                         "gpu_launches": int(e2e_launches)},
                 "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,
                 "kept_instances_per_volume": float(np.mean(keep_counts)),
-                "chain_roofline": {"alg_bytes_per_volume": (3 * kept_crop_bytes / vpr) + 2 * V + alg["nms"] / vpr,
-                                   "frac": ((3 * kept_crop_bytes / vpr) + 2 * V) / (ms_step / vpr * 1e-3) / 1e9 / peak}}
+                "chain_roofline": {"alg_bytes_per_volume": (4 * kept_crop_bytes / vpr) + 2 * V + alg["nms"] / vpr,
+                                   "frac": ((4 * kept_crop_bytes / vpr) + 2 * V) / (ms_step / vpr * 1e-3) / 1e9 / peak}}
         print(json.dumps(line))
 
 

@@ -164,6 +164,21 @@ int b200seg_soma_binarize_dev(const uint8_t* volumes, int n_volumes, int S, int 
                               b200seg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Largest connected component of every instance mask, in place -- replaces tools/binarization_soma.py:97-99
+ * (skimage.measure.label with full = 26-connectivity, then the component with the largest voxel count; equal
+ * counts: the component whose first voxel comes later in raster order, i.e. what a stable argsort()[-1] picks).
+ * masks / crop_off / boxes / det_off / n_max / order / n_valid as in b200seg_soma_binarize_dev; mask bytes are
+ * "set" when non-zero.  status (may be NULL): only instances with status 0 are processed; a mask without any
+ * foreground (the reference raises IndexError there) gets status 5, a degenerate crop whose bookkeeping does not
+ * fit the workspace gets status 6 and an empty mask.  workspace: b200seg_largest_cc_workspace_bytes(total mask bytes).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_largest_cc_workspace_bytes(long long total_mask_bytes);
+int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, long long total_mask_bytes,
+                           int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,
+                           const int32_t* order, const int32_t* n_valid, int32_t* status,
+                           void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Label paste-back -- replaces the inline numpy of tools/binarization_soma.py:100-104 (and
  * binarization_nuclei.py:141-149): instances are visited in order, instance i writes label
  * ids[i] where its mask is set and the label volume is still 0.  seg [n_volumes,S,H,W] uint16 is
@@ -194,13 +209,16 @@ int b200seg_paste_labels_dev(uint16_t* seg, int n_volumes, int S, int H, int W,
  * Outputs: seg [nv,S,H,W] uint16 (label = visit rank + 1, :67), keep / keep_count / rank_order as
  * b200seg_nms3d_dev, masks (packing of prm), b_max[total], status[total] (-1 = suppressed by NMS,
  * else as b200seg_soma_binarize_dev), survive[total] (set b, visit rank r at det_off[b] + r).
- * The largest-connected-component step (:97-99) is not part of the chain.
+ * keep_largest_cc != 0 inserts the largest-connected-component filter of :97-99 (b200seg_largest_cc_dev) between
+ * the binarization and the paste (reference semantics); prm_bytes = crop_off[total] (host-known size of the
+ * packed PRM / mask arrays); the workspace size takes cc_mask_bytes = prm_bytes when the filter is on, else 0.
+ * status additionally reports 5 (mask without foreground) and 6 (degenerate crop) from that step.
  * ---------------------------------------------------------------------------------------------- */
-size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W);
+size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W, long long cc_mask_bytes);
 int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
                               const float* dets, const int32_t* det_off_dev, const int32_t* det_off_host,
                               const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,
-                              float nms_thresh,
+                              long long prm_bytes, float nms_thresh, int keep_largest_cc,
                               uint16_t* seg, int64_t* keep, int32_t* keep_count, int32_t* rank_order,
                               uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive,
                               void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
@@ -208,6 +226,7 @@ int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int 
 int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
                                const float* dets, int n, const int32_t* boxes,
                                const uint8_t* prm, const int64_t* crop_off, float nms_thresh,
+                               int keep_largest_cc,
                                uint16_t* seg, int* n_keep, int32_t* rank_order,
                                int32_t* b_max, int32_t* status, uint8_t* survive);
 
@@ -217,7 +236,7 @@ int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
 int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
                                      const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
                                      const int32_t* const* boxes, const uint8_t* const* prm,
-                                     const int64_t* const* crop_off, float nms_thresh,
+                                     const int64_t* const* crop_off, float nms_thresh, int keep_largest_cc,
                                      uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
                                      int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive);
 

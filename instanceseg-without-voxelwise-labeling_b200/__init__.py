@@ -6,11 +6,11 @@ from . import _lib
 from ._lib import B200SegError, launch_count
 from .boxes_3d import nms_3d, nms_3d_volume, bbox_overlaps_3d, nms_3d_batched
 from .otsu import otsu_py_2d_fast, otsu_2d_batch
-from .binarization import (soma_binarize, paste_labels, SomaPostproc, postproc_soma_host, postproc_soma_host_batch,
+from .binarization import (soma_binarize, largest_cc, paste_labels, SomaPostproc, postproc_soma_host, postproc_soma_host_batch,
                            dets_to_boxes, crop_offsets)
 
 __all__ = ["nms_3d", "nms_3d_volume", "bbox_overlaps_3d", "nms_3d_batched", "otsu_py_2d_fast", "otsu_2d_batch",
-           "soma_binarize", "paste_labels", "SomaPostproc", "postproc_soma_host", "postproc_soma_host_batch", "dets_to_boxes", "crop_offsets",
+           "soma_binarize", "largest_cc", "paste_labels", "SomaPostproc", "postproc_soma_host", "postproc_soma_host_batch", "dets_to_boxes", "crop_offsets",
            "B200SegError", "launch_count"]
 
 

@@ -34,13 +34,15 @@ SIGNATURES = {
     "b200seg_otsu2d_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200seg_otsu2d_host": (_i, [_vp, _vp, _ll, _vp, C.POINTER(C.c_int)]),
     "b200seg_soma_binarize_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200seg_largest_cc_workspace_bytes": (_sz, [_ll]),
+    "b200seg_largest_cc_dev": (_i, [_vp, _vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200seg_paste_labels_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200seg_paste_labels_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "b200seg_postproc_soma_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "b200seg_postproc_soma_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f,
+    "b200seg_postproc_soma_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
+    "b200seg_postproc_soma_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "b200seg_postproc_soma_host_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b200seg_postproc_soma_host": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, C.POINTER(C.c_int),
+    "b200seg_postproc_soma_host_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200seg_postproc_soma_host": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, C.POINTER(C.c_int),
                                         _vp, _vp, _vp, _vp]),
 }
 

@@ -46,6 +46,24 @@ def soma_binarize(volume, boxes, prm, crop_off, order=None, n_valid=None):
     return mask, b_max[:n], status[:n]
 
 
+def largest_cc(masks, crop_off, boxes, status=None, order=None, n_valid=None):
+    """Device op: keep the largest 26-connected component of every packed instance mask, in place
+    (binarization_soma.py:97-99).  masks uint8 packed cuda, crop_off int64 [n+1], boxes int32 [n,6].
+    Returns status int32 [n] (0 ok, 5 = no foreground, 6 = degenerate crop)."""
+    import torch
+    n = boxes.shape[0]
+    L = _lib.lib()
+    if status is None:
+        status = torch.zeros(max(n, 1), dtype=torch.int32, device=masks.device)
+    total = int(masks.numel())
+    ws_bytes = L.b200seg_largest_cc_workspace_bytes(total)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
+    _lib.check(L.b200seg_largest_cc_dev(_lib.ptr(masks), _lib.ptr(crop_off), total, 1, None, n, _lib.ptr(boxes),
+                                        _lib.ptr(order), _lib.ptr(n_valid), _lib.ptr(status), _lib.ptr(ws), ws_bytes,
+                                        _lib.current_stream()), "largest_cc")
+    return status[:n]
+
+
 def paste_labels(seg, boxes, ids, masks, mask_off, order=None, n_valid=None):
     """Device op: seg uint16 [S,H,W] is (over)written once; returns survive uint8 [n] by visit rank."""
     import torch
@@ -64,10 +82,12 @@ def paste_labels(seg, boxes, ids, masks, mask_off, order=None, n_valid=None):
 class SomaPostproc(object):
     """Device-resident chain for a batch of equally shaped volumes (buffers allocated once)."""
 
-    def __init__(self, n_volumes, shape, det_counts, prm_bytes, device="cuda"):
+    def __init__(self, n_volumes, shape, det_counts, prm_bytes, device="cuda", keep_largest_cc=True):
         import torch
         self.torch = torch
         self.nv = int(n_volumes)
+        self.keep_largest_cc = bool(keep_largest_cc)        # binarization_soma.py:97-99 (reference semantics)
+        self.prm_bytes = int(prm_bytes)
         self.S, self.H, self.W = [int(v) for v in shape]
         self.det_off_host = np.zeros(self.nv + 1, dtype=np.int32)
         self.det_off_host[1:] = np.cumsum(det_counts)
@@ -92,20 +112,21 @@ class SomaPostproc(object):
         self.rank_order = self.exchange[7 * t:8 * t]
         self.keep_count = self.exchange[8 * t:8 * t + max(self.nv, 1)]
         self.survive = self.exchange[8 * t + max(self.nv, 1):].view(torch.uint8)[:t]
-        self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(self.nv, self.n_max, self.S, self.H, self.W)
+        self.ws_bytes = _lib.lib().b200seg_postproc_soma_workspace_bytes(
+            self.nv, self.n_max, self.S, self.H, self.W, self.prm_bytes if self.keep_largest_cc else 0)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
     def launches_per_call(self):
-        """Kernels launched by one run(): 3 NMS + iota + binarize + paste bin + paste (all volumes per launch)."""
-        return (3 + 1 + 1 + 1 if self.n_max > 0 else 0) + 1
+        """Kernels launched by one run(): 3 NMS + iota + binarize (+ largest CC) + paste bin + paste (all volumes per launch)."""
+        return (3 + 1 + 1 + 1 + int(self.keep_largest_cc) if self.n_max > 0 else 0) + 1
 
     def run(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
         """All arguments are cuda tensors (volumes uint8 [nv,S,H,W], dets f32 [total,7], boxes int32
         [total,6], prm uint8 packed, crop_off int64 [total+1]).  Enqueues on the current stream."""
         _lib.check(_lib.lib().b200seg_postproc_soma_dev(
             _lib.ptr(volumes), self.nv, self.S, self.H, self.W, _lib.ptr(dets), _lib.ptr(self.det_off_dev),
-            _lib.ptr(self.det_off_host), _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off),
-            float(np.float32(nms_thresh)), _lib.ptr(self.seg), _lib.ptr(self.keep), _lib.ptr(self.keep_count),
+            _lib.ptr(self.det_off_host), _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off), self.prm_bytes,
+            float(np.float32(nms_thresh)), int(self.keep_largest_cc), _lib.ptr(self.seg), _lib.ptr(self.keep), _lib.ptr(self.keep_count),
             _lib.ptr(self.rank_order), _lib.ptr(self.masks), _lib.ptr(self.b_max), _lib.ptr(self.status),
             _lib.ptr(self.survive), _lib.ptr(self.ws), self.ws_bytes, _lib.current_stream()), "postproc_soma_dev")
         return self.seg
@@ -118,12 +139,13 @@ def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
     L = _lib.lib()
     st = _lib.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    spans = {"nms": [], "otsu": [], "paste": []}
+    spans = {"nms": [], "otsu": [], "cc": [], "paste": []}
     if not hasattr(self, "_ids"):
         self._ids = torch.arange(1, max(self.n_max, 1) + 1, dtype=torch.int32, device=self.seg.device).to(torch.uint16)
         self._nms_ws = torch.empty(L.b200seg_nms3d_workspace_bytes(self.nv, self.n_max), dtype=torch.uint8, device=self.seg.device)
         self._paste_ws = torch.empty(L.b200seg_paste_labels_workspace_bytes(self.nv, self.S, self.H, self.W, self.n_max), dtype=torch.uint8,
                                      device=self.seg.device)
+        self._cc_ws = torch.empty(L.b200seg_largest_cc_workspace_bytes(self.prm_bytes), dtype=torch.uint8, device=self.seg.device)
     a, b = ev(), ev()
     a.record()
     _lib.check(L.b200seg_nms3d_dev(_lib.ptr(dets), _lib.ptr(self.det_off_dev), self.nv, self.n_max, float(np.float32(nms_thresh)), 0,
@@ -131,22 +153,29 @@ def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
                                    _lib.ptr(self._nms_ws), self._nms_ws.numel(), st), "nms3d_dev")
     b.record()
     spans["nms"].append((a, b))
-    a, b, c = ev(), ev(), ev()
+    a, b, c, d = ev(), ev(), ev(), ev()
     a.record()
     if self.n_max > 0:
         self.status.fill_(-1)
         self.survive.zero_()
+        self.b_max.zero_()
         _lib.check(L.b200seg_soma_binarize_dev(
             _lib.ptr(volumes), self.nv, self.S, self.H, self.W, _lib.ptr(self.det_off_dev), self.n_max, _lib.ptr(boxes),
             _lib.ptr(prm), _lib.ptr(crop_off), _lib.ptr(self.rank_order), _lib.ptr(self.keep_count), _lib.ptr(self.masks),
             _lib.ptr(self.b_max), _lib.ptr(self.status), st), "soma_binarize")
     b.record()
+    if self.n_max > 0 and self.keep_largest_cc:
+        _lib.check(L.b200seg_largest_cc_dev(
+            _lib.ptr(self.masks), _lib.ptr(crop_off), self.prm_bytes, self.nv, _lib.ptr(self.det_off_dev), self.n_max, _lib.ptr(boxes),
+            _lib.ptr(self.rank_order), _lib.ptr(self.keep_count), _lib.ptr(self.status), _lib.ptr(self._cc_ws), self._cc_ws.numel(), st),
+            "largest_cc")
+    c.record()
     _lib.check(L.b200seg_paste_labels_dev(
         _lib.ptr(self.seg), self.nv, self.S, self.H, self.W, _lib.ptr(self.det_off_dev), self.n_max, _lib.ptr(boxes),
         _lib.ptr(self._ids), _lib.ptr(self.masks), _lib.ptr(crop_off), _lib.ptr(self.rank_order), _lib.ptr(self.keep_count),
         _lib.ptr(self.survive), _lib.ptr(self._paste_ws), self._paste_ws.numel(), st), "paste_labels")
-    c.record()
-    spans["otsu"].append((a, b)); spans["paste"].append((b, c))
+    d.record()
+    spans["otsu"].append((a, b)); spans["cc"].append((b, c)); spans["paste"].append((c, d))
     torch.cuda.synchronize()
     out = {k: sum(x.elapsed_time(y) for x, y in v) for k, v in spans.items()}
     out["n_paste"] = 1
@@ -157,7 +186,7 @@ def _run_profiled(self, volumes, dets, boxes, prm, crop_off, nms_thresh):
 SomaPostproc.run_profiled = _run_profiled
 
 
-def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=None):
+def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=None, keep_largest_cc=True):
     """numpy in / numpy out for ONE volume (H2D and D2H happen inside the C call).
     Returns dict(seg uint16 [S,H,W], n_keep, rank_order, b_max, status, survive, scores [[id, score]])."""
     volume = np.ascontiguousarray(volume, dtype=np.uint8)
@@ -176,7 +205,7 @@ def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=N
     cnt = C.c_int(0)
     _lib.check(_lib.lib().b200seg_postproc_soma_host(
         _lib.ptr(volume), S, H, W, _lib.ptr(dets), n, _lib.ptr(boxes), _lib.ptr(prm), _lib.ptr(crop_off),
-        float(np.float32(nms_thresh)), _lib.ptr(seg), C.byref(cnt), _lib.ptr(rank), _lib.ptr(b_max),
+        float(np.float32(nms_thresh)), int(bool(keep_largest_cc)), _lib.ptr(seg), C.byref(cnt), _lib.ptr(rank), _lib.ptr(b_max),
         _lib.ptr(status), _lib.ptr(survive)), "postproc_soma_host")
     k = cnt.value
     order = rank[:k]
@@ -187,7 +216,7 @@ def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=N
                 survive=alive, scores=scores.astype(np.float32))
 
 
-def postproc_soma_host_batch(cases, nms_thresh, seg_out=None):
+def postproc_soma_host_batch(cases, nms_thresh, seg_out=None, keep_largest_cc=True):
     """numpy in / numpy out for a BATCH of equally shaped volumes (one C call; uploads, kernels and downloads of
     consecutive volumes overlap on three streams -- pass pinned arrays for real overlap).
     cases: list of dict(volume, dets, boxes, prm, crop_off).  Returns a list of dicts like postproc_soma_host."""
@@ -216,7 +245,8 @@ def postproc_soma_host_batch(cases, nms_thresh, seg_out=None):
     keepalive = [parr(a) for a in (vols, dets, boxes, prm, coff, segs, rank, b_max, status, survive)]
     pv, pd, pb, pp, pc, ps, pr, pm, pst, psv = keepalive
     _lib.check(_lib.lib().b200seg_postproc_soma_host_batch(
-        nv, S, H, W, pv, pd, _lib.ptr(n), pb, pp, pc, float(np.float32(nms_thresh)), ps, _lib.ptr(n_keep), pr, pm, pst, psv),
+        nv, S, H, W, pv, pd, _lib.ptr(n), pb, pp, pc, float(np.float32(nms_thresh)), int(bool(keep_largest_cc)), ps,
+        _lib.ptr(n_keep), pr, pm, pst, psv),
         "postproc_soma_host_batch")
     out = []
     for v in range(nv):

@@ -4,9 +4,8 @@
 // (:100-104).  No host round trip between the steps: the NMS survivor count stays on the device
 // and sizes the later launches through `n_valid` pointers.
 //
-// NOTE (documented scope): the reference keeps only the largest connected component of each Otsu
-// mask (skimage.measure.label, :97-99) before pasting.  That step is a "next" row of the scope
-// table and is not part of this chain yet; the chain pastes the Otsu mask itself.
+// The reference keeps only the largest connected component of each Otsu mask (skimage.measure.label, :97-99)
+// before pasting: largest_cc.cu, switched by `keep_largest_cc` (1 = reference semantics).
 #include "common.cuh"
 
 #include <mutex>
@@ -23,15 +22,16 @@ __global__ void iota_u16_kernel(uint16_t* p, int n) {
 
 using namespace b200seg;
 
-extern "C" size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W) {
+extern "C" size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W, long long cc_mask_bytes) {
     return align_up(b200seg_nms3d_workspace_bytes(n_volumes, n_max), 256) + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256) +
-           align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256) + 512;
+           align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256) +
+           (cc_mask_bytes > 0 ? align_up(b200seg_largest_cc_workspace_bytes(cc_mask_bytes), 256) : 0) + 512;
 }
 
 extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, int S, int H, int W,
                                          const float* dets, const int32_t* det_off_dev, const int32_t* det_off_host,
                                          const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off,
-                                         float nms_thresh,
+                                         long long prm_bytes, float nms_thresh, int keep_largest_cc,
                                          uint16_t* seg, int64_t* keep, int32_t* keep_count, int32_t* rank_order,
                                          uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive,
                                          void* workspace, size_t workspace_bytes, b200seg_stream_t stream_) {
@@ -49,7 +49,9 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
     const int total = det_off_host[n_volumes];
     B200_CHECK_ARG(total == 0 || (dets && boxes && prm && crop_off && keep && rank_order && masks && b_max && status && survive),
                    "postproc_soma: null pointer");
-    if (workspace_bytes < b200seg_postproc_soma_workspace_bytes(n_volumes, n_max, S, H, W)) {
+    B200_CHECK_ARG(prm_bytes >= 0, "postproc_soma: negative prm_bytes");
+    const long long cc_bytes = keep_largest_cc ? prm_bytes : 0;
+    if (workspace_bytes < b200seg_postproc_soma_workspace_bytes(n_volumes, n_max, S, H, W, cc_bytes)) {
         set_error("postproc_soma: workspace too small");
         return B200SEG_EWORKSPACE;
     }
@@ -57,7 +59,9 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
     uint16_t* ids = (uint16_t*)ws;
     char* paste_ws = ws + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256);
     const size_t paste_ws_bytes = align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256);
-    char* nms_ws = paste_ws + paste_ws_bytes;
+    char* cc_ws = paste_ws + paste_ws_bytes;
+    const size_t cc_ws_bytes = cc_bytes > 0 ? align_up(b200seg_largest_cc_workspace_bytes(cc_bytes), 256) : 0;
+    char* nms_ws = cc_ws + cc_ws_bytes;
     const size_t nms_ws_bytes = workspace_bytes - (size_t)(nms_ws - (char*)workspace);
 
     int e = b200seg_nms3d_dev(dets, det_off_dev, n_volumes, n_max, nms_thresh, 0, keep, keep_count, rank_order,
@@ -73,6 +77,11 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
         e = b200seg_soma_binarize_dev(volumes, n_volumes, S, H, W, det_off_dev, n_max, boxes, prm, crop_off,
                                       rank_order, keep_count, masks, b_max, status, stream);
         if (e) return e;
+        if (keep_largest_cc) {                               // binarization_soma.py:97-99
+            e = b200seg_largest_cc_dev(masks, crop_off, prm_bytes, n_volumes, det_off_dev, n_max, boxes, rank_order, keep_count,
+                                       status, cc_ws, cc_ws_bytes, stream);
+            if (e) return e;
+        }
     }
     return b200seg_paste_labels_dev(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
                                     rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream);
@@ -84,6 +93,7 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
 extern "C" int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
                                           const float* dets, int n, const int32_t* boxes,
                                           const uint8_t* prm, const int64_t* crop_off, float nms_thresh,
+                                          int keep_largest_cc,
                                           uint16_t* seg, int* n_keep, int32_t* rank_order,
                                           int32_t* b_max, int32_t* status, uint8_t* survive) {
     B200_CHECK_ARG(S > 0 && H > 0 && W > 0 && n >= 0 && volume && seg && n_keep, "postproc_soma_host: bad arguments");
@@ -94,7 +104,7 @@ extern "C" int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, i
     const size_t V = (size_t)S * H * W;
     const size_t nn = n > 0 ? n : 1;
     const size_t prm_bytes = n > 0 ? (size_t)crop_off[n] : 0;
-    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n, S, H, W);
+    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n, S, H, W, keep_largest_cc ? (long long)prm_bytes : 0);
     size_t total = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
                    2 * Carver::need(prm_bytes + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(4) +
                    3 * Carver::need(nn * 4) + Carver::need(nn) + ws_bytes;
@@ -126,7 +136,8 @@ extern "C" int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, i
         B200_CUDA(cudaMemcpyAsync(d_prm, prm, prm_bytes, cudaMemcpyHostToDevice, st));
         B200_CUDA(cudaMemcpyAsync(d_coff, crop_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     }
-    e = b200seg_postproc_soma_dev(d_vol, 1, S, H, W, d_dets, d_off, off, d_boxes, d_prm, d_coff, nms_thresh, d_seg, d_keep,
+    e = b200seg_postproc_soma_dev(d_vol, 1, S, H, W, d_dets, d_off, off, d_boxes, d_prm, d_coff, (long long)prm_bytes, nms_thresh,
+                                  keep_largest_cc, d_seg, d_keep,
                                   d_cnt, d_rank, d_mask, d_bmax, d_stat, d_surv, d_ws, ws_bytes, st);
     if (e) return e;
     int32_t cnt = 0;
@@ -187,7 +198,7 @@ static BatchStreams g_batch;
 extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
                                                 const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
                                                 const int32_t* const* boxes, const uint8_t* const* prm,
-                                                const int64_t* const* crop_off, float nms_thresh,
+                                                const int64_t* const* crop_off, float nms_thresh, int keep_largest_cc,
                                                 uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
                                                 int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive) {
     B200_CHECK_ARG(n_volumes >= 0 && S > 0 && H > 0 && W > 0, "postproc_soma_host_batch: bad sizes");
@@ -209,7 +220,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     std::lock_guard<std::mutex> lock(hc.mu);
     const size_t V = (size_t)S * H * W;
     const size_t nn = n_max > 0 ? n_max : 1;
-    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n_max, S, H, W);
+    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n_max, S, H, W, keep_largest_cc ? (long long)prm_max : 0);
     const int NB = n_volumes < 3 ? n_volumes : 3;
     const size_t slot_bytes = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
                               2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(4) +
@@ -263,7 +274,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
         B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.in_done[k], 0));
         {
             const int32_t off[2] = {0, n};
-            const int ce = b200seg_postproc_soma_dev(s.vol, 1, S, H, W, s.dets, s.off, off, s.boxes, s.prm, s.coff, nms_thresh, s.seg,
+            const int ce = b200seg_postproc_soma_dev(s.vol, 1, S, H, W, s.dets, s.off, off, s.boxes, s.prm, s.coff,
+                                                     n > 0 ? (long long)crop_off[v][n] : 0, nms_thresh, keep_largest_cc, s.seg,
                                                      s.keep, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, s.ws, ws_bytes, s_comp);
             if (ce) { rc = ce; goto done; }
         }

@@ -211,6 +211,25 @@ def paste_labels(seg, boxes, ids, masks):
     return surv[:n].astype(bool)
 
 
+# ------------------------------------------------------------------------------- largest connected component
+def largest_cc(mask):
+    """binarization_soma.py:97-99: `labels = label(box_bi)` (skimage.measure.label, default = full connectivity)
+    then `labels == argsort(bincount(labels.flat)[1:])[-1] + 1`.  PARITY UNPINNED against skimage (not installed
+    in this image, unversioned in the reference README): restated with scipy.ndimage.label and a 3x3x3 structuring
+    element -- both libraries number the components in raster order of their first voxel.  Tie rule (numpy's
+    default argsort is not stable): equal sizes -> the higher label, i.e. what a stable argsort()[-1] returns.
+    Returns the boolean mask of the largest component; raises IndexError on an all-background mask like the
+    reference does."""
+    from scipy import ndimage
+    fg = np.asarray(mask) != 0
+    labels, n = ndimage.label(fg, structure=np.ones((3,) * fg.ndim, dtype=bool))
+    sizes = np.bincount(labels.ravel())[1:]
+    if sizes.size == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    best = np.argsort(sizes, kind="stable")[-1] + 1
+    return labels == best
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

@@ -4,8 +4,8 @@ import numpy as np
 import oracle
 
 
-def oracle_chain(case, nms_thresh=0.23):
-    """binarization_soma.py:57-104 with oracle pieces (no largest-CC step).
+def oracle_chain(case, nms_thresh=0.23, keep_largest_cc=True):
+    """binarization_soma.py:57-104 with oracle pieces (keep_largest_cc: the :97-99 filter, scipy restatement).
     Returns dict(seg, order, status{inst: code}, b_max{inst: b}, survive [by rank])."""
     dets, boxes, prm, off, vol = case["dets"], case["boxes"], case["prm"], case["crop_off"], case["volume"]
     keep = oracle.nms_3d(dets, nms_thresh)
@@ -26,8 +26,14 @@ def oracle_chain(case, nms_thresh=0.23):
         except UnboundLocalError:
             status[int(i)] = 1
             continue
-        status[int(i)] = 0
         bmax[int(i)] = bm
+        if keep_largest_cc:
+            try:
+                m = (oracle.largest_cc(m) * 255).astype(np.uint8)
+            except IndexError:                              # no foreground: the reference raises here
+                status[int(i)] = 5
+                continue
+        status[int(i)] = 0
         pm.append(m); pid.append(rank + 1); pbox.append(b); prank.append(rank)
     surv = np.zeros(len(order), bool)
     if pm:

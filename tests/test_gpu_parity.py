@@ -201,6 +201,39 @@ def test_soma_binarize_vs_oracle(b2, torch_):
 
 
 # ------------------------------------------------------------------------------------------ paste + chain
+def test_largest_cc_vs_oracle(b2, torch_):
+    rng = np.random.default_rng(77)
+    shapes = [(5, 9, 11), (12, 20, 30), (6, 7, 3), (3, 4, 1), (10, 12, 70), (4, 6, 130), (40, 60, 70), (18, 40, 44), (1, 1, 1), (2, 3, 64), (2, 3, 65)]
+    masks = []
+    for i, sh in enumerate(shapes):
+        zz, yy, xx = np.meshgrid(*[np.arange(s) for s in sh], indexing="ij")
+        blob = ((zz - sh[0] / 2) ** 2 / max(sh[0] / 3, 1) ** 2 + (yy - sh[1] / 2) ** 2 / max(sh[1] / 3, 1) ** 2 +
+                (xx - sh[2] / 2) ** 2 / max(sh[2] / 3, 1) ** 2) < 1
+        speck = rng.random(sh) < (0.5 if i == 6 else 0.08)          # crop 6: > 2560 runs and > 2048 rows -> global scratch
+        m = (blob & (rng.random(sh) < 0.9)) | speck
+        masks.append((m * 255).astype(np.uint8))
+    masks.append(np.zeros((4, 5, 6), np.uint8))                     # no foreground: status 5
+    tie = np.zeros((3, 3, 9), np.uint8); tie[0, 0, 0:2] = 255; tie[2, 2, 6:8] = 255                # two components of 2 voxels
+    masks.append(tie)
+    diag = np.zeros((3, 3, 3), np.uint8); diag[0, 0, 0] = diag[1, 1, 1] = diag[2, 2, 2] = 255; diag[0, 2, 0] = 255   # 26-connectivity
+    masks.append(diag)
+    boxes = np.array([[0, 0, 0, m.shape[2] - 1, m.shape[1] - 1, m.shape[0] - 1] for m in masks], np.int32)
+    off = np.zeros(len(masks) + 1, np.int64); off[1:] = np.cumsum([m.size for m in masks])
+    flat = torch_.from_numpy(np.concatenate([m.ravel() for m in masks])).cuda()
+    status = b2.largest_cc(flat, torch_.from_numpy(off).cuda(), torch_.from_numpy(boxes).cuda()).cpu().numpy()
+    out = flat.cpu().numpy()
+    for i, m in enumerate(masks):
+        got = out[off[i]:off[i + 1]].reshape(m.shape)
+        if not m.any():
+            assert status[i] == 5 and not got.any(), i
+            continue
+        ref = oracle.largest_cc(m)
+        assert status[i] == 0, (i, status[i])
+        assert np.array_equal(got != 0, ref), (i, m.shape, int((got != 0).sum()), int(ref.sum()))
+        assert np.array_equal(got[ref], m[ref]), i                  # kept voxels keep their value
+    assert out[off[-3]:off[-2]].reshape(tie.shape)[2, 2, 6] == 255   # tie: the later component wins
+
+
 def test_paste_vs_oracle_overlapping(b2, torch_):
     rng = np.random.default_rng(3)
     S, H, W = 20, 50, 77                                                     # W not a multiple of 8: scalar store path
@@ -223,13 +256,16 @@ def test_paste_vs_oracle_overlapping(b2, torch_):
     assert np.array_equal(surv.cpu().numpy().astype(bool), surv_o)
 
 
-@pytest.mark.parametrize("seed,shape,nb", [(1001, (64, 256, 256), 35), (7, (33, 100, 130), 12)])
-def test_postproc_chain_host_vs_oracle(b2, seed, shape, nb):
-    """BASELINE config 1: one 64x256x256 uint8 volume, exactly 50 boxes, NMS 0.23 + per-instance Otsu + paste."""
+@pytest.mark.parametrize("seed,shape,nb,cc", [(1001, (64, 256, 256), 35, True), (7, (33, 100, 130), 12, True),
+                                              (1001, (64, 256, 256), 35, False)])
+def test_postproc_chain_host_vs_oracle(b2, seed, shape, nb, cc):
+    """BASELINE config 1: one 64x256x256 uint8 volume, exactly 50 boxes, NMS 0.23 + per-instance Otsu
+    (+ largest connected component, binarization_soma.py:97-99) + paste."""
     from b200seg import synth
     case = synth.postproc_case(seed, shape=shape, n_blobs=nb)
-    out = b2.postproc_soma_host(case["volume"], case["dets"], case["boxes"], case["prm"], case["crop_off"], 0.23)
-    ref = oracle_chain(case, 0.23)
+    out = b2.postproc_soma_host(case["volume"], case["dets"], case["boxes"], case["prm"], case["crop_off"], 0.23,
+                                keep_largest_cc=cc)
+    ref = oracle_chain(case, 0.23, keep_largest_cc=cc)
     assert out["n_keep"] == len(ref["order"]) and np.array_equal(out["rank_order"], ref["order"])
     for i, st in ref["status"].items():
         assert out["status"][i] == st, i
