@@ -34,7 +34,9 @@ def short(name):
 
 
 def rows_of(path):
-    rows = list(csv.reader(open(path)))
+    lines = open(path).read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith('"ID"'))      # skip the ==PROF== preamble of --log-file
+    rows = list(csv.reader(lines[start:]))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
         if len(r) == len(hdr):
