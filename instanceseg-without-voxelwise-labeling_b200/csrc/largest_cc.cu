@@ -22,9 +22,9 @@ namespace b200seg {
 
 constexpr int CC_THREADS = 256;
 // dynamic shared memory (72 KB, three CTAs per SM); larger crops spill to their slice of the global scratch
-constexpr int CC_SMEM_WORDS = 3840;        // row bit vectors kept in shared memory (64-bit words)
+constexpr int CC_SMEM_WORDS = 3072;        // row bit vectors kept in shared memory (64-bit words)
 constexpr int CC_SMEM_ROWS = 3072;         // per-row run offsets kept in shared memory
-constexpr int CC_SMEM_RUNS = 2560;         // union-find nodes kept in shared memory (parent, size, run info)
+constexpr int CC_SMEM_RUNS = 2816;         // union-find nodes kept in shared memory (parent, size, interval, row)
 constexpr size_t CC_DYN_BYTES = (size_t)CC_SMEM_WORDS * 8 + (size_t)(CC_SMEM_ROWS + 2) * 4 + (size_t)CC_SMEM_RUNS * 12;
 
 struct CcShared {
@@ -70,120 +70,58 @@ __device__ __forceinline__ bool next_run(const unsigned long long* __restrict__ 
     xe = min(sx, (w << 6) + __ffsll((long long)inv) - 1) - 1;
     return true;
 }
-// ---- a mask row as one or two 64-bit words, with the handful of bit tricks the run arithmetic needs ----------
-template <int W> struct RowBits;
-template <> struct RowBits<1> {
-    unsigned long long v;
-    __device__ static RowBits load(const unsigned long long* p) { return {p[0]}; }
-    __device__ bool any() const { return v != 0ull; }
-    __device__ RowBits operator&(RowBits o) const { return {v & o.v}; }
-    __device__ RowBits operator|(RowBits o) const { return {v | o.v}; }
-    __device__ RowBits operator~() const { return {~v}; }
-    __device__ RowBits shl1() const { return {v << 1}; }
-    __device__ RowBits shr1() const { return {v >> 1}; }
-    __device__ RowBits plus(RowBits o) const { return {v + o.v}; }
-    __device__ RowBits lowbit() const { return {v & (0ull - v)}; }
-    __device__ int ffs() const { return __ffsll((long long)v) - 1; }
-    __device__ int msb() const { return 63 - __clzll((long long)v); }
-    __device__ int popc() const { return __popcll(v); }
-    __device__ static RowBits below(int pos) { return {pos >= 64 ? ~0ull : (1ull << pos) - 1ull}; }
-    __device__ static RowBits bit(int pos) { return {1ull << pos}; }
-};
-template <> struct RowBits<2> {
-    unsigned long long lo, hi;
-    __device__ static RowBits load(const unsigned long long* p) { return {p[0], p[1]}; }
-    __device__ bool any() const { return (lo | hi) != 0ull; }
-    __device__ RowBits operator&(RowBits o) const { return {lo & o.lo, hi & o.hi}; }
-    __device__ RowBits operator|(RowBits o) const { return {lo | o.lo, hi | o.hi}; }
-    __device__ RowBits operator~() const { return {~lo, ~hi}; }
-    __device__ RowBits shl1() const { return {lo << 1, (hi << 1) | (lo >> 63)}; }
-    __device__ RowBits shr1() const { return {(lo >> 1) | (hi << 63), hi >> 1}; }
-    __device__ RowBits plus(RowBits o) const { const unsigned long long s = lo + o.lo; return {s, hi + o.hi + (s < lo ? 1ull : 0ull)}; }
-    __device__ RowBits lowbit() const { return lo ? RowBits{lo & (0ull - lo), 0ull} : RowBits{0ull, hi & (0ull - hi)}; }
-    __device__ int ffs() const { return lo ? __ffsll((long long)lo) - 1 : 63 + __ffsll((long long)hi); }
-    __device__ int msb() const { return hi ? 127 - __clzll((long long)hi) : 63 - __clzll((long long)lo); }
-    __device__ int popc() const { return __popcll(lo) + __popcll(hi); }
-    __device__ static RowBits below(int pos) {
-        if (pos <= 0) return {0ull, 0ull};
-        if (pos < 64) return {(1ull << pos) - 1ull, 0ull};
-        if (pos == 64) return {~0ull, 0ull};
-        return {~0ull, pos >= 128 ? ~0ull : (1ull << (pos - 64)) - 1ull};
-    }
-    __device__ static RowBits bit(int pos) { return pos < 64 ? RowBits{1ull << pos, 0ull} : RowBits{0ull, 1ull << (pos - 64)}; }
-};
-template <int W> __device__ __forceinline__ RowBits<W> lowest_run(RowBits<W> b) { return b & ~b.plus(b.lowbit()); }
-template <int W> __device__ __forceinline__ RowBits<W> span_bits(int xs, int len) { return RowBits<W>::below(xs + len) & ~RowBits<W>::below(xs); }
-// first bit of the run of b that holds bit pos, and that run
-template <int W> __device__ __forceinline__ int run_start(RowBits<W> b, int pos) {
-    const RowBits<W> zeros = ~b & RowBits<W>::below(pos);
-    return zeros.any() ? zeros.msb() + 1 : 0;
-}
-template <int W> __device__ __forceinline__ RowBits<W> run_from(RowBits<W> b, int bs) { return b & ~b.plus(RowBits<W>::bit(bs)); }
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b);
-
-// Union phase for rows of <= 64 * W voxels whose runs fit the shared-memory node tables (T <= CC_SMEM_RUNS):
-//   (0) nodes: parent = self, size = run length, info = (row << 12) | first x
-//   (A) hook every run to the first run it touches in the previous row of its own slice: plain stores, one
-//       outgoing link per node (a forest of chains along y);
-//   (B) pointer jumping flattens those chains in ~log2(sy) uniform rounds -- walking them with find() would cost
-//       their full length per thread;
-//   (C) the remaining relations (other touching runs of that row, the three rows of the slice above) go through
-//       the lock-free union, one (run, neighbour row) pair per thread, on trees that are now one level deep.
-template <int W>
-__device__ __forceinline__ void cc_unions_by_run(const unsigned long long* __restrict__ bits, const int* __restrict__ run_off,
-                                                 int* parent, int* size, int* info, int rows, int sy, int T) {
+// Union phase on INTERVAL LISTS (rows of <= 256 voxels, runs and rows fit the shared-memory tables).  The bit
+// vectors are only used to enumerate the runs once; afterwards a run is the 16-bit interval (first x << 8) | last x
+// and "run A touches run B of a neighbour row" is two integer compares (x ranges dilated by one = 26-connectivity).
+// Components are formed by hooking and pointer jumping (Shiloach-Vishkin style) instead of find() walks -- with
+// every thread of the CTA joining runs at once, find() chains grow as long as the crop is deep and dominate:
+//   (0) nodes: parent = self, size = run length, interval, row
+//   repeat
+//     (H) every (run, earlier neighbour row) pair: for each touching run, hook the larger of the two ROOTS under the
+//         smaller one with atomicMin (parents are roots here: the forest is flat after (J));
+//     (J) pointer jumping until the forest is flat again (~log2 of the longest chain, uniform rounds);
+//   until no hook happened.  The root of a component ends up as its smallest run id = its first run in raster order.
+__device__ __forceinline__ void cc_unions_intervals(const unsigned long long* __restrict__ bits, const int* __restrict__ run_off,
+                                                    int* parent, int* size, unsigned short* iv, unsigned short* rrow,
+                                                    int rows, int sx, int sy, int W64, int T) {
     const int tid = threadIdx.x;
     for (int r = tid; r < rows; r += CC_THREADS) {            // (0)
-        int id = run_off[r];
-        RowBits<W> b = RowBits<W>::load(bits + (size_t)r * W);
-        while (b.any()) {
-            const RowBits<W> run = lowest_run(b);
-            parent[id] = id; size[id] = run.popc(); info[id] = (r << 12) | run.ffs();
-            ++id;
-            b = b & ~run;
+        const unsigned long long* row = bits + (size_t)r * W64;
+        int id = run_off[r], p = 0, xs, xe;
+        while (next_run(row, W64, sx, p, xs, xe)) {
+            parent[id] = id; size[id] = xe - xs + 1; iv[id] = (unsigned short)((xs << 8) | xe); rrow[id] = (unsigned short)r;
+            ++id; p = xe + 2;
         }
     }
     __syncthreads();
     const unsigned int m_sy = 0xFFFFFFFFu / (unsigned)sy + 1u;                // r / sy for r * sy < 2^32
-    auto touching = [&](int id, int zz, int yy, RowBits<W>& b2, int& base2) -> RowBits<W> {
-        if (zz < 0 || yy < 0 || yy >= sy) return RowBits<W>::below(0) & RowBits<W>::below(0);
-        const int inf = info[id];
-        const int r2 = zz * sy + yy;
-        b2 = RowBits<W>::load(bits + (size_t)r2 * W); base2 = run_off[r2];
-        const RowBits<W> run = span_bits<W>(inf & 4095, size[id]);
-        return b2 & (run | run.shl1() | run.shr1());
-    };
-    auto run_id = [&](RowBits<W> b2, int base2, int bs) -> int { return base2 + ((b2 & ~b2.shl1()) & RowBits<W>::below(bs)).popc(); };
-    for (int id = tid; id < T; id += CC_THREADS) {            // (A)
-        const int r = info[id] >> 12;
-        const int z = sy == 1 ? r : (int)__umulhi((unsigned)r, m_sy), y = r - z * sy;
-        RowBits<W> b2; int base2 = 0;
-        const RowBits<W> touch = touching(id, z, y - 1, b2, base2);
-        if (touch.any()) parent[id] = run_id(b2, base2, run_start(b2, touch.ffs()));
-    }
-    __syncthreads();
-    for (int round = 0; round < 20; ++round) {                // (B) 2^20 > any chain length handled here
-        int changed = 0;
-        for (int id = tid; id < T; id += CC_THREADS) {
-            const int p = parent[id];
-            const int gp = parent[p];
-            if (gp != p) { parent[id] = gp; changed = 1; }
+    for (int iter = 0; iter < 64; ++iter) {                   // 64 >> the handful of iterations real masks need; see below
+        int hooked = 0;
+        for (int task = tid; task < 4 * T; task += CC_THREADS) {  // (H)
+            const int id = task >> 2, nb = task & 3;
+            const int r = rrow[id];
+            const int z = sy == 1 ? r : (int)__umulhi((unsigned)r, m_sy), y = r - z * sy;
+            const int zz = nb < 3 ? z - 1 : z, yy = nb < 3 ? y - 1 + nb : y - 1;
+            if (zz < 0 || yy < 0 || yy >= sy) continue;
+            const int r2 = zz * sy + yy;
+            const unsigned int a = iv[id];
+            const int o2 = run_off[r2], e2 = run_off[r2 + 1];
+            for (int j = o2; j < e2; ++j) {
+                const unsigned int b = iv[j];
+                if ((b >> 8) > (a & 255u) + 1u || (b & 255u) + 1u < (a >> 8)) continue;      // x ranges do not touch
+                const int ra = parent[id], rb = parent[j];
+                if (ra != rb) { atomicMin(&parent[max(ra, rb)], min(ra, rb)); hooked = 1; }
+            }
         }
-        if (!__syncthreads_or(changed)) break;
-    }
-    for (int task = tid; task < 4 * T; task += CC_THREADS) {  // (C)
-        const int id = task >> 2, nb = task & 3;
-        const int r = info[id] >> 12;
-        const int z = sy == 1 ? r : (int)__umulhi((unsigned)r, m_sy), y = r - z * sy;
-        RowBits<W> b2; int base2 = 0;
-        RowBits<W> touch = nb < 3 ? touching(id, z - 1, y - 1 + nb, b2, base2) : touching(id, z, y - 1, b2, base2);
-        bool first = nb == 3;                                 // the first touching run of (z, y-1) is the hook of (A)
-        while (touch.any()) {
-            const int bs = run_start(b2, touch.ffs());
-            if (!first) uf_union(parent, id, run_id(b2, base2, bs));
-            first = false;
-            touch = touch & ~run_from(b2, bs);
+        if (!__syncthreads_or(hooked)) break;
+        for (int round = 0; round < 32; ++round) {            // (J)
+            int changed = 0;
+            for (int id = tid; id < T; id += CC_THREADS) {
+                const int p = parent[id];
+                const int gp = parent[p];
+                if (gp != p) { parent[id] = gp; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
         }
     }
 }
@@ -242,7 +180,8 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
     int* sm_run_off = reinterpret_cast<int*>(sm_bits + CC_SMEM_WORDS);
     int* sm_parent = sm_run_off + CC_SMEM_ROWS + 2;
     int* sm_size = sm_parent + CC_SMEM_RUNS;
-    int* sm_info = sm_size + CC_SMEM_RUNS;                    // (row << 12) | first x of the run (rows of <= 64 voxels)
+    unsigned short* sm_iv = reinterpret_cast<unsigned short*>(sm_size + CC_SMEM_RUNS);    // run interval (first x << 8) | last x
+    unsigned short* sm_row = sm_iv + CC_SMEM_RUNS;                                           // row of the run
     const int slot = blockIdx.x, vol = blockIdx.y;
     const int base = det_off ? det_off[vol] : 0;
     const int n_here = det_off ? det_off[vol + 1] - base : n_crops;
@@ -342,13 +281,12 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
     }
     __syncthreads();
 
-    // rows of <= 128 voxels whose runs fit the shared-memory tables: unions are distributed one (run, neighbour row)
-    // pair per thread -- uniform work, almost no divergence.  Everything else walks rows (union_rows).
-    const bool by_run = W64 <= 2 && T <= CC_SMEM_RUNS && rows < (1 << 19) && (unsigned long long)rows * (unsigned long long)sy < 0xFFFFFFFFull;
+    // rows of <= 256 voxels whose runs fit the shared-memory tables take the interval-list path; everything else
+    // walks rows with the generic multi-word helpers (union_rows).
+    const bool by_run = sx <= 256 && T <= CC_SMEM_RUNS && rows < 65536 && (unsigned long long)rows * (unsigned long long)sy < 0xFFFFFFFFull;
     const int sz = rows / sy;
     if (by_run) {
-        if (W64 == 1) cc_unions_by_run<1>(bits, run_off, parent, size, sm_info, rows, sy, T);
-        else cc_unions_by_run<2>(bits, run_off, parent, size, sm_info, rows, sy, T);
+        cc_unions_intervals(bits, run_off, parent, size, sm_iv, sm_row, rows, sx, sy, W64, T);
     } else {
     // generic rows (wider than 128 voxels, or more runs than the shared-memory tables hold): nodes, then
     // (i) inside every z slice one thread walks the rows top to bottom and joins each row with the previous one
@@ -403,21 +341,17 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
     __syncthreads();
     const int best_root = (int)(sh.best & 0xFFFFFFFFull);
     // ---- 4c. clear the runs of every other component ------------------------------------------------------
-    for (int r = tid; r < rows; r += CC_THREADS) {
-        int id = run_off[r];
-        if (W64 == 1) {
-            unsigned long long b = bits[r];
-            while (b) {
-                const unsigned long long run = b & ~(b + (b & (0ull - b)));
-                if (uf_find(parent, id) != best_root) {
-                    const int xs = __ffsll((long long)run) - 1, len = __popcll(run);
-                    for (int x = xs; x < xs + len; ++x) m[(size_t)r * sx + x] = 0;
-                }
-                b &= ~run; ++id;
-            }
-        } else {
-            const unsigned long long* row = bits + r * W64;
-            int p = 0, xs, xe;
+    if (by_run) {
+        for (int id = tid; id < T; id += CC_THREADS) {
+            if (uf_find(parent, id) == best_root) continue;
+            const unsigned int a = sm_iv[id];
+            uint8_t* dst = m + (size_t)sm_row[id] * sx;
+            for (int x = (int)(a >> 8); x <= (int)(a & 255u); ++x) dst[x] = 0;
+        }
+    } else {
+        for (int r = tid; r < rows; r += CC_THREADS) {
+            const unsigned long long* row = bits + (size_t)r * W64;
+            int id = run_off[r], p = 0, xs, xe;
             while (next_run(row, W64, sx, p, xs, xe)) {
                 if (uf_find(parent, id) != best_root) for (int x = xs; x <= xe; ++x) m[(size_t)r * sx + x] = 0;
                 ++id; p = xe + 2;
