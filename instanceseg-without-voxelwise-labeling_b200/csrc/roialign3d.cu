@@ -73,6 +73,31 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Blackwell packed fp32: two independent round-to-nearest FMAs per instruction (FFMA2).  A 128-bit shared-memory
+// load of four weights lands in two aligned register pairs, so the packed operands need no shuffling.
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float((unsigned int)v); }
+__device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float((unsigned int)(v >> 32)); }
+
+// acc[0..PT) += w[0..PT) * v  with w a 16-byte aligned shared-memory row, acc kept as PT/2 packed pairs
+template <int PT>
+__device__ __forceinline__ void axpy_row(unsigned long long (&acc)[PT / 2], const float* __restrict__ wrow, float v) {
+    const unsigned long long vv = pack2(v, v);
+#pragma unroll
+    for (int q = 0; q < PT / 4; ++q) {
+        const ulonglong2 w = reinterpret_cast<const ulonglong2*>(wrow)[q];
+        acc[2 * q] = fma2(w.x, vv, acc[2 * q]);
+        acc[2 * q + 1] = fma2(w.y, vv, acc[2 * q + 1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -213,50 +238,38 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
             const T* fcl = fc + lx;
             float* dst = bufA + lr * RSx + lx;
             const int dstep = rpi * RSx;
-            for (int row = lr; row < rows; row += rpi, dst += dstep) *dst = to_f(fcl[sh.row_off[row]]);
+            int row = lr;
+            for (; row + 3 * rpi < rows; row += 4 * rpi, dst += 4 * dstep) {      // 4 independent loads in flight
+                const int o0 = sh.row_off[row], o1 = sh.row_off[row + rpi], o2 = sh.row_off[row + 2 * rpi], o3 = sh.row_off[row + 3 * rpi];
+                const T v0 = fcl[o0], v1 = fcl[o1], v2 = fcl[o2], v3 = fcl[o3];
+                dst[0] = to_f(v0); dst[dstep] = to_f(v1); dst[2 * dstep] = to_f(v2); dst[3 * dstep] = to_f(v3);
+            }
+            for (; row < rows; row += rpi, dst += dstep) *dst = to_f(fcl[sh.row_off[row]]);
         }
         __syncwarp();
         // ---- pass X: lane = footprint row; PT-vector over pw -------------------------------------------
         for (int row = lane; row < rows; row += 32) {
-            float acc[PT];
+            unsigned long long acc[PT / 2];
 #pragma unroll
-            for (int p = 0; p < PT; ++p) acc[p] = 0.f;
+            for (int p = 0; p < PT / 2; ++p) acc[p] = 0ull;
             const float* src = bufA + row * RSx;
-            for (int x = 0; x < Fx; ++x) {
-                const float v = src[x];
-                const float4* wv = reinterpret_cast<const float4*>(&sh.w[2][x][0]);
+            for (int x = 0; x < Fx; ++x) axpy_row<PT>(acc, &sh.w[2][x][0], src[x]);
 #pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 w4 = wv[q];
-                    acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < PT; ++p) sT1[row * PT + p] = acc[p];
+            for (int p = 0; p < PT / 2; ++p) { sT1[row * PT + 2 * p] = lo2(acc[p]); sT1[row * PT + 2 * p + 1] = hi2(acc[p]); }   // sT1 is only 4-byte aligned
         }
         __syncwarp();
         // ---- pass Y: lane = (z, pw); PT-vector over ph -------------------------------------------------
         {
             const int pw = lane % PT;
             for (int z = lane / PT; z < Fz; z += 32 / PT) {
-                float acc[PT];
+                unsigned long long acc[PT / 2];
 #pragma unroll
-                for (int p = 0; p < PT; ++p) acc[p] = 0.f;
+                for (int p = 0; p < PT / 2; ++p) acc[p] = 0ull;
                 const float* src = sT1 + z * Fy * PT + pw;
-                for (int y = 0; y < Fy; ++y) {
-                    const float v = src[y * PT];
-                    const float4* wv = reinterpret_cast<const float4*>(&sh.w[1][y][0]);
-#pragma unroll
-                    for (int q = 0; q < PT / 4; ++q) {
-                        const float4 w4 = wv[q];
-                        acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
-                    }
-                }
+                for (int y = 0; y < Fy; ++y) axpy_row<PT>(acc, &sh.w[1][y][0], src[y * PT]);
                 float* dst = sT2 + z * PT * PT + pw;
 #pragma unroll
-                for (int p = 0; p < PT; ++p) dst[p * PT] = acc[p];
+                for (int p = 0; p < PT / 2; ++p) { dst[(2 * p) * PT] = lo2(acc[p]); dst[(2 * p + 1) * PT] = hi2(acc[p]); }
             }
         }
         __syncwarp();
@@ -264,20 +277,14 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
 #pragma unroll
         for (int k = 0; k < ZP_ITERS; ++k) {
             if (zp_src[k] < 0) continue;
+            unsigned long long acc2[PT / 2];
+#pragma unroll
+            for (int p = 0; p < PT / 2; ++p) acc2[p] = 0ull;
+            const float* src = sT2 + zp_src[k];
+            for (int z = 0; z < Fz; ++z) axpy_row<PT>(acc2, &sh.w[0][z][0], src[z * PT * PT]);
             float acc[PT];
 #pragma unroll
-            for (int p = 0; p < PT; ++p) acc[p] = 0.f;
-            const float* src = sT2 + zp_src[k];
-            for (int z = 0; z < Fz; ++z) {
-                const float v = src[z * PT * PT];
-                const float4* wv = reinterpret_cast<const float4*>(&sh.w[0][z][0]);
-#pragma unroll
-                for (int q = 0; q < PT / 4; ++q) {
-                    const float4 w4 = wv[q];
-                    acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
-                }
-            }
+            for (int p = 0; p < PT / 2; ++p) { acc[2 * p] = lo2(acc2[p]); acc[2 * p + 1] = hi2(acc2[p]); }
             float* dst = bufA + zp_dst[k];
             if (pow2) {                                    // 1/count already folded into the z table
 #pragma unroll
@@ -367,8 +374,8 @@ roialign3d_prep_kernel(const float* __restrict__ rois, int R, RoiBox* __restrict
 template <int PT>
 __device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float (&g)[PT]) {
     float s0 = 0.f, s1 = 0.f;                                  // two chains: halves the dependent-FMA latency
-#pragma unroll
-    for (int q = 0; q < PT / 4; ++q) {
+#pragma unroll                                                  // (packed FFMA2 was measured slower here: the register
+    for (int q = 0; q < PT / 4; ++q) {                          //  pairs of g cost more moves than the FMAs they save)
         const float4 w4 = reinterpret_cast<const float4*>(wrow)[q];
         s0 = fmaf(w4.x, g[4 * q], s0); s1 = fmaf(w4.y, g[4 * q + 1], s1);
         s0 = fmaf(w4.z, g[4 * q + 2], s0); s1 = fmaf(w4.w, g[4 * q + 3], s1);
