@@ -217,6 +217,24 @@ def bench_ops(torch, peak):
     q = torch.from_numpy(synth.random_dets(rng, 50, extent=(256, 256, 64), side=(10, 40))[:, :6].copy()).to(dev)
     ms = time_op(torch, lambda: b200seg.bbox_overlaps_3d(bx, q), 20, flush)
     ops["iou3d_917504x50"] = entry(ms, 24 * (917504 + 50) + 4 * 917504 * 50, {"pairs_per_s": 917504 * 50 / (ms * 1e-3)})
+    # RLE codec of a 128x512x512 label mask (~200 blobs): encode reads the mask, decode writes it
+    from b200seg import mask_3d, _lib as L_
+    mvol = torch.from_numpy((synth.postproc_case(2000, **CASE_KW)["volume"] > 60).astype(np.uint8)).to(dev)
+    S_, H_, W_ = mvol.shape
+    cap = 1 << 22
+    ms = time_op(torch, lambda: mask_3d._encode_device(mvol, cap), 10, flush)
+    counts, n_c = mask_3d._encode_device(mvol, cap)
+    ops["rle3d_encode_128x512x512"] = entry(ms, mvol.numel() + 8 * n_c, {"gvox_per_s": mvol.numel() / (ms * 1e-3) / 1e9, "runs": n_c,
+                                                                       "note": "two walks over the mask (count, emit) + scan; includes the D2H read of the run count"})
+    lib_ = L_.lib()
+    ws_b = lib_.b200seg_rle3d_workspace_bytes(S_, H_, W_, n_c)
+    ws_t = torch.empty(ws_b, dtype=torch.uint8, device=dev)
+    out_m = torch.empty_like(mvol)
+    cc = counts[:n_c].contiguous()
+    ms = time_op(torch, lambda: L_.check(lib_.b200seg_rle3d_decode_dev(L_.ptr(cc), n_c, L_.ptr(out_m), S_, H_, W_, None, L_.ptr(ws_t), ws_b,
+                                                                       L_.current_stream()), "rle3d_decode"), 10, flush)
+    assert bool((out_m == mvol).all())
+    ops["rle3d_decode_128x512x512"] = entry(ms, mvol.numel() + 8 * n_c, {"gvox_per_s": mvol.numel() / (ms * 1e-3) / 1e9})
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
         d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)

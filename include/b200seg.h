@@ -230,6 +230,21 @@ int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, int W,
                                uint16_t* seg, int* n_keep, int32_t* rank_order,
                                int32_t* b_max, int32_t* status, uint8_t* survive);
 
+/* ----------------------------------------------------------------------------------------------
+ * Run-length codec of binary 3D masks -- replaces lib/utils/mask_3d.py:15-71 (binary_mask_to_rle,
+ * rle_to_binary_mask) and lib/utils/cython_mask_3d.pyx:19-77.  mask [S,H,W] uint8 C-contiguous (set = non-zero);
+ * counts = lengths of the alternating runs of the FORTRAN-order ravel (first axis fastest), starting with a run
+ * of zeros (length 0 when the first element is set); an all-zero mask is the single count S*H*W.
+ * encode: at most `cap` counts are written, *n_counts (device int64) always holds the true number.
+ * decode: writes the whole mask; *sum_out (device int64, may be NULL) = sum of the counts, which the caller
+ * compares with S*H*W like mask_3d.py:53.  workspace: b200seg_rle3d_workspace_bytes(S, H, W, cap or n_counts).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_rle3d_workspace_bytes(int S, int H, int W, long long cap);
+int b200seg_rle3d_encode_dev(const uint8_t* mask, int S, int H, int W, int64_t* counts, long long cap,
+                             int64_t* n_counts, void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+int b200seg_rle3d_decode_dev(const int64_t* counts, long long n_counts, uint8_t* mask, int S, int H, int W,
+                             int64_t* sum_out, void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
 /* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
  * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */

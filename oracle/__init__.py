@@ -230,6 +230,37 @@ def largest_cc(mask):
     return labels == best
 
 
+# ------------------------------------------------------------------------------- RLE codec
+def binary_mask_to_rle(binary_mask):
+    """lib/utils/mask_3d.py:15-46 / cython_mask_3d.pyx:19-50: Fortran-order ravel, alternating run lengths starting
+    with the zeros (0 when the first element is set); blank mask -> [size]."""
+    m = np.asfortranarray(np.asarray(binary_mask) != 0)
+    flat = np.ravel(m, order="F").astype(np.int8)
+    n = flat.size
+    if not flat.any():
+        return {"counts": [int(n)], "size": list(m.shape)}
+    change = np.flatnonzero(np.diff(flat)) + 1               # first index of every run but the first
+    bounds = np.concatenate([[0], change, [n]])
+    counts = np.diff(bounds).tolist()
+    if flat[0]:
+        counts.insert(0, 0)
+    return {"counts": [int(c) for c in counts], "size": list(m.shape)}
+
+
+def rle_to_binary_mask(rle):
+    """lib/utils/mask_3d.py:48-71: runs alternate 0,1,...; a single count is a blank mask; Fortran-order reshape."""
+    counts, size = list(rle["counts"]), list(rle["size"])
+    assert sum(counts) == int(np.prod(size))
+    flat = np.zeros(int(np.prod(size)), dtype=np.uint8)
+    if len(counts) > 1:
+        pos, val = 0, 0
+        for c in counts:
+            flat[pos:pos + c] = val
+            pos += c
+            val ^= 1
+    return flat.reshape(size, order="F")
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

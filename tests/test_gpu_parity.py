@@ -234,6 +234,26 @@ def test_largest_cc_vs_oracle(b2, torch_):
     assert out[off[-3]:off[-2]].reshape(tie.shape)[2, 2, 6] == 255   # tie: the later component wins
 
 
+def test_rle_codec_vs_oracle_and_golden(b2, golden, torch_):
+    from b200seg import mask_3d
+    d = golden("rle.npz")
+    r = mask_3d.binary_mask_to_rle(d["mask"])
+    assert r["counts"] == d["counts"].tolist() and r["size"] == d["size"].tolist()      # mask_3d.py:75-79
+    assert np.array_equal(mask_3d.rle_to_binary_mask(r), d["mask"])
+    rng = np.random.default_rng(5)
+    for sh, dens in [((3, 4, 5), 0.3), ((1, 1, 1), 1.0), ((1, 1, 1), 0.0), ((7, 2, 9), 0.5), ((16, 33, 70), 0.02), ((16, 33, 70), 0.0),
+                     ((16, 33, 70), 1.0), ((40, 64, 96), 0.5), ((128, 40, 50), 0.001)]:
+        m = (rng.random(sh) < dens).astype(np.uint8) * 255
+        a = mask_3d.binary_mask_to_rle(m, cap=64)                # small first guess: exercises the exact second pass
+        o = oracle.binary_mask_to_rle(m)
+        assert a == o, (sh, dens, len(a["counts"]), len(o["counts"]))
+        back = mask_3d.rle_to_binary_mask(a)
+        assert back.dtype == np.uint8 and np.array_equal(back, (m != 0).astype(np.uint8))   # round trip
+    blob = np.zeros((128, 256, 256), np.uint8); blob[30:90, 60:200, 50:180] = 1            # config-sized round trip
+    a = mask_3d.binary_mask_to_rle(blob)
+    assert sum(a["counts"]) == blob.size and np.array_equal(mask_3d.rle_to_binary_mask(a), blob)
+
+
 def test_paste_vs_oracle_overlapping(b2, torch_):
     rng = np.random.default_rng(3)
     S, H, W = 20, 50, 77                                                     # W not a multiple of 8: scalar store path

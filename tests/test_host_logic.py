@@ -37,6 +37,7 @@ def test_shim_installs_reference_names():
     from modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d import RoIAlignFunction_3d
     from modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d import RoIAlign_3d, RoIAlignAvg_3d, RoIAlignMax_3d
     from prm.peak_stimulation_3d import peak_stimulation_3d
+    from utils.cython_mask_3d import binary_mask_to_rle, rle_to_binary_mask
     from otsu import otsu_py, otsu_py_2d, otsu_py_2d_fast      # binarization_soma.py:19, binarization_nuclei.py:12
     import pytest
     with pytest.raises(NotImplementedError):

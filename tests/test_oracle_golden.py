@@ -112,3 +112,23 @@ def test_roialign_oracle_properties():
     g = np.ones((1, 1, 7, 7, 7), np.float32)
     gi = oracle.roialign3d_bwd(g, rois, (1, 1, 6, 7, 8), 0.25, 2)
     np.testing.assert_allclose(gi.sum(), 343.0, rtol=1e-5)
+
+
+def test_rle_golden_and_reference_cython(golden):
+    """lib/utils/mask_3d.py:75-79 is the only known-answer vector of the reference; the Cython twin built by
+    oracle/build_ref.py (when present) pins the restatement on random masks."""
+    d = golden("rle.npz")
+    r = oracle.binary_mask_to_rle(d["mask"])
+    assert r["counts"] == d["counts"].tolist() and r["size"] == d["size"].tolist()
+    assert np.array_equal(oracle.rle_to_binary_mask(r), d["mask"])
+    ref = oracle.ref_module("cython_mask_3d")
+    rng = np.random.default_rng(3)
+    for sh in [(3, 4, 5), (1, 1, 1), (7, 2, 9), (5, 6, 1)]:
+        for dens in (0.0, 0.2, 0.7, 1.0):
+            m = (rng.random(sh) < dens).astype(np.uint8)
+            a = oracle.binary_mask_to_rle(m)
+            assert sum(a["counts"]) == m.size
+            assert np.array_equal(oracle.rle_to_binary_mask(a), m)
+            if ref is not None:
+                b = ref.binary_mask_to_rle(m)
+                assert a["counts"] == [int(x) for x in b["counts"]] and a["size"] == list(b["size"])
