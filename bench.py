@@ -235,6 +235,19 @@ def bench_ops(torch, peak):
                                                                        L_.current_stream()), "rle3d_decode"), 10, flush)
     assert bool((out_m == mvol).all())
     ops["rle3d_decode_128x512x512"] = entry(ms, mvol.numel() + 8 * n_c, {"gvox_per_s": mvol.numel() / (ms * 1e-3) / 1e9})
+    # evaluation: pairwise mask overlaps of two 128x512x512 label volumes (~200 instances each), one joint-histogram pass
+    from b200seg import evaluation
+    rng_e = np.random.default_rng(21)
+    lab_p = np.zeros(SHAPE, np.uint16); lab_g = np.zeros(SHAPE, np.uint16)
+    for lab, shift in ((lab_p, 0), (lab_g, 3)):
+        for i in range(1, 201):
+            c = [int(rng_e.integers(8, s - 40)) for s in SHAPE]; e = [int(rng_e.integers(8, 18)), int(rng_e.integers(16, 40)), int(rng_e.integers(16, 40))]
+            lab[c[0] + shift:c[0] + e[0], c[1]:c[1] + e[1] + shift, c[2]:c[2] + e[2]] = i
+    tp, tg = torch.from_numpy(lab_p).to(dev), torch.from_numpy(lab_g).to(dev)
+    ids = np.arange(1, 201)
+    ms = time_op(torch, lambda: evaluation.mask_overlaps_labels(tp, tg, ids, ids), 10, flush)
+    ops["mask_overlaps_128x512x512_200x200"] = entry(ms, 4 * tp.numel() + 3 * 4 * 200 * 200, {
+        "gvox_per_s": tp.numel() / (ms * 1e-3) / 1e9, "note": "includes the host-side lookup tables and their H2D copies"})
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
         d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)

@@ -245,6 +245,22 @@ int b200seg_rle3d_encode_dev(const uint8_t* mask, int S, int H, int W, int64_t* 
 int b200seg_rle3d_decode_dev(const int64_t* counts, long long n_counts, uint8_t* mask, int S, int H, int W,
                              int64_t* sum_out, void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Pairwise instance-mask overlaps between two label volumes -- replaces tools/evaluation/mask_iou.py:49-109
+ * (mask_iou_fast, mask_ios_fast, mask_iog_fast) as called by eval_instance_segmentation_soma.py:186-197, where the
+ * boolean stacks are cut out of label volumes: pred_masks[i] = (pred == id_i), gt_masks[k] = (gt == id_k).
+ *   pred, gt [n_voxels] uint16 label volumes; lut_pred / lut_gt [65536] int32: label id -> row (0-based) or -1;
+ *   iou / ios / iog [n_pred, n_gt] fp32 (any may be NULL): I/(A+B-I), I/A, I/B with A = pred area, B = gt area, each
+ *   computed as float32(double / double); 0/0 gives NaN (the numba reference raises ZeroDivisionError there).
+ *   inter [(n_pred+1),(n_gt+1)] int64 (row / column 0 = voxels whose id is unlisted or background; cell (0,0)
+ *   excludes the voxels that are background in both volumes), area_pred [n_pred+1], area_gt [n_gt+1]: optional.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_mask_overlaps_workspace_bytes(int n_pred, int n_gt);
+int b200seg_mask_overlaps_dev(const uint16_t* pred, const uint16_t* gt, long long n_voxels,
+                              const int32_t* lut_pred, const int32_t* lut_gt, int n_pred, int n_gt,
+                              float* iou, float* ios, float* iog, int64_t* inter, int64_t* area_pred, int64_t* area_gt,
+                              void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
 /* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
  * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */

@@ -261,6 +261,20 @@ def rle_to_binary_mask(rle):
     return flat.reshape(size, order="F")
 
 
+# ------------------------------------------------------------------------------- mask overlaps (evaluation)
+def mask_overlaps(mask_a, mask_b):
+    """tools/evaluation/mask_iou.py:49-109: for stacks [N,...] and [K,...] of boolean masks, iou = I/U, ios = I/A,
+    iog = I/B with float (fp64) accumulators stored into float32 arrays.  Returns (iou, ios, iog)."""
+    a = np.asarray(mask_a).astype(bool).reshape(len(mask_a), -1)
+    b = np.asarray(mask_b).astype(bool).reshape(len(mask_b), -1)
+    inter = a.astype(np.int64) @ b.astype(np.int64).T
+    A = a.sum(axis=1).astype(np.float64)[:, None]
+    B = b.sum(axis=1).astype(np.float64)[None, :]
+    I = inter.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (I / (A + B - I)).astype(np.float32), (I / A).astype(np.float32), (I / B).astype(np.float32)
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

@@ -10,6 +10,8 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
   peaks.npz     lib/prm/peak_stimulation_3d.py:peak_stimulation_3d on CPU torch, with the median
                 filter of lib/prm/peak_response_mapping_3d.py:45-49
   rle.npz       lib/utils/mask_3d.py literal of :75-79 (the only known-answer in the reference)
+  mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
+                Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
 what the `-m gpu` tests pin the CUDA path against on the GPU box (no /root/reference there).
 """
@@ -147,6 +149,29 @@ def make_peaks():
     print("peaks.npz", len(cases), "cases")
 
 
+def make_mask_iou():
+    """tools/evaluation/mask_iou.py run as plain Python (numba stubbed: nb.jit becomes the identity)."""
+    nb = types.ModuleType("numba")
+    nb.jit = lambda *a, **k: (lambda f: f)
+    sys.modules["numba"] = nb
+    spec = importlib.util.spec_from_file_location("ref_mask_iou", os.path.join(REF, "tools", "evaluation", "mask_iou.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(77)
+    shape = (5, 7, 9)
+    pred = np.zeros(shape, np.uint16); gt = np.zeros(shape, np.uint16)
+    pred[0:3, 0:4, 0:5] = 1; pred[2:5, 4:7, 3:9] = 2; pred[0:2, 5:7, 0:2] = 3
+    gt[0:3, 1:5, 1:6] = 1; gt[3:5, 3:7, 2:8] = 2; gt[0:1, 0:1, 8:9] = 3; gt[4:5, 0:2, 0:2] = 4
+    pred[rng.random(shape) < 0.05] = 0
+    pa = np.stack([pred == i for i in (2, 1, 3)])            # the caller's score order, not id order
+    ga = np.stack([gt == i for i in (1, 2, 3, 4)])
+    out = dict(pred=pred, gt=gt, pred_ids=np.array([2, 1, 3]), gt_ids=np.array([1, 2, 3, 4]),
+               iou=mod.mask_iou_fast(pa, ga), ios=mod.mask_ios_fast(pa, ga), iog=mod.mask_iog_fast(pa, ga),
+               iou_slow=mod.mask_iou(pa, ga))
+    np.savez_compressed(os.path.join(HERE, "mask_iou.npz"), **out)
+    print("mask_iou.npz", out["iou"])
+
+
 def make_rle():
     sys.path.insert(0, os.path.join(REF, "lib", "utils"))
     spec = importlib.util.spec_from_file_location("ref_mask_3d", os.path.join(REF, "lib", "utils", "mask_3d.py"))
@@ -164,3 +189,4 @@ if __name__ == "__main__":
     make_otsu()
     make_peaks()
     make_rle()
+    make_mask_iou()

@@ -234,6 +234,40 @@ def test_largest_cc_vs_oracle(b2, torch_):
     assert out[off[-3]:off[-2]].reshape(tie.shape)[2, 2, 6] == 255   # tie: the later component wins
 
 
+def test_mask_overlaps_vs_oracle_and_golden(b2, golden, torch_):
+    from b200seg import evaluation
+    d = golden("mask_iou.npz")
+    r = evaluation.mask_overlaps_labels(d["pred"], d["gt"], d["pred_ids"], d["gt_ids"])
+    for k in ("iou", "ios", "iog"):
+        assert np.array_equal(r[k].cpu().numpy(), d[k], equal_nan=True), k           # bit-exact float32(double / double)
+    pa = np.stack([d["pred"] == i for i in d["pred_ids"]]); ga = np.stack([d["gt"] == i for i in d["gt_ids"]])
+    assert np.array_equal(evaluation.mask_iou_fast(pa, ga), d["iou"], equal_nan=True)   # the reference's stack signature
+    # random label volumes, odd sizes (scalar tail), ids listed in arbitrary order, unlisted ids, an empty listed id
+    rng = np.random.default_rng(11)
+    for shape, npred, ngt in [((7, 13, 19), 5, 4), ((16, 40, 50), 30, 25), ((33, 65, 70), 200, 180)]:
+        pred = np.zeros(shape, np.uint16); gt = np.zeros(shape, np.uint16)
+        for lab, n in ((pred, npred), (gt, ngt)):
+            for i in range(1, n + 1):
+                c = [rng.integers(0, s) for s in shape]; e = [rng.integers(1, max(2, s // 3)) for s in shape]
+                lab[c[0]:c[0] + e[0], c[1]:c[1] + e[1], c[2]:c[2] + e[2]] = i
+        pid = rng.permutation(np.arange(1, npred + 1))[: max(1, npred - 2)]           # two ids stay unlisted
+        gid = np.concatenate([rng.permutation(np.arange(1, ngt + 1)), [ngt + 7]])     # one listed id that never occurs
+        r = evaluation.mask_overlaps_labels(pred, gt, pid, gid)
+        pa = np.stack([pred == i for i in pid]); ga = np.stack([gt == i for i in gid])
+        iou, ios, iog = oracle.mask_overlaps(pa, ga)
+        assert np.array_equal(r["iou"].cpu().numpy(), iou, equal_nan=True)
+        assert np.array_equal(r["ios"].cpu().numpy(), ios, equal_nan=True)
+        assert np.array_equal(r["iog"].cpu().numpy(), iog, equal_nan=True)
+        assert np.array_equal(r["area_pred"].cpu().numpy(), pa.reshape(len(pid), -1).sum(1))
+        assert np.array_equal(r["area_gt"].cpu().numpy(), ga.reshape(len(gid), -1).sum(1))
+    # full size: checksum property -- the table accounts for every voxel that is not background in both volumes
+    S, H, W = 128, 512, 512
+    pred = torch_.zeros((S, H, W), dtype=torch_.int32, device="cuda"); gt = torch_.zeros_like(pred)
+    pred[10:100, 50:400, 60:300] = 3; pred[20:60, 10:40, 10:500] = 9; gt[30:120, 100:450, 100:350] = 5
+    r = evaluation.mask_overlaps_labels(pred.to(torch_.uint16), gt.to(torch_.uint16), [3, 9], [5])
+    assert int(r["inter"][0, 0]) == int(((pred == 3) & (gt == 5)).sum()) and int(r["area_pred"][1]) == int((pred == 9).sum())
+
+
 def test_rle_codec_vs_oracle_and_golden(b2, golden, torch_):
     from b200seg import mask_3d
     d = golden("rle.npz")

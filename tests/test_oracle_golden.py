@@ -132,3 +132,13 @@ def test_rle_golden_and_reference_cython(golden):
             if ref is not None:
                 b = ref.binary_mask_to_rle(m)
                 assert a["counts"] == [int(x) for x in b["counts"]] and a["size"] == list(b["size"])
+
+
+def test_mask_overlaps_golden(golden):
+    """tools/evaluation/mask_iou.py:10-109 run as plain Python (numba stubbed) generated the fixture."""
+    d = golden("mask_iou.npz")
+    pa = np.stack([d["pred"] == i for i in d["pred_ids"]])
+    ga = np.stack([d["gt"] == i for i in d["gt_ids"]])
+    iou, ios, iog = oracle.mask_overlaps(pa, ga)
+    for k, v in (("iou", iou), ("ios", ios), ("iog", iog), ("iou_slow", iou)):
+        assert np.array_equal(v, d[k], equal_nan=True), k
