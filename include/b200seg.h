@@ -261,6 +261,32 @@ int b200seg_mask_overlaps_dev(const uint16_t* pred, const uint16_t* gt, long lon
                               float* iou, float* ios, float* iog, int64_t* inter, int64_t* area_pred, int64_t* area_gt,
                               void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Whole-volume prefilters and normalisations.
+ *
+ * b200seg_gaussian3d_dev replaces  scipy.ndimage.gaussian_filter(img, sigma)  as called on the raw integer volume by
+ *   tools/binarization_nuclei.py:43 : three separable passes (axis 0, 1, 2), 'reflect' borders, fp64 accumulation in
+ *   scipy's order, every pass truncated to the volume's dtype -- bit exact.  `weights` (HOST pointer) holds the first
+ *   radius+1 taps of the symmetric kernel, weights[radius] = centre; the host side computes them exactly as scipy
+ *   does (radius = int(truncate*sigma + 0.5) <= 8).  elem_bytes: 1 = uint8, 2 = uint16.  in != out.
+ * b200seg_median3d_dev replaces  scipy.ndimage.median_filter(img, size=3)  (tools/binarization_nuclei.py:44).
+ * b200seg_zscore_norm_dev replaces  (im - mean(im[im>0])) / std(im[im>0])  (tools/infer_simple.py:180-183,
+ *   lib/utils/blob.py:180-184).  elem_bytes 1 / 2 = uint8 / uint16 (exact integer moments), 4 = float32 (two-pass
+ *   fp64 moments, deterministic).  out [n] float32 (may be NULL: statistics only); stats [3] double on the device =
+ *   {mean, std, count of non-zero voxels}.
+ * b200seg_prm_to_u8_dev replaces the per-channel  fm -= min; fm /= max; fm *= 255; astype(uint8)  of
+ *   tools/infer_simple.py:233-238 (fp32, same operation order; a constant map gives 0).  in [n_maps, per_map].
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_gaussian3d_dev(const void* in, void* out, int elem_bytes, int S, int H, int W, const double* weights, int radius,
+                           b200seg_stream_t stream);
+int b200seg_median3d_dev(const void* in, void* out, int elem_bytes, int S, int H, int W, b200seg_stream_t stream);
+size_t b200seg_zscore_workspace_bytes(void);
+int b200seg_zscore_norm_dev(const void* in, int elem_bytes, float* out, long long n, double* stats,
+                            void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+size_t b200seg_prm_to_u8_workspace_bytes(int n_maps);
+int b200seg_prm_to_u8_dev(const float* in, uint8_t* out, int n_maps, long long per_map,
+                          void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
 /* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
  * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */

@@ -40,6 +40,12 @@ SIGNATURES = {
     "b200seg_paste_labels_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200seg_mask_overlaps_workspace_bytes": (_sz, [_i, _i]),
     "b200seg_mask_overlaps_dev": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200seg_gaussian3d_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "b200seg_median3d_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200seg_zscore_workspace_bytes": (_sz, []),
+    "b200seg_zscore_norm_dev": (_i, [_vp, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
+    "b200seg_prm_to_u8_workspace_bytes": (_sz, [_i]),
+    "b200seg_prm_to_u8_dev": (_i, [_vp, _vp, _i, _ll, _vp, _sz, _vp]),
     "b200seg_rle3d_workspace_bytes": (_sz, [_i, _i, _i, _ll]),
     "b200seg_rle3d_encode_dev": (_i, [_vp, _i, _i, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
     "b200seg_rle3d_decode_dev": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),

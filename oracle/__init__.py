@@ -275,6 +275,78 @@ def mask_overlaps(mask_a, mask_b):
         return (I / (A + B - I)).astype(np.float32), (I / A).astype(np.float32), (I / B).astype(np.float32)
 
 
+# ------------------------------------------------------------------------------- whole-volume prefilters
+def _reflect_pad_last(x, r):
+    """scipy 'reflect' (d c b a | a b c d | d c b a) along the last axis, any radius."""
+    n = x.shape[-1]
+    idx = np.arange(-r, n + r)
+    if n == 1:
+        idx[:] = 0
+    else:
+        idx = np.mod(idx, 2 * n)
+        idx = np.where(idx < n, idx, 2 * n - 1 - idx)
+    return x[..., idx]
+
+
+def gaussian_kernel1d(sigma, truncate=4.0):
+    """scipy.ndimage._filters._gaussian_kernel1d, order 0 (the arithmetic behind binarization_nuclei.py:43)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (float(sigma) * float(sigma)) * x ** 2)
+    return phi / phi.sum(), radius
+
+
+def gaussian_filter(img, sigma=1, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(img, sigma) on an integer volume (tools/binarization_nuclei.py:43), restated:
+    axis 0, 1, 2 in turn; per output  acc = w[R]*x0; for j = R..1: acc += (x[-j] + x[+j]) * w[R-j]  in fp64 (separate
+    multiply and add), the result cast (truncated) to img.dtype after EVERY pass (scipy filters into the output array)."""
+    w, R = gaussian_kernel1d(sigma, truncate)
+    out = np.asarray(img)
+    if R < 1:
+        return out.copy()
+    for axis in range(out.ndim):
+        x = np.moveaxis(out, axis, -1).astype(np.float64)
+        n = x.shape[-1]
+        xp = _reflect_pad_last(x, R)
+        acc = w[R] * xp[..., R:R + n]
+        for jj in range(-R, 0):
+            acc = acc + (xp[..., R + jj:R + jj + n] + xp[..., R - jj:R - jj + n]) * w[jj + R]
+        out = np.moveaxis(acc, -1, axis).astype(img.dtype)
+    return np.ascontiguousarray(out)
+
+
+def median_filter3(img):
+    """scipy.ndimage.median_filter(img, size=3) (tools/binarization_nuclei.py:44): rank 13 of the 3x3x3 neighbourhood,
+    'reflect' borders."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    a = np.asarray(img)
+    ap = np.pad(a, 1, mode="symmetric")
+    win = sliding_window_view(ap, (3, 3, 3)).reshape(a.shape + (27,))
+    return np.ascontiguousarray(np.partition(win, 13, axis=-1)[..., 13])
+
+
+def zscore_norm(im):
+    """tools/infer_simple.py:180-183: (im - mean(im[im>0])) / std(im[im>0]); returns (float64 array, mean, std)."""
+    im = np.asarray(im)
+    mask = im > 0
+    mean_val = np.mean(im[mask])
+    std_val = np.std(im[mask])
+    return (im - mean_val) / std_val, float(mean_val), float(std_val)
+
+
+def prm_to_uint8(prm):
+    """tools/infer_simple.py:233-238, per channel, in place on a float32 copy: -= min, /= max, *= 255., astype(uint8)."""
+    prm = np.array(prm, dtype=np.float32, copy=True)
+    out = np.empty(prm.shape, np.uint8)
+    for ch in range(prm.shape[0]):
+        fm = prm[ch, :]
+        fm -= np.min(fm)
+        fm /= np.max(fm)
+        fm *= 255.
+        out[ch] = fm.astype(np.uint8)
+    return out
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

@@ -184,7 +184,45 @@ def make_rle():
     print("rle.npz", r)
 
 
+def make_prefilter():
+    """The reference's prefilter / normalisation lines run verbatim on seeded volumes:
+    binarization_nuclei.py:43-44 (scipy.ndimage, the reference's own dependency; version here recorded in the file),
+    infer_simple.py:180-183 (z-score) and :233-238 (PRM -> uint8)."""
+    import scipy
+    from scipy import ndimage
+    rng = np.random.default_rng(4344)
+    out = {"scipy_version": np.array(scipy.__version__)}
+    for name, dtype, hi, shape in (("u16", np.uint16, 65535, (11, 37, 70)), ("u8", np.uint8, 255, (9, 21, 33)), ("thin", np.uint16, 4000, (3, 5, 130))):
+        img = rng.integers(0, hi + 1, shape).astype(dtype)
+        img[rng.random(shape) < 0.3] = 0
+        g = ndimage.gaussian_filter(img, sigma=1)                 # binarization_nuclei.py:43
+        m = ndimage.median_filter(g, size=3)                      # binarization_nuclei.py:44
+        out[name + "_img"], out[name + "_gauss"], out[name + "_median"] = img, g, m
+        if name != "thin":
+            out[name + "_gauss_s2"] = ndimage.gaussian_filter(img, sigma=2)
+    im = out["u16_img"]
+    mask = im > 0                                                 # infer_simple.py:180-183
+    mean_val = np.mean(im[mask])
+    std_val = np.std(im[mask])
+    out["zs_out"] = (im - mean_val) / std_val
+    out["zs_stats"] = np.array([mean_val, std_val])
+    prm = (rng.random((3, 6, 10, 12)) ** 3).astype(np.float32) * np.array([1.0, 37.5, 1e-3], np.float32)[:, None, None, None]
+    prm[1] -= 11.0
+    out["prm_in"] = prm.copy()
+    u8 = np.empty(prm.shape, np.uint8)
+    for ch in range(prm.shape[0]):                                # infer_simple.py:233-238
+        fm_ch = prm[ch, :]
+        fm_ch -= np.min(fm_ch)
+        fm_ch /= np.max(fm_ch)
+        fm_ch *= 255.
+        u8[ch] = fm_ch.astype(np.uint8)
+    out["prm_u8"] = u8
+    np.savez_compressed(os.path.join(HERE, "prefilter.npz"), **out)
+    print("prefilter.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    make_prefilter()
     make_nms_iou()
     make_otsu()
     make_peaks()

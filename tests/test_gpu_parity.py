@@ -584,3 +584,74 @@ def test_roialign_config4_full_size(b2, torch_):
     a = roialign3d_backward(g1, r, feat.shape, 0.125, 2); b = roialign3d_backward(g2, r, feat.shape, 0.125, 2)
     c = roialign3d_backward(g1 + g2, r, feat.shape, 0.125, 2)
     assert float((a + b - c).abs().max()) <= 1e-4 * float(c.abs().max())
+
+
+# ------------------------------------------------------------------------------------------ whole-volume prefilters
+def test_prefilter_golden_and_oracle(b2, golden, torch_):
+    from b200seg import prefilter
+    d = golden("prefilter.npz")
+    for n in ("u16", "u8", "thin"):
+        g = prefilter.gaussian_filter(d[n + "_img"], 1)
+        assert g.dtype == d[n + "_img"].dtype and np.array_equal(g, d[n + "_gauss"]), n                # bit exact vs scipy
+        assert np.array_equal(prefilter.median_filter(g, 3), d[n + "_median"]), n
+        assert np.array_equal(prefilter.prefilter_nuclei(d[n + "_img"]), d[n + "_median"]), n
+        if n != "thin":
+            assert np.array_equal(prefilter.gaussian_filter(d[n + "_img"], 2), d[n + "_gauss_s2"]), n   # radius 8
+    # seeded volumes: odd widths (scalar paths), dims smaller than the radius, tiles that straddle the border, all radii
+    rng = np.random.default_rng(91)
+    for shape, dtype, hi in [((5, 33, 67), np.uint16, 65535), ((13, 70, 129), np.uint8, 255), ((40, 31, 64), np.uint16, 3000),
+                             ((2, 3, 5), np.uint16, 65535), ((1, 1, 1), np.uint8, 255), ((9, 64, 130), np.uint16, 65535)]:
+        img = rng.integers(0, hi + 1, shape).astype(dtype)
+        img[rng.random(shape) < 0.2] = hi                                   # saturated voxels: results must not overflow
+        for sigma in (0.3, 0.5, 0.7, 1, 1.2, 1.5, 1.7, 2):
+            assert np.array_equal(prefilter.gaussian_filter(img, sigma), oracle.gaussian_filter(img, sigma)), (shape, sigma)
+        assert np.array_equal(prefilter.median_filter(img), oracle.median_filter3(img)), shape
+    const = np.full((7, 40, 70), 1000, np.uint16)
+    assert np.array_equal(prefilter.gaussian_filter(const, 1), oracle.gaussian_filter(const, 1))
+    # BASELINE config 2 shape (59 x 350 x 640 uint16): oracle on a z-slab (the filters are local), properties on the rest
+    S, H, W = 59, 350, 640
+    vol = rng.integers(0, 4096, (S, H, W)).astype(np.uint16)
+    vol[:, 100:200, 300:500] += 20000
+    t = torch_.from_numpy(vol).cuda()
+    g = prefilter.gaussian_filter(t, 1)
+    m = prefilter.median_filter(g, 3)
+    gh, mh = g.cpu().numpy(), m.cpu().numpy()
+    ref_g = oracle.gaussian_filter(vol[:24], 1)                          # exact for z < 24 - 4
+    assert np.array_equal(gh[:20], ref_g[:20])
+    assert np.array_equal(mh[:19], oracle.median_filter3(gh[:20])[:19])
+    assert gh.min() >= vol.min() and gh.max() <= vol.max() and mh.min() >= gh.min() and mh.max() <= gh.max()
+    flipped = prefilter.gaussian_filter(torch_.from_numpy(np.ascontiguousarray(vol[::-1, ::-1, ::-1])).cuda(), 1).cpu().numpy()
+    assert np.array_equal(flipped[::-1, ::-1, ::-1], gh)                # the symmetric kernel commutes with mirroring
+    assert np.array_equal(prefilter.median_filter(m, 3).cpu().numpy()[30], oracle.median_filter3(mh[28:33])[2])
+
+
+def test_zscore_and_prm_to_uint8(b2, golden, torch_):
+    from b200seg import prefilter
+    d = golden("prefilter.npz")
+    z, mu, sd = prefilter.zscore_norm(d["u16_img"], return_stats=True)
+    assert mu == d["zs_stats"][0]                                          # exact integer sums: the mean is bit exact
+    assert abs(sd - d["zs_stats"][1]) <= 1e-12 * d["zs_stats"][1]
+    np.testing.assert_allclose(z, d["zs_out"].astype(np.float32), rtol=1e-6, atol=1e-6)
+    assert np.array_equal(prefilter.prm_to_uint8(d["prm_in"]), d["prm_u8"])    # fp32 ops in the reference's order: bit exact
+    rng = np.random.default_rng(17)
+    for dtype, hi in ((np.uint8, 255), (np.uint16, 65535)):
+        im = rng.integers(0, hi + 1, (31, 50, 77)).astype(dtype)
+        im[rng.random(im.shape) < 0.4] = 0
+        ref, rm, rs = oracle.zscore_norm(im)
+        z, mu, sd = prefilter.zscore_norm(im, return_stats=True)
+        assert mu == rm and abs(sd - rs) <= 1e-12 * rs
+        np.testing.assert_allclose(z, ref.astype(np.float32), rtol=1e-6, atol=1e-6)
+    imf = (rng.random((20, 33, 47)).astype(np.float32) * 5000).astype(np.float32)
+    imf[rng.random(imf.shape) < 0.3] = 0
+    mask = imf > 0                                                         # lib/utils/blob.py:180-184 (float32 image)
+    ref = (imf - np.mean(imf[mask])) / np.std(imf[mask])
+    z, mu, sd = prefilter.zscore_norm(imf, return_stats=True)
+    assert abs(mu - np.mean(imf[mask].astype(np.float64))) <= 1e-12 * abs(mu)
+    np.testing.assert_allclose(z, ref, rtol=2e-5, atol=2e-6)               # the reference sums in float32 here
+    z2 = prefilter.zscore_norm(imf)
+    assert np.array_equal(z, z2)                                            # deterministic run to run
+    prm = rng.standard_normal((14, 9, 30, 31)).astype(np.float32) * np.linspace(1e-3, 50, 14, dtype=np.float32)[:, None, None, None]
+    assert np.array_equal(prefilter.prm_to_uint8(prm), oracle.prm_to_uint8(prm))
+    big = torch_.rand((2, 64, 256, 256), device="cuda")
+    u8 = prefilter.prm_to_uint8(big)
+    assert np.array_equal(u8.cpu().numpy(), oracle.prm_to_uint8(big.cpu().numpy()))

@@ -142,3 +142,29 @@ def test_mask_overlaps_golden(golden):
     iou, ios, iog = oracle.mask_overlaps(pa, ga)
     for k, v in (("iou", iou), ("ios", ios), ("iog", iog), ("iou_slow", iou)):
         assert np.array_equal(v, d[k], equal_nan=True), k
+
+
+def test_prefilter_golden(golden):
+    """scipy.ndimage (the reference's dependency for binarization_nuclei.py:43-44) and the reference's inline numpy
+    lines generated the fixture; the oracle restatement must reproduce every array bit for bit."""
+    d = golden("prefilter.npz")
+    for n in ("u16", "u8", "thin"):
+        g = oracle.gaussian_filter(d[n + "_img"], 1)
+        assert g.dtype == d[n + "_img"].dtype and np.array_equal(g, d[n + "_gauss"]), n
+        assert np.array_equal(oracle.median_filter3(g), d[n + "_median"]), n
+        if n != "thin":
+            assert np.array_equal(oracle.gaussian_filter(d[n + "_img"], 2), d[n + "_gauss_s2"]), n
+    z, mu, sd = oracle.zscore_norm(d["u16_img"])
+    assert np.array_equal(z, d["zs_out"]) and mu == d["zs_stats"][0] and sd == d["zs_stats"][1]
+    assert np.array_equal(oracle.prm_to_uint8(d["prm_in"]), d["prm_u8"])
+
+
+def test_prefilter_oracle_vs_scipy_live():
+    """Where scipy is importable the restatement is also checked live on fresh random volumes (odd sizes, dims < radius)."""
+    ndimage = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(5)
+    for shape, dtype, hi in [((6, 9, 11), np.uint16, 65535), ((2, 3, 40), np.uint8, 255), ((17, 8, 5), np.uint16, 700)]:
+        img = rng.integers(0, hi + 1, shape).astype(dtype)
+        for sigma in (0.5, 1, 1.5):
+            assert np.array_equal(oracle.gaussian_filter(img, sigma), ndimage.gaussian_filter(img, sigma=sigma)), (shape, sigma)
+        assert np.array_equal(oracle.median_filter3(img), ndimage.median_filter(img, size=3)), shape
