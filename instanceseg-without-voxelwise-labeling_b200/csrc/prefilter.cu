@@ -15,6 +15,8 @@
 //   zscore     : (im - mean(im[im>0])) / std(im[im>0])  (tools/infer_simple.py:180-183, lib/utils/blob.py:180-184).
 //   prm_to_u8  : per-channel  fm -= min; fm /= max; fm *= 255; astype(uint8)  (tools/infer_simple.py:233-238), fp32
 //                operations in the reference's order, bit exact.
+#include <math.h>
+
 #include "common.cuh"
 #include "median27_net.cuh"
 
@@ -25,10 +27,14 @@ namespace b200seg {
 // =====================================================================================================
 
 constexpr int GA_TY = 32, GA_TX = 64, GA_THREADS = 288, GA_RY = 4, GA_RX = 8, GA_RMAX = 8;
-struct GaussW { double w[GA_RMAX + 1]; };            // w[0..R]: w[R] is the centre tap, w[0] the outermost
+struct GaussW {
+    double w[GA_RMAX + 1];                            // w[0..R]: w[R] is the centre tap, w[0] the outermost
+    unsigned wi[GA_RMAX + 1];                         // min(round(w * 2^32), 2^32 - 1): weights of the fixed-point filter
+};
 
 // scipy 'reflect' (d c b a | a b c d | d c b a), any distance
 __device__ __forceinline__ int reflect_idx(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
     if (n == 1) return 0;
     const int p = 2 * n;
     i %= p;
@@ -41,13 +47,29 @@ __device__ __forceinline__ double u2d(unsigned v) {
     return __dadd_rn(__hiloint2double(0x43300000, (int)v), -4503599627370496.0);
 }
 
-// one output of scipy's symmetric correlate1d: taps v[0..2R] (stride `st` elements of the register array)
+// One output of scipy's symmetric correlate1d over the taps v[0..2R] (values < 2^16).
+//
+// Exact path: fp64 in scipy's order, floor (== C truncation, the sum is >= 0).
+// Fast path: the same sum in 32.32 fixed point, X = sum(wi_j * s_j) / 2^32.  With T the real-valued sum of the double
+// weights, |X - T| <= 2^-32 * sum(s_j) <= 2^-32 * 17 * 65535 < 2.6e-4 and the fp64 result F has |F - T| < 3e-10, so
+// whenever the fraction of X lies in [2^-11, 1 - 2^-11) both floors agree; otherwise (about 1 output in 1000, and
+// every output of a constant non-zero neighbourhood) the exact path decides.  All-zero taps give 0 on both paths.
+template <int R>
+__device__ __forceinline__ unsigned gfilt_exact(const unsigned* v, const GaussW& gw) {
+    double acc = __dmul_rn(gw.w[R], u2d(v[R]));
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc = __dadd_rn(acc, __dmul_rn(u2d(v[j] + v[2 * R - j]), gw.w[j]));
+    return (unsigned)__double2loint(__dadd_rd(acc, 4503599627370496.0));
+}
 template <int R, int ST>
 __device__ __forceinline__ unsigned gfilt(const unsigned* v, const GaussW& gw) {
-    double acc = __dmul_rn(gw.w[R], u2d(v[R * ST]));
+    static_assert(ST == 1, "contiguous windows only");
+    unsigned long long acc = (unsigned long long)gw.wi[R] * v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc = __dadd_rn(acc, __dmul_rn(u2d(v[j * ST] + v[(2 * R - j) * ST]), gw.w[j]));
-    return (unsigned)__double2loint(__dadd_rd(acc, 4503599627370496.0));      // floor == C truncation (acc >= 0)
+    for (int j = 0; j < R; ++j) acc += (unsigned long long)gw.wi[j] * (v[j] + v[2 * R - j]);
+    const unsigned lo = (unsigned)acc;
+    if ((lo - (1u << 21)) < (0u - (1u << 22)) || acc == 0ull) return (unsigned)(acc >> 32);
+    return gfilt_exact<R>(v, gw);
 }
 
 template <int R> struct GaussCfg {
@@ -57,7 +79,7 @@ template <int R> struct GaussCfg {
 };
 
 template <typename T, int R>
-__global__ void __launch_bounds__(GA_THREADS) gauss3d_kernel(const T* __restrict__ in, T* __restrict__ out, int S, int H, int W, int zc,
+__global__ void __launch_bounds__(GA_THREADS, (R <= 4 ? 3 : 1)) gauss3d_kernel(const T* __restrict__ in, T* __restrict__ out, int S, int H, int W, int zc,
                                                              const GaussW gw) {
     using C = GaussCfg<R>;
     constexpr int NS = C::NS, FY = C::FY, FX = C::FX, FXW = C::FXW, BW = C::BW, NE = C::NE;
@@ -114,14 +136,18 @@ __global__ void __launch_bounds__(GA_THREADS) gauss3d_kernel(const T* __restrict
         }
         // ---- z pass: ring -> A -------------------------------------------------------------------
         {
-            const int base = i % NS;
+            int so[NS];                                   // ring slot of tap k, as a word offset
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                int s = i % NS + k;
+                if (s >= NS) s -= NS;
+                so[k] = s * FY * FXW;
+            }
             for (int t = tid; t < FY * FXW; t += GA_THREADS) {
                 unsigned lo[NS], hi[NS];
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
-                    int s = base + k;
-                    if (s >= NS) s -= NS;
-                    const unsigned w = ring[s * FY * FXW + t];
+                    const unsigned w = ring[so[k] + t];
                     lo[k] = w & 0xFFFFu;
                     hi[k] = w >> 16;
                 }
@@ -187,7 +213,7 @@ static int launch_gauss(const void* in, void* out, int S, int H, int W, const Ga
     B200_CUDA(cudaFuncSetAttribute(gauss3d_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     const int gx = (W + GA_TX - 1) / GA_TX, gy = (H + GA_TY - 1) / GA_TY;
     const int per_sm = (int)(200 * 1024 / (C::SMEM + 1024)) > 0 ? (int)(200 * 1024 / (C::SMEM + 1024)) : 1;
-    const long long want = 4ll * num_sms() * per_sm;      // >= 4 waves of CTAs so the tail is short
+    const long long want = 3ll * num_sms() * per_sm;      // >= 3 waves of CTAs so the tail is short
     long long chunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
     if (chunks < 1) chunks = 1;
     int zc = (int)((S + chunks - 1) / chunks);
@@ -219,48 +245,54 @@ static int dispatch_gauss(int R, const void* in, void* out, int S, int H, int W,
 // median3d (3x3x3)
 // =====================================================================================================
 
-constexpr int MD_THREADS = 256, MD_ROWS = MD_THREADS / 32;
+constexpr int MD_THREADS = 256, MD_ROWS = MD_THREADS / 32, MD_LANES = 30;     // lanes 0 and 31 of a warp only carry the x halo
 
 template <typename T, bool EVENW>
-__device__ __forceinline__ unsigned md_pair(const T* row, int x, int W) {
+__device__ __forceinline__ unsigned md_pair(const T* p, bool has_hi) {
     if (EVENW) {
-        if (sizeof(T) == 2) return __ldg(reinterpret_cast<const unsigned*>(row + x));
-        const unsigned w = __ldg(reinterpret_cast<const uint16_t*>(row + x));
+        if (sizeof(T) == 2) return __ldg(reinterpret_cast<const unsigned*>(p));
+        const unsigned w = __ldg(reinterpret_cast<const uint16_t*>(p));
         return (w & 0xFFu) | ((w >> 8) << 16);
     }
-    return (unsigned)__ldg(row + x) | ((unsigned)__ldg(row + min(x + 1, W - 1)) << 16);
+    const unsigned lo = __ldg(p);
+    return lo | ((has_hi ? (unsigned)__ldg(p + 1) : lo) << 16);
 }
 
-// the nine in-plane neighbours of the voxel pair (x, x+1) of row y in plane z, sorted per 16-bit lane
+struct MdRaw { unsigned r[3]; };
+
+// raw voxel pairs (x, x+1) of rows y-1, y, y+1 of one plane
 template <typename T, bool EVENW>
-__device__ __forceinline__ void md_plane(const T* __restrict__ in, int z, int y, int x, int H, int W, int lane, unsigned (&o)[9]) {
+__device__ __forceinline__ MdRaw md_load(const T* const (&rows)[3], size_t plane_off, bool has_hi) {
+    MdRaw m;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m.r[k] = md_pair<T, EVENW>(rows[k] + plane_off, has_hi);
+    return m;
+}
+
+// the nine in-plane neighbours of every lane's voxel pair, sorted per 16-bit half
+__device__ __forceinline__ void md_sort_plane(const MdRaw& m, bool first, bool last, unsigned (&o)[9]) {
     unsigned v[9];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = min(max(y + dy, 0), H - 1);
-        const T* row = in + ((size_t)z * H + yy) * W;
-        const unsigned c = md_pair<T, EVENW>(row, x, W);
+    for (int k = 0; k < 3; ++k) {
+        const unsigned c = m.r[k];
         unsigned prev = __shfl_up_sync(0xFFFFFFFFu, c, 1), next = __shfl_down_sync(0xFFFFFFFFu, c, 1);
-        if (x == 0) prev = c << 16;                                       // clamp: left neighbour of voxel 0 is voxel 0
-        else if (lane == 0) prev = (unsigned)__ldg(row + x - 1) << 16;
-        if (x + 2 >= W) next = c >> 16;                                   // clamp: right neighbour of the last voxel
-        else if (lane == 31) next = (unsigned)__ldg(row + x + 2);
-        v[3 * (dy + 1) + 0] = __funnelshift_l(prev, c, 16);               // (x-1, x)
-        v[3 * (dy + 1) + 1] = c;                                          // (x,   x+1)
-        v[3 * (dy + 1) + 2] = __funnelshift_r(c, next, 16);               // (x+1, x+2)
+        if (first) prev = c << 16;                                        // clamp: left neighbour of voxel 0 is voxel 0
+        if (last) next = c >> 16;                                         // clamp: right neighbour of the last voxel
+        v[3 * k + 0] = __funnelshift_l(prev, c, 16);                      // (x-1, x)
+        v[3 * k + 1] = c;                                                 // (x,   x+1)
+        v[3 * k + 2] = __funnelshift_r(c, next, 16);                      // (x+1, x+2)
     }
     median27_sort9(v, o);
 }
 
 template <typename T, bool EVENW>
-__device__ __forceinline__ void md_store(T* __restrict__ out, int z, int y, int x, int H, int W, unsigned r) {
-    T* q = out + ((size_t)z * H + y) * W + x;
+__device__ __forceinline__ void md_store(T* q, unsigned r, bool has_hi) {
     if (EVENW) {
         if (sizeof(T) == 2) *reinterpret_cast<unsigned*>(q) = r;
         else *reinterpret_cast<uint16_t*>(q) = (uint16_t)((r & 0xFFu) | ((r >> 16) << 8));
     } else {
         q[0] = (T)(r & 0xFFFFu);
-        if (x + 1 < W) q[1] = (T)(r >> 16);
+        if (has_hi) q[1] = (T)(r >> 16);
     }
 }
 
@@ -269,24 +301,42 @@ __global__ void __launch_bounds__(MD_THREADS, 2) median3d_kernel(const T* __rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y = blockIdx.y * MD_ROWS + warp;
     if (y >= H) return;                                   // whole warp; no block barriers below
-    const int xr = (blockIdx.x * 32 + lane) * 2;
-    const bool live = xr < W;
-    const int x = live ? xr : (EVENW ? W - 2 : W - 1);    // dead lanes repeat the last pair (keeps the shuffles convergent)
+    const int npairs = (W + 1) >> 1;
+    const int pi = blockIdx.x * MD_LANES + lane - 1;      // this lane's voxel pair; lanes 0 / 31 hold the neighbours' halo
+    const bool live = lane >= 1 && lane <= MD_LANES && pi < npairs;
+    const int pc = min(max(pi, 0), npairs - 1);
+    const int x = 2 * pc;
+    const bool first = pc == 0, last = pc == npairs - 1, has_hi = x + 1 < W;
+    const size_t ps = (size_t)H * W;
+    const T* rows[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rows[k] = in + (size_t)min(max(y + k - 1, 0), H - 1) * W + x;
+    T* orow = out + (size_t)y * W + x;
     const int z0 = blockIdx.z * zc;
+    auto plane = [&](int k) { return (size_t)min(max(z0 - 1 + k, 0), S - 1) * ps; };       // k-th plane this CTA touches
     unsigned sa[9], sb[9], sc[9], sd[9], m[10];
-    md_plane<T, EVENW>(in, max(z0 - 1, 0), y, x, H, W, lane, sa);
-    md_plane<T, EVENW>(in, z0, y, x, H, W, lane, sb);
+    MdRaw ra, rb;
+    {
+        const MdRaw r0 = md_load<T, EVENW>(rows, plane(0), has_hi), r1 = md_load<T, EVENW>(rows, plane(1), has_hi);
+        ra = md_load<T, EVENW>(rows, plane(2), has_hi);
+        rb = md_load<T, EVENW>(rows, plane(3), has_hi);
+        md_sort_plane(r0, first, last, sa);
+        md_sort_plane(r1, first, last, sb);
+    }
     for (int i = 0; i < zc; i += 2) {
         const int z = z0 + i;
         if (z >= S) break;
-        md_plane<T, EVENW>(in, min(z + 1, S - 1), y, x, H, W, lane, sc);
+        const MdRaw rc = ra, rd = rb;
+        ra = md_load<T, EVENW>(rows, plane(i + 4), has_hi);               // two planes ahead of the arithmetic
+        rb = md_load<T, EVENW>(rows, plane(i + 5), has_hi);
+        md_sort_plane(rc, first, last, sc);
         median27_merge_mid(sb, sc, m);
         const unsigned r0 = median27_select(sa, m);
-        if (live) md_store<T, EVENW>(out, z, y, x, H, W, r0);
+        if (live) md_store<T, EVENW>(orow + (size_t)z * ps, r0, has_hi);
         if (i + 1 >= zc || z + 1 >= S) break;
-        md_plane<T, EVENW>(in, min(z + 2, S - 1), y, x, H, W, lane, sd);
+        md_sort_plane(rd, first, last, sd);
         const unsigned r1 = median27_select(sd, m);
-        if (live) md_store<T, EVENW>(out, z + 1, y, x, H, W, r1);
+        if (live) md_store<T, EVENW>(orow + (size_t)(z + 1) * ps, r1, has_hi);
 #pragma unroll
         for (int k = 0; k < 9; ++k) { sa[k] = sc[k]; sb[k] = sd[k]; }
     }
@@ -294,7 +344,7 @@ __global__ void __launch_bounds__(MD_THREADS, 2) median3d_kernel(const T* __rest
 
 template <typename T, bool EVENW>
 static int launch_median(const void* in, void* out, int S, int H, int W, cudaStream_t stream) {
-    const int gx = (W + 63) / 64, gy = (H + MD_ROWS - 1) / MD_ROWS;
+    const int gx = ((W + 1) / 2 + MD_LANES - 1) / MD_LANES, gy = (H + MD_ROWS - 1) / MD_ROWS;
     const long long want = 8ll * num_sms() * 2;
     long long chunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
     if (chunks < 1) chunks = 1;
@@ -447,7 +497,12 @@ extern "C" int b200seg_gaussian3d_dev(const void* in, void* out, int elem_bytes,
     B200_CHECK_ARG(elem_bytes == 1 || elem_bytes == 2, "gaussian3d: integer volumes only (uint8 / uint16), got %d-byte elements", elem_bytes);
     B200_CHECK_ARG(radius >= 1 && radius <= GA_RMAX, "gaussian3d: radius %d not in 1..%d", radius, GA_RMAX);
     GaussW gw;
-    for (int j = 0; j <= GA_RMAX; ++j) gw.w[j] = j <= radius ? weights[j] : 0.0;
+    for (int j = 0; j <= GA_RMAX; ++j) {
+        gw.w[j] = j <= radius ? weights[j] : 0.0;
+        B200_CHECK_ARG(gw.w[j] >= 0.0 && gw.w[j] <= 1.0, "gaussian3d: weight %d = %g outside [0, 1]", j, gw.w[j]);
+        const double q = nearbyint(gw.w[j] * 4294967296.0);
+        gw.wi[j] = q >= 4294967295.0 ? 0xFFFFFFFFu : (unsigned)q;
+    }
     return elem_bytes == 1 ? dispatch_gauss<uint8_t>(radius, in, out, S, H, W, gw, stream)
                            : dispatch_gauss<uint16_t>(radius, in, out, S, H, W, gw, stream);
 }
