@@ -248,6 +248,20 @@ def bench_ops(torch, peak):
     ms = time_op(torch, lambda: evaluation.mask_overlaps_labels(tp, tg, ids, ids), 10, flush)
     ops["mask_overlaps_128x512x512_200x200"] = entry(ms, 4 * tp.numel() + 3 * 4 * 200 * 200, {
         "gvox_per_s": tp.numel() / (ms * 1e-3) / 1e9, "note": "includes the host-side lookup tables and their H2D copies"})
+    # whole-volume prefilters (binarization_nuclei.py:43-44) on the BASELINE config-2 shape and on the config-3 shape
+    from b200seg import prefilter
+    for shape in ((59, 350, 640), SHAPE):
+        vol = torch.from_numpy(rng_e.integers(0, 4096, shape).astype(np.uint16)).to(dev)
+        tag = "x".join(str(s) for s in shape)
+        for name, fn in (("gaussian_sigma1", lambda: prefilter.gaussian_filter(vol, 1)), ("median3", lambda: prefilter.median_filter(vol, 3))):
+            ms = time_op(torch, fn, 10, flush)
+            ops["%s_u16_%s" % (name, tag)] = entry(ms, 4 * vol.numel(), {"gvox_per_s": vol.numel() / (ms * 1e-3) / 1e9})
+    ms = time_op(torch, lambda: prefilter.zscore_norm(vol), 10, flush)
+    ops["zscore_norm_u16_128x512x512"] = entry(ms, (2 + 2 + 4) * vol.numel(), {"gvox_per_s": vol.numel() / (ms * 1e-3) / 1e9,
+                                               "note": "two reads (moments, apply) + fp32 write; 5 launches"})
+    prm_maps = torch.rand((14, 32, 128, 128), device=dev)
+    ms = time_op(torch, lambda: prefilter.prm_to_uint8(prm_maps), 10, flush)
+    ops["prm_to_uint8_14x32x128x128"] = entry(ms, (4 + 4 + 1) * prm_maps.numel(), {"note": "two reads (min/max, scale) + uint8 write; 3 launches"})
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
         d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)

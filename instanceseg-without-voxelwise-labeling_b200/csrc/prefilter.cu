@@ -16,6 +16,7 @@
 //   prm_to_u8  : per-channel  fm -= min; fm /= max; fm *= 255; astype(uint8)  (tools/infer_simple.py:233-238), fp32
 //                operations in the reference's order, bit exact.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "median27_net.cuh"
@@ -213,7 +214,8 @@ static int launch_gauss(const void* in, void* out, int S, int H, int W, const Ga
     B200_CUDA(cudaFuncSetAttribute(gauss3d_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     const int gx = (W + GA_TX - 1) / GA_TX, gy = (H + GA_TY - 1) / GA_TY;
     const int per_sm = (int)(200 * 1024 / (C::SMEM + 1024)) > 0 ? (int)(200 * 1024 / (C::SMEM + 1024)) : 1;
-    const long long want = 3ll * num_sms() * per_sm;      // >= 3 waves of CTAs so the tail is short
+    static const int waves = getenv("B200SEG_GAUSS_WAVES") ? atoi(getenv("B200SEG_GAUSS_WAVES")) : 3;
+    const long long want = (long long)waves * num_sms() * per_sm;      // >= 3 waves of CTAs so the tail is short
     long long chunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
     if (chunks < 1) chunks = 1;
     int zc = (int)((S + chunks - 1) / chunks);
