@@ -287,6 +287,28 @@ size_t b200seg_prm_to_u8_workspace_bytes(int n_maps);
 int b200seg_prm_to_u8_dev(const float* in, uint8_t* out, int n_maps, long long per_map,
                           void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * RPN proposal generation -- replaces GenerateProposalsOp_3d.forward /
+ * proposals_for_one_image / _filter_boxes_3d (lib/modeling/generate_proposals_3d.py:20-192) with bbox_transform_3d
+ * and clip_tiled_boxes_3d (lib/utils/boxes_3d.py:144-225): top pre_nms_topN scores -> decode -> clip -> filter ->
+ * NMS -> first post_nms_topN, all on the device.
+ *   scores [n_images, A, S, H, W], deltas [n_images, 6A, S, H, W] fp32 on the device;
+ *   im_info [n_images, 4] (slices, height, width, scale) and anchors [A, 6] (cell anchors) on the HOST;
+ *   pre_nms_topN <= 0 or >= A*S*H*W: every anchor is a candidate (:125-126); nms_thresh <= 0: no NMS and no
+ *   post_nms_topN cut (:163); post_nms_topN <= 0: no cut (:166).
+ * Outputs, `cap` = b200seg_generate_proposals_capacity(...) rows per image: rois [n_images*cap, 7]
+ *   (image, x1, y1, z1, x2, y2, z2), probs [n_images*cap], keep_idx [n_images*cap] int64 = index into the image's score
+ *   map flattened in (S,H,W,A) order; image i fills rows [i*cap, i*cap + counts[i]).
+ * Equal scores: the smaller (S,H,W,A) index ranks first (the reference's argpartition/argsort are unstable there).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_generate_proposals_workspace_bytes(int A, int S, int H, int W, int pre_nms_topN, int post_nms_topN, float nms_thresh);
+int b200seg_generate_proposals_capacity(int A, int S, int H, int W, int pre_nms_topN, int post_nms_topN, float nms_thresh);
+int b200seg_generate_proposals_dev(const float* scores, const float* deltas, const float* im_info, int n_images,
+                                   int A, int S, int H, int W, const float* anchors, float feat_stride,
+                                   int pre_nms_topN, int post_nms_topN, float nms_thresh, float min_size,
+                                   float* rois, float* probs, int64_t* keep_idx, int32_t* counts,
+                                   void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
 /* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
  * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */

@@ -11,6 +11,7 @@ registers these modules in sys.modules:
     modeling.roi_xfrom.roi_align_3d.modules.roi_align_3d   -> RoIAlign_3d, RoIAlignAvg_3d, RoIAlignMax_3d
     prm.peak_stimulation_3d      -> peak_stimulation_3d, PeakStimulation
     utils.cython_mask_3d         -> binary_mask_to_rle, rle_to_binary_mask
+    modeling.generate_proposals_3d -> GenerateProposalsOp_3d
     otsu                         -> otsu_py_2d_fast, otsu_py_2d (+ import-compat stubs otsu_py, otsu_mat)
 """
 import sys
@@ -25,7 +26,7 @@ def _module(name, **attrs):
 
 
 def install(overwrite=True):
-    from . import boxes_3d, roi_align_3d, peak_stimulation_3d, otsu, mask_3d
+    from . import boxes_3d, roi_align_3d, peak_stimulation_3d, otsu, mask_3d, generate_proposals_3d
     mods = {
         "utils.cython_nms_3d": _module("utils.cython_nms_3d", nms_3d=boxes_3d._nms_numpy and
                                        (lambda dets, thresh: boxes_3d._nms_numpy(dets, thresh, False)),
@@ -43,6 +44,8 @@ def install(overwrite=True):
                                            PeakStimulation=peak_stimulation_3d.PeakStimulation),
         "utils.cython_mask_3d": _module("utils.cython_mask_3d", binary_mask_to_rle=mask_3d.binary_mask_to_rle,
                                         rle_to_binary_mask=mask_3d.rle_to_binary_mask),
+        "modeling.generate_proposals_3d": _module("modeling.generate_proposals_3d",
+                                                  GenerateProposalsOp_3d=generate_proposals_3d.GenerateProposalsOp_3d),
         "otsu": _module("otsu", otsu_py_2d_fast=otsu.otsu_py_2d_fast, otsu_py_2d=otsu.otsu_py_2d,
                         otsu_py=otsu.otsu_py, otsu_mat=otsu.otsu_mat),
     }

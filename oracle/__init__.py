@@ -347,6 +347,69 @@ def prm_to_uint8(prm):
     return out
 
 
+# ------------------------------------------------------------------------------- RPN proposal generation
+BBOX_XFORM_CLIP = np.float32(np.log(1000. / 16.))            # lib/core/config.py:947, used at float32 (see below)
+
+
+def shifted_anchors(anchors, S, H, W, feat_stride):
+    """generate_proposals_3d.py:66-88: cell anchors [A,6] + (x,y,z,x,y,z) shifts, rows ordered (S,H,W,A)."""
+    sx = np.arange(0, W) * feat_stride
+    sy = np.arange(0, H) * feat_stride
+    sz = np.arange(0, S) * feat_stride
+    zz, yy, xx = np.meshgrid(sz, sy, sx, indexing="ij")
+    shifts = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), xx.ravel(), yy.ravel(), zz.ravel()], axis=1)
+    return (np.asarray(anchors, np.float64)[None, :, :] + shifts[:, None, :]).reshape(-1, 6)
+
+
+def bbox_transform_3d(boxes, deltas):
+    """lib/utils/boxes_3d.py:168-225 with unit weights, every operation in float32 (the arithmetic of the reference's
+    numpy 1.x era: under numpy >= 2 the float64 scalar cfg.BBOX_XFORM_CLIP would silently promote dw/dh/ds to float64)."""
+    b = np.asarray(boxes).astype(np.float32)
+    d = np.asarray(deltas, np.float32)
+    one, half = np.float32(1.0), np.float32(0.5)
+    w = b[:, 3] - b[:, 0] + one
+    h = b[:, 4] - b[:, 1] + one
+    s = b[:, 5] - b[:, 2] + one
+    cx, cy, cz = b[:, 0] + half * w, b[:, 1] + half * h, b[:, 2] + half * s
+    dw, dh, ds = (np.minimum(d[:, k], BBOX_XFORM_CLIP) for k in (3, 4, 5))
+    pcx, pcy, pcz = d[:, 0] * w + cx, d[:, 1] * h + cy, d[:, 2] * s + cz
+    pw, ph, ps = np.exp(dw) * w, np.exp(dh) * h, np.exp(ds) * s
+    out = np.zeros(d.shape, np.float32)
+    out[:, 0], out[:, 1], out[:, 2] = pcx - half * pw, pcy - half * ph, pcz - half * ps
+    out[:, 3], out[:, 4], out[:, 5] = pcx + half * pw - one, pcy + half * ph - one, pcz + half * ps - one
+    return out
+
+
+def generate_proposals(scores, deltas, im_info, anchors, feat_stride, pre_nms_topN, post_nms_topN, nms_thresh, min_size=0):
+    """GenerateProposalsOp_3d.proposals_for_one_image (generate_proposals_3d.py:104-177) + _filter_boxes_3d (:180-192).
+    scores [A,S,H,W], deltas [6A,S,H,W] float32, im_info [slices, height, width, scale].  Ties between equal scores go to
+    the smaller (S,H,W,A) index (the reference's argpartition / argsort are unstable there).
+    Returns (proposals [n,6] f32, scores [n] f32, index into the flattened (S,H,W,A) score map [n] int64)."""
+    scores, deltas = np.asarray(scores, np.float32), np.asarray(deltas, np.float32)
+    im_info = np.asarray(im_info, np.float32)
+    A, S, H, W = scores.shape
+    sc = scores.transpose(1, 2, 3, 0).reshape(-1)
+    dl = deltas.reshape(A, 6, S, H, W).transpose(2, 3, 4, 0, 1).reshape(-1, 6)
+    order = np.argsort(-sc, kind="stable")
+    if 0 < pre_nms_topN < sc.size:
+        order = order[:pre_nms_topN]
+    prop = bbox_transform_3d(shifted_anchors(anchors, S, H, W, feat_stride)[order], dl[order])
+    lim = (im_info[2] - np.float32(1), im_info[1] - np.float32(1), im_info[0] - np.float32(1))
+    for c in range(6):                                                   # clip_tiled_boxes_3d, boxes_3d.py:144-164
+        prop[:, c] = np.maximum(np.minimum(prop[:, c], lim[c % 3]), np.float32(0))
+    ss = prop[:, 3] - prop[:, 0] + np.float32(1)                         # the reference tests the x extent only (:186-192)
+    half_ss = ss / np.float32(2)
+    keep = np.where((ss >= np.float32(min_size) * im_info[3]) & (prop[:, 0] + half_ss < im_info[2]) &
+                    (prop[:, 1] + half_ss < im_info[1]) & (prop[:, 2] + half_ss < im_info[0]))[0]
+    prop, sck, order = prop[keep], sc[order][keep], order[keep]
+    if nms_thresh > 0:
+        k = nms_3d(np.hstack([prop, sck[:, None]]).astype(np.float32), nms_thresh)
+        if post_nms_topN > 0:
+            k = k[:post_nms_topN]
+        prop, sck, order = prop[k], sck[k], order[k]
+    return prop, sck, order.astype(np.int64)
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

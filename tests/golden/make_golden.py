@@ -221,7 +221,48 @@ def make_prefilter():
     print("prefilter.npz", {k: v.shape for k, v in out.items()})
 
 
+def make_proposals():
+    """lib/modeling/generate_proposals_3d.py run unmodified (core.config imported with `nn` stubbed, the Cython NMS from
+    oracle/_ref).  cfg.BBOX_XFORM_CLIP is handed over as a Python float so that numpy >= 2 keeps the float32 arithmetic
+    the reference had under numpy 1.x (a float64 numpy scalar would now promote dw/dh/ds to float64)."""
+    import oracle
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    for n in ("cython_nms_3d", "cython_bbox_3d"):
+        sys.modules["utils." + n] = oracle.ref_module(n)
+    sys.modules["nn"] = types.ModuleType("nn")
+    np.float = float
+    import core.config as cc
+    cc.cfg.BBOX_XFORM_CLIP = float(cc.cfg.BBOX_XFORM_CLIP)
+    spec = importlib.util.spec_from_file_location("ref_gp", os.path.join(REF, "lib", "modeling", "generate_proposals_3d.py"))
+    gp = importlib.util.module_from_spec(spec); spec.loader.exec_module(gp)
+    spec = importlib.util.spec_from_file_location("ref_ga", os.path.join(REF, "lib", "modeling", "generate_anchors.py"))
+    ga = importlib.util.module_from_spec(spec); spec.loader.exec_module(ga)
+    import torch
+    out = {}
+    rng = np.random.default_rng(606)
+    cases = [("a", 4, (12, 20, 30), np.array([[1., 1.], [1., 0.5]]), (6, 10, 12), 300, 100, 0.5),
+             ("b", 8, (16, 24), np.array([[1., 1.]]), (4, 7, 9), 0, 50, 0.3),
+             ("c", 4, (12, 20, 30), np.array([[1., 1.], [1., 0.5]]), (5, 8, 8), 200, 0, 0.7)]
+    for name, stride, sizes, ratios, (S, H, W), pre, post, thr in cases:
+        anchors = ga.generate_anchors_3d(stride=stride, sizes=sizes, aspect_ratios=ratios)
+        A = anchors.shape[0]
+        cc.cfg.TEST.RPN_PRE_NMS_TOP_N, cc.cfg.TEST.RPN_POST_NMS_TOP_N = pre, post
+        cc.cfg.TEST.RPN_NMS_THRESH, cc.cfg.TEST.RPN_MIN_SIZE = thr, 0
+        op = gp.GenerateProposalsOp_3d(anchors, 1.0 / stride).eval()
+        scores = rng.permutation(2 * A * S * H * W).astype(np.float32).reshape(2, A, S, H, W) / np.float32(2 * A * S * H * W)   # distinct
+        deltas = (rng.standard_normal((2, 6 * A, S, H, W)) * 0.4).astype(np.float32)
+        deltas[0, 3::6][:, 0, 0, :3] = 9.0                                # beyond BBOX_XFORM_CLIP
+        im_info = np.array([[S * stride, H * stride, W * stride, 1.0], [S * stride - 3, H * stride - 5, W * stride, 1.0]], np.float32)
+        rois, probs, keep_idx = op(torch.from_numpy(scores), torch.from_numpy(deltas), torch.from_numpy(im_info))
+        out.update({name + "_anchors": anchors, name + "_scores": scores, name + "_deltas": deltas, name + "_im_info": im_info,
+                    name + "_cfg": np.array([stride, pre, post, thr], np.float64), name + "_rois": rois.astype(np.float32),
+                    name + "_probs": probs.astype(np.float32), name + "_keep_idx_last": np.asarray(keep_idx, np.int64)})
+        print(name, "A", A, "rois", rois.shape, "last image keep", len(keep_idx))
+    np.savez_compressed(os.path.join(HERE, "proposals.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_proposals()
     make_prefilter()
     make_nms_iou()
     make_otsu()

@@ -655,3 +655,50 @@ def test_zscore_and_prm_to_uint8(b2, golden, torch_):
     big = torch_.rand((2, 64, 256, 256), device="cuda")
     u8 = prefilter.prm_to_uint8(big)
     assert np.array_equal(u8.cpu().numpy(), oracle.prm_to_uint8(big.cpu().numpy()))
+
+
+# ------------------------------------------------------------------------------------------ RPN proposal generation
+def _proposals_close(got, ref):
+    # boxes: float32 arithmetic in the reference's order; exp() may differ from numpy's float32 exp by one ulp
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=2e-5)
+
+
+def test_generate_proposals_golden_and_oracle(b2, golden, torch_):
+    from b200seg.generate_proposals_3d import GenerateProposalsOp_3d
+    d = golden("proposals.npz")
+    for name in "abc":
+        stride, pre, post, thr = d[name + "_cfg"]
+        op = GenerateProposalsOp_3d(d[name + "_anchors"], 1.0 / stride, pre_nms_topN=int(pre), post_nms_topN=int(post), nms_thresh=float(thr))
+        rois, probs, keep_idx = op(torch_.from_numpy(d[name + "_scores"]).cuda(), torch_.from_numpy(d[name + "_deltas"]).cuda(),
+                                   torch_.from_numpy(d[name + "_im_info"]))
+        assert rois.shape == d[name + "_rois"].shape, name
+        assert np.array_equal(rois[:, 0], d[name + "_rois"][:, 0])
+        _proposals_close(rois, d[name + "_rois"])
+        assert np.array_equal(probs, d[name + "_probs"]), name
+        assert np.array_equal(keep_idx, d[name + "_keep_idx_last"]), name
+    # soma test-tile geometry (14 anchors on 16x40x40, stride 4): every branch against the oracle
+    rng = np.random.default_rng(33)
+    A, S, H, W, stride = 14, 16, 40, 40, 4
+    anchors = np.concatenate([np.stack([-(s / 2 - 2) * np.ones(3), (s / 2 + 1) * np.ones(3)]).reshape(1, 6) * np.array([1, 1, r, 1, 1, r])
+                              for s in (8, 12, 16, 20, 24, 30, 36) for r in (1.0, 0.5)]).astype(np.float32)
+    n = A * S * H * W
+    base = rng.permutation(n).astype(np.float32).reshape(1, A, S, H, W) / np.float32(n)
+    deltas = (rng.standard_normal((1, 6 * A, S, H, W)) * 0.3).astype(np.float32)
+    im_info = np.array([[S * stride, H * stride - 7, W * stride, 1.0]], np.float32)
+    quant = np.round(base * 50) / 50                                           # heavy ties: 51 distinct score values
+    cases = [(base, 1000, 300, 0.23, 0), (base, 2000, 1000, 0.7, 0), (base, 0, 50, 0.5, 0), (base, 500, 0, 0.4, 0), (base, 600, 100, 0.0, 0),
+             (base, 800, 200, 0.3, 14.0), (quant.astype(np.float32), 1000, 300, 0.5, 0), (base, n + 5, 10, 0.9, 0)]
+    for scores, pre, post, thr, min_size in cases:
+        if pre <= 0 or pre >= n:                                               # take-all: keep the quadratic NMS small
+            scores = scores.copy(); scores.reshape(-1)[rng.random(n) < 0.99] *= 0.0
+            scores = scores[:, :2, :4, :10, :10].copy(); dl = deltas.reshape(1, A, 6, S, H, W)[:, :2, :, :4, :10, :10].reshape(1, 12, 4, 10, 10).copy()
+            an = anchors[:2]
+        else:
+            dl, an = deltas, anchors
+        op = GenerateProposalsOp_3d(an, 1.0 / stride, pre_nms_topN=pre, post_nms_topN=post, nms_thresh=thr, min_size=min_size)
+        rois, probs, keep_idx = op(torch_.from_numpy(scores).cuda(), torch_.from_numpy(dl).cuda(), im_info)
+        p, s, k = oracle.generate_proposals(scores[0], dl[0], im_info[0], an, stride, pre, post, thr, min_size)
+        assert np.array_equal(keep_idx, k), (pre, post, thr, min_size, len(keep_idx), len(k))
+        assert np.array_equal(probs[:, 0], s)
+        _proposals_close(rois[:, 1:], p)
+        assert np.all(rois[:, 0] == 0)

@@ -168,3 +168,19 @@ def test_prefilter_oracle_vs_scipy_live():
         for sigma in (0.5, 1, 1.5):
             assert np.array_equal(oracle.gaussian_filter(img, sigma), ndimage.gaussian_filter(img, sigma=sigma)), (shape, sigma)
         assert np.array_equal(oracle.median_filter3(img), ndimage.median_filter(img, size=3)), shape
+
+
+def test_generate_proposals_golden(golden):
+    """lib/modeling/generate_proposals_3d.py, run unmodified by tests/golden/make_golden.py, generated the fixture."""
+    d = golden("proposals.npz")
+    for name in "abc":
+        stride, pre, post, thr = d[name + "_cfg"]
+        rois, probs = [], []
+        for i in range(2):
+            p, s, k = oracle.generate_proposals(d[name + "_scores"][i], d[name + "_deltas"][i], d[name + "_im_info"][i], d[name + "_anchors"],
+                                                stride, int(pre), int(post), float(thr))
+            rois.append(np.hstack([np.full((len(p), 1), i, np.float32), p]))
+            probs.append(s)
+        assert np.array_equal(np.vstack(rois), d[name + "_rois"]), name
+        assert np.array_equal(np.concatenate(probs)[:, None], d[name + "_probs"]), name
+        assert np.array_equal(k, d[name + "_keep_idx_last"]), name
