@@ -262,6 +262,20 @@ def bench_ops(torch, peak):
     prm_maps = torch.rand((14, 32, 128, 128), device=dev)
     ms = time_op(torch, lambda: prefilter.prm_to_uint8(prm_maps), 10, flush)
     ops["prm_to_uint8_14x32x128x128"] = entry(ms, (4 + 4 + 1) * prm_maps.numel(), {"note": "two reads (min/max, scale) + uint8 write; 3 launches"})
+    # RPN proposal generation on the soma test tile: 14 anchors x 16x40x40, pre/post NMS top-N 1000, thresh 0.23
+    from b200seg.generate_proposals_3d import GenerateProposalsOp_3d
+    A_, S_, H_, W_ = 14, 16, 40, 40
+    anchors = np.concatenate([np.stack([-(s / 2 - 2) * np.ones(3), (s / 2 + 1) * np.ones(3)]).reshape(1, 6) * np.array([1, 1, r, 1, 1, r])
+                              for s in (8, 12, 16, 20, 24, 30, 36) for r in (1.0, 0.5)]).astype(np.float32)
+    n_ = A_ * S_ * H_ * W_
+    sc = torch.from_numpy(rng_e.permutation(n_).astype(np.float32).reshape(1, A_, S_, H_, W_) / np.float32(n_)).to(dev)
+    dl = torch.from_numpy((rng_e.standard_normal((1, 6 * A_, S_, H_, W_)) * 0.3).astype(np.float32)).to(dev)
+    info = np.array([[S_ * 4, H_ * 4, W_ * 4, 1.0]], np.float32)
+    gp = GenerateProposalsOp_3d(anchors, 0.25, pre_nms_topN=1000, post_nms_topN=1000, nms_thresh=0.23)
+    ms = time_op(torch, lambda: gp.forward_device(sc, dl, info), 20, flush)
+    ops["generate_proposals_14x16x40x40_top1000"] = {"us": ms * 1e3, "anchors_per_s": n_ / (ms * 1e-3),
+                                                     "note": "latency bound: 5 select passes + collect + rank/decode + compact + 3 NMS launches + gather; "
+                                                             "score and delta maps stay on the device"}
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
         d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)

@@ -410,6 +410,31 @@ def generate_proposals(scores, deltas, im_info, anchors, feat_stride, pre_nms_to
     return prop, sck, order.astype(np.int64)
 
 
+def box_results_with_nms_and_limit(scores, boxes, scores_keep_idx, num_classes, score_thresh, nms, detections_per_im):
+    """lib/core/test.py:806-878 (RPN_ONLY False, soft-NMS and box voting off as in every shipped config).  The limit step
+    selects rows of cls_keep_idx along axis 0 (the reference's `[keep, :]` only works for 2-D index arrays)."""
+    cls_boxes = [[] for _ in range(num_classes)]
+    cls_keep_idx = [[] for _ in range(num_classes)]
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > score_thresh)[0]
+        dets_j = np.hstack((boxes[inds, j * 6:(j + 1) * 6], scores[inds, j][:, None])).astype(np.float32, copy=False)
+        keep = nms_3d(dets_j, nms)
+        cls_boxes[j] = dets_j[keep, :]
+        if scores_keep_idx is not None:
+            cls_keep_idx[j] = scores_keep_idx[inds][keep]
+    if detections_per_im > 0:
+        image_scores = np.hstack([cls_boxes[j][:, -1] for j in range(1, num_classes)])
+        if len(image_scores) > detections_per_im:
+            image_thresh = np.sort(image_scores)[-detections_per_im]
+            for j in range(1, num_classes):
+                keep = np.where(cls_boxes[j][:, -1] >= image_thresh)[0]
+                cls_boxes[j] = cls_boxes[j][keep, :]
+                if scores_keep_idx is not None:
+                    cls_keep_idx[j] = cls_keep_idx[j][keep]
+    im_results = np.vstack([cls_boxes[j] for j in range(1, num_classes)])
+    return im_results[:, -1], im_results[:, :-1], cls_boxes, cls_keep_idx
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

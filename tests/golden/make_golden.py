@@ -261,7 +261,49 @@ def make_proposals():
     np.savez_compressed(os.path.join(HERE, "proposals.npz"), **out)
 
 
+def make_box_results():
+    """box_results_with_nms_and_limit (lib/core/test.py:806-878): core/test.py itself needs cv2 / skimage / pycocotools at
+    import, so only that function's source is compiled, against the reference's own cfg and utils.boxes_3d."""
+    import ast
+    import oracle
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    for n in ("cython_nms_3d", "cython_bbox_3d"):
+        sys.modules["utils." + n] = oracle.ref_module(n)
+    sys.modules["nn"] = types.ModuleType("nn")
+    np.float = float
+    import core.config as cc
+    import utils.boxes_3d as box_utils_3d
+    src = open(os.path.join(REF, "lib", "core", "test.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "box_results_with_nms_and_limit")
+    ns = {"np": np, "cfg": cc.cfg, "box_utils_3d": box_utils_3d}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_core_test", "exec"), ns)
+    rng = np.random.default_rng(808)
+    out = {}
+    for name, R, ncls, per_im, use_idx in (("a", 300, 2, 100, True), ("b", 120, 4, 0, False), ("c", 200, 3, 1000, True)):
+        cc.cfg.MODEL.NUM_CLASSES, cc.cfg.TEST.DETECTIONS_PER_IM = ncls, per_im
+        cc.cfg.TEST.SCORE_THRESH, cc.cfg.TEST.NMS = 0.05, 0.3
+        ctr = rng.uniform(10, 120, (R, 1, 3)) + rng.normal(0, 1.5, (R, ncls, 3))
+        half = rng.uniform(4, 14, (R, ncls, 3))
+        boxes = np.concatenate([ctr - half, ctr + half], axis=2).reshape(R, ncls * 6).astype(np.float32)
+        scores = rng.permutation(R * ncls).reshape(R, ncls).astype(np.float32) / np.float32(R * ncls)
+        idx = rng.permutation(50000)[:R].reshape(R, 1) if use_idx else None          # 2-D, the only shape the reference's limit step accepts
+        if per_im == 100:
+            cc.cfg.TEST.NMS = 0.9                                                     # keep > 100 so that the limit triggers
+        s, b, cls_boxes, cls_idx = ns["box_results_with_nms_and_limit"](scores, boxes, idx)
+        out.update({name + "_scores": scores, name + "_boxes": boxes, name + "_cfg": np.array([ncls, per_im, cc.cfg.TEST.NMS]),
+                    name + "_out_scores": s, name + "_out_boxes": b})
+        if idx is not None:
+            out[name + "_idx"] = idx
+        for j in range(1, ncls):
+            out["%s_cls%d" % (name, j)] = cls_boxes[j]
+            if idx is not None:
+                out["%s_idx%d" % (name, j)] = cls_idx[j]
+        print(name, "dets", s.shape)
+    np.savez_compressed(os.path.join(HERE, "box_results.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_box_results()
     make_proposals()
     make_prefilter()
     make_nms_iou()

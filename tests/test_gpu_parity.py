@@ -702,3 +702,17 @@ def test_generate_proposals_golden_and_oracle(b2, golden, torch_):
         assert np.array_equal(probs[:, 0], s)
         _proposals_close(rois[:, 1:], p)
         assert np.all(rois[:, 0] == 0)
+
+
+def test_box_results_golden(b2, golden):
+    from b200seg.box_results import box_results_with_nms_and_limit
+    from test_oracle_golden import _box_results_check
+    d = golden("box_results.npz")
+
+    def fn(scores, boxes, idx, ncls, thr, nms, per_im):
+        return box_results_with_nms_and_limit(scores, boxes, idx, num_classes=ncls, rpn_only=False, score_thresh=thr, nms=nms,
+                                              detections_per_im=per_im)
+    for name in "abc":
+        _box_results_check(fn, d, name)
+    s, b, cb, ci = fn(np.zeros((5, 2), np.float32), np.zeros((5, 12), np.float32), None, 2, 0.05, 0.3, 100)     # nothing above the threshold
+    assert s.shape == (0,) and b.shape == (0, 6) and cb[1].shape == (0, 7)

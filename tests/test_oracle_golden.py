@@ -184,3 +184,22 @@ def test_generate_proposals_golden(golden):
         assert np.array_equal(np.vstack(rois), d[name + "_rois"]), name
         assert np.array_equal(np.concatenate(probs)[:, None], d[name + "_probs"]), name
         assert np.array_equal(k, d[name + "_keep_idx_last"]), name
+
+
+def _box_results_check(fn, d, name):
+    ncls, per_im, nms = d[name + "_cfg"]
+    ncls = int(ncls)
+    idx = d[name + "_idx"] if name + "_idx" in d.files else None
+    s, b, cb, ci = fn(d[name + "_scores"], d[name + "_boxes"], idx, ncls, 0.05, float(nms), int(per_im))
+    assert np.array_equal(s, d[name + "_out_scores"]) and np.array_equal(b, d[name + "_out_boxes"]), name
+    for j in range(1, ncls):
+        assert np.array_equal(cb[j], d["%s_cls%d" % (name, j)]), (name, j)
+        if idx is not None:
+            assert np.array_equal(ci[j], d["%s_idx%d" % (name, j)]), (name, j)
+
+
+def test_box_results_golden(golden):
+    """lib/core/test.py:806-878 compiled from the reference source generated the fixture."""
+    d = golden("box_results.npz")
+    for name in "abc":
+        _box_results_check(oracle.box_results_with_nms_and_limit, d, name)
