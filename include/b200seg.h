@@ -172,6 +172,11 @@ int b200seg_soma_binarize_dev(const uint8_t* volumes, int n_volumes, int S, int 
  * foreground (the reference raises IndexError there) gets status 5, a degenerate crop whose bookkeeping does not
  * fit the workspace gets status 6 and an empty mask.  workspace: b200seg_largest_cc_workspace_bytes(total mask bytes).
  * ---------------------------------------------------------------------------------------------- */
+/* Diagnostics: how many instances took which path of b200seg_largest_cc_dev since the last reset (synchronises the
+ * device): [0] filled by the warp-per-instance flood fill, [1] geometry outside its limits (rows > 64 voxels, > 32
+ * planes), [2] no foreground, [3] empty centre row, [4] fill not converged, [5] seed component without the majority
+ * ([1]..[5] are finished by the general union-find kernel), [6..7] reserved. */
+int b200seg_largest_cc_path_counts(long long* counts, int reset);
 size_t b200seg_largest_cc_workspace_bytes(long long total_mask_bytes);
 int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, long long total_mask_bytes,
                            int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,

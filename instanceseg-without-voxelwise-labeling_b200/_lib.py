@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200seg_generate_proposals_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _f]),
     "b200seg_generate_proposals_capacity": (_i, [_i, _i, _i, _i, _i, _i, _f]),
     "b200seg_generate_proposals_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200seg_largest_cc_path_counts": (_i, [_vp, _i]),
     "b200seg_rle3d_workspace_bytes": (_sz, [_i, _i, _i, _ll]),
     "b200seg_rle3d_encode_dev": (_i, [_vp, _i, _i, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
     "b200seg_rle3d_decode_dev": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),

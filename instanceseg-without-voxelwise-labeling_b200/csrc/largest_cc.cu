@@ -169,25 +169,194 @@ __device__ __forceinline__ void union_rows(const unsigned long long* __restrict_
 }
 
 // grid = (slots, volumes), like the binarization kernel.  scratch: 8 bytes per mask byte (see the launcher).
-__global__ void __launch_bounds__(CC_THREADS, 3)
-largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, int n_crops,
-                  const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
-                  const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid,
-                  int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes) {
-    __shared__ CcShared sh;
-    extern __shared__ __align__(16) unsigned char cc_dyn[];
+// ---------------------------------------------------------------------------------------------------------
+// Fast path: one small CTA per instance, bit-parallel flood fill from the crop centre.
+//
+// The Otsu mask of a detected instance is almost always one blob around the crop centre plus a few specks.  For
+// crops with rows of <= 64 voxels and <= 32 z planes, lane z of a warp owns plane z: a row is one 64-bit word, filling
+// along x is a carry trick ( up = m & ~(m + s) | s, the same on the bit-reversed words for the other direction ), and
+// warp 0 sweeps the planes forwards and backwards along y in lockstep, the lanes exchanging the fill of the
+// neighbouring planes by shuffle (work-efficient, but a dependent chain).  After every sweep pair all four warps test,
+// on independent rows, whether anything is still reachable; a convex blob is complete after one pair.  The other
+// phases (mask bytes -> row words, counting, clearing) are spread over the four warps.  The converged fill is
+// exactly the 26-connected component of the seed.  If it holds MORE THAN HALF of the foreground it is the unique
+// largest component: everything else is cleared and the instance is marked done (CC_DONE_BIT in status) so that the
+// general kernel below only clears the flag.  Anything else -- wide or deep crops, an empty centre row, a seed component
+// without the majority, a maze that needs more than CCF_MAX_PAIRS sweep pairs -- is left untouched for the general
+// kernel, which also owns the tie rule and the status codes.
+constexpr int CC_DONE_BIT = 0x40000000;
+// path statistics since the last reset (b200seg_largest_cc_path_counts): 0 filled by the fast path, 1 geometry not
+// supported, 2 no foreground, 3 empty centre row, 4 not converged, 5 no majority
+__device__ unsigned long long ccf_counts[8];
+__device__ __forceinline__ void ccf_count(int tid, int k) { if (tid == 0) atomicAdd(&ccf_counts[k], 1ull); }
+constexpr int CCF_WARPS = 4, CCF_ROWS = 1152;                 // rows per instance kept in shared memory (mask + fill words)
+constexpr int CCF_MAX_PAIRS = 6;                              // forward + backward sweeps before a (maze-like) mask is handed on
+
+__device__ __forceinline__ unsigned long long ccf_fill_row(unsigned long long s, unsigned long long m) {
+    // every run of m that contains a bit of s (s subset of m)
+    const unsigned long long up = (m & ~(m + s)) | s;
+    const unsigned long long rm = __brevll(m), rs = __brevll(s);
+    return up | __brevll((rm & ~(rm + rs)) | rs);
+}
+
+// (volume, slot) work item -> instance index, or -1 when the slot is empty / beyond the valid detections
+__device__ __forceinline__ int cc_inst_of(int slot, int vol, int n_crops, const int32_t* __restrict__ det_off,
+                                          const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid) {
+    const int base = det_off ? det_off[vol] : 0;
+    const int n_here = det_off ? det_off[vol + 1] - base : n_crops;
+    if (slot >= n_here || (n_valid && slot >= n_valid[vol])) return -1;
+    return base + (order ? order[base + slot] : slot);
+}
+
+// one sweep step of the fill for row y of every plane (lane = plane); returns the row's new fill word
+__device__ __forceinline__ unsigned long long ccf_seeds(unsigned long long own3, unsigned long long mm) {
+    const unsigned long long nb = own3 | __shfl_up_sync(0xFFFFFFFFu, own3, 1) | __shfl_down_sync(0xFFFFFFFFu, own3, 1);
+    return (nb | (nb << 1) | (nb >> 1)) & mm;
+}
+
+__global__ void __launch_bounds__(CCF_WARPS * 32)
+largest_cc_fill_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, int n_crops,
+                       const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
+                       const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid,
+                       int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes) {
+    extern __shared__ __align__(16) unsigned char ccf_dyn[];
+    __shared__ int s_sum[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = cc_inst_of(blockIdx.x, blockIdx.y, n_crops, det_off, order, n_valid);
+    if (inst < 0 || status[inst] != 0) return;                // CTA-uniform exits
+    const int64_t off = crop_off[inst];
+    const int n = (int)(crop_off[inst + 1] - off);
+    const int32_t* bb = boxes + 6 * (size_t)inst;
+    const int sx = bb[3] - bb[0] + 1, sy = bb[4] - bb[1] + 1;
+    if (n <= 0 || sx <= 0 || sy <= 0 || sx > 64) { ccf_count(tid, 1); return; }
+    const int rows = n / sx, sz = rows / sy;
+    if (sz > 32 || sz < 1 || sz * sy != rows || rows * sx != n) { ccf_count(tid, 1); return; }
+    // plane z keeps its rows at [z * ps, z * ps + sy): an odd stride spreads the lanes (= planes) over the banks
+    const int ps = sy | 1, words = sz * ps;
+    unsigned long long* sm_m;
+    if (words <= CCF_ROWS) sm_m = reinterpret_cast<unsigned long long*>(ccf_dyn);
+    else if ((size_t)words * 2 <= (size_t)n) sm_m = scratch + off;            // large crop: its slice of the global scratch (8 B per voxel)
+    else { ccf_count(tid, 1); return; }
+    unsigned long long* sm_f = sm_m + words;
+    uint8_t* m = mask + off;
+    const uint8_t* mask_safe_end = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(mask + total_mask_bytes) & ~(uintptr_t)7);
+    if (tid < 2) s_sum[tid] = 0;
+    __syncthreads();
+
+    // ---- row words from the mask bytes (all warps); foreground count -------------------------------------------
+    int fg = 0;
+    for (int r = tid; r < rows; r += CCF_WARPS * 32) {
+        const uint8_t* src = m + (size_t)r * sx;
+        unsigned long long word = 0ull;
+#pragma unroll
+        for (int x0 = 0; x0 < 64; x0 += 8) {
+            if (x0 >= sx) break;
+            const int nbytes = min(8, sx - x0);
+            const unsigned long long v = load8_unaligned(src + x0, nbytes, mask_safe_end);
+            const unsigned long long t = ((((v & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | v) & 0x8080808080808080ull) >> 7;
+            unsigned long long b8 = (t * 0x0102040810204080ull) >> 56;
+            if (nbytes < 8) b8 &= (1ull << nbytes) - 1ull;
+            word |= b8 << x0;
+        }
+        const int z = r / sy, w = z * ps + (r - z * sy);
+        sm_m[w] = word;
+        sm_f[w] = 0ull;
+        fg += __popcll(word);
+    }
+    fg = __reduce_add_sync(0xFFFFFFFFu, fg);
+    if (lane == 0 && fg) atomicAdd(&s_sum[0], fg);
+    __syncthreads();
+    fg = s_sum[0];
+    if (fg == 0) { ccf_count(tid, 2); return; }               // status 5 is the general kernel's to report
+    // ---- seed: the foreground voxel of the centre row nearest to the centre column ---------------------------
+    const int yc = sy >> 1, rc = (sz >> 1) * ps + yc, xc = sx >> 1;
+    const unsigned long long mc = sm_m[rc];
+    if (mc == 0ull) { ccf_count(tid, 3); return; }
+    if (tid == 0) {
+        const unsigned long long hi = mc >> xc, lo = xc ? (mc & ((1ull << xc) - 1ull)) : 0ull;
+        const int dh = hi ? __ffsll((long long)hi) - 1 : 1000, dl = lo ? xc - (63 - __clzll((long long)lo)) : 1000;
+        sm_f[rc] = ccf_fill_row(1ull << (dh <= dl ? xc + dh : xc - dl), mc);
+    }
+    __syncthreads();
+    // ---- fill: lane z owns plane z (idle lanes read plane 0 through an empty mask).  Warp 0 sweeps forwards and
+    //      backwards along y (a dependent chain); whether anything is still reachable is then checked by all warps on
+    //      independent rows, so a converged fill costs one sweep pair, not two. -----------------------------------------
+    const bool act = lane < sz;
+    const unsigned long long* pm = sm_m + (size_t)(act ? lane : 0) * ps;
+    unsigned long long* pf = sm_f + (size_t)(act ? lane : 0) * ps;
+    const unsigned long long live = act ? ~0ull : 0ull;
+    for (int pairs = 0;; ++pairs) {
+        if (warp == 0) {
+#pragma unroll 1
+            for (int dir = 0; dir < 2; ++dir) {
+                const int step = dir ? -1 : 1;
+                // nothing above the seed row can change before the first forward sweep reaches it
+                int y = dir ? sy - 1 : (pairs == 0 ? max(yc - 1, 0) : 0);
+                const int nsteps = dir ? sy : sy - y;
+                unsigned long long prev = (y - step >= 0 && y - step < sy) ? pf[y - step] & live : 0ull;
+                unsigned long long cur = pf[y] & live;
+                unsigned long long next = (y + step >= 0 && y + step < sy) ? pf[y + step] & live : 0ull;
+                unsigned long long mm = pm[y] & live;
+                for (int k = 0; k < nsteps; ++k, y += step) {
+                    // rows ahead are only ever written by this lane, later: safe to fetch them early
+                    const int y2 = y + 2 * step, y1 = y + step;
+                    const unsigned long long next2 = (y2 >= 0 && y2 < sy) ? pf[y2] & live : 0ull;
+                    const unsigned long long mm1 = (y1 >= 0 && y1 < sy) ? pm[y1] & live : 0ull;
+                    const unsigned long long seeds = ccf_seeds(prev | cur | next, mm);
+                    unsigned long long fnew = cur;
+                    if (seeds & ~cur) {                           // something new reaches this row
+                        fnew = ccf_fill_row(seeds, mm);
+                        pf[y] = fnew;
+                    }
+                    prev = fnew; cur = next; next = next2; mm = mm1;
+                }
+            }
+        }
+        __syncthreads();
+        int open_rows = 0;
+        for (int y = warp; y < sy; y += CCF_WARPS) {
+            const unsigned long long cur = pf[y] & live;
+            const unsigned long long own3 = cur | (y > 0 ? pf[y - 1] & live : 0ull) | (y + 1 < sy ? pf[y + 1] & live : 0ull);
+            open_rows |= (ccf_seeds(own3, pm[y] & live) & ~cur) != 0ull;
+        }
+        if (!__syncthreads_or(open_rows)) break;
+        if (pairs + 1 >= CCF_MAX_PAIRS) { ccf_count(tid, 4); return; }      // maze-like mask: the general kernel takes it
+    }
+    // ---- majority test; clear everything outside the fill ---------------------------------------------------
+    int cnt = 0;
+    for (int r = tid; r < rows; r += CCF_WARPS * 32) {
+        const int z = r / sy;
+        cnt += __popcll(sm_f[z * ps + (r - z * sy)]);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&s_sum[1], cnt);
+    __syncthreads();
+    if (2 * s_sum[1] <= fg) { ccf_count(tid, 5); return; }    // not a strict majority: the general kernel decides
+    for (int r = tid; r < rows; r += CCF_WARPS * 32) {
+        const int z = r / sy, w = z * ps + (r - z * sy);
+        unsigned long long diff = sm_m[w] & ~sm_f[w];
+        uint8_t* dst = m + (size_t)r * sx;
+        while (diff) {
+            const int x = __ffsll((long long)diff) - 1;
+            dst[x] = 0;
+            diff &= diff - 1ull;
+        }
+    }
+    if (tid == 0) status[inst] = CC_DONE_BIT;
+    ccf_count(tid, 0);
+}
+
+// one instance, whole CTA; every return below is taken by all threads of the CTA
+__device__ __forceinline__ void
+cc_instance(CcShared& sh, unsigned char* cc_dyn, const int inst,
+            uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, const int32_t* __restrict__ boxes,
+            int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes) {
     unsigned long long* sm_bits = reinterpret_cast<unsigned long long*>(cc_dyn);
     int* sm_run_off = reinterpret_cast<int*>(sm_bits + CC_SMEM_WORDS);
     int* sm_parent = sm_run_off + CC_SMEM_ROWS + 2;
     int* sm_size = sm_parent + CC_SMEM_RUNS;
     unsigned short* sm_iv = reinterpret_cast<unsigned short*>(sm_size + CC_SMEM_RUNS);    // run interval (first x << 8) | last x
     unsigned short* sm_row = sm_iv + CC_SMEM_RUNS;                                           // row of the run
-    const int slot = blockIdx.x, vol = blockIdx.y;
-    const int base = det_off ? det_off[vol] : 0;
-    const int n_here = det_off ? det_off[vol + 1] - base : n_crops;
-    if (slot >= n_here || (n_valid && slot >= n_valid[vol])) return;
-    const int inst = base + (order ? order[base + slot] : slot);
-    if (status && status[inst] != 0) return;                 // skipped / failed instances keep their (empty) mask
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t off = crop_off[inst];
     const int n = (int)(crop_off[inst + 1] - off);
@@ -360,9 +529,58 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
     }
 }
 
+// Persistent CTAs claim batches of (volume, slot) work items from a counter.  One thread per item resolves it: an
+// instance the fill kernel finished only has its flag cleared; instances that still need the union-find path are
+// collected and processed by the whole CTA one after the other.
+constexpr int CC_BATCH = 16;
+__global__ void __launch_bounds__(CC_THREADS, 3)
+largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, int n_crops, int n_work,
+                  const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
+                  const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid,
+                  int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes,
+                  unsigned int* __restrict__ work_counter) {
+    __shared__ CcShared sh;
+    __shared__ int s_first, s_n, s_list[CC_BATCH];
+    extern __shared__ __align__(16) unsigned char cc_dyn[];
+    while (true) {
+        __syncthreads();                                     // the previous batch is done with shared memory
+        if (threadIdx.x == 0) { s_first = (int)atomicAdd(work_counter, (unsigned)CC_BATCH); s_n = 0; }
+        __syncthreads();
+        const int first = s_first;
+        if (first >= n_work) break;
+        if (threadIdx.x < CC_BATCH && first + threadIdx.x < n_work) {
+            const int w = first + threadIdx.x;
+            const int inst = cc_inst_of(w % n_crops, w / n_crops, n_crops, det_off, order, n_valid);
+            if (inst >= 0) {
+                const int st = status ? status[inst] : 0;
+                if (st & CC_DONE_BIT) status[inst] = st & ~CC_DONE_BIT;         // already filtered by largest_cc_fill_kernel
+                else if (st == 0) s_list[atomicAdd(&s_n, 1)] = inst;           // skipped / failed instances keep their (empty) mask
+            }
+        }
+        __syncthreads();
+        const int cnt = s_n;
+        for (int k = 0; k < cnt; ++k) {
+            cc_instance(sh, cc_dyn, s_list[k], mask, crop_off, boxes, status, scratch, total_mask_bytes);
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
+
+extern "C" int b200seg_largest_cc_path_counts(long long* counts, int reset) {
+    B200_CHECK_ARG(counts, "largest_cc_path_counts: null pointer");
+    unsigned long long h[8];
+    B200_CUDA(cudaMemcpyFromSymbol(h, ccf_counts, sizeof(h)));
+    for (int i = 0; i < 8; ++i) counts[i] = (long long)h[i];
+    if (reset) {
+        memset(h, 0, sizeof(h));
+        B200_CUDA(cudaMemcpyToSymbol(ccf_counts, h, sizeof(h)));
+    }
+    return 0;
+}
 
 extern "C" size_t b200seg_largest_cc_workspace_bytes(long long total_mask_bytes) {
     if (total_mask_bytes < 0) return 256;
@@ -389,8 +607,25 @@ extern "C" int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, l
         B200_CUDA(cudaFuncSetAttribute(largest_cc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC_DYN_BYTES));
         attr_set = true;
     }
-    dim3 grid(n_max, n_volumes);
-    largest_cc_kernel<<<grid, CC_THREADS, CC_DYN_BYTES, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+    if (status) {                                            // warp-per-instance flood fill first; it marks what it finished
+        const size_t fill_smem = (size_t)2 * CCF_ROWS * 8;
+        static bool fill_attr_set = false;
+        if (!fill_attr_set) {
+            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+            fill_attr_set = true;
+        }
+        dim3 fgrid(n_max, n_volumes);
+        largest_cc_fill_kernel<<<fgrid, CCF_WARPS * 32, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+        B200_LAUNCH_CHECK("largest_cc_fill_kernel");
+    }
+    unsigned int* work_counter = reinterpret_cast<unsigned int*>(scratch + total_mask_bytes);       // inside the 64 spare words
+    B200_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream));
+    const long long n_work = (long long)n_max * n_volumes;
+    B200_CHECK_ARG(n_work < (1ll << 31), "largest_cc: too many instances");
+    const long long batches = (n_work + CC_BATCH - 1) / CC_BATCH;
+    const long long ctas = batches < 3ll * num_sms() ? batches : 3ll * num_sms();
+    largest_cc_kernel<<<(unsigned)ctas, CC_THREADS, CC_DYN_BYTES, stream>>>(masks, crop_off, n_max, (int)n_work, det_off, boxes, order, n_valid, status, scratch,
+                                                                            total_mask_bytes, work_counter);
     B200_LAUNCH_CHECK("largest_cc_kernel");
     return 0;
 }
