@@ -215,13 +215,40 @@ def test_largest_cc_vs_oracle(b2, torch_):
     masks.append(np.zeros((4, 5, 6), np.uint8))                     # no foreground: status 5
     tie = np.zeros((3, 3, 9), np.uint8); tie[0, 0, 0:2] = 255; tie[2, 2, 6:8] = 255                # two components of 2 voxels
     masks.append(tie)
+    i_tie = len(masks) - 1
     diag = np.zeros((3, 3, 3), np.uint8); diag[0, 0, 0] = diag[1, 1, 1] = diag[2, 2, 2] = 255; diag[0, 2, 0] = 255   # 26-connectivity
     masks.append(diag)
+    # every way out of the flood-fill fast path (largest_cc.cu): donut (empty centre row), two blobs where the centre one is
+    # the smaller (no majority), a spiral corridor (more sweep pairs than the cap), 30 planes x 61 rows (row words in
+    # the global scratch), 33 planes (too deep for one lane per plane), and a filled block (one sweep pair)
+    zz, yy, xx = np.meshgrid(np.arange(9), np.arange(21), np.arange(21), indexing="ij")
+    rr = np.sqrt((yy - 10) ** 2 + (xx - 10) ** 2)
+    masks.append((((rr > 4) & (rr < 8)) * 255).astype(np.uint8))
+    two = np.zeros((8, 30, 40), np.uint8); two[2:6, 12:18, 17:23] = 255; two[1:7, 1:9, 1:38] = 255; two[0, 29, 39] = 255
+    masks.append(two)
+    spiral = np.zeros((3, 41, 41), np.uint8)
+    y, x, dy, dx, n = 20, 20, 0, 1, 1
+    for leg in range(38):                                           # unit-width arms two voxels apart: a single long corridor
+        for _ in range(n):
+            spiral[1, y, x] = 255; y += dy; x += dx
+        dy, dx = dx, -dy
+        n += 2 * (leg % 2)
+    masks.append(spiral)
+    big = (rng.random((30, 61, 40)) < 0.7).astype(np.uint8) * 255; big[:, 30, :] = 255
+    masks.append(big)
+    deep = np.zeros((33, 6, 7), np.uint8); deep[:, 2:4, 2:5] = 255; deep[0, 0, 0] = 255
+    masks.append(deep)
+    masks.append(np.full((6, 10, 64), 255, np.uint8))
     boxes = np.array([[0, 0, 0, m.shape[2] - 1, m.shape[1] - 1, m.shape[0] - 1] for m in masks], np.int32)
     off = np.zeros(len(masks) + 1, np.int64); off[1:] = np.cumsum([m.size for m in masks])
     flat = torch_.from_numpy(np.concatenate([m.ravel() for m in masks])).cuda()
+    from b200seg import _lib
+    counts = (ctypes.c_longlong * 8)()
+    _lib.lib().b200seg_largest_cc_path_counts(counts, 1)
     status = b2.largest_cc(flat, torch_.from_numpy(off).cuda(), torch_.from_numpy(boxes).cuda()).cpu().numpy()
     out = flat.cpu().numpy()
+    _lib.lib().b200seg_largest_cc_path_counts(counts, 0)
+    assert sum(counts) == len(masks) and all(c > 0 for c in list(counts)[:6]), list(counts)      # every path was exercised
     for i, m in enumerate(masks):
         got = out[off[i]:off[i + 1]].reshape(m.shape)
         if not m.any():
@@ -231,7 +258,7 @@ def test_largest_cc_vs_oracle(b2, torch_):
         assert status[i] == 0, (i, status[i])
         assert np.array_equal(got != 0, ref), (i, m.shape, int((got != 0).sum()), int(ref.sum()))
         assert np.array_equal(got[ref], m[ref]), i                  # kept voxels keep their value
-    assert out[off[-3]:off[-2]].reshape(tie.shape)[2, 2, 6] == 255   # tie: the later component wins
+    assert out[off[i_tie]:off[i_tie + 1]].reshape(tie.shape)[2, 2, 6] == 255   # tie: the later component wins
 
 
 def test_mask_overlaps_vs_oracle_and_golden(b2, golden, torch_):
