@@ -262,6 +262,26 @@ def bench_ops(torch, peak):
     prm_maps = torch.rand((14, 32, 128, 128), device=dev)
     ms = time_op(torch, lambda: prefilter.prm_to_uint8(prm_maps), 10, flush)
     ops["prm_to_uint8_14x32x128x128"] = entry(ms, (4 + 4 + 1) * prm_maps.numel(), {"note": "two reads (min/max, scale) + uint8 write; 3 launches"})
+    # Mask R-CNN mask paste-back (config 2 tile: 64x200x200, 100 detections, 14^3 masks): resize + threshold + clip, one launch
+    from b200seg import segm, _lib as _bl
+    n_sg, M_sg, (S_sg, H_sg, W_sg) = 100, 14, (64, 200, 200)
+    lo_sg = np.stack([rng_e.uniform(-5, W_sg - 30, n_sg), rng_e.uniform(-5, H_sg - 30, n_sg), rng_e.uniform(-5, S_sg - 15, n_sg)], axis=1)
+    ext_sg = np.stack([rng_e.uniform(25, 60, n_sg), rng_e.uniform(25, 60, n_sg), rng_e.uniform(10, 40, n_sg)], axis=1)
+    bx_sg = np.ascontiguousarray(segm.expand_boxes(np.concatenate([lo_sg, lo_sg + ext_sg], axis=1).astype(np.float32), (M_sg + 2.0) / M_sg).astype(np.int32))
+    _, off_sg = segm.clipped_boxes(bx_sg, S_sg, H_sg, W_sg)
+    mk_sg = torch.from_numpy(rng_e.random((n_sg, 2, M_sg, M_sg, M_sg), dtype=np.float32)).to(dev)
+    ix_sg = torch.arange(n_sg, dtype=torch.int32, device=dev) * 2 + 1
+    d_bx, d_off, d_tab = torch.from_numpy(bx_sg).to(dev), torch.from_numpy(off_sg).to(dev), torch.from_numpy(segm.gauss_table(M_sg)).to(dev)
+    crops_sg = torch.empty(int(off_sg[-1]) + 16, dtype=torch.uint8, device=dev)
+    L_sg = _bl.lib()
+
+    def run_segm():
+        _bl.check(L_sg.b200seg_segm_paste_dev(_bl.ptr(mk_sg), _bl.ptr(ix_sg), _bl.ptr(d_bx), n_sg, M_sg, _bl.ptr(d_tab), 0.5, S_sg, H_sg, W_sg,
+                                              _bl.ptr(crops_sg), _bl.ptr(d_off), _bl.current_stream()), "segm_paste")
+    ms = time_op(torch, run_segm, 20, flush)
+    ops["segm_paste_100x14^3_64x200x200"] = entry(ms, n_sg * M_sg ** 3 * 4 + int(off_sg[-1]) + 36 * n_sg, {
+        "mask_voxels_per_s": int(off_sg[-1]) / (ms * 1e-3), "dets_per_s": n_sg / (ms * 1e-3),
+        "note": "fp64-issue bound by construction: 8 taps x (3 DMUL + DADD) per output voxel in scipy's order; HBM bytes are the 14^3 blocks in and one byte per voxel out"})
     # RPN proposal generation on the soma test tile: 14 anchors x 16x40x40, pre/post NMS top-N 1000, thresh 0.23
     from b200seg.generate_proposals_3d import GenerateProposalsOp_3d
     A_, S_, H_, W_ = 14, 16, 40, 40

@@ -324,6 +324,35 @@ int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
                                      uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
                                      int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive);
 
+/* ----------------------------------------------------------------------------------------------
+ * Mask R-CNN mask paste-back (second row) -- replaces the per-detection body of segm_results
+ * (lib/core/test.py:902-938): zero-pad the M^3 mask block to (M+2)^3, skimage.transform.resize(padded, (s,h,w),
+ * mode='reflect', anti_aliasing=True) (:919), `> THRESH_BINARIZE` (:920), paste the part inside the volume (:921-931).
+ * The resize arithmetic is scipy.ndimage's (gaussian_filter 'mirror' with sigma = max(0, (in/out-1)/2), then
+ * zoom(order=1, 'mirror', grid_mode=True)), reproduced in fp64 in scipy's operation order; see segm_paste.cu.
+ *   masks       fp32 blocks of M*M*M values; detection d uses block mask_index[d]
+ *               (= d*C + class for MRCNN.CLS_SPECIFIC_MASK, d*C otherwise, :903-906)
+ *   ref_boxes   [n,6] int32: boxes after expand_boxes(ref_boxes, (M+2)/M) and .astype(int32) (:895-898) -- host logic
+ *   gauss_w     [(M+2)][2*(M+2)] fp64 (b200seg_segm_gauss_table_size(M) values): row o = the first R+1 taps of the
+ *               normalised Gaussian scipy builds for an axis resized from M+2 to o < M+2 samples
+ *               (sigma = ((M+2)/o - 1)/2, R = int(4*sigma + 0.5), phi = exp(-0.5/sigma^2 * x^2), x = -R..0, / sum(phi));
+ *               rows with R = 0 are unused.  Built by the caller so that exp() is the caller's (numpy's in the Python host).
+ *   crops       packed uint8 {0,1}: detection d owns crop_off[d] .. crop_off[d+1], shape (z1-z0, y1-y0, x1-x0) in C order
+ *               with x0 = max(bx1,0), x1 = min(bx2+1, im_w) ... (:923-928); boxes that miss the volume own 0 bytes
+ *               (the reference's negative slice bounds are undefined there).
+ * b200seg_segm_expand_dev writes the reference's output format: volumes [n, im_s, im_h, im_w] uint8, zero outside the boxes.
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_segm_gauss_table_size(int M);
+int b200seg_segm_paste_dev(const float* masks, const int32_t* mask_index, const int32_t* ref_boxes, int n, int M,
+                           const double* gauss_w, float thresh, int im_s, int im_h, int im_w,
+                           uint8_t* crops, const int64_t* crop_off, b200seg_stream_t stream);
+int b200seg_segm_expand_dev(const uint8_t* crops, const int64_t* crop_off, const int32_t* ref_boxes, int n,
+                            int im_s, int im_h, int im_w, uint8_t* volumes, b200seg_stream_t stream);
+/* numpy seam: every pointer on the host (masks holds n_mask_blocks blocks); crops come back packed. */
+int b200seg_segm_paste_host(const float* masks, long long n_mask_blocks, const int32_t* mask_index, const int32_t* ref_boxes,
+                            int n, int M, const double* gauss_w, float thresh, int im_s, int im_h, int im_w,
+                            uint8_t* crops, const int64_t* crop_off);
+
 #ifdef __cplusplus
 }
 #endif

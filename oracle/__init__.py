@@ -435,6 +435,152 @@ def box_results_with_nms_and_limit(scores, boxes, scores_keep_idx, num_classes, 
     return im_results[:, -1], im_results[:, :-1], cls_boxes, cls_keep_idx
 
 
+# ------------------------------------------------------------------------------- Mask R-CNN mask paste-back
+def _mirror_idx(idx, n):
+    """scipy 'mirror' (d c b | a b c d | c b a) index map for any integer offset."""
+    idx = np.asarray(idx)
+    if n == 1:
+        return np.zeros_like(idx)
+    m = np.mod(idx, 2 * n - 2)
+    return np.where(m < n, m, 2 * n - 2 - m)
+
+
+def gaussian_filter_mirror_f32(a, sigmas, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(a float32, sigmas, mode='mirror') restated: axes in turn, skipped where sigma <= 1e-15,
+    symmetric correlate1d in fp64 (see gaussian_filter above), float32 stored after every pass."""
+    out = np.asarray(a, np.float32)
+    for axis in range(out.ndim):
+        sg = float(sigmas[axis])
+        if sg <= 1e-15:
+            continue
+        w, R = gaussian_kernel1d(sg, truncate)
+        x = np.moveaxis(out, axis, -1).astype(np.float64)
+        n = x.shape[-1]
+        xp = x[..., _mirror_idx(np.arange(-R, n + R), n)]
+        acc = w[R] * xp[..., R:R + n]
+        for jj in range(-R, 0):
+            acc = acc + (xp[..., R + jj:R + jj + n] + xp[..., R - jj:R - jj + n]) * w[jj + R]
+        out = np.moveaxis(acc, -1, axis).astype(np.float32)
+    return np.ascontiguousarray(out)
+
+
+def _zoom_axis_taps(n_in, n_out):
+    """scipy NI_ZoomShift with grid_mode: cc = (o + .5) * (n_in / n_out) - .5, map_coordinate('mirror'), order-1 taps
+    floor(cc), floor(cc)+1 (mirrored) with weights w0 = 1 - frac, w1 = 1 - w0."""
+    zoom = np.float64(n_in) / np.float64(n_out)
+    cc = np.arange(n_out, dtype=np.float64)
+    cc = cc + 0.5
+    cc = cc * zoom
+    cc = cc - 0.5
+    s2 = 2 * n_in - 2
+    c = cc.copy()
+    if n_in <= 1:
+        c[:] = 0
+    else:
+        neg = c < 0
+        cn = c[neg]
+        cn = s2 * np.trunc(-cn / s2) + cn
+        c[neg] = np.where(cn <= 1 - n_in, cn + s2, -cn)
+        big = c > n_in - 1
+        cb = c[big]
+        cb = cb - s2 * np.trunc(cb / s2)
+        c[big] = np.where(cb >= n_in, s2 - cb, cb)
+    f = np.floor(c)
+    w0 = 1.0 - (c - f)
+    w1 = 1.0 - w0
+    i0 = f.astype(np.int64)
+    return _mirror_idx(i0, n_in), _mirror_idx(i0 + 1, n_in), w0, w1
+
+
+def zoom_linear_mirror_f32(a, out_shape):
+    """scipy.ndimage.zoom(a float32, order=1, mode='mirror', grid_mode=True) to out_shape, restated: the eight taps in
+    z-major order, each  ((v * wz) * wy) * wx  in fp64, summed in that order, rounded to float32 once."""
+    tabs = [_zoom_axis_taps(a.shape[d], out_shape[d]) for d in range(3)]
+    a64 = np.asarray(a, np.float32).astype(np.float64)
+    t = np.zeros(out_shape, np.float64)
+    for tz in range(2):
+        for ty in range(2):
+            for tx in range(2):
+                coeff = a64[np.ix_(tabs[0][tz], tabs[1][ty], tabs[2][tx])]
+                coeff = coeff * tabs[0][2 + tz][:, None, None]
+                coeff = coeff * tabs[1][2 + ty][None, :, None]
+                coeff = coeff * tabs[2][2 + tx][None, None, :]
+                t = t + coeff
+    return t.astype(np.float32)
+
+
+def resize_reflect_antialias(image, out_shape):
+    """skimage.transform.resize(image float32, out_shape, mode='reflect', anti_aliasing=True) (order 1, clip=True) as the
+    reference calls it (lib/core/test.py:919).  scikit-image is an un-vendored, unversioned dependency of the reference
+    (README.md:15) and is not installed here: PARITY UNPINNED against skimage itself.  What IS pinned: skimage's resize is
+    a thin wrapper over scipy.ndimage -- gaussian_filter(sigma=max(0,(in/out-1)/2), mode='mirror') then
+    zoom(order=1, mode='mirror', grid_mode=True) (map_coordinates at the same half-pixel-centre coordinates in the 0.14-0.18
+    releases), then np.clip to the input's [min, max] -- and this restatement is bit-identical to those scipy calls
+    (tests/test_oracle_golden.py, tests/golden/segm.npz)."""
+    image = np.asarray(image, np.float32)
+    factors = np.divide(image.shape, out_shape)
+    filtered = gaussian_filter_mirror_f32(image, np.maximum(0, (factors - 1) / 2))
+    out = zoom_linear_mirror_f32(filtered, tuple(int(v) for v in out_shape))
+    return np.clip(out, image.min(), image.max())
+
+
+def expand_boxes(boxes, scale):
+    """lib/utils/boxes_3d.py:271-292."""
+    boxes = np.asarray(boxes)
+    out = np.zeros(boxes.shape)
+    for lo, hi in ((0, 3), (1, 4), (2, 5)):
+        half = (boxes[:, hi] - boxes[:, lo]) * .5
+        ctr = (boxes[:, hi] + boxes[:, lo]) * .5
+        half = half * scale
+        out[:, lo] = ctr - half
+        out[:, hi] = ctr + half
+    return out
+
+
+def segm_results(cls_boxes, masks, ref_boxes, im_s, im_h, im_w, num_classes, cls_specific_mask=True, thresh_binarize=0.5,
+                 resize=None):
+    """lib/core/test.py:886-945.  `resize` defaults to the restatement above (tests also pass the scipy-backed one).
+    Boxes that miss the volume give an all-zero volume (the reference's negative slice bounds misbehave there)."""
+    resize = resize or resize_reflect_antialias
+    masks = np.asarray(masks, np.float32)
+    M = masks.shape[2]
+    cls_segms = [[] for _ in range(num_classes)]
+    mask_ind = 0
+    scale = (M + 2.0) / M
+    ref_boxes = expand_boxes(ref_boxes, scale).astype(np.int32)
+    padded = np.zeros((M + 2, M + 2, M + 2), np.float32)
+    for j in range(1, num_classes):
+        segms = []
+        for _ in range(len(cls_boxes[j])):
+            padded[1:-1, 1:-1, 1:-1] = masks[mask_ind, j if cls_specific_mask else 0]
+            b = ref_boxes[mask_ind]
+            w, h, s = max(b[3] - b[0] + 1, 1), max(b[4] - b[1] + 1, 1), max(b[5] - b[2] + 1, 1)
+            mask = (resize(padded, (s, h, w)) > np.float32(thresh_binarize)).astype(np.uint8)
+            im_mask = np.zeros((im_s, im_h, im_w), np.uint8)
+            x0, x1 = max(b[0], 0), min(b[3] + 1, im_w)
+            y0, y1 = max(b[1], 0), min(b[4] + 1, im_h)
+            z0, z1 = max(b[2], 0), min(b[5] + 1, im_s)
+            if x1 > x0 and y1 > y0 and z1 > z0:
+                im_mask[z0:z1, y0:y1, x0:x1] = mask[z0 - b[2]:z1 - b[2], y0 - b[1]:y1 - b[1], x0 - b[0]:x1 - b[0]]
+            segms.append(im_mask)
+            mask_ind += 1
+        cls_segms[j] = segms
+    assert mask_ind == masks.shape[0]
+    return cls_segms
+
+
+def scipy_resize_reflect_antialias(image, out_shape):
+    """The scipy.ndimage calls skimage.transform.resize makes for (mode='reflect', anti_aliasing=True, order=1): the pin of
+    resize_reflect_antialias.  scipy is the reference's own dependency (unversioned; 1.18.1 in this image)."""
+    from scipy import ndimage as ndi
+    image = np.asarray(image, np.float32)
+    factors = np.divide(image.shape, out_shape)
+    filtered = ndi.gaussian_filter(image, np.maximum(0, (factors - 1) / 2), cval=0, mode="mirror")
+    out = ndi.zoom(filtered, [1 / f for f in factors], order=1, mode="mirror", cval=0, grid_mode=True)
+    assert out.shape == tuple(out_shape)
+    return np.clip(out, image.min(), image.max())
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

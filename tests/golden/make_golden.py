@@ -10,6 +10,7 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
   peaks.npz     lib/prm/peak_stimulation_3d.py:peak_stimulation_3d on CPU torch, with the median
                 filter of lib/prm/peak_response_mapping_3d.py:45-49
   rle.npz       lib/utils/mask_3d.py literal of :75-79 (the only known-answer in the reference)
+  segm.npz      lib/core/test.py:segm_results (its own source, skimage's resize replaced by the scipy.ndimage calls it makes)
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
@@ -302,7 +303,57 @@ def make_box_results():
     np.savez_compressed(os.path.join(HERE, "box_results.npz"), **out)
 
 
+def make_segm():
+    """segm_results (lib/core/test.py:886-945): the function's own source compiled against the reference's cfg and
+    utils.boxes_3d (like make_box_results), with `transform.resize` bound to the scipy.ndimage calls skimage's resize
+    delegates to (oracle.scipy_resize_reflect_antialias) -- scikit-image itself is not installed and unversioned in the
+    reference, so the fixture pins everything except skimage's wrapper."""
+    import ast
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    for n in ("cython_nms_3d", "cython_bbox_3d"):
+        sys.modules["utils." + n] = oracle.ref_module(n)
+    sys.modules["nn"] = types.ModuleType("nn")
+    np.float = float
+    import core.config as cc
+    import utils.boxes_3d as box_utils_3d
+    src = open(os.path.join(REF, "lib", "core", "test.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "segm_results")
+    transform = types.SimpleNamespace(resize=lambda img, shape, mode, anti_aliasing: (
+        oracle.scipy_resize_reflect_antialias(img, shape) if (mode, anti_aliasing) == ("reflect", True) else 1 / 0))
+    ns = {"np": np, "cfg": cc.cfg, "box_utils_3d": box_utils_3d, "transform": transform}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_core_test", "exec"), ns)
+    rng = np.random.default_rng(919)
+    out = {}
+    S, H, W, M = 24, 40, 48, cc.cfg.MRCNN.RESOLUTION
+    for name, ncls, cls_specific in (("a", 3, True), ("b", 2, False)):
+        cc.cfg.MODEL.NUM_CLASSES, cc.cfg.MRCNN.CLS_SPECIFIC_MASK = ncls, cls_specific
+        counts = [0, 5, 4][:ncls] if ncls == 3 else [0, 6]
+        n = sum(counts)
+        lo = np.stack([rng.uniform(-4, W - 10, n), rng.uniform(-4, H - 10, n), rng.uniform(-3, S - 6, n)], axis=1)
+        ext = np.stack([rng.uniform(3, 30, n), rng.uniform(3, 26, n), rng.uniform(0.2, 16, n)], axis=1)
+        ext[0] = (40.0, 9.5, 0.4)                          # one-voxel-thin in z after truncation, wide in x
+        boxes = np.concatenate([lo, lo + ext], axis=1).astype(np.float32)
+        g = np.indices((M, M, M)).astype(np.float64)
+        masks_u8 = np.zeros((n, ncls, M, M, M), np.uint8)
+        for i in range(n):
+            for c in range(ncls):
+                ctr = rng.uniform(4, M - 4, 3)
+                rad = rng.uniform(2.5, 6.0, 3)
+                d2 = sum(((g[k] - ctr[k]) / rad[k]) ** 2 for k in range(3))
+                field = 1.0 / (1.0 + np.exp(3.0 * (d2 - 1.0))) + rng.normal(0, 0.08, (M, M, M))
+                masks_u8[i, c] = np.clip(np.round(field * 256), 0, 255).astype(np.uint8)
+        masks = masks_u8.astype(np.float32) / np.float32(256)
+        cls_boxes = [[]] + [np.zeros((c, 7), np.float32) for c in counts[1:]]
+        segms = ns["segm_results"](cls_boxes, masks, boxes, S, H, W)
+        vols = np.stack([v for j in range(1, ncls) for v in segms[j]])
+        out.update({name + "_masks_u8": masks_u8, name + "_boxes": boxes, name + "_counts": np.array(counts),
+                    name + "_cfg": np.array([ncls, int(cls_specific), M, S, H, W]), name + "_vols_bits": np.packbits(vols.reshape(n, -1), axis=1)})
+        print(name, "dets", n, "foreground voxels", int(vols.sum()))
+    np.savez_compressed(os.path.join(HERE, "segm.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_segm()
     make_box_results()
     make_proposals()
     make_prefilter()

@@ -743,3 +743,50 @@ def test_box_results_golden(b2, golden):
         _box_results_check(fn, d, name)
     s, b, cb, ci = fn(np.zeros((5, 2), np.float32), np.zeros((5, 12), np.float32), None, 2, 0.05, 0.3, 100)     # nothing above the threshold
     assert s.shape == (0,) and b.shape == (0, 6) and cb[1].shape == (0, 7)
+
+
+# ------------------------------------------------------------------------------------------ Mask R-CNN mask paste-back
+def test_segm_results_golden_and_oracle(b2, golden, torch_):
+    """segm_results (core/test.py:886-945): the numpy seam against the fixture produced by the reference's own function, the
+    device form (packed crops + expanded volumes) against the oracle on seeded boxes that upsample, downsample (anti-aliased
+    axes), touch every border of the volume, or miss it."""
+    from b200seg import segm
+    from test_oracle_golden import _segm_case
+    g = golden("segm.npz")
+    for name in ("a", "b"):
+        c = _segm_case(g, name)
+        out = segm.segm_results(c["cls_boxes"], c["masks"], c["boxes"], *c["shape"], num_classes=c["ncls"],
+                                cls_specific_mask=c["cls_specific"], resolution=c["M"])
+        assert [len(out[j]) for j in range(c["ncls"])] == c["counts"]
+        vols = np.stack([v for j in range(1, c["ncls"]) for v in out[j]])
+        assert vols.dtype == np.uint8 and np.array_equal(vols, c["vols"]), name
+    rng = np.random.default_rng(4242)
+    for M, (S, H, W), n in ((14, (32, 48, 64), 40), (7, (16, 16, 32), 12), (26, (8, 24, 16), 5)):
+        ncls = 3
+        counts = [0, n - n // 3, n // 3]
+        lo = np.stack([rng.uniform(-8, W - 4, n), rng.uniform(-8, H - 4, n), rng.uniform(-6, S - 3, n)], axis=1)
+        ext = np.stack([rng.uniform(0, 1.2 * W, n), rng.uniform(0, 1.2 * H, n), rng.uniform(0, 1.5 * S, n)], axis=1)
+        ext[::5] = rng.uniform(0, 6, (len(ext[::5]), 3))                  # small boxes: all three axes anti-aliased
+        boxes = np.concatenate([lo, lo + ext], axis=1).astype(np.float32)
+        boxes[1] = (-40, -30, -20, -12, -9, -7)                            # misses the volume: all-zero output
+        masks = rng.random((n, ncls, M, M, M), dtype=np.float32)
+        masks[2] = 0.25                                                   # constant block below the threshold
+        masks[3] = 0.75
+        cls_boxes = [[]] + [np.zeros((c, 7), np.float32) for c in counts[1:]]
+        ref = oracle.segm_results(cls_boxes, masks, boxes, S, H, W, num_classes=ncls, cls_specific_mask=True, thresh_binarize=0.5)
+        ref = np.stack([v for j in range(1, ncls) for v in ref[j]])
+        dev = segm.segm_results_device(cls_boxes, torch_.from_numpy(masks).cuda(), boxes, S, H, W, expand=True, num_classes=ncls,
+                                       cls_specific_mask=True, thresh_binarize=0.5)
+        torch_.cuda.synchronize()
+        assert np.array_equal(dev["volumes"].cpu().numpy(), ref), (M, n)
+        crops, off, clip = dev["crops"].cpu().numpy(), dev["crop_off"], dev["boxes"]
+        for d in range(n):
+            x0, y0, z0, x1, y1, z1 = clip[d]
+            if off[d + 1] > off[d]:
+                assert np.array_equal(crops[off[d]:off[d + 1]].reshape(z1 - z0, y1 - y0, x1 - x0), ref[d, z0:z1, y0:y1, x0:x1]), d
+        assert off[2] == off[1] and ref[2].sum() == 0 and ref[3].sum() > 0
+        host = segm.segm_results(cls_boxes, masks, boxes, S, H, W, num_classes=ncls, cls_specific_mask=True, thresh_binarize=0.5)
+        assert np.array_equal(np.stack([v for j in range(1, ncls) for v in host[j]]), ref)
+    empty = segm.segm_results([[], np.zeros((0, 7), np.float32)], np.zeros((0, 2, 14, 14, 14), np.float32), np.zeros((0, 6), np.float32),
+                              8, 8, 8, num_classes=2)
+    assert empty == [[], []]

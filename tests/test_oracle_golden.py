@@ -203,3 +203,39 @@ def test_box_results_golden(golden):
     d = golden("box_results.npz")
     for name in "abc":
         _box_results_check(oracle.box_results_with_nms_and_limit, d, name)
+
+
+# ------------------------------------------------------------------------------------------ Mask R-CNN mask paste-back
+def _segm_case(g, name):
+    ncls, cls_specific, M, S, H, W = (int(v) for v in g[name + "_cfg"])
+    counts = [int(c) for c in g[name + "_counts"]]
+    masks = g[name + "_masks_u8"].astype(np.float32) / np.float32(256)
+    cls_boxes = [[]] + [np.zeros((c, 7), np.float32) for c in counts[1:]]
+    vols = np.unpackbits(g[name + "_vols_bits"], axis=1)[:, :S * H * W].reshape(-1, S, H, W)
+    return dict(ncls=ncls, cls_specific=bool(cls_specific), M=M, shape=(S, H, W), counts=counts, masks=masks,
+                boxes=g[name + "_boxes"], cls_boxes=cls_boxes, vols=vols)
+
+
+def test_segm_resize_restatement_is_the_scipy_calls():
+    """skimage.transform.resize == gaussian_filter('mirror') + zoom(order 1, 'mirror', grid_mode) + clip: the restatement
+    must be bit-identical to those scipy calls, upsampling and (anti-aliased) downsampling, every output size 1..40."""
+    rng = np.random.default_rng(31)
+    shapes = [(o, 16 + (o * 7) % 23, 1 + (o * 5) % 37) for o in range(1, 41)] + [(3, 60, 2), (47, 5, 16), (16, 16, 16)]
+    for n_in in (16, 9):
+        img = np.zeros((n_in,) * 3, np.float32)
+        img[1:-1, 1:-1, 1:-1] = rng.random((n_in - 2,) * 3, dtype=np.float32)
+        for shp in shapes:
+            a = oracle.resize_reflect_antialias(img, shp)
+            b = oracle.scipy_resize_reflect_antialias(img, shp)
+            assert a.dtype == b.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_in, shp)
+
+
+def test_segm_results_golden(golden):
+    g = golden("segm.npz")
+    for name in ("a", "b"):
+        c = _segm_case(g, name)
+        out = oracle.segm_results(c["cls_boxes"], c["masks"], c["boxes"], *c["shape"], num_classes=c["ncls"],
+                                  cls_specific_mask=c["cls_specific"])
+        vols = np.stack([v for j in range(1, c["ncls"]) for v in out[j]])
+        assert [len(out[j]) for j in range(c["ncls"])] == c["counts"]
+        assert vols.sum() > 200 and np.array_equal(vols, c["vols"]), name
