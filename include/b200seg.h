@@ -182,6 +182,12 @@ int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, long long to
                            int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,
                            const int32_t* order, const int32_t* n_valid, int32_t* status,
                            void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+/* Same with the tie rule as a parameter: tie_first != 0 -> among equally large components the one whose first voxel comes
+ * FIRST in raster order wins (np.argmax over ascending labels, tools/binarization_nuclei.py:126-130). */
+int b200seg_largest_cc_ex_dev(uint8_t* masks, const int64_t* crop_off, long long total_mask_bytes,
+                              int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,
+                              const int32_t* order, const int32_t* n_valid, int32_t* status, int tie_first,
+                              void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Label paste-back -- replaces the inline numpy of tools/binarization_soma.py:100-104 (and
@@ -352,6 +358,33 @@ int b200seg_segm_expand_dev(const uint8_t* crops, const int64_t* crop_off, const
 int b200seg_segm_paste_host(const float* masks, long long n_mask_blocks, const int32_t* mask_index, const int32_t* ref_boxes,
                             int n, int M, const double* gauss_w, float thresh, int im_s, int im_h, int im_w,
                             uint8_t* crops, const int64_t* crop_off);
+
+/* ----------------------------------------------------------------------------------------------
+ * Per-instance chain of tools/binarization_nuclei.py:92-149 for ONE volume, for the n instances that survived the
+ * detection filters (:72-87: edge filter, nms_3d_volume -> b200seg_nms3d_dev(by_volume = 1), score > 0.4), in visit order:
+ * crop + normalise (:98-121) -> 2D-Otsu (:124) -> largest 26-connected component (:126-130) -> hole filling = all but the
+ * largest 26-connected component of the complement (:132-137) -> binary closing, 6-neighbour cross (:139) -> first-come
+ * label paste with label = visit rank + 1 (:141-147) -> survivor test (:148-149).
+ *   volume [S,H,W] uint8 (elem_bytes 1) or uint16 (2): the prefiltered image (:43-44, b200seg_gaussian3d_dev / median3d_dev);
+ *   boxes [n,6] int32: the clamped boxes (:101-106) in VOLUME coordinates (tile offset added), inclusive;
+ *   prm: uint8 PRM crops (box-shaped [sz,sy,sx]), instance i at crop_off[i] (int64 [n+1], device); total_voxels = crop_off[n].
+ * Outputs: seg [S,H,W] uint16 (fully written), masks (final per-instance masks 0/255, packing of prm), b_max[n], status[n]:
+ *   0 ok; 1 Otsu found no threshold; 2 box outside the volume or crop size mismatch; 4 more than 2048 gray levels;
+ *   5 no foreground / no background left (the reference raises); 6 degenerate crop (see b200seg_largest_cc_dev);
+ *   7 normalisation divides 0 by 0 (gray_max == 0 or constant PRM crop; the reference continues with NaN garbage);
+ *   survive[n]: label present in seg.  Instances with status != 0 paste nothing.
+ * Connected components and closing are cc3d / skimage in the reference (unversioned, not vendored): parity is pinned
+ * against scipy.ndimage (label with the 3x3x3 structure, binary_dilation / binary_erosion(border_value=1)).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200seg_binarize_nuclei_workspace_bytes(int n, long long total_voxels, int S, int H, int W);
+int b200seg_binarize_nuclei_dev(const void* volume, int elem_bytes, int S, int H, int W,
+                                const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, int n, long long total_voxels,
+                                uint16_t* seg, uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive,
+                                void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+/* numpy seam: every pointer on the host; masks may be NULL. */
+int b200seg_binarize_nuclei_host(const void* volume, int elem_bytes, int S, int H, int W,
+                                 const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, int n,
+                                 uint16_t* seg, uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive);
 
 #ifdef __cplusplus
 }

@@ -350,7 +350,7 @@ largest_cc_fill_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ c
 __device__ __forceinline__ void
 cc_instance(CcShared& sh, unsigned char* cc_dyn, const int inst,
             uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, const int32_t* __restrict__ boxes,
-            int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes) {
+            int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes, const int tie_first) {
     unsigned long long* sm_bits = reinterpret_cast<unsigned long long*>(cc_dyn);
     int* sm_run_off = reinterpret_cast<int*>(sm_bits + CC_SMEM_WORDS);
     int* sm_parent = sm_run_off + CC_SMEM_ROWS + 2;
@@ -494,12 +494,12 @@ cc_instance(CcShared& sh, unsigned char* cc_dyn, const int inst,
         } else if (root >= 0) atomicAdd(&size[root], add);
     }
     __syncthreads();
-    // ---- 4b. largest component; ties -> later first voxel (larger root id) --------------------------------
+    // ---- 4b. largest component; ties -> later first voxel (larger root id), or the earlier one with tie_first ----
     {
         unsigned long long bestk = 0ull;
         for (int t = tid; t < T; t += CC_THREADS)
             if (parent[t] == t) {
-                const unsigned long long k = ((unsigned long long)(unsigned)size[t] << 32) | (unsigned)t;
+                const unsigned long long k = ((unsigned long long)(unsigned)size[t] << 32) | (tie_first ? 0xFFFFFFFFu - (unsigned)t : (unsigned)t);
                 bestk = k > bestk ? k : bestk;
             }
 #pragma unroll
@@ -508,7 +508,7 @@ cc_instance(CcShared& sh, unsigned char* cc_dyn, const int inst,
         (void)warp;
     }
     __syncthreads();
-    const int best_root = (int)(sh.best & 0xFFFFFFFFull);
+    const int best_root = tie_first ? (int)(0xFFFFFFFFu - (unsigned)(sh.best & 0xFFFFFFFFull)) : (int)(sh.best & 0xFFFFFFFFull);
     // ---- 4c. clear the runs of every other component ------------------------------------------------------
     if (by_run) {
         for (int id = tid; id < T; id += CC_THREADS) {
@@ -538,7 +538,7 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
                   const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
                   const int32_t* __restrict__ order, const int32_t* __restrict__ n_valid,
                   int32_t* __restrict__ status, unsigned long long* __restrict__ scratch, long long total_mask_bytes,
-                  unsigned int* __restrict__ work_counter) {
+                  unsigned int* __restrict__ work_counter, int tie_first) {
     __shared__ CcShared sh;
     __shared__ int s_first, s_n, s_list[CC_BATCH];
     extern __shared__ __align__(16) unsigned char cc_dyn[];
@@ -560,7 +560,7 @@ largest_cc_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_o
         __syncthreads();
         const int cnt = s_n;
         for (int k = 0; k < cnt; ++k) {
-            cc_instance(sh, cc_dyn, s_list[k], mask, crop_off, boxes, status, scratch, total_mask_bytes);
+            cc_instance(sh, cc_dyn, s_list[k], mask, crop_off, boxes, status, scratch, total_mask_bytes, tie_first);
             __syncthreads();
         }
     }
@@ -591,6 +591,14 @@ extern "C" int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, l
                                       int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,
                                       const int32_t* order, const int32_t* n_valid, int32_t* status,
                                       void* workspace, size_t workspace_bytes, b200seg_stream_t stream_) {
+    return b200seg_largest_cc_ex_dev(masks, crop_off, total_mask_bytes, n_volumes, det_off, n_max, boxes, order, n_valid, status, 0,
+                                     workspace, workspace_bytes, stream_);
+}
+
+extern "C" int b200seg_largest_cc_ex_dev(uint8_t* masks, const int64_t* crop_off, long long total_mask_bytes,
+                                         int n_volumes, const int32_t* det_off, int n_max, const int32_t* boxes,
+                                         const int32_t* order, const int32_t* n_valid, int32_t* status, int tie_first,
+                                         void* workspace, size_t workspace_bytes, b200seg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200_CHECK_ARG(n_max >= 0 && n_volumes >= 0 && total_mask_bytes >= 0, "largest_cc: bad sizes");
     if (n_max == 0 || n_volumes == 0) return 0;
@@ -625,7 +633,7 @@ extern "C" int b200seg_largest_cc_dev(uint8_t* masks, const int64_t* crop_off, l
     const long long batches = (n_work + CC_BATCH - 1) / CC_BATCH;
     const long long ctas = batches < 3ll * num_sms() ? batches : 3ll * num_sms();
     largest_cc_kernel<<<(unsigned)ctas, CC_THREADS, CC_DYN_BYTES, stream>>>(masks, crop_off, n_max, (int)n_work, det_off, boxes, order, n_valid, status, scratch,
-                                                                            total_mask_bytes, work_counter);
+                                                                            total_mask_bytes, work_counter, tie_first ? 1 : 0);
     B200_LAUNCH_CHECK("largest_cc_kernel");
     return 0;
 }

@@ -581,6 +581,75 @@ def scipy_resize_reflect_antialias(image, out_shape):
     return np.clip(out, image.min(), image.max())
 
 
+# ------------------------------------------------------------------------------- nuclei per-instance chain
+def nuclei_normalise(box_img, box_prm):
+    """tools/binarization_nuclei.py:111-121 (numpy 1.x scalar semantics for gray_range: no wrap-around).  Raises
+    ZeroDivisionError where the reference divides 0 by 0 and carries on with NaN-derived values."""
+    g_lo, g_hi = box_img.min(), box_img.max()
+    if int(g_hi) - int(g_lo) + 1 < 400:
+        if g_hi == 0:
+            raise ZeroDivisionError("gray_max == 0")
+        box_img = (box_img.astype(float) / g_hi * 400).astype(np.uint16) + g_lo
+    g_lo, g_hi = box_img.min(), box_img.max()
+    p = box_prm.astype(float)
+    if p.max() == p.min():
+        raise ZeroDivisionError("constant PRM crop")
+    span = (int(g_hi) - int(g_lo)) & 0xFFFF
+    box_prm = np.round((p - p.min()) / (p.max() - p.min()) * span + g_lo).astype(np.uint16)
+    return box_img.astype(np.uint16), box_prm
+
+
+def _largest_first(mask):
+    """largest 26-connected component, ties -> the first label (np.argmax over ascending labels, :126-130);
+    scipy.ndimage.label numbers components in raster order of their first voxel."""
+    from scipy import ndimage as ndi
+    lab, k = ndi.label(mask, structure=np.ones((3, 3, 3), bool))
+    if k == 0:
+        raise ValueError("no component")                     # np.argmax([]) in the reference
+    return lab == (np.argmax(np.bincount(lab.ravel())[1:]) + 1)
+
+
+def binarize_nuclei(volume, boxes, prm_crops):
+    """tools/binarization_nuclei.py:92-149 for already selected instances (boxes int [n,6] in volume coordinates, clamped).
+    cc3d.connected_components / skimage.morphology.binary_closing are unversioned, un-vendored dependencies of the reference
+    and are not installed here: PARITY UNPINNED against them; restated with scipy.ndimage (label with the 3x3x3 structure;
+    binary_closing(selem=None) = binary_dilation then binary_erosion(border_value=True) with the 6-neighbour cross, which
+    is how skimage implements it).  Returns (seg uint16, status list, survive list, masks list)."""
+    from scipy import ndimage as ndi
+    seg = np.zeros(volume.shape, np.uint16)
+    cross = ndi.generate_binary_structure(3, 1)
+    status, survive, masks = [], [], []
+    for i, b in enumerate(np.asarray(boxes)):
+        mask_id = i + 1
+        x1, y1, z1, x2, y2, z2 = (int(v) for v in b)
+        box_img = volume[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1]
+        box_prm = np.asarray(prm_crops[i]).reshape(box_img.shape)
+        st, m = 0, np.zeros(box_img.shape, bool)
+        try:
+            i16, p16 = nuclei_normalise(box_img, box_prm)
+            try:
+                bi, _, _ = otsu_py_2d_fast(i16, p16)
+            except UnboundLocalError:
+                raise RuntimeError(1)
+            try:
+                cc = _largest_first(bi > 0)
+                outside = _largest_first(~cc)
+            except ValueError:
+                raise RuntimeError(5)
+            m = ndi.binary_erosion(ndi.binary_dilation(~outside, structure=cross), structure=cross, border_value=True)
+        except ZeroDivisionError:
+            st = 7
+        except RuntimeError as e:
+            st = int(e.args[0])
+        region = seg[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1]
+        free = region == 0
+        region[free] = (m.astype(np.uint16) * mask_id)[free]
+        status.append(st)
+        masks.append(m)
+        survive.append(bool((seg == mask_id).any()))
+    return seg, status, survive, masks
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

@@ -11,6 +11,8 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
                 filter of lib/prm/peak_response_mapping_3d.py:45-49
   rle.npz       lib/utils/mask_3d.py literal of :75-79 (the only known-answer in the reference)
   segm.npz      lib/core/test.py:segm_results (its own source, skimage's resize replaced by the scipy.ndimage calls it makes)
+  nuclei.npz    tools/binarization_nuclei.py lines 110-139 cut out of the script and executed per crop (cc3d / skimage closing
+                bound to scipy.ndimage)
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
@@ -352,7 +354,55 @@ def make_segm():
     np.savez_compressed(os.path.join(HERE, "segm.npz"), **out)
 
 
+def make_nuclei():
+    """tools/binarization_nuclei.py:110-139 (normalise, otsu_py_2d_fast, largest component, hole filling, closing): the
+    script body cannot be imported (hard-coded paths, tif IO), so exactly those lines are cut out of the file, dedented and
+    executed per crop with the reference's own tools/otsu.py; cc3d.connected_components and skimage's binary_closing (not
+    installed, unversioned) are bound to their scipy.ndimage equivalents."""
+    import textwrap
+    import zlib
+    from scipy import ndimage as ndi
+    ref_otsu = load_ref_otsu()
+    lines = open(os.path.join(REF, "tools", "binarization_nuclei.py")).read().split("\n")
+    body = textwrap.dedent("\n".join(lines[109:139]))           # file lines 110..139
+    assert body.lstrip().startswith("# normalize gray image") and "binary_closing" in body.split("\n")[-1]
+    code = compile(body, "ref_binarization_nuclei_110_139", "exec")
+    morphology = types.SimpleNamespace(binary_closing=lambda m: ndi.binary_erosion(
+        ndi.binary_dilation(m, structure=ndi.generate_binary_structure(3, 1)), structure=ndi.generate_binary_structure(3, 1), border_value=True))
+    connected_components = lambda m: ndi.label(m, structure=np.ones((3, 3, 3), bool))[0]
+    rng = np.random.default_rng(139)
+    c = synth.postproc_case(139, shape=(32, 96, 128), n_blobs=8, n_dup=0, n_false=0)
+    vol = c["volume"].astype(np.int32)
+    for bl in c["blobs"][::2]:                                  # hollow every other blob: cavities for the hole filling
+        cz, cy, cx = bl["c"]
+        zz, yy, xx = np.ogrid[:32, :96, :128]
+        r2 = ((zz - cz) / (0.45 * bl["sz"])) ** 2 + ((yy - cy) / (0.45 * bl["sxy"])) ** 2 + ((xx - cx) / (0.45 * bl["sxy"])) ** 2
+        vol -= (0.9 * bl["amp"] * np.exp(-0.5 * r2)).astype(np.int32)
+    vol = np.clip(vol, 0, 255).astype(np.uint8)
+    out = {"count": 0}
+    k = 0
+    for dtype in (np.uint8, np.uint16):
+        v = vol if dtype == np.uint8 else (vol.astype(np.uint16) * 7 + 11)
+        for i in ((0, 1, 3, 5) if dtype == np.uint8 else (0, 6)):
+            x1, y1, z1, x2, y2, z2 = c["boxes"][i]
+            box_img = v[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1].copy()
+            box_prm = c["prm"][c["crop_off"][i]:c["crop_off"][i + 1]].reshape(box_img.shape).copy()
+            ns = {"np": np, "box_img": box_img.copy(), "box_prm": box_prm.copy(), "otsu_py_2d_fast": ref_otsu.otsu_py_2d_fast,
+                  "connected_components": connected_components, "morphology": morphology}
+            exec(code, ns)
+            out.update({"n%d_img" % k: box_img, "n%d_prm" % k: box_prm, "n%d_crc16" % k: np.array([zlib.crc32(np.ascontiguousarray(ns["box_img"].astype(np.uint16)).tobytes()),
+                                                     zlib.crc32(np.ascontiguousarray(ns["box_prm"].astype(np.uint16)).tobytes())], np.int64),
+                        "n%d_b" % k: np.int32(ns["b"]),
+                        "n%d_mask" % k: np.packbits(ns["largestCC"].ravel())})
+            print("nuclei crop", k, dtype.__name__, box_img.shape, "b", ns["b"], "fg", int(ns["largestCC"].sum()),
+                  "otsu fg", int((ns["labels_out"] > -1).sum()))
+            k += 1
+    out["count"] = k
+    np.savez_compressed(os.path.join(HERE, "nuclei.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_nuclei()
     make_segm()
     make_box_results()
     make_proposals()

@@ -790,3 +790,62 @@ def test_segm_results_golden_and_oracle(b2, golden, torch_):
     empty = segm.segm_results([[], np.zeros((0, 7), np.float32)], np.zeros((0, 2, 14, 14, 14), np.float32), np.zeros((0, 6), np.float32),
                               8, 8, 8, num_classes=2)
     assert empty == [[], []]
+
+
+# ------------------------------------------------------------------------------------------ nuclei per-instance chain
+def test_binarize_nuclei_golden_and_oracle(b2, golden, torch_):
+    """binarization_nuclei.py:92-149: each fixture crop (reference lines executed from the file) as a one-instance volume;
+    then whole volumes (uint8 with stretch, uint16 without) with overlapping boxes, hollow blobs, constant-PRM and
+    out-of-volume rejects against the oracle chain: label volume, final masks, status and survivors bit-exact."""
+    from b200seg import binarization_nuclei as bn, synth
+    from b200seg.binarization import crop_offsets
+    from test_oracle_golden import _nuclei_crops
+    for k, c in enumerate(_nuclei_crops(golden("nuclei.npz"))):
+        S, H, W = c["img"].shape
+        r = bn.binarize_nuclei_host(c["img"], np.array([[0, 0, 0, W - 1, H - 1, S - 1]], np.int32), [c["prm"]], want_masks=True)
+        assert r["status"].tolist() == [0] and r["b_max"].tolist() == [c["b"]] and r["survive"].tolist() == [True], k
+        assert np.array_equal(r["masks"].reshape(c["img"].shape) > 0, c["mask"]) and np.array_equal(r["seg"] > 0, c["mask"]), k
+    for seed, shape, nb, as16 in ((139, (32, 128, 160), 8, False), (140, (24, 120, 150), 6, True), (141, (40, 160, 192), 14, False)):
+        case = synth.postproc_case(seed, shape=shape, n_blobs=nb, n_dup=4, n_false=3, sigma_xy=(9, 13), sigma_z=(3, 6))
+        vol = case["volume"].astype(np.int32)
+        zz, yy, xx = np.ogrid[:shape[0], :shape[1], :shape[2]]
+        for bl in case["blobs"][::2]:                                     # cavities for the hole filling
+            cz, cy, cx = bl["c"]
+            r2 = ((zz - cz) / (0.45 * bl["sz"])) ** 2 + ((yy - cy) / (0.45 * bl["sxy"])) ** 2 + ((xx - cx) / (0.45 * bl["sxy"])) ** 2
+            vol -= (0.9 * bl["amp"] * np.exp(-0.5 * r2)).astype(np.int32)
+        vol = np.clip(vol, 0, 255).astype(np.uint8)
+        if as16:
+            vol = vol.astype(np.uint16) * 7 + 11
+        # selection (:72-87): edge filter, NMS by volume on the GPU, score > 0.4 -- against the same steps with the oracle NMS
+        dets = case["dets"]
+        idx = np.nonzero(bn.nuclei_edge_filter(dets, shape[2]))[0]
+        kept = idx[oracle.nms_3d_volume(np.ascontiguousarray(dets[idx]), 0.15)]
+        assert np.array_equal(bn.nuclei_select(dets, shape[2], nms_thresh=0.15, score_thresh=0.4), kept[dets[kept, -1] > 0.4])
+        sel = np.arange(len(dets))            # the chain itself is exercised on EVERY box: duplicates overlap, false boxes have a constant PRM
+        boxes = bn.nuclei_boxes(case["dets"][sel], np.zeros((len(sel), 3), np.int64), max(shape[1], shape[2]), shape[0])
+        boxes[:, 3] = np.minimum(boxes[:, 3], shape[2] - 1); boxes[:, 4] = np.minimum(boxes[:, 4], shape[1] - 1)
+        off = crop_offsets(boxes)
+        crops = []
+        for i, j in enumerate(sel):
+            ob = case["boxes"][j]
+            full = case["prm"][case["crop_off"][j]:case["crop_off"][j + 1]].reshape(ob[5] - ob[2] + 1, ob[4] - ob[1] + 1, ob[3] - ob[0] + 1)
+            b = boxes[i]
+            crops.append(np.ascontiguousarray(full[b[2] - ob[2]:b[5] - ob[2] + 1, b[1] - ob[1]:b[4] - ob[1] + 1, b[0] - ob[0]:b[3] - ob[0] + 1]))
+        seg, status, survive, masks = oracle.binarize_nuclei(vol, boxes, crops)
+        r = bn.binarize_nuclei_host(vol, boxes, crops, want_masks=True)
+        assert r["status"].tolist() == status, (seed, r["status"].tolist(), status)
+        assert np.array_equal(r["seg"], seg), seed
+        assert r["survive"].tolist() == survive, seed
+        for i in range(len(sel)):
+            assert np.array_equal(r["masks"][off[i]:off[i + 1]].reshape(masks[i].shape) > 0, masks[i]), (seed, i)
+        assert 0 in status and 7 in status and len(np.unique(seg)) > 4
+        d = bn.binarize_nuclei(torch_.from_numpy(vol).cuda(),
+                               torch_.from_numpy(boxes).cuda(), torch_.from_numpy(np.concatenate([c.ravel() for c in crops])).cuda(),
+                               torch_.from_numpy(off).cuda())
+        torch_.cuda.synchronize()
+        assert np.array_equal(d[0].cpu().view(torch_.int16).numpy().view(np.uint16), seg) and d[3].cpu().tolist() == status
+    bad = np.array([[0, 0, 0, 200, 5, 5]], np.int32)                          # box outside the volume: status 2, nothing pasted
+    r = bn.binarize_nuclei_host(np.zeros((8, 16, 16), np.uint8), bad, [np.ones((6, 6, 201), np.uint8)])
+    assert r["status"].tolist() == [2] and not r["seg"].any() and r["survive"].tolist() == [False]
+    r = bn.binarize_nuclei_host(np.zeros((8, 16, 16), np.uint8), np.zeros((0, 6), np.int32), [])
+    assert not r["seg"].any() and len(r["status"]) == 0

@@ -239,3 +239,27 @@ def test_segm_results_golden(golden):
         vols = np.stack([v for j in range(1, c["ncls"]) for v in out[j]])
         assert [len(out[j]) for j in range(c["ncls"])] == c["counts"]
         assert vols.sum() > 200 and np.array_equal(vols, c["vols"]), name
+
+
+# ------------------------------------------------------------------------------------------ nuclei per-instance chain
+def _nuclei_crops(g):
+    import zlib
+    out = []
+    for k in range(int(g["count"])):
+        img, prm = g["n%d_img" % k], g["n%d_prm" % k]
+        mask = np.unpackbits(g["n%d_mask" % k])[:img.size].reshape(img.shape).astype(bool)
+        out.append(dict(img=img, prm=prm, b=int(g["n%d_b" % k]), crc=[int(v) for v in g["n%d_crc16" % k]], mask=mask, crc32=zlib.crc32))
+    return out
+
+
+def test_nuclei_chain_golden(golden):
+    """oracle.binarize_nuclei against binarization_nuclei.py:110-139 executed from the reference file (fixture)."""
+    crops = _nuclei_crops(golden("nuclei.npz"))
+    assert len(crops) >= 6 and {c["img"].dtype for c in crops} == {np.dtype(np.uint8), np.dtype(np.uint16)}
+    for k, c in enumerate(crops):
+        i16, p16 = oracle.nuclei_normalise(c["img"], c["prm"])
+        assert [c["crc32"](np.ascontiguousarray(i16).tobytes()), c["crc32"](np.ascontiguousarray(p16).tobytes())] == c["crc"], k
+        assert oracle.otsu_py_2d_fast(i16, p16)[2] == c["b"], k
+        S, H, W = c["img"].shape
+        seg, status, survive, masks = oracle.binarize_nuclei(c["img"], np.array([[0, 0, 0, W - 1, H - 1, S - 1]]), [c["prm"]])
+        assert status == [0] and survive == [True] and np.array_equal(masks[0], c["mask"]) and np.array_equal(seg > 0, c["mask"]), k
