@@ -12,8 +12,8 @@ registers these modules in sys.modules:
     prm.peak_stimulation_3d      -> peak_stimulation_3d, PeakStimulation
     utils.cython_mask_3d         -> binary_mask_to_rle, rle_to_binary_mask
     modeling.generate_proposals_3d -> GenerateProposalsOp_3d
-    b200seg_core_test            -> box_results_with_nms_and_limit (core/test.py has many other members: bind this one
-                                    name into it, see INTEGRATION.md, instead of replacing the module)
+    b200seg_core_test            -> box_results_with_nms_and_limit, segm_results (core/test.py has many other members: bind
+                                    these names into it, see INTEGRATION.md, instead of replacing the module)
     otsu                         -> otsu_py_2d_fast, otsu_py_2d (+ import-compat stubs otsu_py, otsu_mat)
 """
 import sys
@@ -28,7 +28,7 @@ def _module(name, **attrs):
 
 
 def install(overwrite=True):
-    from . import boxes_3d, roi_align_3d, peak_stimulation_3d, otsu, mask_3d, generate_proposals_3d, box_results
+    from . import boxes_3d, roi_align_3d, peak_stimulation_3d, otsu, mask_3d, generate_proposals_3d, box_results, segm
     mods = {
         "utils.cython_nms_3d": _module("utils.cython_nms_3d", nms_3d=boxes_3d._nms_numpy and
                                        (lambda dets, thresh: boxes_3d._nms_numpy(dets, thresh, False)),
@@ -48,7 +48,8 @@ def install(overwrite=True):
                                         rle_to_binary_mask=mask_3d.rle_to_binary_mask),
         "modeling.generate_proposals_3d": _module("modeling.generate_proposals_3d",
                                                   GenerateProposalsOp_3d=generate_proposals_3d.GenerateProposalsOp_3d),
-        "b200seg_core_test": _module("b200seg_core_test", box_results_with_nms_and_limit=box_results.box_results_with_nms_and_limit),
+        "b200seg_core_test": _module("b200seg_core_test", box_results_with_nms_and_limit=box_results.box_results_with_nms_and_limit,
+                                     segm_results=segm.segm_results),
         "otsu": _module("otsu", otsu_py_2d_fast=otsu.otsu_py_2d_fast, otsu_py_2d=otsu.otsu_py_2d,
                         otsu_py=otsu.otsu_py, otsu_mat=otsu.otsu_mat),
     }
