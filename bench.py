@@ -282,6 +282,21 @@ def bench_ops(torch, peak):
     ops["segm_paste_100x14^3_64x200x200"] = entry(ms, n_sg * M_sg ** 3 * 4 + int(off_sg[-1]) + 36 * n_sg, {
         "mask_voxels_per_s": int(off_sg[-1]) / (ms * 1e-3), "dets_per_s": n_sg / (ms * 1e-3),
         "note": "fp64-issue bound by construction: 8 taps x (3 DMUL + DADD) per output voxel in scipy's order; HBM bytes are the 14^3 blocks in and one byte per voxel out"})
+    # nuclei per-instance chain (config 2 shape: 59x350x640 uint16, ~40 large blobs + 10 duplicate boxes), device resident
+    from b200seg import binarization_nuclei as bn_
+    from b200seg.binarization import crop_offsets as crop_offsets_
+    nshape = (59, 350, 640)
+    ncase = synth.postproc_case(1002, shape=nshape, n_blobs=40, n_dup=10, n_false=0, sigma_xy=(10, 15), sigma_z=(4, 7))
+    nboxes = bn_.nuclei_boxes(ncase["dets"], np.zeros((len(ncase["dets"]), 3), np.int64), max(nshape[1], nshape[2]), nshape[0])
+    nboxes[:, 3] = np.minimum(nboxes[:, 3], nshape[2] - 1); nboxes[:, 4] = np.minimum(nboxes[:, 4], nshape[1] - 1)
+    assert np.array_equal(nboxes, ncase["boxes"])
+    nvol = torch.from_numpy(ncase["volume"].astype(np.uint16) * 7 + 11).to(dev)
+    d_nb, d_np, d_no = torch.from_numpy(nboxes).to(dev), torch.from_numpy(ncase["prm"]).to(dev), torch.from_numpy(ncase["crop_off"]).to(dev)
+    ms = time_op(torch, lambda: bn_.binarize_nuclei(nvol, d_nb, d_np, d_no), 10, flush)
+    nvox = int(ncase["crop_off"][-1])
+    ops["binarize_nuclei_59x350x640_u16_50inst"] = entry(ms, 3 * nvox + nvox + 2 * nvol.numel(), {
+        "gvox_per_s": nvol.numel() / (ms * 1e-3) / 1e9, "crop_voxels": nvox,
+        "note": "14 launches (min/max, normalise, Otsu, 2 x largest component, 2 complements, dilate, erode, paste) + output allocation; latency bound on 50 crops"})
     # RPN proposal generation on the soma test tile: 14 anchors x 16x40x40, pre/post NMS top-N 1000, thresh 0.23
     from b200seg.generate_proposals_3d import GenerateProposalsOp_3d
     A_, S_, H_, W_ = 14, 16, 40, 40

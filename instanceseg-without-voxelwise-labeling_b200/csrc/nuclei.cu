@@ -5,8 +5,8 @@
 //   largest 26-connected component of the complement (:132-137), binary closing with the 6-neighbour cross (:139,
 //   skimage.morphology.binary_closing = dilation with an unset border, then erosion with a set border), first-come
 //   label paste (:141-147) and the survivor test (:148-149).
-// New kernels here: the normalisation (lookup tables built in fp64 in numpy's operation order), the mask complement
-// and the closing; Otsu, connected components and paste are the kernels of the soma chain.
+// New kernels here: the normalisation (min/max pass, then lookup tables built in fp64 in numpy's operation order), the mask
+// complement and the two halves of the closing, each on a grid of (instance, row chunk) CTAs; Otsu, connected components and paste are the kernels of the soma chain.
 //
 // Normalisation, per crop (numpy semantics of :111-121, image dtype uint8 or uint16, PRM uint8):
 //   if (gray_max - gray_min + 1 < 400):  img' = uint16(trunc(img / gray_max * 400)) + gray_min
@@ -21,34 +21,41 @@ namespace b200seg {
 constexpr int NU_THREADS = 256;
 constexpr int NU_NW = NU_THREADS / 32;
 
-template <typename T>
-__global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* __restrict__ vol, int S, int H, int W,
-                                                                       const int32_t* __restrict__ boxes, const uint8_t* __restrict__ prm,
-                                                                       const int64_t* __restrict__ crop_off,
-                                                                       uint16_t* __restrict__ img16, uint16_t* __restrict__ prm16,
-                                                                       int32_t* __restrict__ status) {
-    __shared__ int s_red[4][NU_NW];
-    __shared__ int s_b[4];
-    __shared__ unsigned short s_lut_i[400], s_lut_p[256];
-    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// crop geometry shared by the kernels below; false -> status 2
+struct NuCrop { int bx, by, bz, sx, sy, sz; long long off; };
+__device__ __forceinline__ bool nu_crop(const int32_t* __restrict__ boxes, const int64_t* __restrict__ crop_off, int inst, int S, int H, int W, NuCrop& c) {
     const int32_t* bb = boxes + 6 * (size_t)inst;
-    const int bx = bb[0], by = bb[1], bz = bb[2];
-    const int sx = bb[3] - bx + 1, sy = bb[4] - by + 1, sz = bb[5] - bz + 1;
-    const int64_t off = crop_off[inst];
-    const long long n = crop_off[inst + 1] - off;
-    if (sx <= 0 || sy <= 0 || sz <= 0 || bx < 0 || by < 0 || bz < 0 || bb[3] >= W || bb[4] >= H || bb[5] >= S ||
-        n != (long long)sx * sy * sz || n >= (1ll << 31)) {
-        if (tid == 0) status[inst] = 2;
+    c.bx = bb[0]; c.by = bb[1]; c.bz = bb[2];
+    c.sx = bb[3] - c.bx + 1; c.sy = bb[4] - c.by + 1; c.sz = bb[5] - c.bz + 1;
+    c.off = crop_off[inst];
+    const long long n = crop_off[inst + 1] - c.off;
+    return !(c.sx <= 0 || c.sy <= 0 || c.sz <= 0 || c.bx < 0 || c.by < 0 || c.bz < 0 || bb[3] >= W || bb[4] >= H || bb[5] >= S ||
+             n != (long long)c.sx * c.sy * c.sz || n >= (1ll << 31));
+}
+
+// grid (instances, row chunks): min / max of the image crop and of the PRM crop -> mm[inst] = {gmin, pmin, gmax, pmax}
+// (mins pre-set to 0x7F7F7F7F, maxes to 0 by the launcher)
+template <typename T>
+__global__ void __launch_bounds__(NU_THREADS) nuclei_minmax_kernel(const T* __restrict__ vol, int S, int H, int W,
+                                                                    const int32_t* __restrict__ boxes, const uint8_t* __restrict__ prm,
+                                                                    const int64_t* __restrict__ crop_off, int* __restrict__ mins,
+                                                                    int* __restrict__ maxs, int32_t* __restrict__ nstat) {
+    __shared__ int s_red[4][NU_NW];
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    NuCrop c;
+    if (!nu_crop(boxes, crop_off, inst, S, H, W, c)) {
+        if (tid == 0 && blockIdx.y == 0) nstat[inst] = 2;
         return;
     }
-    const int rows = sy * sz;
+    const int rows = c.sy * c.sz;
+    const int r0 = (int)((long long)rows * blockIdx.y / gridDim.y), r1 = (int)((long long)rows * (blockIdx.y + 1) / gridDim.y);
     const size_t HW = (size_t)H * W;
     int mn_i = 0x7FFFFFFF, mx_i = 0, mn_p = 255, mx_p = 0;
-    for (int r = warp; r < rows; r += NU_NW) {
-        const int z = r / sy, y = r - z * sy;
-        const T* src = vol + (size_t)(bz + z) * HW + (size_t)(by + y) * W + bx;
-        const uint8_t* ps = prm + off + (size_t)r * sx;
-        for (int x = lane; x < sx; x += 32) {
+    for (int r = r0 + warp; r < r1; r += NU_NW) {
+        const int z = r / c.sy, y = r - z * c.sy;
+        const T* src = vol + (size_t)(c.bz + z) * HW + (size_t)(c.by + y) * W + c.bx;
+        const uint8_t* ps = prm + c.off + (size_t)r * c.sx;
+        for (int x = lane; x < c.sx; x += 32) {
             const int v = (int)src[x], p = (int)ps[x];
             mn_i = min(mn_i, v); mx_i = max(mx_i, v); mn_p = min(mn_p, p); mx_p = max(mx_p, p);
         }
@@ -57,16 +64,32 @@ __global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* _
     if (lane == 0) { s_red[0][warp] = mn_i; s_red[1][warp] = mx_i; s_red[2][warp] = mn_p; s_red[3][warp] = mx_p; }
     __syncthreads();
     if (tid == 0) {
-        int a = s_red[0][0], b = s_red[1][0], c = s_red[2][0], d = s_red[3][0];
-        for (int w = 1; w < NU_NW; ++w) { a = min(a, s_red[0][w]); b = max(b, s_red[1][w]); c = min(c, s_red[2][w]); d = max(d, s_red[3][w]); }
-        s_b[0] = a; s_b[1] = b; s_b[2] = c; s_b[3] = d;
+        int a = s_red[0][0], b = s_red[1][0], cc = s_red[2][0], d = s_red[3][0];
+        for (int w = 1; w < NU_NW; ++w) { a = min(a, s_red[0][w]); b = max(b, s_red[1][w]); cc = min(cc, s_red[2][w]); d = max(d, s_red[3][w]); }
+        if (r1 > r0) {
+            atomicMin(&mins[2 * inst], a); atomicMin(&mins[2 * inst + 1], cc);
+            atomicMax(&maxs[2 * inst], b); atomicMax(&maxs[2 * inst + 1], d);
+        }
     }
-    __syncthreads();
-    const int gmin = s_b[0], gmax = s_b[1], pmin = s_b[2], pmax = s_b[3];
+}
+
+// grid (instances, row chunks): the two normalisation maps as shared-memory tables, then two lookups per voxel
+template <typename T>
+__global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* __restrict__ vol, int S, int H, int W,
+                                                                       const int32_t* __restrict__ boxes, const uint8_t* __restrict__ prm,
+                                                                       const int64_t* __restrict__ crop_off, const int* __restrict__ mins,
+                                                                       const int* __restrict__ maxs,
+                                                                       uint16_t* __restrict__ img16, uint16_t* __restrict__ prm16,
+                                                                       int32_t* __restrict__ nstat) {
+    __shared__ unsigned short s_lut_i[400], s_lut_p[256];
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    NuCrop c;
+    if (!nu_crop(boxes, crop_off, inst, S, H, W, c)) return;                 // status 2 already reported
+    const int gmin = mins[2 * inst], pmin = mins[2 * inst + 1], gmax = maxs[2 * inst], pmax = maxs[2 * inst + 1];
     // gray_range = gray_max - gray_min + 1 with numpy 1.x scalar semantics (the sum is promoted, no wrap-around)
     const bool stretch = gmax - gmin + 1 < 400;
     if (pmax == pmin || (stretch && gmax == 0)) {
-        if (tid == 0) status[inst] = 7;
+        if (tid == 0 && blockIdx.y == 0) nstat[inst] = 7;
         return;
     }
     auto f_img = [&](int v) -> int {                           // (box_img / gray_max * 400).astype(uint16) + gray_min
@@ -82,11 +105,14 @@ __global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* _
         s_lut_p[tid] = (tid >= pmin && tid <= pmax) ? (unsigned short)(int)rint(t) : (unsigned short)0;
     }
     __syncthreads();
-    for (int r = warp; r < rows; r += NU_NW) {
-        const int z = r / sy, y = r - z * sy;
-        const T* src = vol + (size_t)(bz + z) * HW + (size_t)(by + y) * W + bx;
-        const size_t o = (size_t)off + (size_t)r * sx;
-        for (int x = lane; x < sx; x += 32) {
+    const int rows = c.sy * c.sz;
+    const int r0 = (int)((long long)rows * blockIdx.y / gridDim.y), r1 = (int)((long long)rows * (blockIdx.y + 1) / gridDim.y);
+    const size_t HW = (size_t)H * W;
+    for (int r = r0 + warp; r < r1; r += NU_NW) {
+        const int z = r / c.sy, y = r - z * c.sy;
+        const T* src = vol + (size_t)(c.bz + z) * HW + (size_t)(c.by + y) * W + c.bx;
+        const size_t o = (size_t)c.off + (size_t)r * c.sx;
+        for (int x = lane; x < c.sx; x += 32) {
             const int v = (int)src[x];
             img16[o + x] = stretch ? s_lut_i[v - gmin] : (unsigned short)v;
             prm16[o + x] = s_lut_p[prm[o + x]];
@@ -100,50 +126,50 @@ __global__ void __launch_bounds__(256) mask_complement_kernel(uint8_t* __restric
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m[i] = m[i] ? (uint8_t)0 : (uint8_t)255;
 }
 
-// binary closing with the 6-neighbour cross, one CTA per instance: tmp = dilate(mask) (outside = unset),
-// mask = erode(tmp) (outside = set).  Instances whose status is not 0 end with an empty mask (they paste nothing).
-__global__ void __launch_bounds__(NU_THREADS) nuclei_closing_kernel(uint8_t* mask, uint8_t* tmp,
-                                                                     const int32_t* __restrict__ boxes, const int64_t* __restrict__ crop_off,
-                                                                     const int32_t* __restrict__ status) {
+// one half of the binary closing with the 6-neighbour cross, grid (instances, row chunks):
+// ERODE = false: dst = dilate(src) (outside the crop = unset); ERODE = true: dst = erode(src) (outside = set).
+// The erosion pass also empties the masks of instances whose status is not 0 (they paste nothing).
+template <bool ERODE>
+__global__ void __launch_bounds__(NU_THREADS) nuclei_morph_kernel(const uint8_t* __restrict__ src_all, uint8_t* __restrict__ dst_all,
+                                                                   const int32_t* __restrict__ boxes, const int64_t* __restrict__ crop_off,
+                                                                   const int32_t* __restrict__ status) {
     const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t off = crop_off[inst];
     const long long n = crop_off[inst + 1] - off;
-    uint8_t* m = mask + off;
-    uint8_t* t = tmp + off;
+    const uint8_t* s = src_all + off;
+    uint8_t* d = dst_all + off;
     if (status[inst] != 0) {
-        for (long long j = tid; j < n; j += NU_THREADS) m[j] = 0;
+        if (ERODE) {
+            const long long j0 = n * blockIdx.y / gridDim.y, j1 = n * (blockIdx.y + 1) / gridDim.y;
+            for (long long j = j0 + tid; j < j1; j += NU_THREADS) d[j] = 0;
+        }
         return;
     }
     const int32_t* bb = boxes + 6 * (size_t)inst;
     const int sx = bb[3] - bb[0] + 1, sy = bb[4] - bb[1] + 1, sz = bb[5] - bb[2] + 1;
     const int rows = sy * sz, plane = sy * sx;
-    for (int r = warp; r < rows; r += NU_NW) {
+    const int r0 = (int)((long long)rows * blockIdx.y / gridDim.y), r1 = (int)((long long)rows * (blockIdx.y + 1) / gridDim.y);
+    for (int r = r0 + warp; r < r1; r += NU_NW) {
         const int z = r / sy, y = r - z * sy;
-        const uint8_t* c = m + (size_t)r * sx;
+        const uint8_t* c = s + (size_t)r * sx;
         for (int x = lane; x < sx; x += 32) {
             unsigned v = c[x];
-            if (x > 0) v |= c[x - 1];
-            if (x + 1 < sx) v |= c[x + 1];
-            if (y > 0) v |= c[x - sx];
-            if (y + 1 < sy) v |= c[x + sx];
-            if (z > 0) v |= c[x - plane];
-            if (z + 1 < sz) v |= c[x + plane];
-            t[(size_t)r * sx + x] = v ? (uint8_t)255 : (uint8_t)0;
-        }
-    }
-    __syncthreads();                                          // one CTA owns the crop: global writes above are visible after the barrier
-    for (int r = warp; r < rows; r += NU_NW) {
-        const int z = r / sy, y = r - z * sy;
-        const uint8_t* c = t + (size_t)r * sx;
-        for (int x = lane; x < sx; x += 32) {
-            unsigned v = c[x];
-            if (x > 0) v &= c[x - 1];
-            if (x + 1 < sx) v &= c[x + 1];
-            if (y > 0) v &= c[x - sx];
-            if (y + 1 < sy) v &= c[x + sx];
-            if (z > 0) v &= c[x - plane];
-            if (z + 1 < sz) v &= c[x + plane];
-            m[(size_t)r * sx + x] = v ? (uint8_t)255 : (uint8_t)0;
+            if (ERODE) {
+                if (x > 0) v &= c[x - 1];
+                if (x + 1 < sx) v &= c[x + 1];
+                if (y > 0) v &= c[x - sx];
+                if (y + 1 < sy) v &= c[x + sx];
+                if (z > 0) v &= c[x - plane];
+                if (z + 1 < sz) v &= c[x + plane];
+            } else {
+                if (x > 0) v |= c[x - 1];
+                if (x + 1 < sx) v |= c[x + 1];
+                if (y > 0) v |= c[x - sx];
+                if (y + 1 < sy) v |= c[x + sx];
+                if (z > 0) v |= c[x - plane];
+                if (z + 1 < sz) v |= c[x + plane];
+            }
+            d[(size_t)r * sx + x] = v ? (uint8_t)255 : (uint8_t)0;
         }
     }
 }
@@ -159,7 +185,7 @@ __global__ void nuclei_merge_status_kernel(const int32_t* __restrict__ nstat, in
     if (i < n && nstat[i] != 0) { status[i] = nstat[i]; b_max[i] = 0; }
 }
 
-struct NucleiWs { size_t img16, prm16, tmp, ginfo, nstat, ids, cc, cc_bytes, paste, paste_bytes, total; };
+struct NucleiWs { size_t img16, prm16, tmp, ginfo, nstat, mins, maxs, ids, cc, cc_bytes, paste, paste_bytes, total; };
 static NucleiWs nuclei_ws(int n, long long total_vox, int S, int H, int W) {
     NucleiWs w;
     const size_t tv = (size_t)(total_vox > 0 ? total_vox : 0), nn = (size_t)(n > 0 ? n : 1);
@@ -169,6 +195,8 @@ static NucleiWs nuclei_ws(int n, long long total_vox, int S, int H, int W) {
     w.tmp = o; o += align_up(tv + 16, 256);
     w.ginfo = o; o += align_up(nn * 16, 256);
     w.nstat = o; o += align_up(nn * 4, 256);
+    w.mins = o; o += align_up(nn * 8, 256);
+    w.maxs = o; o += align_up(nn * 8, 256);
     w.ids = o; o += align_up(nn * 2, 256);
     w.cc_bytes = align_up(b200seg_largest_cc_workspace_bytes((long long)tv), 256);
     w.cc = o; o += w.cc_bytes;
@@ -208,10 +236,22 @@ extern "C" int b200seg_binarize_nuclei_dev(const void* volume, int elem_bytes, i
         B200_CUDA(cudaMemsetAsync(nstat, 0, sizeof(int32_t) * (size_t)n, stream));
         B200_CUDA(cudaMemsetAsync(img16, 0, (size_t)total_voxels * 2, stream));     // rejected crops stay constant
         B200_CUDA(cudaMemsetAsync(prm16, 0, (size_t)total_voxels * 2, stream));
-        if (elem_bytes == 1)
-            nuclei_normalise_kernel<uint8_t><<<n, NU_THREADS, 0, stream>>>((const uint8_t*)volume, S, H, W, boxes, prm, crop_off, img16, prm16, nstat);
-        else
-            nuclei_normalise_kernel<uint16_t><<<n, NU_THREADS, 0, stream>>>((const uint16_t*)volume, S, H, W, boxes, prm, crop_off, img16, prm16, nstat);
+        int* mins = (int*)(ws + w.mins);
+        int* maxs = (int*)(ws + w.maxs);
+        B200_CUDA(cudaMemsetAsync(mins, 0x7F, sizeof(int) * 2 * (size_t)n, stream));
+        B200_CUDA(cudaMemsetAsync(maxs, 0, sizeof(int) * 2 * (size_t)n, stream));
+        int nch = (4 * num_sms() + n - 1) / n;                // row chunks per instance: ~4 CTAs per SM in total
+        nch = nch < 1 ? 1 : (nch > 64 ? 64 : nch);
+        const dim3 cgrid2((unsigned)n, (unsigned)nch);
+        if (elem_bytes == 1) {
+            nuclei_minmax_kernel<uint8_t><<<cgrid2, NU_THREADS, 0, stream>>>((const uint8_t*)volume, S, H, W, boxes, prm, crop_off, mins, maxs, nstat);
+            B200_LAUNCH_CHECK("nuclei_minmax_kernel");
+            nuclei_normalise_kernel<uint8_t><<<cgrid2, NU_THREADS, 0, stream>>>((const uint8_t*)volume, S, H, W, boxes, prm, crop_off, mins, maxs, img16, prm16, nstat);
+        } else {
+            nuclei_minmax_kernel<uint16_t><<<cgrid2, NU_THREADS, 0, stream>>>((const uint16_t*)volume, S, H, W, boxes, prm, crop_off, mins, maxs, nstat);
+            B200_LAUNCH_CHECK("nuclei_minmax_kernel");
+            nuclei_normalise_kernel<uint16_t><<<cgrid2, NU_THREADS, 0, stream>>>((const uint16_t*)volume, S, H, W, boxes, prm, crop_off, mins, maxs, img16, prm16, nstat);
+        }
         B200_LAUNCH_CHECK("nuclei_normalise_kernel");
         int e = b200seg_otsu2d_dev(img16, prm16, crop_off, n, masks, b_max, ginfo, status, nullptr, nullptr, stream);      // :124
         if (e) return e;
@@ -229,8 +269,10 @@ extern "C" int b200seg_binarize_nuclei_dev(const void* volume, int elem_bytes, i
         }
         mask_complement_kernel<<<cgrid, 256, 0, stream>>>(masks, total_voxels);
         B200_LAUNCH_CHECK("mask_complement_kernel");
-        nuclei_closing_kernel<<<n, NU_THREADS, 0, stream>>>(masks, tmp, boxes, crop_off, status);                          // :139
-        B200_LAUNCH_CHECK("nuclei_closing_kernel");
+        nuclei_morph_kernel<false><<<cgrid2, NU_THREADS, 0, stream>>>(masks, tmp, boxes, crop_off, status);               // :139 dilation
+        B200_LAUNCH_CHECK("nuclei_morph_kernel<dilate>");
+        nuclei_morph_kernel<true><<<cgrid2, NU_THREADS, 0, stream>>>(tmp, masks, boxes, crop_off, status);                // :139 erosion
+        B200_LAUNCH_CHECK("nuclei_morph_kernel<erode>");
         nuclei_iota_u16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, n);                                                 // mask_id, :93-94
         B200_LAUNCH_CHECK("nuclei_iota_u16_kernel");
     }
