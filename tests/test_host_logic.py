@@ -105,3 +105,58 @@ def test_gather_detections_gloo_world2():
         assert shapes == {0: 1, 1: 2, 2: 3, 3: 4, 4: 5}
         assert vals == {v: float(v) for v in range(5)}
         assert cnt == [5, 15, 2]
+
+
+def test_segm_host_logic_matches_oracle_and_scipy():
+    """expand_boxes / clipped crops / the anti-aliasing tap table of segm.py against the oracle restatement and scipy."""
+    import oracle
+    from b200seg import segm
+    rng = np.random.default_rng(12)
+    boxes = (rng.uniform(-20, 200, (50, 6))).astype(np.float32)
+    boxes[:, 3:] = boxes[:, :3] + rng.uniform(0, 60, (50, 3)).astype(np.float32)
+    scale = (14 + 2.0) / 14
+    a, b = segm.expand_boxes(boxes, scale), oracle.expand_boxes(boxes, scale)
+    assert a.dtype == np.float64 and np.array_equal(a, b)
+    ib = a.astype(np.int32)
+    clip, off = segm.clipped_boxes(ib, 64, 100, 150)
+    for d in range(len(ib)):
+        x0, x1 = max(ib[d, 0], 0), min(ib[d, 3] + 1, 150)
+        y0, y1 = max(ib[d, 1], 0), min(ib[d, 4] + 1, 100)
+        z0, z1 = max(ib[d, 2], 0), min(ib[d, 5] + 1, 64)
+        vol = (x1 - x0) * (y1 - y0) * (z1 - z0) if (x1 > x0 and y1 > y0 and z1 > z0) else 0
+        assert off[d + 1] - off[d] == vol
+        if vol:
+            assert clip[d].tolist() == [x0, y0, z0, x1, y1, z1]
+    tab = segm.gauss_table(14)
+    assert tab.shape == (16, 32)
+    for o in range(1, 16):
+        sigma = max(0, (16 / o - 1) / 2)
+        w, R = oracle.gaussian_kernel1d(sigma) if sigma > 0 else (np.ones(1), 0)
+        if R >= 1:
+            assert np.array_equal(tab[o, :R + 1], w[:R + 1]) and not tab[o, R + 1:].any()
+        else:
+            assert not tab[o].any()
+
+
+def test_nuclei_host_logic():
+    """Edge filter (binarization_nuclei.py:72-77, as written) and box clamping (:96-106) against a literal per-row evaluation."""
+    from b200seg import binarization_nuclei as bn
+    rng = np.random.default_rng(13)
+    n, width, norm_side, slices = 200, 640, 200, 59
+    lo = np.stack([rng.uniform(0, 600, n), rng.uniform(0, 600, n), rng.uniform(0, 50, n)], axis=1)
+    dets = np.concatenate([lo, lo + rng.uniform(5, 60, (n, 3)), rng.random((n, 1))], axis=1).astype(np.float32)
+    keep = bn.nuclei_edge_filter(dets, width)
+    for i, d in enumerate(dets):
+        c1 = d[0] > 10 and d[3] < width - 10 and d[3] - d[0] + 1 < 32
+        c2 = d[1] > 10 and d[4] < width - 10 and d[4] - d[1] + 1 < 32
+        assert keep[i] == (not (c1 or c2))
+    tile = np.stack([rng.integers(0, 440, n), rng.integers(0, 150, n), np.zeros(n, np.int64)], axis=1)
+    boxes = bn.nuclei_boxes(dets, tile, norm_side, slices)
+    for i in range(n):
+        w, h, s = tile[i]
+        rel = (dets[i] - np.array([w, h, s, w, h, s, 0]))[:6].astype(int)
+        x1, y1, z1 = max(0, rel[0]), max(0, rel[1]), max(0, rel[2])
+        x2, y2, z2 = min(norm_side - 1, rel[3]), min(norm_side - 1, rel[4]), min(slices - 1, rel[5])
+        assert boxes[i].tolist() == [x1 + w, y1 + h, z1 + s, x2 + w, y2 + h, z2 + s]
+    rows = bn.id_det_rows(boxes[:5], dets[:5, -1], [True, False, True, True, False])
+    assert rows.shape == (3, 8) and rows[:, 0].tolist() == [1.0, 3.0, 4.0] and rows.dtype == np.float32
