@@ -14,9 +14,9 @@
 // Only the voxels inside the volume are computed; they are written as packed uint8 crops (one per detection, C order),
 // from which segm_expand_kernel builds the reference's one-volume-per-detection output where that is wanted.
 //
-// One CTA per (detection, z slab): the padded block lives in shared memory (two float buffers for the Gaussian
+// One CTA per (detection, slice of the crop's (y, x) columns): the padded block lives in shared memory (two float buffers for the Gaussian
 // ping-pong), each thread owns (y, x) columns of the crop -- consecutive threads write consecutive bytes -- and walks the
-// slab in z with the z taps staged in shared memory.  All fp64 arithmetic uses the _rn intrinsics so that nothing is
+// column in z with the z taps staged in shared memory.  All fp64 arithmetic uses the _rn intrinsics so that nothing is
 // contracted into an FMA (scipy's C code is not).
 #include "common.cuh"
 
@@ -81,8 +81,12 @@ __global__ void __launch_bounds__(SG_THREADS) segm_resize_paste_kernel(const flo
     const int z0 = max(bz0, 0), z1 = min(bz1 + 1, im_s);
     const int cw = x1 - x0, ch = y1 - y0, cs = z1 - z0;
     if (cw <= 0 || ch <= 0 || cs <= 0) return;
-    const int zlo = z0 + (int)((long long)cs * blockIdx.y / zsplit), zhi = z0 + (int)((long long)cs * (blockIdx.y + 1) / zsplit);
-    if (zhi <= zlo) return;
+    // the CTAs of one detection split the (y, x) columns of the crop, not its z extent: a thread's per-column setup (two axis
+    // taps, one division) is then amortised over the whole column
+    const int plane = ch * cw;
+    const int col_lo = (int)((long long)plane * blockIdx.y / zsplit), col_hi = (int)((long long)plane * (blockIdx.y + 1) / zsplit);
+    if (col_hi <= col_lo) return;
+    const int zlo = z0, zhi = z1;
 
     // padded block (core/test.py:899, :906-908) + its min / max for the final clip
     const float* src = masks + (size_t)mask_index[d] * (size_t)(M * M * M);
@@ -133,7 +137,6 @@ __global__ void __launch_bounds__(SG_THREADS) segm_resize_paste_kernel(const flo
 
     const double zoom_z = __ddiv_rn((double)M2, (double)os), zoom_y = __ddiv_rn((double)M2, (double)oh), zoom_x = __ddiv_rn((double)M2, (double)ow);
     uint8_t* dst = out + out_off[d];
-    const int plane = ch * cw;
     for (int zc = zlo; zc < zhi; zc += SG_ZT) {
         const int nz = min(SG_ZT, zhi - zc);
         __syncthreads();
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(SG_THREADS) segm_resize_paste_kernel(const flo
             s_zi[2 * k] = t.i0 * M2sq; s_zi[2 * k + 1] = t.i1 * M2sq;
         }
         __syncthreads();
-        for (int col = tid; col < plane; col += SG_THREADS) {
+        for (int col = col_lo + tid; col < col_hi; col += SG_THREADS) {
             const int yy = col / cw, xx = col - yy * cw;
             const AxisTap ty = axis_tap(y0 + yy - by0, zoom_y, M2), tx = axis_tap(x0 + xx - bx0, zoom_x, M2);
             const int o00 = ty.i0 * M2 + tx.i0, o01 = ty.i0 * M2 + tx.i1, o10 = ty.i1 * M2 + tx.i0, o11 = ty.i1 * M2 + tx.i1;

@@ -849,3 +849,29 @@ def test_binarize_nuclei_golden_and_oracle(b2, golden, torch_):
     assert r["status"].tolist() == [2] and not r["seg"].any() and r["survive"].tolist() == [False]
     r = bn.binarize_nuclei_host(np.zeros((8, 16, 16), np.uint8), np.zeros((0, 6), np.int32), [])
     assert not r["seg"].any() and len(r["status"]) == 0
+
+
+def test_config2_sizes_segm_and_nuclei(b2, torch_):
+    """BASELINE configs[1] sizes: 100 detections with 14^3 masks on a 64x200x200 tile (segm_results) and the nuclei chain
+    on a 59x350x640 uint16 volume with 50 large instances -- both against the oracle, bit-exact."""
+    from b200seg import segm, synth, binarization_nuclei as bn
+    rng = np.random.default_rng(2002)
+    n, M, (S, H, W) = 100, 14, (64, 200, 200)
+    lo = np.stack([rng.uniform(-5, W - 30, n), rng.uniform(-5, H - 30, n), rng.uniform(-5, S - 15, n)], axis=1)
+    ext = np.stack([rng.uniform(25, 60, n), rng.uniform(25, 60, n), rng.uniform(10, 40, n)], axis=1)
+    boxes = np.concatenate([lo, lo + ext], axis=1).astype(np.float32)
+    masks = rng.random((n, 2, M, M, M), dtype=np.float32)
+    cls_boxes = [[], np.zeros((n, 7), np.float32)]
+    ref = np.stack(oracle.segm_results(cls_boxes, masks, boxes, S, H, W, num_classes=2)[1])
+    dev = segm.segm_results_device(cls_boxes, torch_.from_numpy(masks).cuda(), boxes, S, H, W, expand=True, num_classes=2)
+    torch_.cuda.synchronize()
+    assert ref.sum() > 1e6 and np.array_equal(dev["volumes"].cpu().numpy(), ref)
+    shape = (59, 350, 640)
+    case = synth.postproc_case(1002, shape=shape, n_blobs=40, n_dup=10, n_false=0, sigma_xy=(10, 15), sigma_z=(4, 7))
+    vol = case["volume"].astype(np.uint16) * 7 + 11
+    off = case["crop_off"]
+    crops = [case["prm"][off[i]:off[i + 1]] for i in range(len(case["boxes"]))]
+    seg, status, survive, _ = oracle.binarize_nuclei(vol, case["boxes"], crops)
+    r = bn.binarize_nuclei_host(vol, case["boxes"], case["prm"])
+    assert r["status"].tolist() == status and r["survive"].tolist() == survive and np.array_equal(r["seg"], seg)
+    assert status.count(0) >= 45 and len(np.unique(seg)) > 40
