@@ -239,10 +239,13 @@ def bench_ops(torch, peak):
     from b200seg import evaluation
     rng_e = np.random.default_rng(21)
     lab_p = np.zeros(SHAPE, np.uint16); lab_g = np.zeros(SHAPE, np.uint16)
+    ev_box_list = []
     for lab, shift in ((lab_p, 0), (lab_g, 3)):
         for i in range(1, 201):
             c = [int(rng_e.integers(8, s - 40)) for s in SHAPE]; e = [int(rng_e.integers(8, 18)), int(rng_e.integers(16, 40)), int(rng_e.integers(16, 40))]
             lab[c[0] + shift:c[0] + e[0], c[1]:c[1] + e[1] + shift, c[2]:c[2] + e[2]] = i
+            if shift == 0:
+                ev_box_list.append([c[2], c[1], c[0], c[2] + e[2] - 1, c[1] + e[1] - 1, c[0] + e[0] - 1])
     tp, tg = torch.from_numpy(lab_p).to(dev), torch.from_numpy(lab_g).to(dev)
     ids = np.arange(1, 201)
     ms = time_op(torch, lambda: evaluation.mask_overlaps_labels(tp, tg, ids, ids), 10, flush)
@@ -297,6 +300,20 @@ def bench_ops(torch, peak):
     ops["binarize_nuclei_59x350x640_u16_50inst"] = entry(ms, 3 * nvox + nvox + 2 * nvol.numel(), {
         "gvox_per_s": nvol.numel() / (ms * 1e-3) / 1e9, "crop_voxels": nvox,
         "note": "14 launches (min/max, normalise, Otsu, 2 x largest component, 2 complements, dilate, erode, paste) + output allocation; latency bound on 50 crops"})
+    # evaluation helpers on a 128x512x512 label volume pair (np.unique replacement; nuclei voxel counts with 200 matched boxes)
+    L_ev = _bl.lib()
+    present = torch.empty(65536, dtype=torch.uint8, device=dev)
+    ms = time_op(torch, lambda: _bl.check(L_ev.b200seg_label_presence_dev(_bl.ptr(tp), tp.numel(), _bl.ptr(present), _bl.current_stream()), "presence"), 20, flush)
+    ops["label_presence_128x512x512"] = entry(ms, 2 * tp.numel(), {"gvox_per_s": tp.numel() / (ms * 1e-3) / 1e9})
+    ev_boxes = torch.from_numpy(np.ascontiguousarray(np.array(ev_box_list, np.int32))).to(dev)
+    ev_counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    ev_wsb = L_ev.b200seg_eval_voxel_counts_workspace_bytes(tp.numel())
+    ev_ws = torch.empty(ev_wsb, dtype=torch.uint8, device=dev)
+    ms = time_op(torch, lambda: _bl.check(L_ev.b200seg_eval_voxel_counts_dev(_bl.ptr(tp), _bl.ptr(tg), SHAPE[0], SHAPE[1], SHAPE[2], _bl.ptr(ev_boxes),
+                                                                             int(ev_boxes.shape[0]), _bl.ptr(ev_counts), _bl.ptr(ev_ws), ev_wsb,
+                                                                             _bl.current_stream()), "voxel_counts"), 20, flush)
+    ops["eval_voxel_counts_128x512x512_200boxes"] = entry(ms, 4 * tp.numel() + tp.numel() // 8, {"gvox_per_s": tp.numel() / (ms * 1e-3) / 1e9,
+                                                                                                "note": "bit-volume memset + box rasterisation + count pass"})
     # RPN proposal generation on the soma test tile: 14 anchors x 16x40x40, pre/post NMS top-N 1000, thresh 0.23
     from b200seg.generate_proposals_3d import GenerateProposalsOp_3d
     A_, S_, H_, W_ = 14, 16, 40, 40

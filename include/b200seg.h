@@ -386,6 +386,22 @@ int b200seg_binarize_nuclei_host(const void* volume, int elem_bytes, int S, int 
                                  const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, int n,
                                  uint16_t* seg, uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive);
 
+/* ----------------------------------------------------------------------------------------------
+ * Evaluation helpers: the volume-sized parts of tools/evaluation/eval_instance_segmentation_soma.py
+ * and tools/evaluation/evaluation_nuclei_f1score_seg.py; the greedy matching on the (few hundred) rows stays on the host.
+ * b200seg_label_presence_dev: present[65536] uint8 (device), present[v] = 1 <=> label v occurs in labels[n] -- replaces
+ *   np.unique(label volume) (eval_instance_segmentation_soma.py:177-181).
+ * b200seg_eval_voxel_counts_dev: counts[3] uint64 (device) = { tp_pixel, gt_pixel, pre_pixel } of
+ *   evaluation_nuclei_f1score_seg.py:86-89 / :124-130: gt_pixel = #(gt > 0), pre_pixel = #(pred > 0),
+ *   tp_pixel = #(pred > 0 and gt > 0 and inside the box of a matched detection); boxes [n_boxes,6] int32 = the matched
+ *   detections' bbox.astype(int), inclusive, clipped to the volume here (device).
+ * ---------------------------------------------------------------------------------------------- */
+int b200seg_label_presence_dev(const uint16_t* labels, long long n, uint8_t* present, b200seg_stream_t stream);
+size_t b200seg_eval_voxel_counts_workspace_bytes(long long n_voxels);
+int b200seg_eval_voxel_counts_dev(const uint16_t* pred, const uint16_t* gt, int S, int H, int W,
+                                  const int32_t* boxes, int n_boxes, unsigned long long* counts,
+                                  void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

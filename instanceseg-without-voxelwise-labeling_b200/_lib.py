@@ -57,6 +57,9 @@ SIGNATURES = {
     "b200seg_binarize_nuclei_workspace_bytes": (_sz, [_i, _ll, _i, _i, _i]),
     "b200seg_binarize_nuclei_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200seg_binarize_nuclei_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "b200seg_label_presence_dev": (_i, [_vp, _ll, _vp, _vp]),
+    "b200seg_eval_voxel_counts_workspace_bytes": (_sz, [_ll]),
+    "b200seg_eval_voxel_counts_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "b200seg_segm_gauss_table_size": (_i, [_i]),
     "b200seg_segm_paste_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _f, _i, _i, _i, _vp, _vp, _vp]),
     "b200seg_segm_expand_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -650,6 +650,64 @@ def binarize_nuclei(volume, boxes, prm_crops):
     return seg, status, survive, masks
 
 
+# ------------------------------------------------------------------------------- evaluation records
+def eval_volume_soma(pred_mask, gt_mask, pred_score, iou_thresh=0.3):
+    """tools/evaluation/eval_instance_segmentation_soma.py:166-216 for one image -> (score list, match list, n_pos)."""
+    pred_score = np.asarray(pred_score, dtype=np.float64).reshape(-1, 2)
+    pred_score = pred_score[pred_score[:, 1].argsort()[::-1], :]
+    score = list(pred_score[:, 1])
+    pred_ids = [v for v in np.unique(pred_mask).tolist() if v != 0]
+    gt_ids = [v for v in np.unique(gt_mask).tolist() if v != 0]
+    if len(pred_score) == 0:
+        return score, [], len(gt_ids)
+    if len(gt_ids) == 0:
+        return score, [0] * len(pred_ids), 0
+    pm = np.stack([pred_mask == i for i in pred_score[:, 0]])
+    gm = np.stack([gt_mask == i for i in gt_ids])
+    iou = mask_overlaps(pm, gm)[0]
+    gt_index = iou.argmax(axis=1)
+    gt_index[iou.max(axis=1) < iou_thresh] = -1
+    selec = np.zeros(len(gt_ids), dtype=bool)
+    match = []
+    for gi in gt_index:
+        if gi >= 0:
+            match.append(0 if selec[gi] else 1)
+            selec[gi] = True
+        else:
+            match.append(0)
+    return score, match, len(gt_ids)
+
+
+def eval_volume_nuclei(pred_mask, gt_mask, dets_bbox, gt_bbox, ovthresh=0.4):
+    """tools/evaluation/evaluation_nuclei_f1score_seg.py:70-131 for one image -> (tp, fp, tp_pixel, gt_pixel, pre_pixel)."""
+    gt_bbox = np.asarray(gt_bbox, dtype=float).reshape(-1, 6)
+    dets_bbox = np.asarray(dets_bbox, dtype=float).reshape(-1, 6)
+    detected = np.zeros(gt_bbox.shape[0], dtype=bool)
+    tp, fp = np.zeros(dets_bbox.shape[0]), np.zeros(dets_bbox.shape[0])
+    gt_b, pred_b = gt_mask > 0, pred_mask > 0
+    keep = np.zeros(pred_mask.shape, dtype=bool)
+    tp_pixel = 0
+    if gt_bbox.shape[0] > 0:
+        for ib, bbox in enumerate(dets_bbox):
+            iw = np.maximum(np.minimum(gt_bbox[:, 3], bbox[3]) - np.maximum(gt_bbox[:, 0], bbox[0]) + 1., 0.)
+            ih = np.maximum(np.minimum(gt_bbox[:, 4], bbox[4]) - np.maximum(gt_bbox[:, 1], bbox[1]) + 1., 0.)
+            iss = np.maximum(np.minimum(gt_bbox[:, 5], bbox[5]) - np.maximum(gt_bbox[:, 2], bbox[2]) + 1., 0.)
+            inters = iw * ih * iss
+            uni = ((bbox[3] - bbox[0] + 1.) * (bbox[4] - bbox[1] + 1.) * (bbox[5] - bbox[2] + 1.) +
+                   (gt_bbox[:, 3] - gt_bbox[:, 0] + 1.) * (gt_bbox[:, 4] - gt_bbox[:, 1] + 1.) * (gt_bbox[:, 5] - gt_bbox[:, 2] + 1.) - inters)
+            overlaps = inters / uni
+            jmax = np.argmax(overlaps)
+            if overlaps[jmax] > ovthresh and not detected[jmax]:
+                tp[ib] = 1.
+                detected[jmax] = True
+                x1, y1, z1, x2, y2, z2 = (max(int(v), 0) for v in bbox.astype(int))
+                keep[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1] = pred_b[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1]
+            else:
+                fp[ib] = 1.
+        tp_pixel = int(np.sum(keep & gt_b))
+    return tp, fp, tp_pixel, int(gt_b.sum()), int(pred_b.sum())
+
+
 # ------------------------------------------------------------------------------- reference builds
 def ref_module(name):
     """Import a reference Cython module built into oracle/_ref (None when it is not there)."""

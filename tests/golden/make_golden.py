@@ -13,6 +13,8 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
   segm.npz      lib/core/test.py:segm_results (its own source, skimage's resize replaced by the scipy.ndimage calls it makes)
   nuclei.npz    tools/binarization_nuclei.py lines 110-139 cut out of the script and executed per crop (cc3d / skimage closing
                 bound to scipy.ndimage)
+  eval.npz      tools/evaluation/eval_instance_segmentation_soma.py (calc_instance_segmentation_voc_prec_rec, voc_ap, unmodified,
+                file IO bound to in-memory volumes) and evaluation_nuclei_f1score_seg.py (per-image body, lines 82-133)
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
@@ -401,7 +403,89 @@ def make_nuclei():
     np.savez_compressed(os.path.join(HERE, "nuclei.npz"), **out)
 
 
+def _eval_images(rng):
+    """two small images: ground-truth / predicted label volumes with shifted, missing and spurious instances + scores + boxes"""
+    imgs = []
+    for k in range(2):
+        S, H, W = 12, 40, 48
+        gt = np.zeros((S, H, W), np.uint16); pred = np.zeros((S, H, W), np.uint16)
+        gt_boxes, det_boxes, score = [], [], []
+        n = 7 + k
+        for i in range(n):
+            z, y, x = int(rng.integers(0, S - 6)), int(rng.integers(0, H - 12)), int(rng.integers(0, W - 12))
+            d, h, w = int(rng.integers(4, 7)), int(rng.integers(7, 12)), int(rng.integers(7, 12))
+            region = gt[z:z + d, y:y + h, x:x + w]
+            region[region == 0] = i + 1
+            gt_boxes.append([x, y, z, x + w - 1, y + h - 1, z + d - 1])
+            if i % 4 != 3:                                            # every fourth instance is missed
+                dz, dy, dx = (int(v) for v in rng.integers(-1, 2, 3))
+                z2, y2, x2 = max(z + dz, 0), max(y + dy, 0), max(x + dx, 0)
+                region = pred[z2:z2 + d, y2:y2 + h, x2:x2 + w]
+                region[region == 0] = 10 + i
+                det_boxes.append([x2, y2, z2, min(x2 + w, W) - 1, min(y2 + h, H) - 1, min(z2 + d, S) - 1])
+                score.append([10 + i, float(rng.random())])
+        pred[0:2, 0:3, W - 4:W][pred[0:2, 0:3, W - 4:W] == 0] = 99   # a spurious prediction
+        det_boxes.append([W - 4, 0, 0, W - 1, 2, 1]); score.append([99, 0.05 + 0.1 * k])
+        present = set(np.unique(pred).tolist())
+        keep = [j for j, sc in enumerate(score) if int(sc[0]) in present]     # fully overwritten predictions carry no score row
+        imgs.append(dict(gt=gt, pred=pred, gt_boxes=np.array(gt_boxes, np.float32), det_boxes=np.array(det_boxes, np.float32)[keep],
+                         score=np.array(score, np.float64)[keep]))
+    return imgs
+
+
+def make_eval():
+    """tools/evaluation/eval_instance_segmentation_soma.py: calc_instance_segmentation_voc_prec_rec + voc_ap run unmodified
+    (skimage.io.imread / np.load bound to in-memory volumes, numba stubbed for mask_iou.py), and
+    tools/evaluation/evaluation_nuclei_f1score_seg.py: the per-image body (file lines 82-133) cut out of the script and executed."""
+    import tempfile
+    import textwrap
+    nb = types.ModuleType("numba"); nb.jit = lambda *a, **k: (lambda f: f); sys.modules["numba"] = nb
+    store = {}
+    sk, skio = types.ModuleType("skimage"), types.ModuleType("skimage.io")
+    skio.imread = lambda path: store[path]
+    sk.io = skio
+    sys.modules["skimage"], sys.modules["skimage.io"] = sk, skio
+    sys.path.insert(0, os.path.join(REF, "tools", "evaluation"))
+    spec = importlib.util.spec_from_file_location("ref_eval_soma", os.path.join(REF, "tools", "evaluation", "eval_instance_segmentation_soma.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(216)
+    imgs = _eval_images(rng)
+    out = {"count": len(imgs)}
+    with tempfile.TemporaryDirectory() as tmp:
+        names = []
+        for k, im in enumerate(imgs):
+            name = "img%d" % k
+            names.append(name)
+            store[os.path.join(tmp, name + ".tif")] = im["pred"]
+            store[os.path.join("gt", name, name + ".tif")] = im["gt"]
+            np.save(os.path.join(tmp, name + ".npy"), im["score"])
+            for key, v in im.items():
+                out["%s_%s" % (name, key)] = v
+        prec, rec = mod.calc_instance_segmentation_voc_prec_rec(tmp, "gt", names, 0.3)
+        _, _, ap = mod.voc_ap(rec, prec, use_07_metric=False)
+    out.update(prec=prec, rec=rec, ap=np.float64(ap))
+    print("soma eval: ap", ap, "rows", len(prec))
+    lines = open(os.path.join(REF, "tools", "evaluation", "evaluation_nuclei_f1score_seg.py")).read().split("\n")
+    body = textwrap.dedent("\n".join(lines[81:133]))                  # file lines 82..133
+    assert body.startswith("tp = np.zeros") and body.rstrip().split("\n")[-1].lstrip().startswith("tp_pixel +=")
+    code = compile(body, "ref_evaluation_nuclei_82_133", "exec")
+    for k, im in enumerate(imgs):
+        store.clear()
+        store["GT"] = im["gt"]; store["PRED"] = im["pred"]
+        io = types.SimpleNamespace(imread=lambda path: store["GT"] if "man_seg" in path else store["PRED"])
+        ns = {"np": np, "os": os, "io": io, "src_path": "s", "res_path": "r", "track": "01", "img_name": "01_t000", "ovthresh": 0.4,
+              "dets_bbox": im["det_boxes"].astype(float), "gt_bbox": im["gt_boxes"].astype(float),
+              "detected": np.zeros(len(im["gt_boxes"]), dtype=bool), "gt_pixel": 0, "pre_pixel": 0, "tp_pixel": 0, "print": lambda *a, **k: None}
+        exec(code, ns)
+        out.update({"img%d_tp" % k: ns["tp"], "img%d_fp" % k: ns["fp"],
+                    "img%d_pixels" % k: np.array([ns["tp_pixel"], ns["gt_pixel"], ns["pre_pixel"]], np.int64)})
+        print("nuclei eval img", k, "tp", int(ns["tp"].sum()), "fp", int(ns["fp"].sum()), "pixels", ns["tp_pixel"], ns["gt_pixel"], ns["pre_pixel"])
+    np.savez_compressed(os.path.join(HERE, "eval.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_eval()
     make_nuclei()
     make_segm()
     make_box_results()

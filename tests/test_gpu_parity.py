@@ -875,3 +875,42 @@ def test_config2_sizes_segm_and_nuclei(b2, torch_):
     r = bn.binarize_nuclei_host(vol, case["boxes"], case["prm"])
     assert r["status"].tolist() == status and r["survive"].tolist() == survive and np.array_equal(r["seg"], seg)
     assert status.count(0) >= 45 and len(np.unique(seg)) > 40
+
+
+# ------------------------------------------------------------------------------------------ evaluation records
+def test_eval_records_golden_and_oracle(b2, golden, torch_):
+    """Label presence, overlap-matrix matching and voxel counts behind eval_volume_soma / eval_volume_nuclei: the fixture
+    produced by the reference's evaluation code, then a 64x256x256 volume pair (BASELINE configs[0] shape) against the oracle."""
+    from b200seg import evaluation as ev, synth
+    from test_oracle_golden import _eval_images
+    g = golden("eval.npz")
+    score, match, n_pos = [], [], 0
+    for im in _eval_images(g):
+        assert np.array_equal(ev.label_ids(im["pred"]), np.unique(im["pred"])[1:])
+        r = ev.eval_volume_soma(im["pred"], im["gt"], im["score"], 0.3)
+        score += r["score"]; match += r["match"]; n_pos += r["n_pos"]
+        n = ev.eval_volume_nuclei(im["pred"], im["gt"], im["det_boxes"], im["gt_boxes"], 0.4)
+        assert np.array_equal(n["tp"], im["tp"]) and np.array_equal(n["fp"], im["fp"])
+        assert [n["tp_pixel"], n["gt_pixel"], n["pre_pixel"]] == im["pixels"].tolist()
+    prec, rec = ev.precision_recall(score, match, n_pos)
+    assert np.array_equal(prec, g["prec"]) and np.array_equal(rec, g["rec"]) and ev.voc_ap(rec, prec) == float(g["ap"])
+    # the chain's own label volume as the prediction, a shifted copy as ground truth
+    case = synth.postproc_case(1001, shape=(64, 256, 256), n_blobs=35, n_dup=10, n_false=5)
+    out = b2.postproc_soma_host(case["volume"], case["dets"], case["boxes"], case["prm"], case["crop_off"], 0.23)
+    pred = out["seg"]
+    ps = out["scores"].astype(np.float64)
+    drop = int(ps[3, 0])
+    gt = np.roll(pred, (1, 2, -2), axis=(0, 1, 2)).copy()
+    gt[gt == drop] = 0                                                     # one ground truth instance removed
+    assert np.array_equal(ev.label_ids(gt), np.unique(gt)[1:])
+    r = ev.eval_volume_soma(pred, gt, ps, 0.3)
+    s0, m0, n0 = oracle.eval_volume_soma(pred, gt, ps, 0.3)
+    assert r["score"] == s0 and r["match"] == m0 and r["n_pos"] == n0 and sum(m0) > 20 and 0 in m0
+    ids = ps[:, 0].astype(int)
+    det_boxes = case["boxes"][out["rank_order"][ids - 1]].astype(np.float32)
+    gt_boxes = det_boxes + np.array([-2, 2, 1, -2, 2, 1], np.float32)
+    gt_boxes = gt_boxes[ids != drop]
+    n = ev.eval_volume_nuclei(pred, gt, det_boxes, gt_boxes, 0.4)
+    tp, fp, tpp, gtp, prp = oracle.eval_volume_nuclei(pred, gt, det_boxes, gt_boxes, 0.4)
+    assert np.array_equal(n["tp"], tp) and np.array_equal(n["fp"], fp) and [n["tp_pixel"], n["gt_pixel"], n["pre_pixel"]] == [tpp, gtp, prp]
+    assert tp.sum() > 20 and fp.sum() >= 1 and 0 < tpp < prp

@@ -263,3 +263,27 @@ def test_nuclei_chain_golden(golden):
         S, H, W = c["img"].shape
         seg, status, survive, masks = oracle.binarize_nuclei(c["img"], np.array([[0, 0, 0, W - 1, H - 1, S - 1]]), [c["prm"]])
         assert status == [0] and survive == [True] and np.array_equal(masks[0], c["mask"]) and np.array_equal(seg > 0, c["mask"]), k
+
+
+# ------------------------------------------------------------------------------------------ evaluation records
+def _eval_images(g):
+    return [dict(gt=g["img%d_gt" % k], pred=g["img%d_pred" % k], gt_boxes=g["img%d_gt_boxes" % k], det_boxes=g["img%d_det_boxes" % k],
+                 score=g["img%d_score" % k], tp=g["img%d_tp" % k], fp=g["img%d_fp" % k], pixels=g["img%d_pixels" % k])
+            for k in range(int(g["count"]))]
+
+
+def test_eval_records_golden(golden):
+    """oracle.eval_volume_soma / eval_volume_nuclei against the reference's evaluation code run on in-memory volumes (fixture)."""
+    g = golden("eval.npz")
+    imgs = _eval_images(g)
+    score, match, n_pos = [], [], 0
+    for im in imgs:
+        s, m, n = oracle.eval_volume_soma(im["pred"], im["gt"], im["score"], 0.3)
+        score += s; match += m; n_pos += n
+        tp, fp, tpp, gtp, prp = oracle.eval_volume_nuclei(im["pred"], im["gt"], im["det_boxes"], im["gt_boxes"], 0.4)
+        assert np.array_equal(tp, im["tp"]) and np.array_equal(fp, im["fp"]) and [tpp, gtp, prp] == im["pixels"].tolist()
+    order = np.asarray(score).argsort()[::-1]
+    m = np.asarray(match, np.int8)[order]
+    tp, fp = np.cumsum(m == 1), np.cumsum(m == 0)
+    assert np.array_equal(tp / (fp + tp), g["prec"]) and np.array_equal(tp / n_pos, g["rec"])
+    assert sum(int(im["tp"].sum()) for im in imgs) >= 4 and sum(int(im["fp"].sum()) for im in imgs) >= 2
