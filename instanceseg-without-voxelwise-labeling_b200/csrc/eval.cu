@@ -11,7 +11,17 @@
 
 namespace b200seg {
 
+// Each CTA collects the labels it sees in a 65536-bit shared-memory bitmap (test before set: the same few labels are seen
+// thousands of times) and publishes the set bits once at the end, so global memory sees at most one byte store per
+// (CTA, label) instead of one per sighting.
 __global__ void __launch_bounds__(256) label_presence_kernel(const uint16_t* __restrict__ lab, long long n, uint8_t* present) {
+    __shared__ uint32_t s_bits[2048];
+    for (int i = threadIdx.x; i < 2048; i += 256) s_bits[i] = 0u;
+    __syncthreads();
+    auto mark = [&](uint32_t a) {
+        const uint32_t bit = 1u << (a & 31);
+        if (!(s_bits[a >> 5] & bit)) atomicOr(&s_bits[a >> 5], bit);
+    };
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long nvec = n >> 3;
     const bool aligned = (reinterpret_cast<uintptr_t>(lab) & 15) == 0;
@@ -24,15 +34,22 @@ __global__ void __launch_bounds__(256) label_presence_kernel(const uint16_t* __r
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t a = w[k] & 0xFFFFu, b = w[k] >> 16;
-                // plain byte stores (benign race: every writer stores 1).  A test-before-set through L2 (__ldcg) was measured
-                // 3x slower: the dependent load costs more than the redundant stores it avoids.
-                if (a != last) { present[a] = 1; last = a; }
-                if (b != last) { present[b] = 1; last = b; }
+                if (a != last) { mark(a); last = a; }
+                if (b != last) { mark(b); last = b; }
             }
         }
     }
     const long long tail0 = aligned ? nvec * 8 : 0;
-    for (long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) present[lab[i]] = 1;
+    for (long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mark(lab[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += 256) {
+        uint32_t m = s_bits[i];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            present[i * 32 + bit] = 1;                                    // benign race: every writer stores 1
+        }
+    }
 }
 
 // one CTA per matched box: set the bits of its voxels (volume-clipped) in `bits` (1 bit per voxel, flat index)
