@@ -438,11 +438,27 @@ __global__ void zs_finish_f32_kernel(const double* __restrict__ part_s, const do
     else stats[1] = sqrt(ts / tn);
 }
 
+// (v - mean) / sd in fp64, rounded to float once (numpy keeps the float64 quotient, the network reads it as float32).
+// Eight elements per thread: one 8- or 16-byte (32-byte for float input) streaming load, two 16-byte streaming stores; the
+// division stays a true fp64 division (bit-identical to numpy for a given mean / sd), its cost hides behind the stores.
 template <typename T>
 __global__ void __launch_bounds__(ZS_THREADS) zs_apply_kernel(const T* __restrict__ in, float* __restrict__ out, long long n, const double* __restrict__ stats) {
     const double mean = stats[0], sd = stats[1];
     const long long stride = (long long)gridDim.x * ZS_THREADS;
-    for (long long i = (long long)blockIdx.x * ZS_THREADS + threadIdx.x; i < n; i += stride)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const long long nvec = aligned ? n >> 3 : 0;
+    for (long long g = (long long)blockIdx.x * ZS_THREADS + threadIdx.x; g < nvec; g += stride) {
+        alignas(16) T v[8];
+        if (sizeof(T) == 1) *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(in + g * 8);
+        else if (sizeof(T) == 2) *reinterpret_cast<uint4*>(v) = ld_stream_u4(in + g * 8);
+        else { reinterpret_cast<uint4*>(v)[0] = ld_stream_u4(in + g * 8); reinterpret_cast<uint4*>(v)[1] = ld_stream_u4(in + g * 8 + 4); }
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = (float)(((double)v[k] - mean) / sd);
+        st_stream_u4(out + g * 8, make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3])));
+        st_stream_u4(out + g * 8 + 4, make_uint4(__float_as_uint(r[4]), __float_as_uint(r[5]), __float_as_uint(r[6]), __float_as_uint(r[7])));
+    }
+    for (long long i = nvec * 8 + (long long)blockIdx.x * ZS_THREADS + threadIdx.x; i < n; i += stride)
         out[i] = (float)(((double)in[i] - mean) / sd);
 }
 
