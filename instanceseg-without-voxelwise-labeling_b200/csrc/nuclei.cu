@@ -123,7 +123,17 @@ __global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* _
 // mask byte -> its complement (0 -> 255, set -> 0)
 __global__ void __launch_bounds__(256) mask_complement_kernel(uint8_t* __restrict__ m, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m[i] = m[i] ? (uint8_t)0 : (uint8_t)255;
+    const long long nvec = (reinterpret_cast<uintptr_t>(m) & 15) == 0 ? n >> 4 : 0;                 // 16 mask bytes per thread
+    auto inv = [](unsigned x) -> unsigned {                  // per byte: 0 -> 0xFF, non-zero -> 0
+        const unsigned t = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;                    // bit 7 = byte != 0
+        return ~((t >> 7) * 0xFFu);
+    };
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < nvec; g += stride) {
+        uint4 v = *reinterpret_cast<const uint4*>(m + g * 16);
+        v.x = inv(v.x); v.y = inv(v.y); v.z = inv(v.z); v.w = inv(v.w);
+        *reinterpret_cast<uint4*>(m + g * 16) = v;
+    }
+    for (long long i = nvec * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m[i] = m[i] ? (uint8_t)0 : (uint8_t)255;
 }
 
 // one half of the binary closing with the 6-neighbour cross, grid (instances, row chunks):

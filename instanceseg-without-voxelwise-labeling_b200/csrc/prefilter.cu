@@ -473,7 +473,15 @@ __global__ void __launch_bounds__(256) prm_minmax_kernel(const float* __restrict
     const float* p = in + (size_t)map * per_map;
     unsigned lo = 0xFFFFFFFFu, hi = 0u;
     const long long stride = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per_map; i += stride) {
+    const long long nvec = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? per_map >> 2 : 0;          // four floats per 128-bit load
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < nvec; g += stride) {
+        const uint4 v = ld_stream_u4(p + g * 4);
+        const unsigned k0 = ordered_key(__uint_as_float(v.x)), k1 = ordered_key(__uint_as_float(v.y));
+        const unsigned k2 = ordered_key(__uint_as_float(v.z)), k3 = ordered_key(__uint_as_float(v.w));
+        lo = min(min(lo, min(k0, k1)), min(k2, k3));
+        hi = max(max(hi, max(k0, k1)), max(k2, k3));
+    }
+    for (long long i = nvec * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < per_map; i += stride) {
         const unsigned k = ordered_key(p[i]);
         lo = min(lo, k);
         hi = max(hi, k);
@@ -497,10 +505,24 @@ __global__ void __launch_bounds__(256) prm_scale_kernel(const float* __restrict_
     const float* p = in + (size_t)map * per_map;
     uint8_t* q = out + (size_t)map * per_map;
     const long long stride = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per_map; i += stride) {
-        const float r = __fmul_rn(__fdiv_rn(__fsub_rn(p[i], mn), mx), 255.0f);
-        q[i] = r == r ? (uint8_t)(int)r : (uint8_t)0;                    // constant map: 0/0 -> 0
+    auto scale = [&](float v) -> unsigned {
+        const float r = __fmul_rn(__fdiv_rn(__fsub_rn(v, mn), mx), 255.0f);
+        return r == r ? (unsigned)(uint8_t)(int)r : 0u;                  // constant map: 0/0 -> 0
+    };
+    // 16 values per thread: four 128-bit streaming loads, one 128-bit streaming store
+    const long long nvec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q)) & 15) == 0 ? per_map >> 4 : 0;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < nvec; g += stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = ld_stream_u4(p + g * 16 + k * 4);
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = scale(__uint_as_float(v[k].x)) | scale(__uint_as_float(v[k].y)) << 8 | scale(__uint_as_float(v[k].z)) << 16 |
+                   scale(__uint_as_float(v[k].w)) << 24;
+        st_stream_u4(q + g * 16, make_uint4(w[0], w[1], w[2], w[3]));
     }
+    for (long long i = nvec * 16 + (long long)blockIdx.x * 256 + threadIdx.x; i < per_map; i += stride) q[i] = (uint8_t)scale(p[i]);
 }
 
 }  // namespace b200seg
