@@ -370,7 +370,24 @@ template <typename T>
 __global__ void __launch_bounds__(ZS_THREADS) zs_sums_int_kernel(const T* __restrict__ in, long long n, unsigned long long* __restrict__ acc) {
     unsigned long long s1 = 0, s2 = 0, cnt = 0;
     const long long stride = (long long)gridDim.x * ZS_THREADS;
-    for (long long i = (long long)blockIdx.x * ZS_THREADS + threadIdx.x; i < n; i += stride) {
+    // one 128-bit streaming load = 16 uint8 / 8 uint16 values; their sum and non-zero count fit 32 bits per group
+    constexpr int PER = 16 / (int)sizeof(T);
+    const long long nvec = (reinterpret_cast<uintptr_t>(in) & 15) == 0 ? n / PER : 0;
+    for (long long g = (long long)blockIdx.x * ZS_THREADS + threadIdx.x; g < nvec; g += stride) {
+        alignas(16) T v[PER];
+        *reinterpret_cast<uint4*>(v) = ld_stream_u4(in + g * PER);
+        unsigned a = 0, c = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const unsigned x = v[k];
+            a += x;
+            c += x != 0;
+            s2 += (unsigned long long)(x * x);                // x <= 65535: the product fits 32 bits
+        }
+        s1 += a;
+        cnt += c;
+    }
+    for (long long i = nvec * PER + (long long)blockIdx.x * ZS_THREADS + threadIdx.x; i < n; i += stride) {
         const unsigned v = in[i];
         s1 += v;
         s2 += (unsigned long long)v * v;

@@ -46,13 +46,21 @@ rle_walk_kernel(const uint8_t* __restrict__ mask, int S, int H, int W, int32_t* 
     int n = 0;
     long long pos = MODE == 1 ? (long long)offs[c] : 0;
     const long long f0 = (long long)c * S;
-    for (int s = 0; s < S; ++s) {
-        const int v = p[(size_t)s * HW] != 0;
-        if (prev >= 0 && v != prev) {
-            if (MODE == 1) { if (pos < cap) starts[pos] = f0 + s; ++pos; }
-            ++n;
+    // eight independent loads in flight per thread (the walk is latency bound: one byte per step and column)
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        uint8_t buf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) buf[k] = s0 + k < S ? p[(size_t)(s0 + k) * HW] : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (s0 + k >= S) break;
+            const int v = buf[k] != 0;
+            if (prev >= 0 && v != prev) {
+                if (MODE == 1) { if (pos < cap) starts[pos] = f0 + s0 + k; ++pos; }
+                ++n;
+            }
+            prev = v;
         }
-        prev = v;
     }
     if (MODE == 0) cnt[c] = n;
 }
