@@ -1,6 +1,6 @@
 // nms3d.cu -- batched 3D greedy NMS on the GPU (replaces lib/utils/cython_nms_3d.pyx:39-159).
 //
-// Three launches per batch of detection sets, no host round trip:
+// Three launches per batch of detection sets (one for sets of at most 64 boxes, nms_small_kernel), no host round trip:
 //   1. nms_rank_kernel   rank sort: rank(i) = #{j : key_j > key_i or (key_j == key_i and j < i)}
 //                        (O(n^2) compares, trivially parallel, deterministic, stable tie rule) and
 //                        scatter of {box, volume, original index} into visit order.
@@ -278,6 +278,70 @@ nms_reduce_kernel(const SortedBox* __restrict__ sorted_all, const unsigned long 
     }
 }
 
+// Sets of at most 64 boxes (the per-class NMS of box_results, config 1's 50 boxes): the three steps in ONE launch, one
+// 64-thread CTA per set -- rank by counting, scatter into visit order in shared memory, one 64-bit suppression word per row,
+// and a 64-step serial resolve by thread 0.  Same arithmetic, tie rule and outputs as the three-kernel path.
+__global__ void __launch_bounds__(64)
+nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ offsets, int by_volume, float thresh,
+                 int64_t* __restrict__ keep, int32_t* __restrict__ keep_count, int32_t* __restrict__ rank_order) {
+    __shared__ uint32_t s_key[64];
+    __shared__ SortedBox s_box[64];
+    __shared__ unsigned long long s_mask[64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int off = offsets[b];
+    const int n = min(offsets[b + 1] - off, 64);            // n_max <= 64 is the caller's promise
+    float my[7];
+    uint32_t ki = 0;
+    float vi = 0.f;
+    if (t < n) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) my[k] = dets[((size_t)off + t) * 7 + k];
+        vi = box_volume_f32(my);
+        ki = ordered_key(by_volume ? vi : my[6]);
+    }
+    s_key[t] = ki;
+    __syncthreads();
+    if (t < n) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t k = s_key[j];
+            rank += (k > ki) || (k == ki && j < t);
+        }
+        SortedBox sb;
+        sb.x1 = my[0]; sb.y1 = my[1]; sb.z1 = my[2]; sb.x2 = my[3]; sb.y2 = my[4]; sb.z2 = my[5];
+        sb.vol = vi; sb.orig = t;
+        s_box[rank] = sb;
+    }
+    __syncthreads();
+    if (t < n) {
+        const SortedBox rbox = s_box[t];
+        unsigned long long word = 0ull;
+        for (int c = t + 1; c < n; ++c)
+            if (suppresses(rbox, s_box[c], thresh)) word |= 1ull << c;
+        s_mask[t] = word;
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long removed = 0ull, flags = 0ull;
+        int nk = 0;
+        for (int r = 0; r < n; ++r) {
+            if ((removed >> r) & 1ull) continue;
+            const int orig = s_box[r].orig;
+            flags |= 1ull << orig;
+            if (rank_order) rank_order[off + nk] = orig;
+            ++nk;
+            removed |= s_mask[r];
+        }
+        keep_count[b] = nk;
+        int pos = 0;
+        while (flags) {                                       // kept ORIGINAL indices, ascending (np.where(suppressed == 0))
+            const int bit = __ffsll((long long)flags) - 1;
+            flags &= flags - 1ull;
+            keep[off + pos++] = (int64_t)bit;
+        }
+    }
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -306,6 +370,11 @@ extern "C" int b200seg_nms3d_dev(const float* dets, const int32_t* offsets, int 
         set_error("nms3d: workspace too small (%zu < %zu)", workspace_bytes,
                   b200seg_nms3d_workspace_bytes(batch, n_max));
         return B200SEG_EWORKSPACE;
+    }
+    if (n_max <= 64) {                                        // small sets: everything in one launch
+        nms_small_kernel<<<batch, 64, 0, stream>>>(dets, offsets, by_volume, thresh, keep, keep_count, rank_order);
+        B200_LAUNCH_CHECK("nms_small_kernel");
+        return 0;
     }
     const int w64 = (n_max + 63) / 64;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
