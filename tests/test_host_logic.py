@@ -160,3 +160,27 @@ def test_nuclei_host_logic():
         assert boxes[i].tolist() == [x1 + w, y1 + h, z1 + s, x2 + w, y2 + h, z2 + s]
     rows = bn.id_det_rows(boxes[:5], dets[:5, -1], [True, False, True, True, False])
     assert rows.shape == (3, 8) and rows[:, 0].tolist() == [1.0, 3.0, 4.0] and rows.dtype == np.float32
+
+
+def test_eval_host_logic_golden(golden):
+    """The host parts of evaluation.py (greedy matching, precision / recall, AP, box matching) against the fixture produced
+    by the reference's evaluation code; no GPU involved (overlaps come from the oracle here)."""
+    import oracle
+    from b200seg import evaluation as ev
+    g = golden("eval.npz")
+    score, match, n_pos = [], [], 0
+    for k in range(int(g["count"])):
+        pred, gt, ps = g["img%d_pred" % k], g["img%d_gt" % k], g["img%d_score" % k]
+        ps = ps[ps[:, 1].argsort()[::-1]]
+        gt_ids = np.unique(gt)[1:]
+        iou = oracle.mask_overlaps(np.stack([pred == i for i in ps[:, 0]]), np.stack([gt == i for i in gt_ids]))[0]
+        m = ev.match_by_iou(iou, 0.3)
+        assert m == oracle.eval_volume_soma(pred, gt, ps, 0.3)[1]
+        score += ps[:, 1].tolist(); match += m; n_pos += len(gt_ids)
+        tp, fp, matched = ev.match_boxes_tp_fp(g["img%d_det_boxes" % k], g["img%d_gt_boxes" % k], 0.4)
+        assert np.array_equal(tp, g["img%d_tp" % k]) and np.array_equal(fp, g["img%d_fp" % k]) and np.array_equal(matched, tp == 1)
+    prec, rec = ev.precision_recall(score, match, n_pos)
+    assert np.array_equal(prec, g["prec"]) and np.array_equal(rec, g["rec"]) and ev.voc_ap(rec, prec) == float(g["ap"])
+    assert ev.match_by_iou(np.zeros((3, 0)), 0.3) == [0, 0, 0]
+    tp, fp, matched = ev.match_boxes_tp_fp(np.zeros((2, 6)), np.zeros((0, 6)), 0.4)
+    assert not tp.any() and not fp.any() and not matched.any()          # the script leaves tp / fp at 0 without ground truth
