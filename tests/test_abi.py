@@ -42,6 +42,20 @@ def test_argument_validation_without_gpu(built_lib):
     assert L.b200seg_nms3d_workspace_bytes(2, 1000) > 2 * 1000 * 16 * 8
     assert L.b200seg_roialign3d_workspace_bytes(512, 8, 32, 32, 7) >= 512 * (32 + 72 * 8 * 4)
     assert L.b200seg_paste_labels_workspace_bytes(2, 128, 512, 512, 800) >= 2 * 8192 * 25 * 4
+    # entry points added later in the round: same contract (negative code + message, empty work is a no-op)
+    assert L.b200seg_segm_paste_dev(None, None, None, 3, 0, None, 0.5, 8, 8, 8, None, None, None) == -1
+    assert b"segm_paste" in L.b200seg_last_error()
+    assert L.b200seg_segm_paste_dev(None, None, None, 0, 14, None, 0.5, 8, 8, 8, None, None, None) == 0
+    assert L.b200seg_segm_paste_dev(None, None, None, 2, 14, None, 0.5, 8, 8, 8, None, None, None) == -1      # null pointers
+    assert L.b200seg_segm_gauss_table_size(14) == 16 * 32
+    assert L.b200seg_segm_expand_dev(None, None, None, 0, 8, 8, 8, None, None) == 0
+    assert L.b200seg_binarize_nuclei_dev(None, 3, 8, 8, 8, None, None, None, 0, 0, None, None, None, None, None, None, 0, None) == -1
+    assert b"binarize_nuclei" in L.b200seg_last_error()
+    assert L.b200seg_binarize_nuclei_workspace_bytes(50, 3000000, 59, 350, 640) > 3000000 * (2 + 2 + 1 + 8)
+    assert L.b200seg_eval_voxel_counts_workspace_bytes(128 * 512 * 512) >= 128 * 512 * 512 // 8
+    assert L.b200seg_eval_voxel_counts_dev(None, None, 8, 8, 8, None, 0, None, None, 0, None) == -1
+    assert L.b200seg_label_presence_dev(None, -1, None, None) == -1
+    assert L.b200seg_largest_cc_ex_dev(None, None, -1, 1, None, 4, None, None, None, None, 1, None, 0, None) == -1
 
 
 def test_no_cpu_fallback():
