@@ -102,8 +102,12 @@ def binarize_nuclei(volume, boxes, prm, crop_off):
 
 
 def id_det_rows(boxes, scores, survive):
-    """:148-151: one float32 row [mask_id, x1, y1, z1, x2, y2, z2, score] per instance whose label survives in the volume."""
-    boxes, scores, survive = np.asarray(boxes), np.asarray(scores), np.asarray(survive, dtype=bool)
-    ids = np.arange(1, len(boxes) + 1)
-    rows = np.concatenate([ids[:, None], boxes, scores[:, None]], axis=1)[survive]
-    return rows.astype(np.float32).reshape(-1, 8)
+    """:148-151: one row [mask_id, x1, y1, z1, x2, y2, z2, score] per instance whose label survives in the volume.  float64 like
+    the array the script saves (np.concatenate promotes its float32 accumulator on the first row; the score is the float32
+    detection score widened)."""
+    boxes, survive = np.asarray(boxes, dtype=np.float64).reshape(-1, 6), np.asarray(survive, dtype=bool)
+    scores = np.asarray(scores, dtype=np.float32).astype(np.float64)
+    ids = np.arange(1, len(boxes) + 1, dtype=np.float64)
+    if not survive.any():
+        return np.zeros((0, 8), dtype=np.float32)              # the script's untouched accumulator
+    return np.concatenate([ids[:, None], boxes, scores[:, None]], axis=1)[survive]

@@ -15,6 +15,7 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
                 bound to scipy.ndimage)
   eval.npz      tools/evaluation/eval_instance_segmentation_soma.py (calc_instance_segmentation_voc_prec_rec, voc_ap, unmodified,
                 file IO bound to in-memory volumes) and evaluation_nuclei_f1score_seg.py (per-image body, lines 82-133)
+  nuclei_script.npz  tools/binarization_nuclei.py lines 73-148 (selection + the whole per-instance loop) executed on one small volume
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
@@ -484,7 +485,72 @@ def make_eval():
     np.savez_compressed(os.path.join(HERE, "eval.npz"), **out)
 
 
+def make_nuclei_script():
+    """tools/binarization_nuclei.py file lines 73-148 (edge filter, nms_3d_volume, score cut, the whole per-instance loop with
+    tile-relative clamping, first-come paste and the survivor table) cut out of the script and executed on one small synthetic
+    volume: PRM tifs are served from memory, otsu is the reference's tools/otsu.py, nms_3d_volume the reference's Cython
+    (oracle/_ref); cc3d / skimage closing are bound to scipy.ndimage as in make_nuclei."""
+    import textwrap
+    from scipy import ndimage as ndi
+    ref_otsu = load_ref_otsu()
+    lines = open(os.path.join(REF, "tools", "binarization_nuclei.py")).read().split("\n")
+    body = textwrap.dedent("\n".join(lines[72:148]))             # file lines 73..148
+    assert body.startswith("# remove broken boxes at edges") and "id_det = np.concatenate" in body.rstrip().split("\n")[-1]
+    code = compile(body, "ref_binarization_nuclei_73_148", "exec")
+    cross = ndi.generate_binary_structure(3, 1)
+    morphology = types.SimpleNamespace(binary_closing=lambda m: ndi.binary_erosion(ndi.binary_dilation(m, structure=cross), structure=cross, border_value=True))
+    connected_components = lambda m: ndi.label(m, structure=np.ones((3, 3, 3), bool))[0]
+    nms_mod = oracle.ref_module("cython_nms_3d")
+    box_utils_3d = types.SimpleNamespace(nms_3d_volume=lambda d, t: nms_mod.nms_3d_volume(np.ascontiguousarray(d, dtype=np.float32), np.float32(t)))
+    from b200seg.binarization import dets_to_boxes, crop_offsets
+    rng = np.random.default_rng(148)
+    S, H, W, norm_side = 16, 160, 256, 64
+    vol = rng.uniform(0, 40, (S, H, W))
+    blobs, bx = [], []
+    zz, yy, xx = np.ogrid[:S, :H, :W]
+    for gy in (40, 120):
+        for gx in (32, 96, 160, 224):
+            cz, cy, cx = 8 + rng.uniform(-1, 1), gy + rng.uniform(-6, 6), gx + rng.uniform(-6, 6)
+            sz, sxy, amp = rng.uniform(2.5, 3.5), rng.uniform(8, 10), rng.uniform(120, 200)
+            vol += amp * np.exp(-0.5 * (((zz - cz) / sz) ** 2 + ((yy - cy) / sxy) ** 2 + ((xx - cx) / sxy) ** 2))
+            blobs.append(dict(c=(cz, cy, cx), sz=sz, sxy=sxy, amp=amp))
+            bx.append([cx - 2 * sxy, cy - 2 * sxy, cz - 2 * sz, cx + 2 * sxy, cy + 2 * sxy, cz + 2 * sz])
+    owners = list(range(8)) + [1, 5] + [0, 3]
+    bx = np.array(bx)
+    allb = np.concatenate([bx, bx[[1, 5]] + rng.uniform(-2, 2, (2, 6)), np.array([[100., 60., 2., 140., 100., 9.], [200., 20., 5., 236., 58., 12.]])])
+    scores = np.array([0.9, 0.5, 0.8, 0.3, 0.7, 0.95, 0.6, 0.45, 0.55, 0.35, 0.25, 0.85])   # the false box with a constant PRM crop stays below the 0.4 cut (the script divides 0 by 0 there)
+    dets = np.hstack([allb, scores[:, None]]).astype(np.float32)
+    img = (np.clip(vol, 0, 255).astype(np.uint8) // 32 * 32).astype(np.uint8)       # coarse gray levels: a small fixture
+    boxes0 = dets_to_boxes(dets, (S, H, W))
+    off0 = crop_offsets(boxes0)
+    c = dict(boxes=boxes0, crop_off=off0, prm=np.concatenate([synth.prm_crop(blobs[owners[i]], boxes0[i]).ravel() for i in range(len(dets))]))
+    n = len(dets)
+    # tile of every detection: the 32-aligned tile origin that keeps the box centre inside
+    cx, cy = (dets[:, 0] + dets[:, 3]) / 2, (dets[:, 1] + dets[:, 4]) / 2
+    tw = np.clip((cx // 32 - 1) * 32, 0, W - norm_side).astype(int)
+    th = np.clip((cy // 32 - 1) * 32, 0, H - norm_side).astype(int)
+    instance_idex = np.stack([np.arange(n), np.zeros(n, int), tw, th, np.zeros(n, int)], axis=1).astype(int)
+    tiles = np.zeros((n, S, norm_side, norm_side), np.uint8)
+    for i in range(n):                                            # the PRM "tif" of instance i: its response inside its tile
+        ob, full = c["boxes"][i], None
+        full = c["prm"][c["crop_off"][i]:c["crop_off"][i + 1]].reshape(ob[5] - ob[2] + 1, ob[4] - ob[1] + 1, ob[3] - ob[0] + 1)
+        for z in range(ob[2], ob[5] + 1):
+            for y in range(max(ob[1], th[i]), min(ob[4] + 1, th[i] + norm_side)):
+                x0, x1 = max(ob[0], tw[i]), min(ob[3] + 1, tw[i] + norm_side)
+                if x1 > x0:
+                    tiles[i, z, y - th[i], x0 - tw[i]:x1 - tw[i]] = full[z - ob[2], y - ob[1], x0 - ob[0]:x1 - ob[0]]
+    io = types.SimpleNamespace(imread=lambda path: tiles[int(path.split("/")[-2])].copy())
+    ns = {"np": np, "os": os, "io": io, "dets": dets.copy(), "instance_idex": instance_idex.copy(), "width": W, "nms_thresh": 0.15,
+          "img": img, "norm_side": norm_side, "slices": S, "prm_path": "p", "img_name": "x", "box_utils_3d": box_utils_3d,
+          "otsu_py_2d_fast": ref_otsu.otsu_py_2d_fast, "connected_components": connected_components, "morphology": morphology}
+    exec(code, ns)
+    print("nuclei script: visited", len(ns["dets"]), "of", n, "kept rows", ns["id_det"].shape, "labels", len(np.unique(ns["seg"])) - 1)
+    np.savez_compressed(os.path.join(HERE, "nuclei_script.npz"), img=img, dets=dets, instance_idex=instance_idex, tiles=tiles,
+                        cfg=np.array([W, norm_side, S]), seg=ns["seg"], id_det=ns["id_det"], visited_dets=ns["dets"])
+
+
 if __name__ == "__main__":
+    make_nuclei_script()
     make_eval()
     make_nuclei()
     make_segm()

@@ -914,3 +914,16 @@ def test_eval_records_golden_and_oracle(b2, golden, torch_):
     tp, fp, tpp, gtp, prp = oracle.eval_volume_nuclei(pred, gt, det_boxes, gt_boxes, 0.4)
     assert np.array_equal(n["tp"], tp) and np.array_equal(n["fp"], fp) and [n["tp_pixel"], n["gt_pixel"], n["pre_pixel"]] == [tpp, gtp, prp]
     assert tp.sum() > 20 and fp.sum() >= 1 and 0 < tpp < prp
+
+
+def test_nuclei_script_golden_cuda(b2, golden):
+    """binarization_nuclei.py:73-148 executed from the reference file (fixture) against the CUDA path end to end:
+    selection with the GPU NMS by volume, clamped boxes, the per-instance chain, label volume and survivor table."""
+    from b200seg import binarization_nuclei as bn
+    from test_oracle_golden import _nuclei_script_inputs
+    g = golden("nuclei_script.npz")
+    sel, boxes, crops = _nuclei_script_inputs(g, b2.nms_3d_volume)
+    assert np.array_equal(g["dets"][sel], g["visited_dets"])
+    r = bn.binarize_nuclei_host(g["img"], boxes, crops)
+    assert r["status"].tolist() == [0] * len(sel) and np.array_equal(r["seg"], g["seg"])
+    assert np.array_equal(bn.id_det_rows(boxes, g["dets"][sel, -1], r["survive"]), g["id_det"])

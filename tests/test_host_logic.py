@@ -159,7 +159,7 @@ def test_nuclei_host_logic():
         x2, y2, z2 = min(norm_side - 1, rel[3]), min(norm_side - 1, rel[4]), min(slices - 1, rel[5])
         assert boxes[i].tolist() == [x1 + w, y1 + h, z1 + s, x2 + w, y2 + h, z2 + s]
     rows = bn.id_det_rows(boxes[:5], dets[:5, -1], [True, False, True, True, False])
-    assert rows.shape == (3, 8) and rows[:, 0].tolist() == [1.0, 3.0, 4.0] and rows.dtype == np.float32
+    assert rows.shape == (3, 8) and rows[:, 0].tolist() == [1.0, 3.0, 4.0] and rows.dtype == np.float64
 
 
 def test_eval_host_logic_golden(golden):

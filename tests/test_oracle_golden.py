@@ -287,3 +287,35 @@ def test_eval_records_golden(golden):
     tp, fp = np.cumsum(m == 1), np.cumsum(m == 0)
     assert np.array_equal(tp / (fp + tp), g["prec"]) and np.array_equal(tp / n_pos, g["rec"])
     assert sum(int(im["tp"].sum()) for im in imgs) >= 4 and sum(int(im["fp"].sum()) for im in imgs) >= 2
+
+
+def _nuclei_script_inputs(g, nms_volume):
+    """Selection (:72-87), clamped boxes (:96-106) and PRM crops of the fixture volume, through the package's host helpers;
+    nms_volume = the NMS to use (oracle on CPU, CUDA on the GPU)."""
+    from b200seg import binarization_nuclei as bn
+    dets, idx5, tiles = g["dets"], g["instance_idex"], g["tiles"]
+    W, norm_side, S = (int(v) for v in g["cfg"])
+    sel = np.nonzero(bn.nuclei_edge_filter(dets, W))[0]
+    d = np.ascontiguousarray(dets[sel], dtype=np.float32)
+    keep = np.asarray(nms_volume(d, 0.15), dtype=np.int64)
+    sel, d = sel[keep], d[keep]
+    sel = sel[d[:, -1] > 0.4]
+    boxes = bn.nuclei_boxes(dets[sel], idx5[sel][:, 2:5], norm_side, S)
+    crops = []
+    for i, b in zip(sel, boxes):
+        w, h = idx5[i, 2], idx5[i, 3]
+        crops.append(np.ascontiguousarray(tiles[idx5[i, 0]][b[2]:b[5] + 1, b[1] - h:b[4] - h + 1, b[0] - w:b[3] - w + 1]))
+    return sel, boxes, crops
+
+
+def test_nuclei_script_golden(golden):
+    """binarization_nuclei.py:73-148 executed from the reference file (selection, tile-relative clamping, per-instance chain,
+    first-come paste, survivor table) against the host helpers + the oracle chain."""
+    from b200seg import binarization_nuclei as bn
+    g = golden("nuclei_script.npz")
+    sel, boxes, crops = _nuclei_script_inputs(g, oracle.nms_3d_volume)
+    assert np.array_equal(g["dets"][sel], g["visited_dets"]) and len(sel) >= 6
+    seg, status, survive, _ = oracle.binarize_nuclei(g["img"], boxes, crops)
+    assert status == [0] * len(sel) and np.array_equal(seg, g["seg"])
+    rows = bn.id_det_rows(boxes, g["dets"][sel, -1], survive)
+    assert rows.dtype == g["id_det"].dtype and np.array_equal(rows, g["id_det"])
