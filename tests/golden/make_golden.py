@@ -16,6 +16,7 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
   eval.npz      tools/evaluation/eval_instance_segmentation_soma.py (calc_instance_segmentation_voc_prec_rec, voc_ap, unmodified,
                 file IO bound to in-memory volumes) and evaluation_nuclei_f1score_seg.py (per-image body, lines 82-133)
   nuclei_script.npz  tools/binarization_nuclei.py lines 73-148 (selection + the whole per-instance loop) executed on one small volume
+  soma_script.npz    tools/binarization_soma.py lines 57-104 (NMS, visit order, the whole per-instance loop, score table) executed on one small volume
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
 The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
@@ -549,7 +550,49 @@ def make_nuclei_script():
                         cfg=np.array([W, norm_side, S]), seg=ns["seg"], id_det=ns["id_det"], visited_dets=ns["dets"])
 
 
+def make_soma_script():
+    """tools/binarization_soma.py file lines 57-104 (nms_3d, visit in descending score, mask_id bookkeeping, the per-instance
+    loop with tile crops, normalisation, otsu_py_2d_fast, largest component, first-come paste and the score table) cut out of
+    the script and executed on one small synthetic volume: PRM tifs served from memory, nms_3d = the reference's Cython
+    (oracle/_ref), otsu = the reference's tools/otsu.py; skimage.measure.label bound to scipy.ndimage.label (3x3x3)."""
+    import textwrap
+    from scipy import ndimage as ndi
+    ref_otsu = load_ref_otsu()
+    lines = open(os.path.join(REF, "tools", "binarization_soma.py")).read().split("\n")
+    body = textwrap.dedent("\n".join(lines[56:104]))             # file lines 57..104
+    assert body.startswith("keep = box_utils_3d.nms_3d(dets, nms_thresh)") and body.rstrip().split("\n")[-1].lstrip().startswith("scores = np.concatenate")
+    code = compile(body, "ref_binarization_soma_57_104", "exec")
+    nms_mod = oracle.ref_module("cython_nms_3d")
+    box_utils_3d = types.SimpleNamespace(nms_3d=lambda d, t: nms_mod.nms_3d(np.ascontiguousarray(d, dtype=np.float32), np.float32(t)))
+    label = lambda m: ndi.label(m, structure=np.ones((3, 3, 3), bool))[0]
+    rng = np.random.default_rng(104)
+    shape = (40, 120, 144)
+    c = synth.postproc_case(104, shape=shape, n_blobs=9, n_dup=4, n_false=3)
+    img = (c["volume"] // 32 * 32).astype(np.uint8)               # coarse gray levels: a small fixture
+    dets, n = c["dets"], len(c["dets"])
+    # tile origins like the script's (ws, hs, ss): any tile that contains the box will do
+    b = c["boxes"]
+    ws = np.minimum(b[:, 0] // 48 * 48, 48); hs = np.minimum(b[:, 1] // 40 * 40, 40); ss = np.minimum(b[:, 2] // 16 * 16, 16)
+    instance_idex = np.stack([np.arange(n), np.zeros(n, int), ws, hs, ss], axis=1).astype(int)
+    tiles = []
+    for i in range(n):                                            # the PRM "tif" of instance i = its response inside its tile
+        t = np.zeros((min(64, shape[0] - ss[i]), min(160, shape[1] - hs[i]), min(160, shape[2] - ws[i])), np.uint8)
+        ob = b[i]
+        full = c["prm"][c["crop_off"][i]:c["crop_off"][i + 1]].reshape(ob[5] - ob[2] + 1, ob[4] - ob[1] + 1, ob[3] - ob[0] + 1)
+        t[ob[2] - ss[i]:ob[5] + 1 - ss[i], ob[1] - hs[i]:ob[4] + 1 - hs[i], ob[0] - ws[i]:ob[3] + 1 - ws[i]] = full
+        tiles.append(t)
+    io = types.SimpleNamespace(imread=lambda path: tiles[int(path.split("/")[-2])].copy())
+    ns = {"np": np, "os": os, "io": io, "dets": dets.copy(), "instance_idex": instance_idex.copy(), "nms_thresh": 0.23, "img": img,
+          "seg": np.zeros(img.shape, np.uint16), "mask_id": 0, "prm_path": "p", "im_name": "x", "box_utils_3d": box_utils_3d,
+          "otsu_py_2d_fast": ref_otsu.otsu_py_2d_fast, "label": label}
+    exec(code, ns)
+    print("soma script: visited", len(ns["dets"]), "of", n, "score rows", ns["scores"].shape, "labels", len(np.unique(ns["seg"])) - 1)
+    np.savez_compressed(os.path.join(HERE, "soma_script.npz"), img=img, dets=dets, boxes=c["boxes"], prm=c["prm"], crop_off=c["crop_off"],
+                        seg=ns["seg"], scores=ns["scores"], visited_dets=ns["dets"])
+
+
 if __name__ == "__main__":
+    make_soma_script()
     make_nuclei_script()
     make_eval()
     make_nuclei()

@@ -927,3 +927,13 @@ def test_nuclei_script_golden_cuda(b2, golden):
     r = bn.binarize_nuclei_host(g["img"], boxes, crops)
     assert r["status"].tolist() == [0] * len(sel) and np.array_equal(r["seg"], g["seg"])
     assert np.array_equal(bn.id_det_rows(boxes, g["dets"][sel, -1], r["survive"]), g["id_det"])
+
+
+def test_soma_script_golden_cuda(b2, golden):
+    """binarization_soma.py:57-104 executed from the reference file (fixture) against the CUDA chain through the host entry:
+    visit order, label volume and the [[id, score]] table."""
+    g = golden("soma_script.npz")
+    out = b2.postproc_soma_host(g["img"], g["dets"], g["boxes"], g["prm"], g["crop_off"], 0.23)
+    assert np.array_equal(g["dets"][out["rank_order"]], g["visited_dets"])
+    assert np.array_equal(out["seg"], g["seg"])
+    assert np.array_equal(out["scores"].astype(np.float64), g["scores"])

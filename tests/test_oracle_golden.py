@@ -319,3 +319,19 @@ def test_nuclei_script_golden(golden):
     assert status == [0] * len(sel) and np.array_equal(seg, g["seg"])
     rows = bn.id_det_rows(boxes, g["dets"][sel, -1], survive)
     assert rows.dtype == g["id_det"].dtype and np.array_equal(rows, g["id_det"])
+
+
+def test_soma_script_golden(golden):
+    """binarization_soma.py:57-104 executed from the reference file (NMS, descending-score visit order, mask ids that count
+    skipped instances, tile crops, normalisation, Otsu, largest component, first-come paste, score table) against the
+    oracle chain the GPU tests use as their checker."""
+    from helpers import oracle_chain
+    g = golden("soma_script.npz")
+    case = dict(volume=g["img"], dets=g["dets"], boxes=g["boxes"], prm=g["prm"], crop_off=g["crop_off"])
+    oc = oracle_chain(case, nms_thresh=0.23, keep_largest_cc=True)
+    assert np.array_equal(g["dets"][oc["order"]], g["visited_dets"])
+    assert np.array_equal(oc["seg"], g["seg"]) and len(np.unique(g["seg"])) > 6
+    alive = np.asarray(oc["survive"][:len(oc["order"])], bool)
+    ids = np.arange(1, len(oc["order"]) + 1)[alive]
+    rows = np.stack([ids.astype(np.float64), g["dets"][oc["order"], 6][alive].astype(np.float64)], axis=1)
+    assert np.array_equal(rows, g["scores"]) and 3 in oc["status"].values()          # an empty-PRM instance was skipped
