@@ -19,7 +19,7 @@ oracle/build_ref.py):   python tests/golden/make_golden.py
   soma_script.npz    tools/binarization_soma.py lines 57-104 (NMS, visit order, the whole per-instance loop, score table) executed on one small volume
   mask_iou.npz  tools/evaluation/mask_iou.py (mask_iou, mask_iou_fast, mask_ios_fast, mask_iog_fast) run as plain
                 Python with numba stubbed, on stacks cut out of two small label volumes
-The fixtures are small (< 1 MB total) and are what `-m "not gpu"` tests pin the oracle against and
+The fixtures are small (about 2 MB in total) and are what `-m "not gpu"` tests pin the oracle against and
 what the `-m gpu` tests pin the CUDA path against on the GPU box (no /root/reference there).
 """
 import importlib.util
