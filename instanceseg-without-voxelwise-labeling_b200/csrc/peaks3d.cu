@@ -3,40 +3,48 @@
 //
 // The reference runs pad(-inf) -> max_pool3d(return_indices) -> (indices == own index) ->
 // (input >= median) -> nonzero, i.e. five full-volume torch kernels plus an int64 index volume.
-// Here:
-//   peaks_scan_kernel    one pass over the map: halo tile in shared memory, the ATen arg-max rule
-//                        evaluated directly as a raster-order-aware local-max predicate ("earlier
-//                        neighbours strictly smaller, later neighbours not larger"), candidate bits
-//                        OR-ed into a 1 bit/voxel mask, and the level-1 (top 12 key bits) radix
-//                        histogram for the exact median accumulated in shared memory.
-//   peaks_refine_kernel  two more radix levels (12 + 8 bits) with 128-bit streaming loads; every CTA
-//                        re-derives the previous level's selected bin from the global histogram
-//                        (no separate "select" launches).
-//   peaks_filter_kernel  applies input >= threshold to the candidate bits, counts per chunk and
-//                        accumulates the aggregation partial sums (deterministic order).
-//   peaks_offsets_kernel exclusive scan of the chunk counts, final aggregation, total count.
-//   peaks_emit_kernel    expands bits to (b,a,z,y,x) int64 rows in lexicographic order --
-//                        ordered stream compaction, no sort, no int64 index volume.
+// Here (round 2 layout: one memset + four launches, no host round trip, every map of the batch per launch):
+//   peaks_scan3_kernel     window 3: one pass over the maps with NO shared-memory tile.  A warp owns a strip of
+//                          32 x-positions x 4 rows and marches along z; rows arrive as coalesced 128-byte loads
+//                          straight into registers, x-neighbours by warp shuffle, and the ATen arg-max rule is
+//                          evaluated on ordered integer keys with three-input maxima.  The candidate bits of a row
+//                          are one warp ballot = one 32-bit word of the 1 bit/voxel mask (plain store), and the
+//                          level-1 (top 12 key bits) radix histogram of the exact median lives in shared memory.
+//                          The last CTA of each map selects the level-1 bin (no separate select launch).
+//   peaks_scan_kernel<5|7> generic halo-tile kernel for the larger windows.
+//   peaks_refine_kernel    two more radix levels (12 + 8 bits) over the L2-resident maps with 128-bit streaming
+//                          loads; the last CTA of a map selects the next prefix / the final threshold.
+//   peaks_finalize_kernel  filter (input >= threshold) + count + single-pass chained scan (decoupled look-back,
+//                          work items handed out by ticket) + ordered emission of the (b,a,z,y,x) int64 rows +
+//                          aggregation partial sums; the last CTA reduces them per map in a fixed order.
 // Exact lower median = element of rank (V-1)/2 of the ascending order (torch.median).
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace b200seg {
 
 constexpr int PK_TX = 32, PK_TY = 8, PK_TZ = 8;
 constexpr int PK_THREADS = 256;
+constexpr int PK_NW = PK_THREADS / 32;
 constexpr int PK_BINS1 = 4096;
-constexpr int PK_CHUNK_WORDS = 1024;               // bitmask words (32 voxels each) per filter/emit CTA
+constexpr int PK_CHUNK_WORDS = 1024;               // bitmask words (32 voxels each) per finalize work item: four per thread
+constexpr int PK_RF_THREADS = 512;                 // refine kernels
 
 struct PeakWs {
-    uint32_t* hist1;      // [BA][4096]
-    uint32_t* hist2;      // [BA][4096]
-    uint32_t* hist3;      // [BA][256]
-    uint32_t* nan_cnt;    // [BA]
+    uint32_t* hist1;      // [BA][4096]   key bits 31..20
+    uint32_t* hist2;      // [BA][4096]   key bits 19..8 of the members of the level-1 bin
+    uint32_t* hist3;      // [BA][256]    key bits 7..0 of the members of the level-2 bin
+    uint32_t* ticket;     // [BA][4]      per-map CTA tickets of the scan / refine<2> / refine<3> kernels
+    uint32_t* gticket;    // [4]          finalize: work-item ticket, done counter
+    unsigned long long* look;   // [BA * nchunks]  look-back state of the chained scan (flag << 62 | count)
     uint32_t* bits;       // [BA][words]
+    unsigned long long* sel;    // [BA][2]  (prefix, remaining rank) handed from one radix level to the next
+    uint32_t* list;       // [BA][list_cap]  low 20 key bits of the members of the level-1 bin (list mode)
+    uint32_t* list_n;     // [BA]  (zeroed per call)
+    long long list_cap;
     uint32_t* chunk_cnt;  // [BA][nchunks]
     float* chunk_sum;     // [BA][nchunks]
-    uint32_t* chunk_off;  // [BA][nchunks]
     float* thr;           // [BA]
     size_t zero_bytes;    // prefix of the workspace that must be cleared per call
     size_t total_bytes;
@@ -52,28 +60,42 @@ static PeakWs peak_layout(void* base, int BA, long long V) {
     w.hist1 = (uint32_t*)take((size_t)BA * PK_BINS1 * 4);
     w.hist2 = (uint32_t*)take((size_t)BA * PK_BINS1 * 4);
     w.hist3 = (uint32_t*)take((size_t)BA * 256 * 4);
-    w.nan_cnt = (uint32_t*)take((size_t)BA * 4);
+    w.ticket = (uint32_t*)take((size_t)BA * 4 * 4);
+    w.gticket = (uint32_t*)take(16);
+    w.list_n = (uint32_t*)take((size_t)BA * 4);
+    w.look = (unsigned long long*)take((size_t)BA * w.nchunks * 8);
     w.bits = (uint32_t*)take((size_t)BA * w.words * 4);
     w.zero_bytes = (size_t)(p - (char*)base);
+    w.sel = (unsigned long long*)take((size_t)BA * 2 * 8);
     w.chunk_cnt = (uint32_t*)take((size_t)BA * w.nchunks * 4);
     w.chunk_sum = (float*)take((size_t)BA * w.nchunks * 4);
-    w.chunk_off = (uint32_t*)take((size_t)BA * w.nchunks * 4);
     w.thr = (float*)take((size_t)BA * 4);
+    // member list of the level-1 bin: room for a quarter of the map (a map whose median bin holds more falls back to
+    // full passes over the map, decided on the device)
+    w.list_cap = V < 65536 ? V : (V / 4 < 65536 ? 65536 : (V / 4 > 131072 ? 131072 : V / 4));
+    w.list = (uint32_t*)take((size_t)BA * (size_t)w.list_cap * 4);
     w.total_bytes = (size_t)(p - (char*)base);
     return w;
 }
 
-// Finds the bin holding ascending rank k in hist[nbins]; returns bin and the rank inside it.
-// Must be called by all PK_THREADS threads; s_tmp has PK_THREADS+2 entries.  Block-wide prefix sum of per-thread
-// bin groups (warp shuffles + one shared-memory hop); the single thread whose group contains rank k resolves it.
-__device__ void select_bin(const uint32_t* __restrict__ hist, int nbins, unsigned long long k,
+// Finds the bin holding ascending rank k in hist[nbins] (read through L2: the counts were produced by atomics of
+// other CTAs); returns bin and the rank inside it.  Must be called by all NT threads of the CTA; s_tmp has NT/32+2
+// entries.  Block-wide prefix sum of per-thread bin groups (warp shuffles + one shared-memory hop); the single
+// thread whose group contains rank k resolves it.
+template <int NT>
+__device__ void select_bin(const uint32_t* hist, int nbins, unsigned long long k,
                            unsigned long long* s_tmp, int* out_bin, unsigned long long* out_k) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = PK_THREADS / 32;
-    const int per = (nbins + PK_THREADS - 1) / PK_THREADS;
-    const int b0 = min(nbins, tid * per), b1 = min(nbins, b0 + per);
+    constexpr int NW = NT / 32;
+    constexpr int PER = (PK_BINS1 + NT - 1) / NT;          // nbins <= PK_BINS1: a thread's bins sit in registers
+    const int per = (nbins + NT - 1) / NT;
+    const int b0 = min(nbins, tid * per);
+    uint32_t h[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) h[j] = (j < per && b0 + j < nbins) ? __ldcg(hist + b0 + j) : 0u;     // independent loads
     unsigned long long local = 0;
-    for (int b = b0; b < b1; ++b) local += hist[b];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) local += h[j];
     unsigned long long incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -89,7 +111,11 @@ __device__ void select_bin(const uint32_t* __restrict__ hist, int nbins, unsigne
     if (k >= excl && k < excl + local) {                   // exactly one thread (groups are disjoint, local > 0 here)
         unsigned long long acc = excl;
         int b = b0;
-        for (; b < b1; ++b) { const unsigned long long h = hist[b]; if (acc + h > k) break; acc += h; }
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (!done) { if (acc + h[j] > k) done = true; else { acc += h[j]; ++b; } }
+        }
         s_tmp[NW] = (unsigned long long)b;
         s_tmp[NW + 1] = k - acc;
     }
@@ -97,6 +123,78 @@ __device__ void select_bin(const uint32_t* __restrict__ hist, int nbins, unsigne
     *out_bin = (int)s_tmp[NW];
     *out_k = s_tmp[NW + 1];
     __syncthreads();
+}
+
+template <int NT>
+__device__ void select_bin_smem(const uint32_t* hist, int nbins, unsigned long long k,
+                           unsigned long long* s_tmp, int* out_bin, unsigned long long* out_k) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    constexpr int PER = (PK_BINS1 + NT - 1) / NT;          // nbins <= PK_BINS1: a thread's bins sit in registers
+    const int per = (nbins + NT - 1) / NT;
+    const int b0 = min(nbins, tid * per);
+    uint32_t h[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) h[j] = (j < per && b0 + j < nbins) ? hist[b0 + j] : 0u;     // independent loads
+    unsigned long long local = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) local += h[j];
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    if (tid == 0) { s_tmp[NW] = (unsigned long long)(nbins - 1); s_tmp[NW + 1] = 0ull; }   // fallback: rank beyond the total
+    __syncthreads();
+    unsigned long long before = 0;
+    for (int w = 0; w < warp; ++w) before += s_tmp[w];
+    const unsigned long long excl = before + incl - local;
+    if (k >= excl && k < excl + local) {                   // exactly one thread (groups are disjoint, local > 0 here)
+        unsigned long long acc = excl;
+        int b = b0;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (!done) { if (acc + h[j] > k) done = true; else { acc += h[j]; ++b; } }
+        }
+        s_tmp[NW] = (unsigned long long)b;
+        s_tmp[NW + 1] = k - acc;
+    }
+    __syncthreads();
+    *out_bin = (int)s_tmp[NW];
+    *out_k = s_tmp[NW + 1];
+    __syncthreads();
+}
+
+// "last CTA of the map" protocol: every CTA adds its shared-memory histogram to the map's global one, then takes
+// a ticket; the CTA that draws the last ticket sees every contribution (fence + atomics are ordered through L2).
+template <int NT>
+__device__ bool flush_hist_and_vote(const uint32_t* s_hist, int nbins, uint32_t* gh, uint32_t* ticket, int* s_flag) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += NT) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&gh[i], c); }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u);
+        *s_flag = (t == gridDim.x - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+// epilogue of the scan kernels: publish the level-1 histogram; the last CTA selects the bin of the median
+template <int NT = PK_THREADS>
+__device__ void flush_level1(const uint32_t* s_hist, int ba, long long V, PeakWs ws) {
+    __shared__ unsigned long long s_tmp[NT / 32 + 2];
+    __shared__ int s_flag;
+    uint32_t* gh = ws.hist1 + (size_t)ba * PK_BINS1;
+    if (!flush_hist_and_vote<NT>(s_hist, PK_BINS1, gh, ws.ticket + ba * 4 + 0, &s_flag)) return;
+    int bin1; unsigned long long k1;
+    select_bin<NT>(gh, PK_BINS1, (unsigned long long)((V - 1) / 2), s_tmp, &bin1, &k1);
+    if (threadIdx.x == 0) { ws.sel[ba * 2] = (unsigned long long)bin1; ws.sel[ba * 2 + 1] = k1; }
 }
 
 template <int WIN>
@@ -113,7 +211,6 @@ peaks_scan_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x
     uint32_t* bits = ws.bits + (size_t)ba * ws.words;
     const int tid = threadIdx.x, lane = tid & 31;
     if (do_hist) for (int i = tid; i < PK_BINS1; i += PK_THREADS) s_hist[i] = 0u;
-    unsigned nan_local = 0;
     const int ntiles = tiles_x * tiles_y * tiles_z;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, tz = tile / (tiles_x * tiles_y);
@@ -153,7 +250,6 @@ peaks_scan_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x
             }
             if (do_hist) {                                   // warp-uniform: every lane reaches the match
                 const uint32_t bin = inb ? (ordered_key(v) >> 20) : 0xFFFFFFFFu;
-                if (inb && v != v) ++nan_local;
                 // warp aggregation for the contended case (all lanes in one bin); otherwise plain atomics
                 const uint32_t b0 = __shfl_sync(0xffffffffu, bin, 0);
                 if (__all_sync(0xffffffffu, bin == b0)) { if (lane == 0 && b0 != 0xFFFFFFFFu) atomicAdd(&s_hist[b0], 32u); }
@@ -165,156 +261,405 @@ peaks_scan_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x
             }
         }
     }
-    if (do_hist) {
-        __syncthreads();
-        uint32_t* gh = ws.hist1 + (size_t)ba * PK_BINS1;
-        for (int i = tid; i < PK_BINS1; i += PK_THREADS) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&gh[i], c); }
-        if (nan_local) atomicAdd(&ws.nan_cnt[ba], nan_local);
+    if (do_hist) flush_level1(s_hist, ba, V, ws);
+}
+
+// ---- window 3 (the reference default, peak_response_mapping_3d.py:29): register marching, no shared tile ----
+// Values are handled as ORDERED KEYS (monotone uint32 image of the float, every NaN = 0xFFFFFFFF, -0 = +0), so
+// the ATen arg-max rule becomes integer arithmetic: with Kb / Ka the unsigned maxima over the 13 neighbours that
+// come earlier / later in the (z,y,x) window scan,
+//     v not NaN:  peak <=> v != -inf  and  Kb < key(v)  and  Ka <= key(v)      (a NaN neighbour has the largest key)
+//     v NaN:      peak <=> Ka != key(NaN)                                       (the LAST NaN of a window wins)
+// The 13 + 13 split is separable: with m3(z,y,x) = max over x-1..x+1 and m9(z,y,x) = max over y-1..y+1 of m3,
+//     Kb = max(m9(z-1,y,x), m3(z,y-1,x), key(z,y,x-1)),   Ka = max(m9(z+1,y,x), m3(z,y+1,x), key(z,y,x+1)).
+// A warp owns 32 consecutive x (one lane each) x P3_R rows and marches along z.  Per plane it loads P3_R + 2 rows
+// (coalesced 128-byte segments; lanes 0 / 31 also fetch the two x-halo elements), converts them to keys once,
+// gets the x-neighbours by shuffle, and keeps m9 of the previous plane, the centre plane and the next plane in
+// registers; the next plane's loads are issued one iteration ahead.  Out-of-volume elements are -inf (the padding
+// of peak_stimulation_3d.py:14-16).
+constexpr uint32_t KEY_NAN = 0xFFFFFFFFu, KEY_NINF = 0x007FFFFFu;          // ordered_key(-inf) = ~0xFF800000
+
+// Same map as ordered_key() in three instructions: the add canonicalises -0 to +0 AND every NaN (any sign, any
+// payload) to the GPU's canonical NaN 0x7FFFFFFF, whose key is 0xFFFFFFFF.
+__device__ __forceinline__ uint32_t fkey(float f) {
+    const uint32_t u = __float_as_uint(__fadd_rn(f, 0.0f));
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+
+template <int P3_R> struct P3Raw { float v[P3_R + 2], h[P3_R + 2]; };
+template <int P3_R> struct P3Plane { uint32_t k[P3_R], l[P3_R], r[P3_R], m3[P3_R + 2], m9[P3_R]; };
+
+// per-unit constants of a lane: row offsets inside a z plane and which rows / halo elements exist
+template <int P3_R> struct P3Unit {
+    int roff[P3_R + 2];          // (y0 - 1 + j) * W + gx
+    int mywoff;                  // ALIGNED: lane i < P3_R stores the mask word of row y0 + i: its word index inside a z plane (-1: none)
+    uint32_t vmask, hmask;       // bit j: row j is inside the map and this lane's element / halo element exists
+    int hoff;
+    bool interior, h_ok;         // interior (warp-uniform): every row and every lane of the unit is inside the map
+};
+
+template <int P3_R>
+__device__ __forceinline__ void p3_load(P3Raw<P3_R>& rw, const float* __restrict__ vol, int z, int S, size_t HW,
+                                        const P3Unit<P3_R>& u) {
+    if (z < 0 || z >= S) {                                  // warp-uniform: the -inf padding plane
+#pragma unroll
+        for (int j = 0; j < P3_R + 2; ++j) { rw.v[j] = -CUDART_INF_F; rw.h[j] = -CUDART_INF_F; }
+        return;
+    }
+    const float* p = vol + (size_t)z * HW;
+    const float* ph = p + u.hoff;
+    if (u.interior) {
+#pragma unroll
+        for (int j = 0; j < P3_R + 2; ++j) {
+            rw.v[j] = __ldg(p + u.roff[j]);
+            rw.h[j] = u.h_ok ? __ldg(ph + u.roff[j]) : -CUDART_INF_F;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < P3_R + 2; ++j) {
+            rw.v[j] = (u.vmask >> j) & 1u ? __ldg(p + u.roff[j]) : -CUDART_INF_F;
+            rw.h[j] = (u.hmask >> j) & 1u ? __ldg(ph + u.roff[j]) : -CUDART_INF_F;
+        }
     }
 }
 
-// ---- window 3 (the reference default, peak_response_mapping_3d.py:29): register sliding window ----------
-// The tile is stored as ORDERED KEYS (monotone uint32 image of the float, every NaN = 0xFFFFFFFF), so the ATen
-// arg-max rule becomes integer arithmetic: with Kb / Ka the unsigned maxima over the 13 neighbours that come
-// earlier / later in the (z,y,x) window scan,
-//     v not NaN:  peak <=> v != -inf  and  Kb < key(v)  and  Ka <= key(v)      (a NaN neighbour has the largest key)
-//     v NaN:      peak <=> Ka != key(NaN)                                       (the LAST NaN of a window wins)
-// A thread owns one (x,y) column of the tile and marches along z keeping three plane summaries in registers
-// (max of the 9, max of the upper row, max of the lower row, left, centre, right): 9 shared loads, 6 three-input
-// integer maxima and two compares per voxel, no branches.  The level-1 radix histogram of the exact median
-// uses the key's top 12 bits directly.
-constexpr int P3_TX = 32, P3_TY = 8, P3_TZ = 16;
-constexpr int P3_HX = P3_TX + 2, P3_HY = P3_TY + 2, P3_HZ = P3_TZ + 2;
-
-struct PlaneStat { uint32_t m9, top3, bot3, l, c, r; };
-
-__device__ __forceinline__ PlaneStat plane_stat(const uint32_t* __restrict__ p) {   // p -> key (dy=0, dx=0) of the 3x3 patch
-    PlaneStat s;
-    s.top3 = __vimax3_u32(p[0], p[1], p[2]);
-    s.l = p[P3_HX]; s.c = p[P3_HX + 1]; s.r = p[P3_HX + 2];
-    s.bot3 = __vimax3_u32(p[2 * P3_HX], p[2 * P3_HX + 1], p[2 * P3_HX + 2]);
-    s.m9 = __vimax3_u32(s.top3, s.bot3, __vimax3_u32(s.l, s.c, s.r));
-    return s;
+template <int P3_R>
+__device__ __forceinline__ void p3_process(P3Plane<P3_R>& pl, const P3Raw<P3_R>& rw, int lane) {
+#pragma unroll
+    for (int j = 0; j < P3_R + 2; ++j) {
+        const uint32_t kk = fkey(rw.v[j]), hk = fkey(rw.h[j]);
+        uint32_t l = __shfl_up_sync(0xffffffffu, kk, 1), r = __shfl_down_sync(0xffffffffu, kk, 1);
+        l = lane == 0 ? hk : l;
+        r = lane == 31 ? hk : r;
+        pl.m3[j] = __vimax3_u32(l, kk, r);
+        if (j >= 1 && j <= P3_R) { pl.k[j - 1] = kk; pl.l[j - 1] = l; pl.r[j - 1] = r; }
+    }
+#pragma unroll
+    for (int i = 0; i < P3_R; ++i) pl.m9[i] = __vimax3_u32(pl.m3[i], pl.m3[i + 1], pl.m3[i + 2]);
 }
 
-__global__ void __launch_bounds__(PK_THREADS)
-peaks_scan3_kernel(const float* __restrict__ in, int S, int H, int W, int tiles_x, int tiles_y, int tiles_z,
+// outputs of plane z (centre plane `cur`, previous plane summarised by m9p, next plane `nxt`).
+// peak <=> v != -inf, no later NaN unless... in key arithmetic (see above):
+//   kv != key(-inf)  and  (Kb < kv or kv is NaN)  and  Ka <= kv  and  Ka is not NaN
+// (for a non-NaN centre Ka <= kv already implies that Ka is not NaN; for a NaN centre Ka <= kv always holds).
+template <int P3_R, bool ALIGNED>
+__device__ __forceinline__ void p3_outputs(const uint32_t (&m9p)[P3_R], const P3Plane<P3_R>& cur, const P3Plane<P3_R>& nxt,
+                                           int z, int y0, int x0, int H, int W, size_t HW, int lane, uint32_t omask,
+                                           uint32_t rowmask, const P3Unit<P3_R>& u, uint32_t* __restrict__ bits,
+                                           uint32_t* __restrict__ bz, uint32_t* s_hist, int do_hist) {
+    uint32_t myword = 0;
+#pragma unroll
+    for (int i = 0; i < P3_R; ++i) {
+        const uint32_t kb = __vimax3_u32(m9p[i], cur.m3[i], cur.l[i]);
+        const uint32_t ka = __vimax3_u32(nxt.m9[i], cur.m3[i + 2], cur.r[i]);
+        const uint32_t kv = cur.k[i];
+        const bool inb = (omask >> i) & 1u;
+        const bool peak = inb & (kv != KEY_NINF) & ((kb < kv) | (kv == KEY_NAN)) & (ka <= kv) & (ka != KEY_NAN);
+        const uint32_t word = __ballot_sync(0xffffffffu, peak);
+        const bool row = (rowmask >> i) & 1u;               // warp-uniform: row y0 + i exists
+        if (ALIGNED) {                                      // W % 32 == 0: the word belongs to this row segment alone
+            myword = lane == i ? word : myword;
+        } else if (row && word) {
+            const long long flat0 = ((long long)z * H + (y0 + i)) * W + x0;
+            uint32_t* wp = bits + (flat0 >> 5);
+            const int sh = (int)(flat0 & 31);
+            if (lane == 0) atomicOr(wp, word << sh);
+            if (lane == 1 && sh && (word >> (32 - sh))) atomicOr(wp + 1, word >> (32 - sh));
+        }
+        if (do_hist && inb) atomicAdd(&s_hist[kv >> 20], 1u);           // NaN keys land in the last bin
+    }
+    if (ALIGNED && u.mywoff >= 0) bz[u.mywoff] = myword;
+}
+
+// grid (ctas per map, BA).  Work unit of a warp = (z chunk, x strip, row group); adjacent warps take adjacent row
+// groups of one strip, so the two halo rows they share are L1 hits.  H * W < 2^31 (checked by the launcher).
+template <int P3_R, bool ALIGNED, int MINB>
+__global__ void __launch_bounds__(PK_THREADS, MINB)
+peaks_scan3_kernel(const float* __restrict__ in, int S, int H, int W, int nstrips, int nrowg, int nzc, int tz,
                    int do_hist, PeakWs ws) {
-    __shared__ uint32_t s_key[P3_HZ * P3_HY * P3_HX];
     __shared__ uint32_t s_hist[PK_BINS1];
     const int ba = blockIdx.y;
-    const long long V = (long long)S * H * W;
+    const size_t HW = (size_t)H * W;
+    const long long V = (long long)S * (long long)HW;
     const float* vol = in + (size_t)ba * V;
     uint32_t* bits = ws.bits + (size_t)ba * ws.words;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t KEY_NAN = 0xFFFFFFFFu, KEY_NINF = 0x007FFFFFu;          // ordered_key(-inf) = ~0xFF800000
     if (do_hist) for (int i = tid; i < PK_BINS1; i += PK_THREADS) s_hist[i] = 0u;
-    unsigned nan_local = 0;
-    const int ntiles = tiles_x * tiles_y * tiles_z;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, tz = tile / (tiles_x * tiles_y);
-        const int x0 = tx * P3_TX, y0 = ty * P3_TY, z0 = tz * P3_TZ;
-        __syncthreads();
-        // ---- load: one warp per halo row; lanes 0,1 also fetch the two halo columns --------------------
-        constexpr int NWARP = PK_THREADS / 32, RU = 4;    // RU rows per warp in flight: the loads of a batch are independent
-        for (int rb = warp; rb < P3_HY * P3_HZ; rb += NWARP * RU) {
-            float v[RU], vh[RU];
-            bool ok[RU], okh[RU];
+    __syncthreads();
+    const int nunits = nstrips * nrowg * nzc;
+    for (int unit = blockIdx.x * PK_NW + warp; unit < nunits; unit += gridDim.x * PK_NW) {
+        const int rowg = unit % nrowg;
+        const int t = unit / nrowg;
+        const int strip = t % nstrips, zc = t / nstrips;
+        const int x0 = strip * 32, y0 = rowg * P3_R, z0 = zc * tz, z1 = min(S, z0 + tz);
+        const int gx = x0 + lane;
+        const bool col_ok = gx < W;
+        P3Unit<P3_R> u;
+        u.h_ok = (lane == 0 && x0 > 0) || (lane == 31 && x0 + 32 < W);
+        u.hoff = lane == 0 ? -1 : 1;
+        uint32_t rows = 0;                                  // bit j: row y0 - 1 + j is inside the map
 #pragma unroll
-            for (int j = 0; j < RU; ++j) {
-                const int rr = rb + j * NWARP;
-                const int hz = rr / P3_HY, hy = rr - hz * P3_HY;
-                const int gy = y0 + hy - 1, gz = z0 + hz - 1;
-                const bool row_ok = rr < P3_HY * P3_HZ && gy >= 0 && gy < H && gz >= 0 && gz < S;   // warp-uniform
-                const float* row = vol + ((size_t)(row_ok ? gz : 0) * H + (row_ok ? gy : 0)) * W;
-                const int gx = x0 + lane;
-                const int hxg = lane == 0 ? x0 - 1 : x0 + P3_TX;
-                ok[j] = row_ok && gx < W;
-                okh[j] = row_ok && lane < 2 && hxg >= 0 && hxg < W;
-                v[j] = ok[j] ? row[gx] : 0.f;
-                vh[j] = okh[j] ? row[hxg] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < RU; ++j) {
-                const int rr = rb + j * NWARP;
-                if (rr < P3_HY * P3_HZ) {
-                    uint32_t* dst = s_key + rr * P3_HX;
-                    dst[1 + lane] = ok[j] ? ordered_key(v[j]) : KEY_NINF;
-                    if (lane < 2) dst[lane == 0 ? 0 : P3_HX - 1] = okh[j] ? ordered_key(vh[j]) : KEY_NINF;
-                }
-            }
+        for (int j = 0; j < P3_R + 2; ++j) {
+            const int gy = y0 - 1 + j;
+            u.roff[j] = gy * W + gx;
+            if (gy >= 0 && gy < H) rows |= 1u << j;
         }
-        __syncthreads();
-        // ---- compute: thread = (x, y) column, march along z -------------------------------------------
-        const int lx = lane, ly = warp;                   // 32 x 8 threads
-        const int gx = x0 + lx, gy = y0 + ly;
-        const bool col_ok = gx < W && gy < H;
-        const uint32_t* colp = s_key + ly * P3_HX + lx;   // (dy = 0, dx = 0) of the patch in halo plane 0
-        PlaneStat prev = plane_stat(colp), cur = plane_stat(colp + P3_HY * P3_HX);
-#pragma unroll 4
-        for (int lz = 0; lz < P3_TZ; ++lz) {
-            const PlaneStat next = plane_stat(colp + (lz + 2) * P3_HY * P3_HX);
-            const uint32_t kb = __vimax3_u32(prev.m9, cur.top3, cur.l);
-            const uint32_t ka = __vimax3_u32(next.m9, cur.bot3, cur.r);
-            const uint32_t kv = cur.c;
-            const int gz = z0 + lz;
-            const bool inb = col_ok && gz < S;
-            const bool peak = inb && (kv == KEY_NAN ? ka != KEY_NAN : (kv != KEY_NINF && kb < kv && ka <= kv));
-            if (do_hist && inb) {
-                if (kv == KEY_NAN) ++nan_local;
-                atomicAdd(&s_hist[kv >> 20], 1u);
-            }
-            if (peak) {
-                const long long flat = ((long long)gz * H + gy) * W + gx;
-                atomicOr(&bits[flat >> 5], 1u << (flat & 31));
-            }
-            prev = cur; cur = next;
+        u.mywoff = (lane < P3_R && y0 + lane < H) ? ((y0 + lane) * W + x0) >> 5 : -1;
+        u.vmask = col_ok ? rows : 0u;
+        u.hmask = u.h_ok ? rows : 0u;
+        u.interior = rows == (1u << (P3_R + 2)) - 1u && x0 + 32 <= W;
+        const uint32_t rowmask = rows >> 1;                 // bit i: centre row y0 + i
+        const uint32_t omask = col_ok ? rowmask : 0u;
+
+        P3Raw<P3_R> ra, rb;
+        P3Plane<P3_R> pa, pb;
+        uint32_t m9p[P3_R];
+        p3_load(ra, vol, z0 - 1, S, HW, u);
+        p3_process(pa, ra, lane);
+#pragma unroll
+        for (int i = 0; i < P3_R; ++i) m9p[i] = pa.m9[i];
+        p3_load(ra, vol, z0, S, HW, u);
+        p3_process(pa, ra, lane);
+        p3_load(ra, vol, z0 + 1, S, HW, u);
+        int z = z0;
+        const size_t HW32 = HW >> 5;
+        uint32_t* bz = bits + (size_t)z0 * HW32;            // ALIGNED: first word of plane z
+        while (true) {                                      // two planes per trip: the plane / raw buffers swap roles
+            if (z + 2 <= z1) p3_load(rb, vol, z + 2, S, HW, u);                 // one plane ahead
+            p3_process(pb, ra, lane);
+            p3_outputs<P3_R, ALIGNED>(m9p, pa, pb, z, y0, x0, H, W, HW, lane, omask, rowmask, u, bits, bz, s_hist, do_hist);
+#pragma unroll
+            for (int i = 0; i < P3_R; ++i) m9p[i] = pa.m9[i];
+            bz += HW32;
+            if (++z >= z1) break;
+            if (z + 2 <= z1) p3_load(ra, vol, z + 2, S, HW, u);
+            p3_process(pa, rb, lane);
+            p3_outputs<P3_R, ALIGNED>(m9p, pb, pa, z, y0, x0, H, W, HW, lane, omask, rowmask, u, bits, bz, s_hist, do_hist);
+#pragma unroll
+            for (int i = 0; i < P3_R; ++i) m9p[i] = pb.m9[i];
+            bz += HW32;
+            if (++z >= z1) break;
         }
     }
-    if (do_hist) {
-        __syncthreads();
-        uint32_t* gh = ws.hist1 + (size_t)ba * PK_BINS1;
-        for (int i = tid; i < PK_BINS1; i += PK_THREADS) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&gh[i], c); }
-        if (nan_local) atomicAdd(&ws.nan_cnt[ba], nan_local);
+    if (do_hist) flush_level1(s_hist, ba, V, ws);
+}
+
+// ---- window 3, rows that are multiples of 128 voxels: four consecutive x per lane ---------------------------------
+// Same algorithm as peaks_scan3_kernel with a 128-voxel strip per warp: a lane owns x0 + 4*lane .. +3, a row is ONE
+// 128-bit load per lane, three of the four x-neighbour pairs live in the lane's own registers and only the two
+// edge elements travel by shuffle (the two strip-edge lanes fetch one halo element).  Per plane a warp loads
+// PW_R + 2 rows and emits PW_R rows of 128 voxels.  Planes without a NaN in reach (one vote per plane) use the
+// two-compare form of the predicate: Kb < kv (which already excludes kv = -inf: every Kb >= key(-inf)) and Ka <= kv.
+constexpr int PW_R = 2;
+constexpr int PW_THREADS = 128, PW_NW = PW_THREADS / 32, PW_MINB = 3;
+
+struct PWRaw { uint4 v[PW_R + 2]; float h[PW_R + 2]; };
+struct PWPlane {
+    uint32_t k[PW_R][4], le[PW_R], re[PW_R];   // centre rows: keys, left neighbour of element 0, right neighbour of element 3
+    uint32_t m3[PW_R + 2][4], m9[PW_R][4];
+};
+
+// pz = first voxel of the plane to load (only dereferenced when z_ok); all_rows: every row of the unit is inside the map
+__device__ __forceinline__ void pw_load(PWRaw& rw, const float* __restrict__ pz, bool z_ok, const int (&roff)[PW_R + 2],
+                                        uint32_t rows, bool all_rows, bool h_ok, int hoff) {
+    const uint32_t NINF_BITS = 0xFF800000u;
+#pragma unroll
+    for (int j = 0; j < PW_R + 2; ++j) { rw.v[j] = make_uint4(NINF_BITS, NINF_BITS, NINF_BITS, NINF_BITS); rw.h[j] = -CUDART_INF_F; }
+    if (!z_ok) return;                                      // warp-uniform: the -inf padding plane
+    if (all_rows) {
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            const float* q;
+            asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(q) : "r"(roff[j]), "l"(pz));
+            rw.v[j] = __ldg(reinterpret_cast<const uint4*>(q));
+            if (h_ok) rw.h[j] = __ldg(q + hoff);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            if ((rows >> j) & 1u) {                         // warp-uniform
+                const float* q;
+                asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(q) : "r"(roff[j]), "l"(pz));
+                rw.v[j] = __ldg(reinterpret_cast<const uint4*>(q));
+                if (h_ok) rw.h[j] = __ldg(q + hoff);
+            }
+        }
     }
 }
 
-// LEVEL 2: bins = key bits 19..8 of elements whose top 12 bits match the level-1 bin.
-// LEVEL 3: bins = key bits 7..0 of elements whose top 24 bits match.
-template <int LEVEL>
-__global__ void __launch_bounds__(PK_THREADS)
-peaks_refine_kernel(const float* __restrict__ in, long long V, PeakWs ws) {
-    __shared__ uint32_t s_hist[PK_BINS1];
-    __shared__ unsigned long long s_tmp[PK_THREADS + 2];
-    const int ba = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned long long k = (unsigned long long)((V - 1) / 2);
-    int bin1; unsigned long long k1;
-    select_bin(ws.hist1 + (size_t)ba * PK_BINS1, PK_BINS1, k, s_tmp, &bin1, &k1);
-    uint32_t prefix = (uint32_t)bin1;
-    int shift = 20;
-    if (LEVEL == 3) {
-        int bin2; unsigned long long k2;
-        select_bin(ws.hist2 + (size_t)ba * PK_BINS1, PK_BINS1, k1, s_tmp, &bin2, &k2);
-        prefix = ((uint32_t)bin1 << 12) | (uint32_t)bin2;
-        shift = 8;
+// returns (warp-uniform) whether some key of the plane's PW_R + 2 rows (with the x halo) is NaN
+__device__ __forceinline__ bool pw_process(PWPlane& pl, const PWRaw& rw, int lane) {
+    uint32_t mx = 0u;
+#pragma unroll
+    for (int j = 0; j < PW_R + 2; ++j) {
+        const uint32_t k0 = fkey(__uint_as_float(rw.v[j].x)), k1 = fkey(__uint_as_float(rw.v[j].y));
+        const uint32_t k2 = fkey(__uint_as_float(rw.v[j].z)), k3 = fkey(__uint_as_float(rw.v[j].w));
+        const uint32_t hk = fkey(rw.h[j]);
+        uint32_t le = __shfl_up_sync(0xffffffffu, k3, 1), re = __shfl_down_sync(0xffffffffu, k0, 1);
+        le = lane == 0 ? hk : le;
+        re = lane == 31 ? hk : re;
+        pl.m3[j][0] = __vimax3_u32(le, k0, k1);
+        pl.m3[j][1] = __vimax3_u32(k0, k1, k2);
+        pl.m3[j][2] = __vimax3_u32(k1, k2, k3);
+        pl.m3[j][3] = __vimax3_u32(k2, k3, re);
+        mx = __vimax3_u32(mx, pl.m3[j][0], pl.m3[j][3]);    // covers le, k0..k3, re
+        if (j >= 1 && j <= PW_R) {
+            pl.k[j - 1][0] = k0; pl.k[j - 1][1] = k1; pl.k[j - 1][2] = k2; pl.k[j - 1][3] = k3;
+            pl.le[j - 1] = le; pl.re[j - 1] = re;
+        }
     }
+#pragma unroll
+    for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pl.m9[i][e] = __vimax3_u32(pl.m3[i][e], pl.m3[i + 1][e], pl.m3[i + 2][e]);
+    return __any_sync(0xffffffffu, mx == KEY_NAN);
+}
+
+template <bool HIST, bool SLOW>
+__device__ __forceinline__ void pw_outputs(const uint32_t (&m9p)[PW_R][4], const PWPlane& cur, const PWPlane& nxt,
+                                           uint32_t rowmask, int lane, int mywoff, int w32, uint32_t* __restrict__ bz, uint32_t hist_addr) {
+#pragma unroll
+    for (int i = 0; i < PW_R; ++i) {
+        if (!((rowmask >> i) & 1u)) continue;               // warp-uniform: row y0 + i is outside the map
+        uint32_t nib = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t left = e == 0 ? cur.le[i] : cur.k[i][e - 1], right = e == 3 ? cur.re[i] : cur.k[i][e + 1];
+            const uint32_t kb = __vimax3_u32(m9p[i][e], cur.m3[i][e], left);
+            const uint32_t ka = __vimax3_u32(nxt.m9[i][e], cur.m3[i + 2][e], right);
+            const uint32_t kv = cur.k[i][e];
+            bool peak;
+            if (!SLOW) peak = (kb < kv) & (ka <= kv);
+            else peak = ((kb < kv) | (kv == KEY_NAN)) & (ka <= kv) & (ka != KEY_NAN) & (kv != KEY_NINF);
+            nib |= peak ? (1u << e) : 0u;
+            if (HIST) {                                     // NaN keys land in the last bin
+                const uint32_t a = hist_addr + ((kv >> 18) & 0x3FFCu);
+                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(1u) : "memory");
+            }
+        }
+        uint32_t w = nib << (4 * (lane & 7));               // 8 lanes = one 32-voxel word of the mask
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0) bz[mywoff + i * w32] = w;
+    }
+}
+
+// grid (ctas per map, BA); W % 128 == 0, maps 16-byte aligned, H * W < 2^31 (checked by the launcher).
+// Work unit of a warp = (z chunk, 128-voxel strip, pair of rows); adjacent warps take adjacent row pairs.
+// Per trip: issue the loads of plane z + 2, emit plane z from the planes already in registers (this hides the
+// load latency), then turn the loaded rows into plane z + 2 in the registers plane z just vacated.
+template <bool HIST>
+__global__ void __launch_bounds__(PW_THREADS, PW_MINB)
+peaks_scan3w_kernel(const float* __restrict__ in, int S, int H, int W, int nstrips, int nrowg, int nzc, int tz, PeakWs ws) {
+    __shared__ uint32_t s_hist[PK_BINS1];
+    const int ba = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    const long long V = (long long)S * (long long)HW;
+    const float* vol = in + (size_t)ba * V;
+    uint32_t* bits = ws.bits + (size_t)ba * ws.words;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (HIST) for (int i = tid; i < PK_BINS1; i += PW_THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const int w32 = W >> 5;
+    const size_t HW32 = HW >> 5;
+    const int nunits = nstrips * nrowg * nzc;
+    for (int unit = blockIdx.x * PW_NW + warp; unit < nunits; unit += gridDim.x * PW_NW) {
+        const int rowg = unit % nrowg;
+        const int t = unit / nrowg;
+        const int strip = t % nstrips, zc = t / nstrips;
+        const int x0 = strip * 128, y0 = rowg * PW_R, z0 = zc * tz, z1 = min(S, z0 + tz);
+        const bool h_ok = (lane == 0 && x0 > 0) || (lane == 31 && x0 + 128 < W);
+        const int hoff = lane == 0 ? -1 : 4;
+        int roff[PW_R + 2];
+        uint32_t rows = 0;                                  // bit j: row y0 - 1 + j is inside the map
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            const int gy = y0 - 1 + j;
+            roff[j] = gy * W + x0 + 4 * lane;
+            if (gy >= 0 && gy < H) rows |= 1u << j;
+        }
+        const bool all_rows = rows == (1u << (PW_R + 2)) - 1u;
+        const uint32_t rowmask = rows >> 1;                 // bit i: centre row y0 + i
+        const int mywoff = ((y0 * W + x0) >> 5) + (lane >> 3);
+
+        PWRaw rw;
+        PWPlane pa, pb;
+        uint32_t m9p[PW_R][4];
+        uint32_t nanbits;                                   // bit 0: plane z - 1, bit 1: plane z, bit 2: plane z + 1 holds a NaN
+        pw_load(rw, vol + (ptrdiff_t)(z0 - 1) * (ptrdiff_t)HW, z0 >= 1, roff, rows, all_rows, h_ok, hoff);
+        nanbits = pw_process(pa, rw, lane) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m9p[i][e] = pa.m9[i][e];
+        pw_load(rw, vol + (size_t)z0 * HW, true, roff, rows, all_rows, h_ok, hoff);
+        nanbits |= pw_process(pa, rw, lane) ? 2u : 0u;
+        pw_load(rw, vol + (size_t)(z0 + 1) * HW, z0 + 1 < S, roff, rows, all_rows, h_ok, hoff);
+        nanbits |= pw_process(pb, rw, lane) ? 4u : 0u;
+        int z = z0;
+        const float* pz = vol + (size_t)(z0 + 2) * HW;     // plane z + 2
+        uint32_t* bz = bits + (size_t)z0 * HW32;            // first mask word of plane z
+        while (true) {                                      // two planes per trip: pa / pb swap roles
+            const bool more = z + 1 < z1;                   // plane z + 2 is needed (as the next plane of plane z + 1)
+            if (more) pw_load(rw, pz, z + 2 < S, roff, rows, all_rows, h_ok, hoff);
+            if (nanbits) pw_outputs<HIST, true>(m9p, pa, pb, rowmask, lane, mywoff, w32, bz, hist_addr);     // warp-uniform
+            else pw_outputs<HIST, false>(m9p, pa, pb, rowmask, lane, mywoff, w32, bz, hist_addr);
+            if (!more) break;
+#pragma unroll
+            for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m9p[i][e] = pa.m9[i][e];
+            nanbits = (nanbits >> 1) | (pw_process(pa, rw, lane) ? 4u : 0u);
+            ++z; pz += HW; bz += HW32;
+            const bool more2 = z + 1 < z1;
+            if (more2) pw_load(rw, pz, z + 2 < S, roff, rows, all_rows, h_ok, hoff);
+            if (nanbits) pw_outputs<HIST, true>(m9p, pb, pa, rowmask, lane, mywoff, w32, bz, hist_addr);
+            else pw_outputs<HIST, false>(m9p, pb, pa, rowmask, lane, mywoff, w32, bz, hist_addr);
+            if (!more2) break;
+#pragma unroll
+            for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m9p[i][e] = pb.m9[i][e];
+            nanbits = (nanbits >> 1) | (pw_process(pb, rw, lane) ? 4u : 0u);
+            ++z; pz += HW; bz += HW32;
+        }
+    }
+    if (HIST) flush_level1<PW_THREADS>(s_hist, ba, V, ws);
+}
+
+// LEVEL 2: bins = key bits 19..8 of elements whose top 12 bits match the level-1 bin.
+// LEVEL 3: bins = key bits 7..0 of elements whose top 24 bits match.  The prefix and the remaining rank come from
+// ws.sel (written by the last CTA of the previous level); the last CTA of this level writes the next one, and at
+// level 3 the final threshold (NaN when the map holds a NaN: torch.median propagates it).
+template <int LEVEL>
+__global__ void __launch_bounds__(PK_RF_THREADS)
+peaks_refine_kernel(const float* __restrict__ in, long long V, PeakWs ws, float* __restrict__ thr_out) {
     constexpr int NB = LEVEL == 2 ? PK_BINS1 : 256;
-    for (int i = tid; i < NB; i += PK_THREADS) s_hist[i] = 0u;
+    __shared__ uint32_t s_hist[NB];
+    __shared__ unsigned long long s_tmp[PK_RF_THREADS / 32 + 2];
+    __shared__ int s_flag;
+    const int ba = blockIdx.y;
+    const int tid = threadIdx.x;
+    if (ws.ticket[ba * 4 + 1]) return;                      // list mode: the collect kernel has produced this map's threshold
+    const uint32_t prefix = (uint32_t)ws.sel[ba * 2];
+    constexpr int shift = LEVEL == 2 ? 20 : 8;
+    for (int i = tid; i < NB; i += PK_RF_THREADS) s_hist[i] = 0u;
     __syncthreads();
     const float* vol = in + (size_t)ba * V;
     const bool vec = ((((uintptr_t)vol) & 15) == 0);
     const long long nvec = vec ? (V >> 2) : 0;
-    auto add = [&](float f) {
-        const uint32_t key = ordered_key(f);
-        if ((key >> shift) == prefix) {
-            const uint32_t bin = LEVEL == 2 ? ((key >> 8) & 0xFFFu) : (key & 0xFFu);
-            atomicAdd(&s_hist[bin], 1u);
-        }
+    const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+    auto add = [&](float f) {                              // predicated shared-memory reduction, no branch
+        const uint32_t key = fkey(f);
+        const uint32_t a = hist_addr + (LEVEL == 2 ? ((key >> 6) & 0x3FFCu) : ((key << 2) & 0x3FCu));
+        asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, %1; @p red.shared.add.u32 [%2], %3; }"
+                     :: "r"(key >> shift), "r"(prefix), "r"(a), "r"(1u) : "memory");
     };
     {
-        const long long stride = (long long)gridDim.x * PK_THREADS;
-        long long i = (long long)blockIdx.x * PK_THREADS + tid;
+        const long long stride = (long long)gridDim.x * PK_RF_THREADS;
+        long long i = (long long)blockIdx.x * PK_RF_THREADS + tid;
         for (; i + 3 * stride < nvec; i += 4 * stride) {           // 4 independent 128-bit loads in flight
             uint4 u[4];
 #pragma unroll
@@ -329,155 +674,315 @@ peaks_refine_kernel(const float* __restrict__ in, long long V, PeakWs ws) {
             add(__uint_as_float(u.x)); add(__uint_as_float(u.y)); add(__uint_as_float(u.z)); add(__uint_as_float(u.w));
         }
     }
-    for (long long i = (nvec << 2) + (long long)blockIdx.x * PK_THREADS + tid; i < V; i += (long long)gridDim.x * PK_THREADS)
+    for (long long i = (nvec << 2) + (long long)blockIdx.x * PK_RF_THREADS + tid; i < V; i += (long long)gridDim.x * PK_RF_THREADS)
         add(vol[i]);
-    (void)lane;
-    __syncthreads();
     uint32_t* gh = (LEVEL == 2 ? ws.hist2 + (size_t)ba * PK_BINS1 : ws.hist3 + (size_t)ba * 256);
-    for (int i = tid; i < NB; i += PK_THREADS) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&gh[i], c); }
+    if (!flush_hist_and_vote<PK_RF_THREADS>(s_hist, NB, gh, ws.ticket + ba * 4 + LEVEL, &s_flag)) return;
+    int bin; unsigned long long kk;
+    select_bin<PK_RF_THREADS>(gh, NB, ws.sel[ba * 2 + 1], s_tmp, &bin, &kk);
+    if (tid == 0) {
+        if (LEVEL == 2) {
+            ws.sel[ba * 2] = ((unsigned long long)prefix << 12) | (unsigned long long)bin;
+            ws.sel[ba * 2 + 1] = kk;
+        } else {
+            const uint32_t key = (prefix << 8) | (uint32_t)bin;
+            const uint32_t nan_cnt = __ldcg(ws.hist1 + (size_t)ba * PK_BINS1 + (PK_BINS1 - 1));   // only NaN keys reach the last bin
+            const float thr = nan_cnt ? CUDART_NAN_F : key_to_float(key);
+            ws.thr[ba] = thr;
+            if (thr_out) thr_out[ba] = thr;
+        }
+    }
 }
 
-// grid (nchunks, BA).  filter_mode 1: derive the median threshold from the three histograms;
-// 2: thresholds in thr_in; 0: no filter.
-__global__ void __launch_bounds__(PK_THREADS)
-peaks_filter_kernel(const float* __restrict__ in, long long V, int filter_mode, const float* __restrict__ thr_in,
-                    PeakWs ws, float* __restrict__ thr_out) {
-    __shared__ unsigned long long s_tmp[PK_THREADS + 2];
-    __shared__ float s_thr;
-    __shared__ uint32_t s_cnt[PK_THREADS / 32];
-    __shared__ float s_sum[PK_THREADS / 32];
-    const int ba = blockIdx.y, chunk = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float thr = 0.f;
-    if (filter_mode == 1) {
-        const unsigned long long k = (unsigned long long)((V - 1) / 2);
-        int b1, b2, b3; unsigned long long k1, k2, k3;
-        select_bin(ws.hist1 + (size_t)ba * PK_BINS1, PK_BINS1, k, s_tmp, &b1, &k1);
-        select_bin(ws.hist2 + (size_t)ba * PK_BINS1, PK_BINS1, k1, s_tmp, &b2, &k2);
-        select_bin(ws.hist3 + (size_t)ba * 256, 256, k2, s_tmp, &b3, &k3);
-        if (tid == 0) {
-            const uint32_t key = ((uint32_t)b1 << 20) | ((uint32_t)b2 << 8) | (uint32_t)b3;
-            s_thr = ws.nan_cnt[ba] ? CUDART_NAN_F : key_to_float(key);
-        }
+// ---- list mode of the exact median (the common case) -------------------------------------------------------------
+// After the scan the level-1 bin of the median and its population are known.  When the population fits the list
+// (a quarter of the map, at most 131072 entries: one CTA finishes it), ONE more pass over the (L2-resident) map gathers the low 20 key bits of the bin's members:
+// matches are staged in shared memory (slot = shared-memory atomic) and appended to the map's list with one global
+// atomic per flush.  The last CTA of the map then finishes the selection on the list alone: 12-bit histogram, bin,
+// 8-bit histogram, bin -> threshold.  Maps whose bin is too crowded are left to the two full refinement passes
+// (peaks_refine_kernel<2>, <3>), which return at once for list-mode maps.
+constexpr int PK_STAGE = 16 * PK_RF_THREADS;          // worst case of one round: 4 x 128-bit loads per thread, all matching
+
+__device__ __forceinline__ bool list_mode(const PeakWs& ws, int ba) {
+    const uint32_t bin1 = (uint32_t)ws.sel[ba * 2];
+    return (long long)__ldcg(ws.hist1 + (size_t)ba * PK_BINS1 + bin1) <= ws.list_cap;
+}
+
+__global__ void __launch_bounds__(PK_RF_THREADS)
+peaks_collect_kernel(const float* __restrict__ in, long long V, PeakWs ws, float* __restrict__ thr_out) {
+    __shared__ uint32_t s_stage[PK_STAGE];                 // 32 KB; reused as the histograms of the finishing step
+    __shared__ unsigned long long s_tmp[PK_RF_THREADS / 32 + 2];
+    __shared__ uint32_t s_n, s_base;
+    __shared__ int s_flag;
+    uint32_t* s_hist = s_stage;
+    const int ba = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t prefix = (uint32_t)ws.sel[ba * 2];
+    const float* vol = in + (size_t)ba * V;
+    const bool vec = ((((uintptr_t)vol) & 15) == 0);
+    const long long nvec = vec ? (V >> 2) : 0;
+    const long long stride = (long long)gridDim.x * PK_RF_THREADS;
+    if (!list_mode(ws, ba)) {
+        // ---- crowded level-1 bin (uniform per map): this pass is the level-2 histogram (key bits 19..8); the last CTA
+        // selects the level-2 bin and peaks_refine_kernel<3> finishes with one more pass over the map
+        for (int i = tid; i < PK_BINS1; i += PK_RF_THREADS) s_hist[i] = 0u;
         __syncthreads();
-        thr = s_thr;
-    } else if (filter_mode == 2) {
-        thr = thr_in[ba];
+        const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+        auto add2 = [&](float f) {
+            const uint32_t key = fkey(f);
+            if ((key >> 20) == prefix) atomicAdd(&s_hist[(key >> 8) & 0xFFFu], 1u);
+        };
+        (void)hist_addr;
+        for (long long i = (long long)blockIdx.x * PK_RF_THREADS + tid; i < nvec; i += stride) {
+            const uint4 u = ld_stream_u4(vol + (i << 2));
+            add2(__uint_as_float(u.x)); add2(__uint_as_float(u.y)); add2(__uint_as_float(u.z)); add2(__uint_as_float(u.w));
+        }
+        for (long long i = (nvec << 2) + (long long)blockIdx.x * PK_RF_THREADS + tid; i < V; i += stride) add2(vol[i]);
+        uint32_t* gh = ws.hist2 + (size_t)ba * PK_BINS1;
+        if (!flush_hist_and_vote<PK_RF_THREADS>(s_hist, PK_BINS1, gh, ws.ticket + ba * 4 + 2, &s_flag)) return;
+        int bin; unsigned long long kk;
+        select_bin<PK_RF_THREADS>(gh, PK_BINS1, ws.sel[ba * 2 + 1], s_tmp, &bin, &kk);
+        if (tid == 0) {
+            ws.sel[ba * 2] = ((unsigned long long)prefix << 12) | (unsigned long long)bin;
+            ws.sel[ba * 2 + 1] = kk;
+        }
+        return;
     }
-    if (chunk == 0 && tid == 0) { ws.thr[ba] = thr; if (thr_out) thr_out[ba] = thr; }
+    uint32_t* list = ws.list + (size_t)ba * (size_t)ws.list_cap;
+    if (tid == 0) s_n = 0u;
+    __syncthreads();
+    // One round = 4 x 128-bit loads per thread.  A thread first marks its matches among the 16 values, the warp agrees on
+    // slots with one prefix sum and ONE shared-memory atomic per round, then the matches are written to the stage.
+    auto round16 = [&](const uint32_t (&val)[16], uint32_t okmask) {
+        uint32_t mm = 0u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) mm |= ((fkey(__uint_as_float(val[e])) >> 20) == prefix) ? (1u << e) : 0u;
+        mm &= okmask;
+        const uint32_t c = __popc(mm);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += a; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {                                        // warp-uniform
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&s_n, total);
+            uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if ((mm >> e) & 1u) s_stage[pos++] = fkey(__uint_as_float(val[e])) & 0xFFFFFu;
+        }
+    };
+    auto flush = [&]() {                                    // called by all threads: stage -> the map's list
+        __syncthreads();
+        const uint32_t n = s_n;
+        if (n) {                                            // uniform
+            if (tid == 0) s_base = atomicAdd(ws.list_n + ba, n);
+            __syncthreads();
+            const uint32_t base = s_base;
+            for (uint32_t i = tid; i < n; i += PK_RF_THREADS) list[base + i] = s_stage[i];
+            __syncthreads();
+            if (tid == 0) s_n = 0u;
+            __syncthreads();
+        }
+    };
+    {
+        const long long rounds = (nvec + 4 * stride - 1) / (4 * stride);
+        long long i = (long long)blockIdx.x * PK_RF_THREADS + tid;
+        for (long long r = 0; r < rounds; ++r, i += 4 * stride) {           // 4 independent 128-bit loads in flight
+            uint32_t val[16];
+            uint32_t okmask = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long idx = i + j * stride;
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (idx < nvec) { u = ld_stream_u4(vol + (idx << 2)); okmask |= 0xFu << (4 * j); }
+                val[4 * j] = u.x; val[4 * j + 1] = u.y; val[4 * j + 2] = u.z; val[4 * j + 3] = u.w;
+            }
+            round16(val, okmask);
+            flush();
+        }
+    }
+    for (long long i0 = (nvec << 2) + (long long)blockIdx.x * PK_RF_THREADS; i0 < V; i0 += stride * 16) {     // unaligned maps / tails
+        uint32_t val[16];
+        uint32_t okmask = 0u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const long long i = i0 + e * stride + tid;
+            val[e] = 0u;
+            if (i < V) { val[e] = __float_as_uint(vol[i]); okmask |= 1u << e; }
+        }
+        round16(val, okmask);
+        flush();
+    }
+    // ---- last CTA of the map: finish the selection on the list ---------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { s_flag = (atomicAdd(ws.ticket + ba * 4 + 1, 1u) == gridDim.x - 1); __threadfence(); }
+    __syncthreads();
+    if (!s_flag) return;
+    const uint32_t n = __ldcg(ws.list_n + ba);
+    __syncthreads();
+    for (int i = tid; i < PK_BINS1; i += PK_RF_THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += PK_RF_THREADS) atomicAdd(&s_hist[__ldcg(list + i) >> 8], 1u);
+    __syncthreads();
+    int bin2; unsigned long long k2;
+    select_bin_smem<PK_RF_THREADS>(s_hist, PK_BINS1, ws.sel[ba * 2 + 1], s_tmp, &bin2, &k2);
+    for (int i = tid; i < 256; i += PK_RF_THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += PK_RF_THREADS) {
+        const uint32_t lo = __ldcg(list + i);
+        if ((lo >> 8) == (uint32_t)bin2) atomicAdd(&s_hist[lo & 0xFFu], 1u);
+    }
+    __syncthreads();
+    int bin3; unsigned long long k3;
+    select_bin_smem<PK_RF_THREADS>(s_hist, 256, k2, s_tmp, &bin3, &k3);
+    if (tid == 0) {
+        const uint32_t key = (prefix << 20) | ((uint32_t)bin2 << 8) | (uint32_t)bin3;
+        const uint32_t nan_cnt = __ldcg(ws.hist1 + (size_t)ba * PK_BINS1 + (PK_BINS1 - 1));   // only NaN keys reach the last bin
+        const float thr = nan_cnt ? CUDART_NAN_F : key_to_float(key);
+        ws.thr[ba] = thr;
+        if (thr_out) thr_out[ba] = thr;
+    }
+}
+
+// One launch for filter + count + scan + emit.  Work item = PK_ITEM_WORDS consecutive words of one map's candidate
+// mask (4 per thread), items ordered (map, chunk) = the lexicographic order of the output rows.  A CTA draws its item
+// by ticket, so every predecessor of a running item is running or finished; an item publishes its count as soon as
+// it is known and obtains its output offset by summing the counts of ALL its predecessors (a few hundred words
+// read by the whole CTA in parallel) -- no chain of dependent look-backs.
+// filter_mode 1: threshold = ws.thr (median, written by the refine<3> kernel); 2: thr_in; 0: no filter.
+constexpr int PK_PER = 4;
+constexpr int PK_ITEM_WORDS = PK_PER * PK_THREADS;
+constexpr unsigned long long LB_READY = 1ull << 63, LB_MASK = (1ull << 63) - 1;
+
+__global__ void __launch_bounds__(PK_THREADS)
+peaks_finalize_kernel(const float* __restrict__ in, int BA, int A, int H, int W, long long V, int filter_mode,
+                      const float* __restrict__ thr_in, PeakWs ws, int64_t* __restrict__ peaks, int cap,
+                      int32_t* __restrict__ n_peaks, float* __restrict__ agg, float* __restrict__ thr_out) {
+    __shared__ int s_item, s_last;
+    __shared__ uint32_t s_cnt[PK_NW];
+    __shared__ float s_sum[PK_NW];
+    __shared__ unsigned long long s_part[PK_NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nitems = BA * ws.nchunks;
+    if (tid == 0) s_item = (int)atomicAdd(ws.gticket, 1u);
+    __syncthreads();
+    const int item = s_item;
+    const int ba = item / ws.nchunks, chunk = item - ba * ws.nchunks;
+    float thr = 0.f;
+    if (filter_mode == 1) thr = ws.thr[ba];
+    else if (filter_mode == 2) thr = thr_in[ba];
+    if (filter_mode != 1 && chunk == 0 && tid == 0) { ws.thr[ba] = thr; if (thr_out) thr_out[ba] = thr; }
 
     const float* vol = in + (size_t)ba * V;
-    uint32_t* bits = ws.bits + (size_t)ba * ws.words;
+    const uint32_t* bits = ws.bits + (size_t)ba * ws.words;
+    const int w0 = chunk * PK_ITEM_WORDS + tid * PK_PER;   // a thread owns PK_PER consecutive words
+    uint32_t g[PK_PER], keep[PK_PER];
+    float sm[PK_PER];
+#pragma unroll
+    for (int j = 0; j < PK_PER; ++j) { g[j] = (w0 + j) < ws.words ? __ldg(bits + w0 + j) : 0u; keep[j] = 0u; sm[j] = 0.f; }
+    while (g[0] | g[1] | g[2] | g[3]) {                     // one candidate of every word per trip: 4 independent loads in flight
+        float v[PK_PER];
+        int bit[PK_PER];
+#pragma unroll
+        for (int j = 0; j < PK_PER; ++j) {
+            bit[j] = __ffs(g[j]) - 1;
+            v[j] = 0.f;
+            if (g[j]) { v[j] = __ldg(vol + (long long)(w0 + j) * 32 + bit[j]); g[j] &= g[j] - 1; }
+        }
+#pragma unroll
+        for (int j = 0; j < PK_PER; ++j)
+            if (bit[j] >= 0 && (filter_mode == 0 || v[j] >= thr)) { keep[j] |= 1u << bit[j]; sm[j] += v[j]; }
+    }
     uint32_t cnt = 0;
     float sum = 0.f;
-    const int w0 = chunk * PK_CHUNK_WORDS;
-    for (int wi = tid; wi < PK_CHUNK_WORDS; wi += PK_THREADS) {
-        const int w = w0 + wi;
-        if (w >= ws.words) break;
-        uint32_t m = bits[w];
-        if (m) {
-            uint32_t keepm = 0;
-            uint32_t g = m;
-            while (g) {
-                const int bit = __ffs(g) - 1;
-                g &= g - 1;
-                const float v = vol[(long long)w * 32 + bit];
-                if (filter_mode == 0 || v >= thr) { keepm |= 1u << bit; sum += v; ++cnt; }
+#pragma unroll
+    for (int j = 0; j < PK_PER; ++j) { cnt += __popc(keep[j]); sum += sm[j]; }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += a; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);          // deterministic tree
+    if (lane == 31) s_cnt[warp] = incl;
+    if (lane == 0) s_sum[warp] = sum;
+    __syncthreads();
+    volatile unsigned long long* look = ws.look;
+    if (tid == 0) {
+        uint32_t T = 0; float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < PK_NW; ++i) { T += s_cnt[i]; t += s_sum[i]; }
+        ws.chunk_cnt[item] = T;
+        ws.chunk_sum[item] = t;
+        look[item] = LB_READY | (unsigned long long)T;     // the count is the whole message: one 64-bit store
+    }
+    // output offset = sum of the counts of all predecessors (spin until each has been published)
+    unsigned long long part = 0;
+    for (int j = tid; j < item; j += PK_THREADS) {
+        unsigned long long st;
+        do { st = look[j]; } while (!(st & LB_READY));
+        part += st & LB_MASK;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    unsigned long long prefix = 0;
+#pragma unroll
+    for (int i = 0; i < PK_NW; ++i) prefix += s_part[i];
+    if (cnt && cap > 0) {
+        unsigned long long pos = prefix + (incl - cnt);
+        for (int i = 0; i < warp; ++i) pos += s_cnt[i];
+        const int b = ba / A, a = ba - b * A;
+        // (z, y, x) of the first voxel of the thread's first word: one division per thread, then increments (a word never
+        // leaves its row when W % 32 == 0; in general the carry loops run a few times)
+        const long long flat0 = (long long)w0 * 32;
+        int x = (int)(flat0 % W);
+        const long long t0 = flat0 / W;
+        int y = (int)(t0 % H), z = (int)(t0 / H);
+#pragma unroll
+        for (int j = 0; j < PK_PER; ++j) {
+            for (uint32_t q = keep[j]; q;) {
+                const int bit = __ffs(q) - 1;
+                q &= q - 1;
+                if (pos < (unsigned long long)cap) {
+                    int xx = x + bit, yy = y, zz = z;
+                    while (xx >= W) { xx -= W; if (++yy == H) { yy = 0; ++zz; } }
+                    int64_t* row = peaks + pos * 5;
+                    row[0] = b; row[1] = a; row[2] = zz; row[3] = yy; row[4] = xx;
+                }
+                ++pos;
             }
-            if (keepm != m) bits[w] = keepm;
+            x += 32;
+            while (x >= W) { x -= W; if (++y == H) { y = 0; ++z; } }
         }
     }
-    // deterministic tree reduction
+    // ---- the last CTA reduces the per-chunk sums per map (fixed order) and publishes the total ----------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { s_last = (atomicAdd(ws.gticket + 1, 1u) == (uint32_t)(nitems - 1)); __threadfence(); }
+    __syncthreads();
+    if (!s_last) return;
+    unsigned long long tot = 0;
+    for (int m2 = tid; m2 < BA; m2 += PK_THREADS) {
+        float s2 = 0.f, c = 0.f;
+        for (int jc = 0; jc < ws.nchunks; ++jc) {
+            const uint32_t cc = __ldcg(ws.chunk_cnt + (size_t)m2 * ws.nchunks + jc);
+            s2 += __ldcg(ws.chunk_sum + (size_t)m2 * ws.nchunks + jc);
+            c += (float)cc;
+            tot += cc;
+        }
+        if (agg) agg[m2] = s2 / c;      // 0/0 = NaN when the map has no peak, as in the reference
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); sum += __shfl_down_sync(0xffffffffu, sum, o); }
-    if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum; }
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = tot;
     __syncthreads();
     if (tid == 0) {
-        uint32_t c = 0; float s = 0.f;
-        for (int i = 0; i < PK_THREADS / 32; ++i) { c += s_cnt[i]; s += s_sum[i]; }
-        ws.chunk_cnt[(size_t)ba * ws.nchunks + chunk] = c;
-        ws.chunk_sum[(size_t)ba * ws.nchunks + chunk] = s;
-    }
-}
-
-// single CTA: exclusive scan over [BA][nchunks] counts in lexicographic order, aggregation per map
-__global__ void __launch_bounds__(PK_THREADS)
-peaks_offsets_kernel(int BA, PeakWs ws, int32_t* __restrict__ n_peaks, float* __restrict__ agg) {
-    __shared__ unsigned long long s_scan[PK_THREADS];
-    const int tid = threadIdx.x;
-    const long long total = (long long)BA * ws.nchunks;
-    unsigned long long base = 0;
-    for (long long i0 = 0; i0 < total; i0 += PK_THREADS) {
-        const long long i = i0 + tid;
-        const unsigned long long c = i < total ? ws.chunk_cnt[i] : 0u;
-        s_scan[tid] = c;
-        __syncthreads();
-        for (int d = 1; d < PK_THREADS; d <<= 1) {
-            const unsigned long long v = tid >= d ? s_scan[tid - d] : 0ull;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        if (i < total) {
-            const unsigned long long off = base + s_scan[tid] - c;
-            ws.chunk_off[i] = (uint32_t)(off > 0xFFFFFFFFull ? 0xFFFFFFFFull : off);
-        }
-        base += s_scan[PK_THREADS - 1];
-        __syncthreads();
-    }
-    if (tid == 0) *n_peaks = (int32_t)(base > 0x7FFFFFFFull ? 0x7FFFFFFFull : base);
-    if (agg) {
-        for (int ba = tid; ba < BA; ba += PK_THREADS) {
-            float s = 0.f, c = 0.f;
-            for (int j = 0; j < ws.nchunks; ++j) {
-                s += ws.chunk_sum[(size_t)ba * ws.nchunks + j];
-                c += (float)ws.chunk_cnt[(size_t)ba * ws.nchunks + j];
-            }
-            agg[ba] = s / c;            // 0/0 = NaN when the map has no peak, as in the reference
-        }
-    }
-}
-
-__global__ void __launch_bounds__(PK_THREADS)
-peaks_emit_kernel(int A, int H, int W, PeakWs ws, int64_t* __restrict__ peaks, int cap) {
-    __shared__ uint32_t s_scan[PK_THREADS];
-    const int ba = blockIdx.y, chunk = blockIdx.x;
-    const int tid = threadIdx.x;
-    const size_t ci = (size_t)ba * ws.nchunks + chunk;
-    if (ws.chunk_cnt[ci] == 0) return;
-    const uint32_t* bits = ws.bits + (size_t)ba * ws.words;
-    constexpr int PER = PK_CHUNK_WORDS / PK_THREADS;      // consecutive words per thread
-    const int w0 = chunk * PK_CHUNK_WORDS + tid * PER;
-    uint32_t m[PER];
-    uint32_t c = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) { m[j] = (w0 + j) < ws.words ? bits[w0 + j] : 0u; c += __popc(m[j]); }
-    s_scan[tid] = c;
-    __syncthreads();
-    for (int d = 1; d < PK_THREADS; d <<= 1) {
-        const uint32_t v = tid >= d ? s_scan[tid - d] : 0u;
-        __syncthreads();
-        s_scan[tid] += v;
-        __syncthreads();
-    }
-    long long pos = (long long)ws.chunk_off[ci] + s_scan[tid] - c;
-    const int b = ba / A, a = ba % A;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        uint32_t g = m[j];
-        while (g) {
-            const int bit = __ffs(g) - 1;
-            g &= g - 1;
-            if (pos < cap) {
-                const long long flat = (long long)(w0 + j) * 32 + bit;
-                const int x = (int)(flat % W);
-                const long long t = flat / W;
-                const int y = (int)(t % H), z = (int)(t / H);
-                int64_t* row = peaks + pos * 5;
-                row[0] = b; row[1] = a; row[2] = z; row[3] = y; row[4] = x;
-            }
-            ++pos;
-        }
+        unsigned long long total = 0;
+        for (int i = 0; i < PK_NW; ++i) total += s_part[i];
+        *n_peaks = (int32_t)(total > 0x7FFFFFFFull ? 0x7FFFFFFFull : total);
     }
 }
 
@@ -527,42 +1032,73 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         set_error("peaks3d: workspace too small");
         return B200SEG_EWORKSPACE;
     }
+    B200_CHECK_ARG((long long)BA * ws.nchunks < (1ll << 31), "peaks3d: too many work items");
     B200_CUDA(cudaMemsetAsync(base, 0, ws.zero_bytes, stream));
     const int sms = num_sms();
     const int do_hist = filter_mode == 1;
-    {
-        const int TX = win == 3 ? P3_TX : PK_TX, TY = win == 3 ? P3_TY : PK_TY, TZ = win == 3 ? P3_TZ : PK_TZ;
-        const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, tiles_z = (S + TZ - 1) / TZ;
+    static const int stop_after = getenv("B200SEG_PEAKS_STOP") ? atoi(getenv("B200SEG_PEAKS_STOP")) : 99;    // profiling aid: run only the first k kernels
+    if (stop_after < 1) return 0;
+    if (win == 3) {
+        static const int variant = getenv("B200SEG_PEAKS_VARIANT") ? atoi(getenv("B200SEG_PEAKS_VARIANT")) : 0;
+        B200_CHECK_ARG((long long)H * W < (1ll << 31) - 256, "peaks3d: H * W too large");
+        const bool wide = variant < 10 && (W % 128) == 0 && (((uintptr_t)input) & 15) == 0;
+        const int xs = wide ? 128 : 32, R = wide ? PW_R : 4, minb = wide ? PW_MINB : 2, nw = wide ? PW_NW : PK_NW;
+        const int nstrips = (W + xs - 1) / xs, nrowg = (H + R - 1) / R;
+        // persistent CTAs: 2 resident CTAs per SM in total, spread over the B*A maps
+        int per_map = (sms * minb) / BA;                   // never more CTAs than resident slots: a second wave would double the time
+        if (per_map < 1) per_map = 1;
+        // z chunk: a warp's time is (units per warp) x (planes per unit + 2 halo planes); pick the cheapest split
+        int best_tz = S;
+        long long best_cost = -1;
+        for (int tz = S;; tz = (tz + 1) / 2) {
+            const long long nzc = (S + tz - 1) / tz, units = (long long)nstrips * nrowg * nzc;
+            const long long warps = (long long)per_map * nw;
+            const long long cost = ((units + warps - 1) / warps) * (tz + 2);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tz = tz; }
+            if (tz <= 4) break;
+        }
+        const int tz = best_tz, nzc = (S + tz - 1) / tz;
+        const long long units = (long long)nstrips * nrowg * nzc;
+        B200_CHECK_ARG(units < (1ll << 31), "peaks3d: too many work units");
+        if ((long long)per_map * nw > units) per_map = (int)((units + nw - 1) / nw);
+        dim3 g1((unsigned)per_map, BA);
+        if (wide) {
+            if (do_hist) peaks_scan3w_kernel<true><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            else peaks_scan3w_kernel<false><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+        } else if ((W % 32) == 0) peaks_scan3_kernel<4, true, 2><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, do_hist, ws);
+        else peaks_scan3_kernel<4, false, 2><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, do_hist, ws);
+        B200_LAUNCH_CHECK("peaks_scan3_kernel");
+    } else {
+        const int tiles_x = (W + PK_TX - 1) / PK_TX, tiles_y = (H + PK_TY - 1) / PK_TY, tiles_z = (S + PK_TZ - 1) / PK_TZ;
         const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
         B200_CHECK_ARG(ntiles < (1ll << 31), "peaks3d: too many tiles");
-        // persistent CTAs: about 5 resident CTAs per SM in total, spread over the B*A maps
         long long per_map = ((long long)sms * 5 + BA - 1) / BA;
         if (per_map > ntiles) per_map = ntiles;
         if (per_map < 1) per_map = 1;
         dim3 g1((unsigned)per_map, BA);
-        if (win == 3) peaks_scan3_kernel<<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
-        else if (win == 5) peaks_scan_kernel<5><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
+        if (win == 5) peaks_scan_kernel<5><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
         else peaks_scan_kernel<7><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, tiles_x, tiles_y, tiles_z, do_hist, ws);
         B200_LAUNCH_CHECK("peaks_scan_kernel");
     }
+    if (stop_after < 2) return 0;
     if (filter_mode == 1) {
-        long long want = (V / 4 + PK_THREADS - 1) / PK_THREADS;
-        int gr = (int)(want < 1 ? 1 : (want > (long long)sms * 8 / BA + 1 ? (long long)sms * 8 / BA + 1 : want));
+        // a few fat CTAs per map: the fixed cost per CTA (clear + publish a 4096-bin histogram) must stay small
+        // against its share of the stream
+        long long want = (V / 4 + (long long)PK_RF_THREADS * 8 - 1) / ((long long)PK_RF_THREADS * 8);
+        long long lim = ((long long)sms * 2) / BA;
+        int gr = (int)(want < 1 ? 1 : (want > lim ? lim : want));
+        if (gr < 1) gr = 1;
         dim3 g2(gr, BA);
-        peaks_refine_kernel<2><<<g2, PK_THREADS, 0, stream>>>(input, V, ws);
-        B200_LAUNCH_CHECK("peaks_refine_kernel<2>");
-        peaks_refine_kernel<3><<<g2, PK_THREADS, 0, stream>>>(input, V, ws);
+        peaks_collect_kernel<<<g2, PK_RF_THREADS, 0, stream>>>(input, V, ws, thr_out);
+        B200_LAUNCH_CHECK("peaks_collect_kernel");
+        if (stop_after < 3) return 0;
+        peaks_refine_kernel<3><<<g2, PK_RF_THREADS, 0, stream>>>(input, V, ws, thr_out);
         B200_LAUNCH_CHECK("peaks_refine_kernel<3>");
     }
-    dim3 g3(ws.nchunks, BA);
-    peaks_filter_kernel<<<g3, PK_THREADS, 0, stream>>>(input, V, filter_mode, thr_in, ws, thr_out);
-    B200_LAUNCH_CHECK("peaks_filter_kernel");
-    peaks_offsets_kernel<<<1, PK_THREADS, 0, stream>>>(BA, ws, n_peaks, agg);
-    B200_LAUNCH_CHECK("peaks_offsets_kernel");
-    if (cap > 0) {
-        peaks_emit_kernel<<<g3, PK_THREADS, 0, stream>>>(A, H, W, ws, peaks, cap);
-        B200_LAUNCH_CHECK("peaks_emit_kernel");
-    }
+    if (stop_after < 4) return 0;
+    peaks_finalize_kernel<<<BA * ws.nchunks, PK_THREADS, 0, stream>>>(input, BA, A, H, W, V, filter_mode, thr_in, ws, peaks, cap,
+                                                                     n_peaks, agg, thr_out);
+    B200_LAUNCH_CHECK("peaks_finalize_kernel");
     return 0;
 }
 

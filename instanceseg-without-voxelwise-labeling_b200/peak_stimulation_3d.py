@@ -19,39 +19,55 @@ def median_filter(input):
     return thr.contiguous().view(b, c, 1, 1, 1)
 
 
+class PeaksPlan(object):
+    """Pre-allocated, allocation-free and sync-free form of the op for a fixed input shape (what the batched chain and
+    bench.py use): `run(input)` enqueues one memset + four kernels on the current stream and returns device buffers
+    (peaks [cap,5] int64, n int32[1] = total number of peaks, agg [B,A] or None, thr [B,A]); nothing is read back."""
+
+    def __init__(self, shape, device, win_size=3, filter_mode=0, want_agg=True, cap=None):
+        assert win_size % 2 == 1, 'Window size for peak finding must be odd.'
+        B, A, S, H, W = [int(v) for v in shape]
+        self.shape, self.win, self.mode = (B, A, S, H, W), int(win_size), int(filter_mode)
+        L = _lib.lib()
+        V = S * H * W
+        if cap is None:
+            cap = min(B * A * V, max(1 << 16, (B * A * V) // 8))
+        self.cap = int(cap)
+        self.peaks = torch.empty((max(self.cap, 1), 5), dtype=torch.int64, device=device)
+        self.n = torch.zeros(1, dtype=torch.int32, device=device)
+        self.agg = torch.empty((B, A), dtype=torch.float32, device=device) if want_agg else None
+        self.thr = torch.empty((B, A), dtype=torch.float32, device=device)
+        self.ws_bytes = L.b200seg_peaks3d_workspace_bytes(B, A, S, H, W)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+
+    def run(self, input, thr_in=None):
+        B, A, S, H, W = self.shape
+        assert tuple(input.shape) == self.shape and input.is_cuda and input.dtype == torch.float32 and input.is_contiguous()
+        _lib.check(_lib.lib().b200seg_peaks3d_dev(_lib.ptr(input), B, A, S, H, W, self.win, self.mode, _lib.ptr(thr_in),
+                                                  _lib.ptr(self.peaks), self.cap, _lib.ptr(self.n), _lib.ptr(self.agg),
+                                                  _lib.ptr(self.thr), _lib.ptr(self.ws), self.ws_bytes, _lib.current_stream()),
+                   "peaks3d")
+        return self.peaks, self.n, self.agg, self.thr
+
+
 def peaks_forward(input, win_size=3, filter_mode=0, thresholds=None, want_agg=True, cap=None):
-    """Device op.  Returns (peaks int64 [Npk,5], agg [B,A] or None, thr [B,A])."""
+    """Device op with the reference's result shape.  Returns (peaks int64 [Npk,5], agg [B,A] or None, thr [B,A]); the
+    exact-size peak list needs the count on the host (one 4-byte read, like torch.nonzero in the reference)."""
     assert input.is_cuda and input.dtype == torch.float32 and input.dim() == 5
-    assert win_size % 2 == 1, 'Window size for peak finding must be odd.'
-    L = _lib.lib()
     input = input.contiguous()
-    B, A, S, H, W = input.shape
-    dev = input.device
-    V = S * H * W
-    if cap is None:
-        cap = min(B * A * V, max(1 << 16, (B * A * V) // 8))
-    peaks = torch.empty((max(cap, 1), 5), dtype=torch.int64, device=dev)
-    n = torch.zeros(1, dtype=torch.int32, device=dev)
-    agg = torch.empty((B, A), dtype=torch.float32, device=dev) if want_agg else None
-    thr = torch.empty((B, A), dtype=torch.float32, device=dev)
-    ws_bytes = L.b200seg_peaks3d_workspace_bytes(B, A, S, H, W)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    B, A = input.shape[:2]
+    plan = PeaksPlan(input.shape, input.device, win_size, filter_mode, want_agg, cap)
     thr_in = None
     if filter_mode == 2:
-        thr_in = torch.as_tensor(thresholds, dtype=torch.float32, device=dev).reshape(-1)
+        thr_in = torch.as_tensor(thresholds, dtype=torch.float32, device=input.device).reshape(-1)
         thr_in = thr_in.expand(B * A).contiguous() if thr_in.numel() == 1 else thr_in.contiguous()
         assert thr_in.numel() == B * A
-
-    def run(cap_, peaks_):
-        _lib.check(L.b200seg_peaks3d_dev(_lib.ptr(input), B, A, S, H, W, int(win_size), int(filter_mode),
-                                         _lib.ptr(thr_in), _lib.ptr(peaks_), cap_, _lib.ptr(n), _lib.ptr(agg),
-                                         _lib.ptr(thr), _lib.ptr(ws), ws_bytes, _lib.current_stream()), "peaks3d")
-    run(cap, peaks)
-    npk = int(n.item())
-    if npk > cap:                       # rare: more peaks than the default capacity, rerun with room
-        peaks = torch.empty((npk, 5), dtype=torch.int64, device=dev)
-        run(npk, peaks)
-    return peaks[:npk], agg, thr
+    plan.run(input, thr_in)
+    npk = int(plan.n.item())
+    if npk > plan.cap:                  # rare: more peaks than the default capacity, rerun with room
+        plan = PeaksPlan(input.shape, input.device, win_size, filter_mode, want_agg, npk)
+        plan.run(input, thr_in)
+    return plan.peaks[:npk], plan.agg, plan.thr
 
 
 class PeakStimulation(Function):

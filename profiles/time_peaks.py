@@ -1,0 +1,28 @@
+"""Times the peak-stimulation op (device part only, CUDA events, L2 flushed) on the BASELINE config-3 maps."""
+import os, sys, json
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+import b200seg
+from b200seg import synth
+from b200seg.peak_stimulation_3d import PeaksPlan
+
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+out = {}
+for name, shape, ch, nv in (("14x32x128x128", (32, 128, 128), 14, 1), ("8x14x32x128x128", (32, 128, 128), 14, 8), ("1x128x512x512", (128, 512, 512), 1, 1)):
+    x = torch.from_numpy(synth.response_map(np.random.default_rng(1003), shape, n_peaks=60, channels=ch)).to(dev)
+    if nv > 1:
+        x = x.repeat(nv, 1, 1, 1, 1).contiguous()
+    plan = PeaksPlan(x.shape, dev, 3, 1)
+    for _ in range(3):
+        plan.run(x)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); plan.run(x); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    out[name] = {"ms_median": float(np.median(ts)), "ms_min": float(min(ts)), "n_peaks": int(plan.n.item()),
+                 "gbs_8V": 8 * x.numel() / (np.median(ts) * 1e-3) / 1e9}
+print(json.dumps({"variant": os.environ.get("B200SEG_PEAKS_VARIANT", "0"), "peaks": out}))

@@ -462,6 +462,49 @@ def test_peaks_vs_oracle_random_edge_cases(b2, torch_):
             assert np.array_equal(pl.cpu().numpy(), op)
 
 
+def test_peaks_aligned_rows_nan_signs_and_plateaus(b2, torch_):
+    """Row widths that are multiples of 32 take the ballot-word store path of the window-3 scan; heights that are not
+    multiples of the row group, both NaN signs with non-canonical payloads, -inf, signed zeros and plateaus."""
+    from b200seg.peak_stimulation_3d import peaks_forward
+    rng = np.random.default_rng(77)
+    for t, (S, H, W) in enumerate([(5, 7, 32), (9, 13, 64), (3, 4, 96), (17, 6, 32), (1, 1, 32), (2, 33, 64), (12, 9, 128)]):
+        x = rng.normal(size=(2, 2, S, H, W)).astype(np.float32)
+        if t % 3 == 0:
+            x = np.round(x * 2) / 2
+        if t % 2 == 1:
+            x[x < -1] = -0.0
+            x.flat[rng.integers(0, x.size, 4)] = -np.inf
+        xn = x.copy()
+        if t in (1, 3, 6):                                             # NaNs of both signs, odd payloads
+            u = xn.view(np.uint32)
+            idx = rng.integers(0, x.size, 6)
+            u.flat[idx[:2]] = 0xFFC00000; u.flat[idx[2:4]] = 0x7FC00001; u.flat[idx[4:]] = 0xFF800123
+        for arr in (x, xn):
+            for mode, name in ((0, None), (1, "median")):
+                p, agg, thr = peaks_forward(torch_.from_numpy(arr).cuda(), 3, mode)
+                op, oagg, othr = oracle.peak_stimulation_3d(arr, win_size=3, filter_mode=name)
+                assert np.array_equal(p.cpu().numpy(), op), (t, mode, arr.shape)
+                np.testing.assert_allclose(agg.cpu().numpy(), oagg, rtol=1e-5, atol=1e-6, equal_nan=True)
+                if mode == 1:
+                    assert np.array_equal(thr.cpu().numpy(), othr, equal_nan=True), (t, thr, othr)
+
+
+def test_peaks_full_resolution_map(b2, torch_):
+    """(1,1,128,512,512) fp32 map (BASELINE config 3, full-resolution variant): exact peak list and threshold vs the oracle."""
+    from b200seg import synth
+    from b200seg.peak_stimulation_3d import peaks_forward
+    x = synth.response_map(np.random.default_rng(1003), (128, 512, 512), n_peaks=200, channels=1)
+    p, agg, thr = peaks_forward(torch_.from_numpy(x).cuda(), 3, 1)
+    op, oagg, othr = oracle.peak_stimulation_3d(x, win_size=3, filter_mode="median")
+    assert np.array_equal(thr.cpu().numpy(), othr)
+    assert p.shape[0] == op.shape[0] and np.array_equal(p.cpu().numpy(), op)
+    # aggregation = mean of the map over its peaks: an fp32 sum of 1.2 M terms is order dependent (torch reduces pairwise,
+    # the oracle sequentially, the kernel per 8192-voxel chunk), so it is checked against the fp64 mean at 1e-5 relative
+    exact = x[op[:, 0], op[:, 1], op[:, 2], op[:, 3], op[:, 4]].astype(np.float64).mean()
+    np.testing.assert_allclose(agg.cpu().numpy().ravel()[0], exact, rtol=1e-5)
+    np.testing.assert_allclose(oagg.ravel()[0], exact, rtol=5e-3)
+
+
 def test_peaks_config3_size_and_backward(b2, torch_):
     """(1,14,32,128,128) fp32 response map (BASELINE config 3 @stride 4): exact peaks vs oracle; backward."""
     from b200seg import synth
