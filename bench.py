@@ -2,24 +2,26 @@
 """bench.py -- headline benchmark of the b200seg hot path (contract: see the task statement).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code for the path, all host cores
 
-A "step" = one pass of the post-processing chain (tools/binarization_soma.py:57-104: 3D NMS ->
-visit order -> per-instance crop/normalise/2D-Otsu -> largest connected component -> label paste-back) over one batch of
-synthetic 128x512x512 uint8 volumes (BASELINE.json configs[2]/[4]; ~200 blob instances and ~800
-candidate detections per volume).  Each rank owns `--volumes-per-rank` volumes (8 by default, so
-8 GPUs process the 64-volume batch of configs[4]); scaling is weak, no data-path collective except
-the all-gather of the surviving detections at the end of each step (N > 1).
+A "step" = one pass of the post-processing pipeline of BASELINE.json configs[2]/[4] over the batch of `--volumes`
+(64) synthetic 128x512x512 uint8 volumes (~200 blob instances, 800 candidate detections, one (14,32,128,128) fp32
+response map each): PRM peak stimulation (lib/prm/peak_stimulation_3d.py, median filter) -> tools/binarization_soma.py
+:57-104 (3D NMS -> visit order -> per-instance crop/normalise/2D-Otsu -> largest connected component -> label
+paste-back).  STRONG scaling by default: the 64 volumes are split over the N ranks (np.array_split, the reference's
+my_subprocess.py:56), so N = 1 processes all 64; `--scaling weak --volumes-per-rank V` keeps V volumes per rank.
+No data-path collective; the only exchange is the all-gather of the surviving detections at the end of each step.
 
 One JSON line is printed by rank 0:
-  value          Gvox/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e            same metric through the host-buffer C-ABI call (pinned host memory in, H2D + D2H
-                 inside the timed region)
-  roofline       dominant kernel: algorithmic bytes per launch / measured launch time vs the
-                 measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline   the oracle port of the reference chain on the host cores (bounded sample)
-  ops            per-operator numbers: RoIAlign3D fwd/bwd RoIs/s (config 4), peak stimulation,
-                 IoU matrix, NMS -- each with its own roofline fraction
+  value          Gvox/s, inputs resident in HBM, CUDA-event timed, max over ranks (peak stimulation included;
+                 `value_without_peaks` = the binarization chain alone)
+  e2e            the binarization chain through the host-buffer C-ABI call (pinned host memory in, H2D + D2H inside)
+  roofline       dominant kernel: algorithmic bytes per launch / measured launch time vs the measured HBM peak
+  cpu_baseline   kind "reference": the reference's own Python (tools/otsu.py + Cython NMS + the script's numpy, staged in
+                 oracle/_ref) on a bounded sample; `port` = the C restatement (oracle/) beside it
+  parity_checked number of this run's volumes whose GPU result was compared bit for bit with the oracle chain
+  ops            per-operator numbers (RoIAlign3D fwd/bwd incl. the reference's own CUDA kernel, peaks, IoU, NMS, ...),
+                 each with its roofline fraction and, where the reference has a CPU implementation, its time beside it
 """
 import argparse
 import json
@@ -104,56 +106,101 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation of the chain (oracle port), all host cores
+# reference arm: the reference's own CPU code for the chain, all host cores
 # ------------------------------------------------------------------------------------------------
 _CASES = {}
+REF_SAMPLE_INSTANCES = 24          # detections of the script's own visit order processed per volume and step (bounded sample)
 
 
-def _ref_worker(seed):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import oracle_chain
+def volume_split(n_volumes, world, rank):
+    """Volumes of rank `rank`: np.array_split(range(n), world)[rank] (my_subprocess.py:56)."""
+    return [int(v) for v in np.array_split(np.arange(n_volumes), world)[rank]]
+
+
+def load_oracle_in_parent():
+    """Load the oracle libraries in THIS process (before forking workers) so that a loaded-library record shows them."""
+    import oracle
+    oracle.lib()
+    try:
+        oracle.ref_module("cython_nms_3d"); oracle.ref_module("cython_bbox_3d")
+    except Exception:
+        pass
+    return oracle
+
+
+def _ref_worker(job):
+    """One volume, the reference's own code: tools/binarization_soma.py:57-104 (Cython NMS + tools/otsu.py + numpy paste)
+    on the first `k` detections of its visit order.  Returns (seconds, volume fraction done, seconds of the C port or None)."""
+    seed, k, want_port = job
+    from oracle import refpy
     if seed not in _CASES:
         _CASES[seed] = make_case(seed)
+    c = _CASES[seed]
     t = time.perf_counter()
-    r = oracle_chain(_CASES[seed], NMS_THRESH)
-    return time.perf_counter() - t, int(len(r["order"]))
+    r = refpy.run_soma_script(c, NMS_THRESH, max_instances=k)
+    dt = time.perf_counter() - t
+    frac = r["n_visited"] / max(r["n_after_nms"], 1)
+    tp = None
+    if want_port:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle_chain
+        t = time.perf_counter()
+        oracle_chain(c, NMS_THRESH)
+        tp = time.perf_counter() - t
+    return dt, frac, tp
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
+    from oracle import refpy
+    load_oracle_in_parent()
+    if not refpy.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/py (staged reference Python) is missing: run build() where /root/reference exists"}))
+        return
     cores = os.cpu_count() or 1
-    per_step = max(1, min(args.volumes_per_rank, cores))
-    seeds = [2000 + i for i in range(per_step)]
+    workers = max(1, min(cores, args.volumes))
+    seeds = [args.seed_base + i for i in range(workers)]
+    V = int(np.prod(SHAPE))
     ctx = mp.get_context("fork")
-    with ctx.Pool(per_step) as pool:
-        pool.map(_ref_worker, seeds)                      # builds the cases inside the workers + 1 warm run
+    with ctx.Pool(workers) as pool:
+        first = pool.map(_ref_worker, [(s_, 2, True) for s_ in seeds])                # builds the cases + times the C port once
         for _ in range(max(0, args.warmup - 1)):
-            pool.map(_ref_worker, seeds)
+            pool.map(_ref_worker, [(s_, 2, False) for s_ in seeds])
         t0 = time.perf_counter()
+        fr = []
         for _ in range(args.steps):
-            pool.map(_ref_worker, seeds)
+            fr.append(pool.map(_ref_worker, [(s_, REF_SAMPLE_INSTANCES, False) for s_ in seeds]))
         dt = time.perf_counter() - t0
-    vox = per_step * np.prod(SHAPE) * args.steps
-    val = vox / dt / 1e9
+    # volumes' worth of work done per step = sum over workers of the fraction of the visit list they processed
+    vol_equiv = float(np.mean([sum(f for _, f, _ in step) for step in fr]))
+    val = vol_equiv * V * args.steps / dt / 1e9
+    port = workers * V / max(t for _, _, t in first) / 1e9
     line = {"impl": "reference", "metric": "postproc_gvox_per_s", "value": val, "unit": "Gvox/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, world, per_step),
-            "cpu_baseline": {"value": val, "unit": "Gvox/s", "cores": per_step, "kind": "port",
-                             "sample": "%d volumes of 128x512x512 per step, one per worker process (oracle C port of "
-                                       "cython NMS + otsu_py_2d_fast + numpy paste), host has %d cores" % (per_step, cores)},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world, len(volume_split(args.volumes, world, 0)) if args.scaling == "strong" else args.volumes_per_rank),
+            "cpu_baseline": {"value": val, "unit": "Gvox/s", "cores": workers, "kind": "reference",
+                             "sample": "per step every one of %d worker processes runs tools/binarization_soma.py:57-104 (reference Cython nms_3d, "
+                                       "tools/otsu.py otsu_py_2d_fast, the script's numpy crop / paste / np.unique; skimage label -> scipy) on one "
+                                       "128x512x512 volume for the first %d of ~390 detections of its visit order; value = volume fractions done x "
+                                       "voxels / time; peak stimulation not included; host has %d cores" % (workers, REF_SAMPLE_INSTANCES, cores),
+                             "port": {"value": port, "unit": "Gvox/s", "cores": workers,
+                                      "note": "the oracle's C restatement of the same chain, whole volumes, one per worker"}},
             "e2e": {"value": val, "unit": "Gvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 def workload_config(args, world, vpr):
-    return {"workload": "postproc_soma_chain: 3D NMS(0.23) + per-instance 2D-Otsu + largest connected component + label paste-back on synthetic uint8 "
-                        "128x512x512 volumes, ~200 blobs, 800 candidate detections each (BASELINE configs[2]/[4])",
-            "volumes_per_rank": vpr, "global_volumes_per_step": vpr * world, "volume_shape": list(SHAPE),
-            "dets_per_volume": CASE_KW["n_blobs"] + CASE_KW["n_dup"] + CASE_KW["n_false"], "nms_thresh": NMS_THRESH,
+    nd = CASE_KW["n_blobs"] + CASE_KW["n_dup"] + CASE_KW["n_false"]
+    return {"workload": "postproc_soma_chain: PRM peak stimulation (14x32x128x128 fp32 map, win 3, median) + 3D NMS(0.23) + per-instance 2D-Otsu + "
+                        "largest connected component + label paste-back on synthetic uint8 128x512x512 volumes, ~200 blobs, %d candidate "
+                        "detections each (BASELINE configs[2]/[4])" % nd,
+            "scaling": args.scaling, "global_volumes_per_step": vpr * world if args.scaling == "weak" else args.volumes,
+            "volumes_per_rank": vpr, "volume_shape": list(SHAPE), "response_map_shape": [14, 32, 128, 128],
+            "dets_per_volume": nd, "nms_thresh": NMS_THRESH,
             "l2": "per-step inputs+outputs (%.0f MB per rank) exceed the 126 MB L2; no explicit flush in the chain loop, "
                   "explicit 256 MB flush between iterations of the per-operator timings" % (vpr * 3 * np.prod(SHAPE) / 1e6),
             "parallelism": "volumes sharded by rank (np.array_split), dp%d" % world}
@@ -177,12 +224,27 @@ def time_op(torch, fn, iters, flush):
     return tot / iters
 
 
-def bench_ops(torch, peak):
-    """Per-operator timings on the BASELINE shapes (rank-local)."""
+def _ref_roialign_lib():
+    """The reference's own CUDA kernels (roi_align_kernel_3d.cu compiled unmodified into oracle/_ref): "the kernel to beat"."""
+    import ctypes
+    p_ = os.path.join(ROOT, "oracle", "_ref", "libref_roialign3d.so")
+    if not os.path.exists(p_):
+        return None
+    L = ctypes.CDLL(p_)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.ROIAlignForwardLaucher_3d.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.ROIAlignBackwardLaucher_3d.argtypes = [vp, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    return L
+
+
+def bench_ops(torch, peak, with_cpu=True):
+    """Per-operator timings on the BASELINE shapes (rank-local).  with_cpu: also time the reference's CPU implementation
+    of the operators that have one (Cython NMS / IoU from oracle/_ref, CPU-torch peak_stimulation_3d) on this host."""
+    import ctypes
     import b200seg
     from b200seg import synth
     from b200seg.roi_align_3d import roialign3d_forward, roialign3d_backward
-    from b200seg.peak_stimulation_3d import peaks_forward
+    from b200seg.peak_stimulation_3d import peaks_forward, PeaksPlan
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ops = {}
@@ -192,6 +254,21 @@ def bench_ops(torch, peak):
         d = {"ms": ms, "alg_bytes": bytes_alg, "achieved_gbs": gbs, "roofline_frac": gbs / peak}
         d.update(extra)
         return d
+
+    def cpu_time(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+
+    ref_nms = ref_bbox = None
+    if with_cpu:
+        try:
+            import oracle
+            ref_nms, ref_bbox = oracle.ref_module("cython_nms_3d"), oracle.ref_module("cython_bbox_3d")
+        except Exception:
+            pass
 
     # RoIAlign3D, config 4: 512 RoIs x 256 ch x 7^3 on (2,256,8,32,32), scale 1/8, sr 2
     feat, rois = synth.roialign_case(1004)
@@ -206,17 +283,69 @@ def bench_ops(torch, peak):
     fb = f.bfloat16()
     ms = time_op(torch, lambda: roialign3d_forward(fb, r, P, P, P, 0.125, 2), 20, flush)
     ops["roialign3d_fwd_bf16"] = entry(ms, (out_b + feat_b) // 2 + 28 * R, {"rois_per_s": R / (ms * 1e-3)})
+    gb = g.bfloat16()
+    ms = time_op(torch, lambda: roialign3d_backward(gb, r, feat.shape, 0.125, 2), 20, flush)
+    ops["roialign3d_bwd_bf16"] = entry(ms, (out_b + feat_b) // 2 + 28 * R, {"rois_per_s": R / (ms * 1e-3)})
+    # the reference's own CUDA kernels on the same inputs (launchers roi_align_kernel_3d.cu:153-172, :340-360; the caller
+    # zero-fills both outputs first, functions/roi_align_3d.py:26-28, :41-42 -- included, it is part of the reference's op)
+    RL = _ref_roialign_lib()
+    if RL is not None:
+        vp, cf = ctypes.c_void_p, ctypes.c_float
+        B_, _, S_, H_, W_ = feat.shape
+        out_ref = torch.empty((R, C, P, P, P), device=dev)
+        gin_ref = torch.empty(feat.shape, device=dev)
+
+        def ref_fwd():
+            out_ref.zero_()
+            RL.ROIAlignForwardLaucher_3d(vp(f.data_ptr()), cf(0.125), R, S_, H_, W_, C, P, P, P, 2, vp(r.data_ptr()), vp(out_ref.data_ptr()),
+                                         vp(torch.cuda.current_stream().cuda_stream))
+
+        def ref_bwd():
+            gin_ref.zero_()
+            RL.ROIAlignBackwardLaucher_3d(vp(g.data_ptr()), cf(0.125), B_, R, S_, H_, W_, C, P, P, P, 2, vp(r.data_ptr()), vp(gin_ref.data_ptr()),
+                                          vp(torch.cuda.current_stream().cuda_stream))
+        for nm, fn, ours in (("roialign3d_fwd_f32_reference_kernel", ref_fwd, "roialign3d_fwd_f32"), ("roialign3d_bwd_f32_reference_kernel", ref_bwd, "roialign3d_bwd_f32")):
+            ms = time_op(torch, fn, 20, flush)
+            ops[nm] = entry(ms, out_b + feat_b + 28 * R, {"rois_per_s": R / (ms * 1e-3),
+                                                          "note": "reference roi_align_kernel_3d.cu compiled unmodified for sm_100a (oracle/_ref), incl. the caller's zero fill"})
+            ops[ours]["vs_ref_kernel"] = ms / ops[ours]["ms"]
     # peak stimulation, config 3: fp32 (1,14,32,128,128), win 3, median filter
     x = torch.from_numpy(synth.response_map(np.random.default_rng(1003), (32, 128, 128), n_peaks=60, channels=14)).to(dev)
-    ms = time_op(torch, lambda: peaks_forward(x, 3, 1), 10, flush)
+    pplan = PeaksPlan(x.shape, dev, 3, 1)
+    ms = time_op(torch, lambda: pplan.run(x), 10, flush)
     ops["peaks3d_f32_14x32x128x128"] = entry(ms, 8 * x.numel(), {"gvox_per_s": x.numel() / (ms * 1e-3) / 1e9,
-                                                                  "note": "includes the D2H read of the peak count"})
+                                                                  "note": "device op (memset + 4 launches, count stays on the device)"})
+    ms2 = time_op(torch, lambda: peaks_forward(x, 3, 1), 10, flush)
+    ops["peaks3d_f32_14x32x128x128"]["ms_with_exact_size_list"] = ms2
+    x8 = x.repeat(8, 1, 1, 1, 1).contiguous()
+    pplan8 = PeaksPlan(x8.shape, dev, 3, 1)
+    ms = time_op(torch, lambda: pplan8.run(x8), 10, flush)
+    ops["peaks3d_f32_8x14x32x128x128"] = entry(ms, 8 * x8.numel(), {"gvox_per_s": x8.numel() / (ms * 1e-3) / 1e9, "note": "8 volumes' maps in one call"})
+    xf = torch.from_numpy(synth.response_map(np.random.default_rng(1003), (128, 512, 512), n_peaks=200, channels=1)).to(dev)
+    pplanf = PeaksPlan(xf.shape, dev, 3, 1)
+    ms = time_op(torch, lambda: pplanf.run(xf), 10, flush)
+    ops["peaks3d_f32_1x128x512x512"] = entry(ms, 8 * xf.numel(), {"gvox_per_s": xf.numel() / (ms * 1e-3) / 1e9, "note": "full-resolution variant of config 3"})
+    del x8, xf, pplan8, pplanf
+    if with_cpu:
+        try:
+            from oracle import refpy
+            rp = refpy.load_peaks()
+            xc = x.cpu()
+            medf = lambda inp: torch.median(inp.view(inp.size(0), inp.size(1), -1), dim=2)[0].contiguous().view(inp.size(0), inp.size(1), 1, 1, 1)
+            ops["peaks3d_f32_14x32x128x128"]["cpu_ref_ms"] = cpu_time(lambda: rp.peak_stimulation_3d(xc, win_size=3, peak_filter=medf), 2)
+            ops["peaks3d_f32_14x32x128x128"]["cpu_ref"] = "lib/prm/peak_stimulation_3d.py on CPU torch (%d threads)" % torch.get_num_threads()
+        except Exception as e:                                   # staged file missing
+            ops["peaks3d_f32_14x32x128x128"]["cpu_ref"] = "unavailable: %s" % e
     # IoU matrix: anchors x gt (917504 x 50)
     rng = np.random.default_rng(10)
-    bx = torch.from_numpy(synth.random_dets(rng, 917504, extent=(256, 256, 64), side=(8, 64))[:, :6].copy()).to(dev)
-    q = torch.from_numpy(synth.random_dets(rng, 50, extent=(256, 256, 64), side=(10, 40))[:, :6].copy()).to(dev)
+    bx_np = synth.random_dets(rng, 917504, extent=(256, 256, 64), side=(8, 64))[:, :6].copy()
+    q_np = synth.random_dets(rng, 50, extent=(256, 256, 64), side=(10, 40))[:, :6].copy()
+    bx, q = torch.from_numpy(bx_np).to(dev), torch.from_numpy(q_np).to(dev)
     ms = time_op(torch, lambda: b200seg.bbox_overlaps_3d(bx, q), 20, flush)
     ops["iou3d_917504x50"] = entry(ms, 24 * (917504 + 50) + 4 * 917504 * 50, {"pairs_per_s": 917504 * 50 / (ms * 1e-3)})
+    if ref_bbox is not None:
+        ops["iou3d_917504x50"]["cpu_ref_ms"] = cpu_time(lambda: ref_bbox.bbox_overlaps_3d(bx_np, q_np), 2)
+        ops["iou3d_917504x50"]["cpu_ref"] = "reference cython_bbox_3d.bbox_overlaps_3d (oracle/_ref), 1 core"
     # RLE codec of a 128x512x512 label mask (~200 blobs): encode reads the mask, decode writes it
     from b200seg import mask_3d, _lib as L_
     mvol = torch.from_numpy((synth.postproc_case(2000, **CASE_KW)["volume"] > 60).astype(np.uint8)).to(dev)
@@ -330,25 +459,52 @@ def bench_ops(torch, peak):
                                                              "score and delta maps stay on the device"}
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
-        d = torch.from_numpy(synth.random_dets(rng, n, extent=(256, 256, 64))).to(dev)
+        d_np = synth.random_dets(rng, n, extent=(256, 256, 64))
+        d = torch.from_numpy(d_np).to(dev)
         off = torch.tensor([0, n], dtype=torch.int32, device=dev)
         ms = time_op(torch, lambda: b200seg.nms_3d_batched(d, off, n, NMS_THRESH), 20, flush)
         ops["nms3d_n%d" % n] = {"us": ms * 1e3, "pairs_per_s": n * (n - 1) / 2 / (ms * 1e-3),
-                                "note": "latency bound, %s (includes the wrapper's output allocations)" % ("1 launch" if n <= 64 else "3 launches")}
+                                "note": "latency bound (includes the wrapper's output allocations)"}
+        if ref_nms is not None:
+            ops["nms3d_n%d" % n]["cpu_ref_us"] = cpu_time(lambda: ref_nms.nms_3d(d_np, np.float32(NMS_THRESH)), 5) * 1e3
+            ops["nms3d_n%d" % n]["cpu_ref"] = "reference cython_nms_3d.nms_3d (oracle/_ref), 1 core"
     return ops
+
+
+def make_cases(seeds):
+    """Synthetic volumes are independent: build them on a thread pool (numpy releases the GIL in the heavy parts)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(seeds), os.cpu_count() or 1, 16))) as ex:
+        return list(ex.map(make_case, seeds))
+
+
+def make_response_maps(ids):
+    from concurrent.futures import ThreadPoolExecutor
+    from b200seg import synth
+    f = lambda i: synth.response_map(np.random.default_rng(5000 + i), (32, 128, 128), n_peaks=60, channels=14)[0]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(ids), os.cpu_count() or 1, 16))) as ex:
+        return np.stack(list(ex.map(f, ids)))
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import b200seg
+    from b200seg.peak_stimulation_3d import PeaksPlan
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     peak, peak_src = hbm_peak()
-    vpr = args.volumes_per_rank
     V = int(np.prod(SHAPE))
+    if args.scaling == "strong":
+        vol_ids = volume_split(args.volumes, world, rank)
+    else:
+        vol_ids = list(range(rank * args.volumes_per_rank, (rank + 1) * args.volumes_per_rank))
+    vpr = len(vol_ids)
+    n_global = args.volumes if args.scaling == "strong" else args.volumes_per_rank * world
+    assert vpr > 0, "fewer volumes than ranks"
 
-    cases = [make_case(args.seed_base + rank * vpr + i) for i in range(vpr)]
+    cases = make_cases([args.seed_base + i for i in vol_ids])
+    maps_np = make_response_maps(vol_ids)                              # [vpr,14,32,128,128] fp32
     counts = [c["dets"].shape[0] for c in cases]
     prm_np = np.concatenate([c["prm"] for c in cases])
     offs, base = [], 0
@@ -360,24 +516,33 @@ def run_ours(args, rank, world, local_rank):
     boxes = torch.from_numpy(np.concatenate([c["boxes"] for c in cases])).to(dev)
     prm = torch.from_numpy(prm_np).to(dev)
     crop_off = torch.from_numpy(crop_off_np).to(dev)
+    maps = torch.from_numpy(maps_np).to(dev)
     pp = b200seg.SomaPostproc(vpr, SHAPE, counts, prm_np.size, device=dev)
-    n_max = max(counts)
+    plan = PeaksPlan(maps.shape, dev, 3, 1, want_agg=True, cap=maps.numel() // 16)
     # the detections live inside the chain's exchange buffer: the per-step gather needs no packing
     pp.dets_in.copy_(dets)
     dets = pp.dets_in
-    gather_out = torch.zeros((world, pp.exchange.numel()), dtype=torch.int32, device=dev) if world > 1 else None
+    # exchange buffers of all ranks have different sizes under strong scaling (array_split): gather into a padded buffer
+    ex_words = torch.tensor([pp.exchange.numel()], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ex_words, op=dist.ReduceOp.MAX)
+    ex_max = int(ex_words.item())
+    gather_out = torch.zeros((world, ex_max), dtype=torch.int32, device=dev) if world > 1 else None
     # The exchange of step i runs on a side stream and overlaps the (latency-bound) NMS phase of step i+1: the
     # chain's exchange buffer is snapshotted (0.2 MB device copy) so the next step may overwrite it.
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    snap = torch.empty_like(pp.exchange) if world > 1 else None
+    snap = torch.zeros(ex_max, dtype=torch.int32, device=dev) if world > 1 else None
     ev_chain, ev_gather = torch.cuda.Event(), torch.cuda.Event()
+    with_peaks = [True]
 
     def step():
+        if with_peaks[0]:
+            plan.run(maps)                                      # peak list, count, aggregation stay on the device
         pp.run(vols, dets, boxes, prm, crop_off, NMS_THRESH)
         if world > 1:
             main = torch.cuda.current_stream()
             main.wait_event(ev_gather)                      # the previous gather has finished reading `snap`
-            snap.copy_(pp.exchange)
+            snap[:pp.exchange.numel()].copy_(pp.exchange)
             ev_chain.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev_chain)
@@ -397,32 +562,63 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_block(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(nsteps):
+            step()
+        finish_steps()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                                     # before the barrier: spawning nvidia-smi must not skew rank 0
-    barrier()
     l0 = b200seg.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    finish_steps()
-    e1.record()
-    barrier()
+    # The timed region is K steps between barriers (max over ranks).  One block of K steps of this workload lasts only
+    # milliseconds, so the block is repeated until >= 0.5 s have been timed; ms_per_step is the mean over all blocks.
+    blocks = [timed_block(args.steps)]
+    while sum(blocks) < args.min_timed_ms and len(blocks) < 200:
+        blocks.append(timed_block(args.steps))
     launches = b200seg.launch_count() - l0
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    ms_step = sum(blocks) / (len(blocks) * args.steps)
+    lt = torch.tensor([launches // len(blocks)], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms_step = float(ms_total.item()) / args.steps
-    value = vpr * world * V / (ms_step * 1e-3) / 1e9
+    value = n_global * V / (ms_step * 1e-3) / 1e9
+    # ---- NCCL exchange content check: every rank's slot of the gathered buffer must equal that rank's own exchange data
+    exchange_ok = None
+    if world > 1:
+        torch.cuda.synchronize()
+        mine = torch.zeros(ex_max, dtype=torch.int32, device=dev)
+        mine[:pp.exchange.numel()].copy_(pp.exchange)
+        cks = torch.stack([mine.to(torch.int64).sum(), (mine.to(torch.int64) * torch.arange(1, ex_max + 1, device=dev)).sum()])
+        all_cks = [torch.zeros_like(cks) for _ in range(world)]
+        dist.all_gather(all_cks, cks)
+        got = gather_out.to(torch.int64)
+        ar = torch.arange(1, ex_max + 1, device=dev)
+        exchange_ok = all(int(got[r].sum()) == int(all_cks[r][0]) and int((got[r] * ar).sum()) == int(all_cks[r][1]) for r in range(world))
+        assert bool(torch.equal(gather_out[rank], mine)), "all-gather slot of this rank differs from its own exchange buffer"
+        assert exchange_ok, "all-gathered exchange buffer does not match the ranks' checksums"
+    # the chain alone (without peak stimulation), same protocol, one block
+    with_peaks[0] = False
+    step()
+    ms_nopeaks = timed_block(args.steps) / args.steps
+    with_peaks[0] = True
+    step()
+    torch.cuda.synchronize()
     keep_counts = pp.keep_count.cpu().numpy()
+    rank_order_np = pp.rank_order.cpu().numpy()
     kept_crop_bytes = 0
     for v in range(vpr):
-        order = pp.rank_order.cpu().numpy()[pp.det_off_host[v]:pp.det_off_host[v] + keep_counts[v]]
+        order = rank_order_np[pp.det_off_host[v]:pp.det_off_host[v] + keep_counts[v]]
         kept_crop_bytes += int(np.diff(cases[v]["crop_off"])[order].sum())
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (same inputs, same launches) -------
@@ -433,20 +629,45 @@ def run_ours(args, rank, world, local_rank):
         r = pp.run_profiled(vols, dets, boxes, prm, crop_off, NMS_THRESH)
         for k in prof:
             prof[k] += r[k] / reps
+    # peak stimulation kernel by kernel: the C-ABI's profiling knob stops the op after its first k launches
+    L = b200seg._lib.lib()
+    stage_ms = []
+    for k in (0, 1, 2, 3, 99):
+        L.b200seg_set_option(b"peaks_stop_after", k)
+        for _ in range(2):
+            plan.run(maps)
+        torch.cuda.synchronize()
+        tt = []
+        for _ in range(reps):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); plan.run(maps); b_.record(); torch.cuda.synchronize()
+            tt.append(a_.elapsed_time(b_))
+        stage_ms.append(float(np.median(tt)))
+    L.b200seg_set_option(b"peaks_stop_after", 99)
+    prof["peaks_scan"] = max(stage_ms[1] - stage_ms[0], 0.0)
+    prof["peaks_median"] = max(stage_ms[3] - stage_ms[1], 0.0)
+    prof["peaks_emit"] = max(stage_ms[4] - stage_ms[3], 0.0)
+    Vm = int(maps.numel())
+    n_pk = int(plan.n.item())
     # one launch covers every volume of the rank's batch
     alg = {"paste": 2 * V * vpr + kept_crop_bytes,                   # label volumes written once + mask bytes read
            "otsu": 3 * kept_crop_bytes,                              # image + prm read, mask written (uint8)
            "cc": kept_crop_bytes,                                    # masks read once (cleared runs are a few % more)
-           "nms": sum(28 * c + 16 * c * ((c + 63) // 64) + 8 * c for c in counts)}
-    per_launch_ms = {"paste": prof["paste"], "otsu": prof["otsu"], "cc": prof["cc"], "nms": prof["nms"]}
-    kernels = {k: {"ms_per_step": prof[k], "share": prof[k] / max(sum(prof.values()), 1e-9),
-                   "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (per_launch_ms[k] * 1e-3) / 1e9 if per_launch_ms[k] > 0 else None}
+           "nms": sum(28 * c + 16 * c * ((c + 63) // 64) + 8 * c for c in counts),
+           "peaks_scan": 4 * Vm + Vm // 8,                           # the map read once + the 1 bit / voxel candidate mask
+           "peaks_median": 4 * Vm,                                   # the second read of the map (8 B / voxel in total)
+           "peaks_emit": Vm // 8 + 4 * n_pk + 40 * n_pk}             # mask read, candidate values, int64 rows written
+    names = {"paste": "paste_labels_kernel", "otsu": "soma_binarize_kernel", "cc": "largest_cc_fill_kernel", "nms": "nms3d (3 kernels)",
+             "peaks_scan": "peaks_scan3w_kernel", "peaks_median": "peaks_collect_kernel", "peaks_emit": "peaks_finalize_kernel"}
+    tot_prof = max(sum(prof.values()), 1e-9)
+    kernels = {k: {"kernel": names[k], "ms_per_step": prof[k], "share": prof[k] / tot_prof,
+                   "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (prof[k] * 1e-3) / 1e9 if prof[k] > 0 else None}
                for k in prof}
     dom = max(prof, key=lambda k: prof[k])
-    roof = {"bound": "hbm", "kernel": {"paste": "paste_labels_kernel", "otsu": "soma_binarize_kernel", "cc": "largest_cc_fill_kernel", "nms": "nms3d (3 kernels)"}[dom],
+    roof = {"bound": "hbm", "kernel": names[dom],
             "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-            "launch_ms": per_launch_ms[dom], "alg_bytes_per_launch": alg[dom]}
+            "launch_ms": prof[dom], "alg_bytes_per_launch": alg[dom]}
     tr = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes per launch from the committed ncu capture
     if os.path.exists(tr):
         try:
@@ -456,8 +677,8 @@ def run_ours(args, rank, world, local_rank):
 
     if args.chain_only:
         if rank == 0:
-            print(json.dumps({"metric": "postproc_gvox_per_s", "value": value, "ms_per_step": ms_step, "kernels": kernels,
-                              "gpu_launches": int(lt.item()), "note": "chain-only profiling run"}))
+            print(json.dumps({"metric": "postproc_gvox_per_s", "value": value, "ms_per_step": ms_step, "ms_per_step_without_peaks": ms_nopeaks,
+                              "kernels": kernels, "gpu_launches": int(lt.item()), "note": "chain-only profiling run"}))
         return
     # ---- e2e: host-buffer C-ABI call, pinned memory, H2D + D2H inside the timed region --------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -471,58 +692,94 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_step():
         # one C call for the rank's batch: uploads, kernels and downloads of consecutive volumes overlap
-        b200seg.postproc_soma_host_batch(e2e_cases, NMS_THRESH, seg_out=e2e_segs)
+        return b200seg.postproc_soma_host_batch(e2e_cases, NMS_THRESH, seg_out=e2e_segs)
     for _ in range(2):
-        e2e_step()
+        e2e_out = e2e_step()
+    e2e_steps = max(2, min(args.steps, int(np.ceil(640.0 / max(vpr, 1)))))         # about 10 passes over 64 volumes at most
     barrier()
     l1 = b200seg.launch_count()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = vpr * world * V * args.steps / float(dt.item()) / 1e9
-    e2e_launches = b200seg.launch_count() - l1
+    e2e_val = n_global * V * e2e_steps / float(dt.item()) / 1e9
+    e2e_launches = (b200seg.launch_count() - l1) // e2e_steps
     h2d = sum(c["volume"].nbytes + c["dets"].nbytes + c["boxes"].nbytes + c["prm"].nbytes + c["crop_off"].nbytes + 8 for c in cases)
     d2h = sum(2 * V + 4 + c["dets"].shape[0] * 13 for c in cases)
     clocks = sampler.stop() if rank == 0 else None
-    # correctness guard on the e2e output (cheap): labels present == survivors of volume 0
-    assert np.array_equal(h_seg[0].numpy(), pp.seg[0].cpu().numpy()), "e2e and device-resident chains disagree"
 
-    ops = bench_ops(torch, peak) if rank == 0 or world > 1 else {}
+    # ---- parity of THIS run's workload against the oracle (and the CPU baselines, which are the same computation) ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_chain
+    oracle = load_oracle_in_parent()
+    n_check = min(vpr, args.parity_volumes)
+    t_port, checked = 0.0, 0
+    seg_dev = pp.seg
+    surv_np = pp.survive.cpu().numpy()
+    for v in range(n_check):
+        t0 = time.perf_counter()
+        o = oracle_chain(cases[v], NMS_THRESH)
+        t_port += time.perf_counter() - t0
+        lo = int(pp.det_off_host[v]); k = int(keep_counts[v])
+        assert np.array_equal(rank_order_np[lo:lo + k], o["order"]), "bench parity: NMS / visit order of volume %d differs from the oracle" % v
+        assert np.array_equal(surv_np[lo:lo + k].astype(bool), o["survive"]), "bench parity: survivor flags of volume %d differ" % v
+        assert np.array_equal(seg_dev[v].cpu().numpy(), o["seg"]), "bench parity: label volume %d (device chain) differs from the oracle" % v
+        assert np.array_equal(e2e_segs[v], o["seg"]), "bench parity: label volume %d (host-buffer call) differs from the oracle" % v
+        assert np.array_equal(e2e_out[v]["rank_order"], o["order"]), "bench parity: e2e visit order of volume %d differs" % v
+        checked += 1
+    peaks_checked = 0
+    if rank == 0 and not args.no_cpu_baseline:
+        op, oagg, othr = oracle.peak_stimulation_3d(maps_np[:1], win_size=3, filter_mode="median")
+        rows = plan.peaks[:n_pk].cpu().numpy()
+        assert np.array_equal(rows[rows[:, 0] == 0], op), "bench parity: peak list of volume 0 differs from the oracle"
+        assert np.array_equal(plan.thr[0].cpu().numpy(), othr[0]), "bench parity: median thresholds of volume 0 differ"
+        peaks_checked = 1
+
+    ops = bench_ops(torch, peak, with_cpu=(rank == 0 and not args.no_cpu_baseline)) if rank == 0 or world > 1 else {}
     if world > 1:                                           # replicas: aggregate RoIs/s over ranks
-        for k in ("roialign3d_fwd_f32", "roialign3d_bwd_f32", "roialign3d_fwd_bf16"):
+        for k in ("roialign3d_fwd_f32", "roialign3d_bwd_f32", "roialign3d_fwd_bf16", "roialign3d_bwd_bf16"):
             t = torch.tensor([ops[k]["ms"]], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ops[k]["rois_per_s_all_ranks"] = 512 * world / (float(t.item()) * 1e-3)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import oracle_chain
-        t0, n_done = time.perf_counter(), 0
-        for c in cases:
-            oracle_chain(c, NMS_THRESH)
-            n_done += 1
-            if time.perf_counter() - t0 > 12.0:
-                break
-        dtc = time.perf_counter() - t0
-        cpu = {"value": n_done * V / dtc / 1e9, "unit": "Gvox/s", "cores": 1, "kind": "port",
-               "sample": "%d of the %d volumes of this step, oracle C port of the reference chain (cython NMS, otsu_py_2d_fast, "
-                         "numpy paste) on 1 of %d host cores, %.1f s" % (n_done, vpr, os.cpu_count() or 1, dtc)}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import refpy
+        port = {"value": n_check * V / t_port / 1e9, "unit": "Gvox/s", "cores": 1,
+                "note": "oracle C restatement of the chain (cython NMS, otsu_py_2d_fast, scipy label, numpy paste) on %d whole volumes of this "
+                        "step, %.1f s -- the same runs that produced parity_checked" % (n_check, t_port)}
+        if refpy.available():
+            k_inst = 64
+            r = refpy.run_soma_script(cases[0], NMS_THRESH, max_instances=k_inst)
+            frac = r["n_visited"] / max(r["n_after_nms"], 1)
+            tref = r["t_nms"] + r["t_loop"]
+            cpu = {"value": frac * V / tref / 1e9, "unit": "Gvox/s", "cores": 1, "kind": "reference",
+                   "sample": "tools/binarization_soma.py:57-104 executed as is (reference Cython nms_3d, tools/otsu.py otsu_py_2d_fast, the script's numpy "
+                             "crop / paste / np.unique; skimage label -> scipy) on volume 0 of this step for the first %d of %d detections of its visit "
+                             "order, %.1f s on 1 of %d host cores; value = fraction of the visit list x voxels / time; peak stimulation: see "
+                             "ops.peaks3d.cpu_ref_ms" % (r["n_visited"], r["n_after_nms"], tref, os.cpu_count() or 1),
+                   "port": port}
+        else:
+            cpu = dict(port, kind="port", sample=port["note"])
     if rank == 0:
         line = {"metric": "postproc_gvox_per_s", "value": value, "unit": "Gvox/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world, vpr),
+                "timed_blocks": len(blocks), "timed_region_s": sum(blocks) / 1e3,
+                "value_without_peaks": n_global * V / (ms_nopeaks * 1e-3) / 1e9, "ms_per_step_without_peaks": ms_nopeaks,
+                "parity_checked": checked, "peaks_parity_checked": peaks_checked, "exchange_checked": exchange_ok,
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "Gvox/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "gpu_launches": int(e2e_launches)},
+                        "gpu_launches": int(e2e_launches), "steps": e2e_steps,
+                        "note": "binarization chain through b200seg_postproc_soma_host_batch; the peak finder's input is the network's "
+                                "response map, which never exists on the host in the reference flow (peak_response_mapping_3d.py:150)"},
                 "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,
-                "kept_instances_per_volume": float(np.mean(keep_counts)),
-                "chain_roofline": {"alg_bytes_per_volume": (4 * kept_crop_bytes / vpr) + 2 * V + alg["nms"] / vpr,
-                                   "frac": ((4 * kept_crop_bytes / vpr) + 2 * V) / (ms_step / vpr * 1e-3) / 1e9 / peak}}
+                "kept_instances_per_volume": float(np.mean(keep_counts)), "peaks_per_volume": n_pk / vpr,
+                "chain_roofline": {"alg_bytes_per_volume": (4 * kept_crop_bytes / vpr) + 2 * V + alg["nms"] / vpr + 8 * Vm / vpr,
+                                   "frac": ((4 * kept_crop_bytes / vpr) + 2 * V + 8 * Vm / vpr) / (ms_step / vpr * 1e-3) / 1e9 / peak}}
         print(json.dumps(line))
 
 
@@ -532,7 +789,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--volumes-per-rank", type=int, default=8)
+    ap.add_argument("--volumes", type=int, default=64, help="volumes per step over ALL ranks (strong scaling, BASELINE configs[4])")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--volumes-per-rank", type=int, default=8, help="weak scaling only")
+    ap.add_argument("--parity-volumes", type=int, default=8, help="volumes of this run checked against the oracle chain")
+    ap.add_argument("--min-timed-ms", type=float, default=500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed-base", type=int, default=2000, help="seed of the first synthetic volume (volume i of rank r: base + r*vpr + i)")
     ap.add_argument("--chain-only", action="store_true", help="profiling aid: time only the device-resident chain")

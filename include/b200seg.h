@@ -44,6 +44,10 @@ const char* b200seg_last_error(void);
 int b200seg_version(void);
 /* Number of kernels launched by this library in the calling process so far (all entry points). */
 long long b200seg_launch_count(void);
+/* Profiling knobs (no effect on results unless stated).  "peaks_stop_after" = k: b200seg_peaks3d_dev returns after its
+ * first k kernel launches (0 = memset only, 99 = the whole op, the default), so that a caller can time the op kernel by
+ * kernel with CUDA events; outputs are incomplete while k < 99.  Unknown names return B200SEG_EINVAL. */
+int b200seg_set_option(const char* name, int value);
 
 /* ----------------------------------------------------------------------------------------------
  * 3D NMS  -- replaces lib/utils/cython_nms_3d.pyx:39-96 (nms_3d) and :102-159 (nms_3d_volume),

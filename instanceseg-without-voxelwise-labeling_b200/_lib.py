@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200seg_last_error": (C.c_char_p, []),
     "b200seg_version": (_i, []),
     "b200seg_launch_count": (_ll, []),
+    "b200seg_set_option": (_i, [C.c_char_p, _i]),
     "b200seg_nms3d_workspace_bytes": (_sz, [_i, _i]),
     "b200seg_nms3d_dev": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200seg_nms3d_host": (_i, [_vp, _i, _f, _i, _vp, C.POINTER(C.c_int)]),

@@ -62,6 +62,11 @@ int HostCtx::ensure(size_t bytes) {
 static HostCtx g_host;
 HostCtx& host_ctx() { return g_host; }
 
+// profiling knobs (b200seg_set_option)
+static std::atomic<int> g_peaks_stop_after{99};
+int opt_peaks_stop_after() { return g_peaks_stop_after.load(std::memory_order_relaxed); }
+void opt_set_peaks_stop_after(int v) { g_peaks_stop_after.store(v, std::memory_order_relaxed); }
+
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -69,6 +74,13 @@ using namespace b200seg;
 extern "C" const char* b200seg_last_error(void) { return g_err; }
 extern "C" int b200seg_version(void) { return B200SEG_VERSION; }
 extern "C" long long b200seg_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b200seg_set_option(const char* name, int value) {
+    B200_CHECK_ARG(name, "set_option: null name");
+    if (!strcmp(name, "peaks_stop_after")) { opt_set_peaks_stop_after(value); return 0; }
+    set_error("set_option: unknown option '%s'", name);
+    return B200SEG_EINVAL;
+}
 
 extern "C" int b200seg_nms3d_host(const float* dets, int n, float thresh, int by_volume, int64_t* keep, int* n_keep) {
     B200_CHECK_ARG(n >= 0 && n_keep, "nms3d_host: bad arguments");

@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int opt_peaks_stop_after();          // profiling knob: peaks3d stops after its first k kernels (99 = run all)
 
 #define B200_CHECK_ARG(cond, ...)                         \
     do {                                                  \

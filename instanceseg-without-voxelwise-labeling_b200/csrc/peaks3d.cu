@@ -1036,7 +1036,7 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
     B200_CUDA(cudaMemsetAsync(base, 0, ws.zero_bytes, stream));
     const int sms = num_sms();
     const int do_hist = filter_mode == 1;
-    static const int stop_after = getenv("B200SEG_PEAKS_STOP") ? atoi(getenv("B200SEG_PEAKS_STOP")) : 99;    // profiling aid: run only the first k kernels
+    const int stop_after = opt_peaks_stop_after();        // profiling aid (b200seg_set_option): run only the first k kernels
     if (stop_after < 1) return 0;
     if (win == 3) {
         static const int variant = getenv("B200SEG_PEAKS_VARIANT") ? atoi(getenv("B200SEG_PEAKS_VARIANT")) : 0;

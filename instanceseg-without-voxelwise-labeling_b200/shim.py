@@ -56,16 +56,33 @@ def install(overwrite=True):
     installed = []
     for name, mod in mods.items():
         if overwrite or name not in sys.modules:
-            sys.modules[name] = mod
-            installed.append(name)
-            # make `import a.b.c` work when the parents are absent: create empty parent packages
             parts = name.split(".")
+            # Parents first.  The reference's own packages (lib/utils, lib/modeling, lib/prm: they have __init__.py and hold
+            # many modules this layer does not replace -- utils.boxes_3d, utils.net, modeling.model_builder, ...) must stay
+            # importable, so a parent is taken from sys.path when it is there and only fabricated when it is not; a
+            # fabricated parent still points its __path__ at any matching directory found on sys.path.
             for i in range(1, len(parts)):
                 parent = ".".join(parts[:i])
                 if parent not in sys.modules:
-                    pm = types.ModuleType(parent)
-                    pm.__path__ = []
-                    pm.__b200seg_shim__ = True
-                    sys.modules[parent] = pm
-                setattr(sys.modules[parent], parts[i], sys.modules.get(".".join(parts[:i + 1]), None) or mod)
+                    sys.modules[parent] = _import_or_fabricate(parent)
+            sys.modules[name] = mod
+            installed.append(name)
+            for i in range(1, len(parts)):
+                setattr(sys.modules[".".join(parts[:i])], parts[i], sys.modules[".".join(parts[:i + 1])])
     return installed
+
+
+def _import_or_fabricate(parent):
+    import importlib
+    import os
+    try:
+        return importlib.import_module(parent)          # the real package (e.g. the reference's lib/utils) wins
+    except Exception:
+        pass
+    pm = types.ModuleType(parent)
+    rel = parent.split(".")
+    grand = ".".join(rel[:-1])
+    roots = list(getattr(sys.modules.get(grand), "__path__", [])) if grand else list(sys.path)
+    pm.__path__ = [d for d in (os.path.join(r or ".", rel[-1]) for r in roots) if os.path.isdir(d)]
+    pm.__b200seg_shim__ = True
+    return pm

@@ -67,6 +67,9 @@ def postproc_case(seed, shape=(64, 256, 256), n_blobs=35, n_dup=10, n_false=5, s
         owners += [int(s) for s in src]
     if n_false:
         fd = random_dets(rng, n_false, extent=(W, H, S), side=(6, 24))[:, :6]
+        # detections reach the scripts clipped to the tile (boxes_3d.py:144-225 clip_tiled_boxes_3d); the reference script
+        # indexes with the raw int() box and fails on a box that leaves the volume
+        fd = np.clip(fd, 0, np.array([W - 1, H - 1, S - 1, W - 1, H - 1, S - 1], dtype=np.float32))
         allb.append(fd)
         owners += [int(v) for v in rng.integers(0, n_blobs, n_false)]
     allb = np.concatenate(allb, axis=0)

@@ -19,6 +19,9 @@ What is built (reference file -> output):
 The C is compiled with plain `gcc -O2` and no -march flag, i.e. baseline x86-64 without FMA
 contraction, which is what a stock `python setup.py build_ext` of the reference produces.
 
+Besides the shared objects, oracle/refpy.py:stage() copies five reference .py files byte for byte into oracle/_ref/py/
+(same status: git-ignored build output that travels to the GPU box).
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 load anything from oracle/.
 """
@@ -60,8 +63,13 @@ def build_ref(force=False):
     wanted.append(os.path.join(OUT, "libref_roialign3d.so"))
     if not os.path.isdir(REF):
         return [w for w in wanted if os.path.exists(w)]
+    # the reference's Python on this path (otsu.py, the two binarization scripts, boxes_3d.py, peak_stimulation_3d.py),
+    # staged byte for byte next to the compiled modules: the GPU box has no /root/reference (oracle/refpy.py)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import refpy
+    staged = refpy.stage()
     if not force and all(os.path.exists(w) for w in wanted):
-        return wanted
+        return wanted + staged
     scratch = tempfile.mkdtemp(prefix="b200seg_ref_")
     try:
         utils = os.path.join(REF, "lib", "utils")
@@ -85,7 +93,7 @@ def build_ref(force=False):
               "-o", os.path.join(OUT, "libref_roialign3d.so")])
     finally:
         shutil.rmtree(scratch, ignore_errors=True)
-    return wanted
+    return wanted + staged
 
 
 if __name__ == "__main__":

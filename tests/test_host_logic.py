@@ -184,3 +184,33 @@ def test_eval_host_logic_golden(golden):
     assert ev.match_by_iou(np.zeros((3, 0)), 0.3) == [0, 0, 0]
     tp, fp, matched = ev.match_boxes_tp_fp(np.zeros((2, 6)), np.zeros((0, 6)), 0.4)
     assert not tp.any() and not fp.any() and not matched.any()          # the script leaves tp / fp at 0 without ground truth
+
+
+def test_shim_keeps_the_reference_packages_importable(tmp_path):
+    """install() must not shadow the reference's own `utils` / `modeling` / `prm` packages.  A fake lib tree
+    with utils/boxes_3d.py (importing the shimmed Cython names) and utils/net.py must import after install()."""
+    import subprocess
+    lib = tmp_path / "lib"
+    (lib / "utils").mkdir(parents=True)
+    (lib / "utils" / "__init__.py").write_text("")
+    (lib / "utils" / "boxes_3d.py").write_text(
+        "import utils.cython_bbox_3d as cython_bbox_3d\nimport utils.cython_nms_3d as cython_nms_3d\n"
+        "bbox_overlaps_3d = cython_bbox_3d.bbox_overlaps_3d\n"
+        "def nms_3d(dets, thresh):\n    return [] if dets.shape[0] == 0 else cython_nms_3d.nms_3d(dets, thresh)\n")
+    (lib / "utils" / "net.py").write_text("X = 1\n")
+    (lib / "prm").mkdir()
+    (lib / "prm" / "__init__.py").write_text("")
+    (lib / "prm" / "peak_backprop_3d.py").write_text("Y = 2\n")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import b200seg.shim as shim; shim.install()\n"
+            "import utils.boxes_3d, utils.net, prm.peak_backprop_3d, prm.peak_stimulation_3d\n"
+            "import utils, prm\n"
+            "assert utils.__file__.startswith(%r) and utils.net.X == 1 and prm.peak_backprop_3d.Y == 2\n"
+            "assert getattr(utils.boxes_3d.cython_nms_3d, '__b200seg_shim__', False)\n"
+            "assert hasattr(prm.peak_stimulation_3d, 'peak_stimulation_3d')\n"
+            "import modeling.roi_xfrom.roi_align_3d.functions.roi_align_3d as f\n"
+            "assert hasattr(f, 'RoIAlignFunction_3d')\n"
+            "import numpy as np; assert utils.boxes_3d.nms_3d(np.zeros((0, 7), np.float32), 0.3) == []\n"
+            "print('ok')\n") % (ROOT, str(lib), str(lib))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

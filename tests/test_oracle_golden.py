@@ -335,3 +335,76 @@ def test_soma_script_golden(golden):
     ids = np.arange(1, len(oc["order"]) + 1)[alive]
     rows = np.stack([ids.astype(np.float64), g["dets"][oc["order"], 6][alive].astype(np.float64)], axis=1)
     assert np.array_equal(rows, g["scores"]) and 3 in oc["status"].values()          # an empty-PRM instance was skipped
+
+
+# ------------------------------------------------------------------------------------------ round 2: the oracle against the
+# reference's own Python, live (the staged files of oracle/_ref/py travel with the repo; skipped when they were never staged)
+def test_oracle_otsu_vs_reference_python_1000_crops():
+    """oracle.otsu_py_2d_fast == tools/otsu.py:otsu_py_2d_fast (b_max and mask) on >= 10^3 seeded crops: soma-normalised blob
+    crops, few-level crops with exact ties in the criterion, noise and correlated attributes (same generator family as the GPU
+    stress test, which checks the CUDA path against the oracle on >= 10^4 crops)."""
+    from oracle import refpy
+    if not refpy.available():
+        pytest.skip("oracle/_ref/py not staged")
+    ref = refpy.load_otsu().otsu_py_2d_fast
+    rng = np.random.default_rng(2718)
+    old = np.seterr(all="ignore")
+    n_ok = n_raise = 0
+    try:
+        for i in range(1000):
+            shape = tuple(int(v) for v in rng.integers(3, 9, 3))
+            kind = i % 4
+            if kind == 0:
+                zz, yy, xx = np.meshgrid(*[np.arange(s_) for s_ in shape], indexing="ij")
+                c = [s_ / 2 + rng.uniform(-1, 1) for s_ in shape]
+                r2 = sum(((g_ - c_) / (s_ / 3 + 0.5)) ** 2 for g_, c_, s_ in zip((zz, yy, xx), c, shape))
+                v = np.clip(rng.uniform(0, 40, shape) + rng.uniform(80, 200) * np.exp(-0.5 * r2), 0, 255).astype(np.uint8)
+                p = (255 * np.exp(-0.5 * r2 / 0.64)).astype(np.uint8)
+                if p.max() == 0 or v.max() == 0:
+                    p[tuple(s_ // 2 for s_ in shape)] = 200; v[tuple(s_ // 2 for s_ in shape)] = 100
+                # fewer levels than the soma range keep the reference's Python loop over b short
+                a = (v // 4).astype(np.uint16) + 30; b = (p // 4).astype(np.uint16) + 30
+            elif kind == 1:
+                a = rng.integers(0, int(rng.integers(2, 6)), shape).astype(np.uint16) * int(rng.integers(1, 12)) + int(rng.integers(0, 300))
+                b = rng.integers(0, int(rng.integers(2, 6)), shape).astype(np.uint16) * int(rng.integers(1, 12)) + int(rng.integers(0, 300))
+            elif kind == 2:
+                a = rng.integers(0, int(rng.integers(5, 70)), shape).astype(np.uint16)
+                b = rng.integers(0, int(rng.integers(5, 70)), shape).astype(np.uint16)
+            else:
+                a = rng.integers(0, 60, shape).astype(np.uint16)
+                b = (a // int(rng.integers(1, 5)) + rng.integers(0, 3, shape)).astype(np.uint16)
+            try:
+                rm, _, rb = ref(a, b)
+            except (NameError, UnboundLocalError):
+                with pytest.raises(UnboundLocalError):
+                    oracle.otsu_py_2d_fast(a, b)
+                n_raise += 1
+                continue
+            om, _, ob = oracle.otsu_py_2d_fast(a, b)
+            assert ob == rb, (i, ob, rb)
+            assert np.array_equal(om, rm), i
+            n_ok += 1
+    finally:
+        np.seterr(**old)
+    assert n_ok >= 900
+
+
+def test_oracle_chain_vs_reference_script_live():
+    """The oracle chain that checks every GPU chain test == the reference script's own lines 57-104 executed on a fresh seeded
+    case with the reference's Cython NMS and tools/otsu.py (a second, independent case besides tests/golden/soma_script.npz)."""
+    import sys, os
+    from oracle import refpy
+    if not refpy.available():
+        pytest.skip("oracle/_ref/py not staged")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import oracle_chain
+    # no false boxes: the script indexes with the raw int() box and breaks on boxes that leave the volume (negative start
+    # = empty numpy slice); the detector clips boxes to the tile (boxes_3d.py:144-225), dets_to_boxes mirrors that clip
+    c = synth.postproc_case(77, shape=(24, 80, 96), n_blobs=6, n_dup=3, n_false=0)
+    c["volume"] = (c["volume"] // 16 * 16).astype(np.uint8)       # coarse gray levels keep the Python Otsu loop short
+    r = refpy.run_soma_script(c, 0.23)
+    o = oracle_chain(c, 0.23)
+    assert np.array_equal(r["seg"], o["seg"])
+    assert np.array_equal(r["visited_dets"], c["dets"][o["order"]])
+    ids = np.flatnonzero(o["survive"]) + 1
+    assert np.array_equal(r["scores"][:, 0], ids.astype(np.float64))
