@@ -17,8 +17,10 @@
  *     internal stream with grow-only device scratch, and return when the result is in host memory.
  *     They are what the reference's numpy call sites bind to.
  *   - Boxes are (x1,y1,z1,x2,y2,z2) with inclusive "+1" extents, as in the reference.
- *   - Tie rule for equal sort keys (scores / volumes): key descending, then original index
- *     ascending (numpy's default argsort, cython_nms_3d.pyx:49, is unstable and platform dependent).
+ *   - Tie rule for equal sort keys (scores / volumes) in NMS and in the visit order: key descending, then original
+ *     index DESCENDING.  The reference takes `argsort()[::-1]` (cython_nms_3d.pyx:49, binarization_soma.py:60); numpy's
+ *     default sort is stable below 17 elements (ties ascending, so the reversal puts the higher index first) and
+ *     build dependent above -- the rule reproduces the reference wherever that sort is stable.
  */
 #ifndef B200SEG_H_
 #define B200SEG_H_
@@ -375,7 +377,8 @@ int b200seg_segm_paste_host(const float* masks, long long n_mask_blocks, const i
  * Outputs: seg [S,H,W] uint16 (fully written), masks (final per-instance masks 0/255, packing of prm), b_max[n], status[n]:
  *   0 ok; 1 Otsu found no threshold; 2 box outside the volume or crop size mismatch; 4 more than 2048 gray levels;
  *   5 no foreground / no background left (the reference raises); 6 degenerate crop (see b200seg_largest_cc_dev);
- *   7 normalisation divides 0 by 0 (gray_max == 0 or constant PRM crop; the reference continues with NaN garbage);
+ *   (where the script's normalisation divides 0 by 0 -- gray_max == 0 under the stretch, constant PRM crop -- numpy's NaN
+ *   becomes 0 in the uint16 cast and the script carries on; the kernels do the same, status 7 of round 1 is gone);
  *   survive[n]: label present in seg.  Instances with status != 0 paste nothing.
  * Connected components and closing are cc3d / skimage in the reference (unversioned, not vendored): parity is pinned
  * against scipy.ndimage (label with the 3x3x3 structure, binary_dilation / binary_erosion(border_value=1)).

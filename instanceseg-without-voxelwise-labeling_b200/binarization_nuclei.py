@@ -73,6 +73,11 @@ def binarize_nuclei_host(volume, boxes, prm_crops, seg_out=None, want_masks=Fals
     _lib.check(_lib.lib().b200seg_binarize_nuclei_host(_lib.ptr(volume), volume.dtype.itemsize, S, H, W, _lib.ptr(boxes), _lib.ptr(prm),
                                                        _lib.ptr(off), n, _lib.ptr(seg), _lib.ptr(masks), _lib.ptr(b_max), _lib.ptr(status),
                                                        _lib.ptr(survive)), "b200seg_binarize_nuclei_host")
+    if (status[:n] == 4).any():
+        # the generic 2D-Otsu kernel holds at most 2048 gray levels in shared memory; the reference would binarize such a crop
+        # (uint16 data whose range exceeds 2048 levels inside one box): refuse loudly instead of dropping the instance
+        raise _lib.B200SegError("binarize_nuclei_host: instance(s) %s span more than 2048 gray levels (unsupported by the 2D-Otsu kernel)"
+                                % np.flatnonzero(status[:n] == 4).tolist())
     out = dict(seg=seg, status=status[:n], b_max=b_max[:n], survive=survive[:n].astype(bool), crop_off=off)
     if want_masks:
         out["masks"] = masks[:int(off[-1])]
@@ -81,7 +86,8 @@ def binarize_nuclei_host(volume, boxes, prm_crops, seg_out=None, want_masks=Fals
 
 def binarize_nuclei(volume, boxes, prm, crop_off):
     """Device form: volume uint8 / uint16 cuda [S,H,W], boxes int32 cuda [n,6], prm uint8 cuda (packed), crop_off int64 cuda
-    [n+1].  Returns (seg uint16 cuda, masks uint8 cuda, b_max, status int32 cuda, survive uint8 cuda); no synchronisation."""
+    [n+1].  Returns (seg uint16 cuda, masks uint8 cuda, b_max, status int32 cuda, survive uint8 cuda); no synchronisation -- the
+    caller must check `status`: 4 = more than 2048 gray levels in the box (unsupported, nothing pasted)."""
     import torch
     S, H, W = volume.shape
     n = int(boxes.shape[0])

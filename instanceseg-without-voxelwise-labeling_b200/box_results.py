@@ -12,6 +12,13 @@ from . import boxes_3d
 def _settings(kw):
     try:
         from core.config import cfg
+        # the reference switches to soft_nms_3d / box_voting under these flags (core/test.py:839-861); neither is built
+        # (both off in every shipped config, and the soft-NMS call site names a function that does not exist): fail loudly
+        # instead of silently returning hard-NMS results
+        if getattr(getattr(cfg.TEST, "SOFT_NMS", None), "ENABLED", False):
+            raise NotImplementedError("cfg.TEST.SOFT_NMS.ENABLED is set: soft_nms_3d is not implemented by b200seg")
+        if getattr(getattr(cfg.TEST, "BBOX_VOTE", None), "ENABLED", False):
+            raise NotImplementedError("cfg.TEST.BBOX_VOTE.ENABLED is set: box voting is not implemented by b200seg")
         d = dict(num_classes=cfg.MODEL.NUM_CLASSES, rpn_only=cfg.MODEL.RPN_ONLY, score_thresh=cfg.TEST.SCORE_THRESH, nms=cfg.TEST.NMS,
                  detections_per_im=cfg.TEST.DETECTIONS_PER_IM)
     except ImportError:

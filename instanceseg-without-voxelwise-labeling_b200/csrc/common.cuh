@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <atomic>
 
 #include "../../include/b200seg.h"
 
@@ -40,6 +41,19 @@ int opt_peaks_stop_after();          // profiling knob: peaks3d stops after its 
         int _e = ::b200seg::check_cuda(cudaGetLastError(), name);    \
         if (_e) return _e;                                           \
     } while (0)
+
+// "do this once per device" flag for per-function attributes (cudaFuncSetAttribute is per device): one bit per device ordinal,
+// lock-free; a lost race only repeats an idempotent call.
+struct OncePerDevice {
+    std::atomic<unsigned long long> done{0ull};
+    bool needed(int* dev_out) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *dev_out = -1; return true; }
+        *dev_out = dev;
+        return !(done.load(std::memory_order_acquire) & (1ull << dev));
+    }
+    void mark(int dev) { if (dev >= 0) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -610,17 +610,19 @@ extern "C" int b200seg_largest_cc_ex_dev(uint8_t* masks, const int64_t* crop_off
         return B200SEG_EWORKSPACE;
     }
     unsigned long long* scratch = (unsigned long long*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr;
+    int attr_dev;
+    if (attr.needed(&attr_dev)) {
         B200_CUDA(cudaFuncSetAttribute(largest_cc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC_DYN_BYTES));
-        attr_set = true;
+        attr.mark(attr_dev);
     }
     if (status) {                                            // warp-per-instance flood fill first; it marks what it finished
         const size_t fill_smem = (size_t)2 * CCF_ROWS * 8;
-        static bool fill_attr_set = false;
-        if (!fill_attr_set) {
+        static OncePerDevice fill_attr;
+        int fill_dev;
+        if (fill_attr.needed(&fill_dev)) {
             B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-            fill_attr_set = true;
+            fill_attr.mark(fill_dev);
         }
         dim3 fgrid(n_max, n_volumes);
         largest_cc_fill_kernel<<<fgrid, CCF_WARPS * 32, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);

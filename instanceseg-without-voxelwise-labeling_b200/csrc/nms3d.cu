@@ -1,7 +1,8 @@
 // nms3d.cu -- batched 3D greedy NMS on the GPU (replaces lib/utils/cython_nms_3d.pyx:39-159).
 //
 // Three launches per batch of detection sets (one for sets of at most 64 boxes, nms_small_kernel), no host round trip:
-//   1. nms_rank_kernel   rank sort: rank(i) = #{j : key_j > key_i or (key_j == key_i and j < i)}
+//   1. nms_rank_kernel   rank sort: rank(i) = #{j : key_j > key_i or (key_j == key_i and j > i)}  (equal keys: higher index first =
+//                        what the reference's `argsort()[::-1]` yields wherever numpy's sort is stable)
 //                        (O(n^2) compares, trivially parallel, deterministic, stable tie rule) and
 //                        scatter of {box, volume, original index} into visit order.
 //   2. nms_mask_kernel   upper-triangular 64x64 tiles of the suppression relation; one warp owns a
@@ -97,7 +98,7 @@ nms_rank_kernel(const float* __restrict__ dets, const int32_t* __restrict__ offs
         if (i < n) {
             for (int t = 0; t < lim; ++t) {
                 const uint32_t k = s_key[t];
-                rank += (k > ki) || (k == ki && (j0 + t) < i);
+                rank += (k > ki) || (k == ki && (j0 + t) > i);
             }
         }
     }
@@ -305,7 +306,7 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ off
         int rank = 0;
         for (int j = 0; j < n; ++j) {
             const uint32_t k = s_key[j];
-            rank += (k > ki) || (k == ki && j < t);
+            rank += (k > ki) || (k == ki && j > t);
         }
         SortedBox sb;
         sb.x1 = my[0]; sb.y1 = my[1]; sb.z1 = my[2]; sb.x2 = my[3]; sb.y2 = my[4]; sb.z2 = my[5];

@@ -88,12 +88,13 @@ __global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* _
     const int gmin = mins[2 * inst], pmin = mins[2 * inst + 1], gmax = maxs[2 * inst], pmax = maxs[2 * inst + 1];
     // gray_range = gray_max - gray_min + 1 with numpy 1.x scalar semantics (the sum is promoted, no wrap-around)
     const bool stretch = gmax - gmin + 1 < 400;
-    if (pmax == pmin || (stretch && gmax == 0)) {
-        if (tid == 0 && blockIdx.y == 0) nstat[inst] = 7;
-        return;
-    }
+    // Where the script divides 0 by 0 -- gray_max == 0 under the stretch (an all-zero crop), or a constant PRM crop -- numpy
+    // yields NaN and the following .astype(np.uint16) turns it into 0 (x86-64 / aarch64); the script carries on with the
+    // zeros and so do these tables (round 1 reported status 7 here).
+    const bool img_nan = stretch && gmax == 0, prm_nan = pmax == pmin;
     auto f_img = [&](int v) -> int {                           // (box_img / gray_max * 400).astype(uint16) + gray_min
         if (!stretch) return v;
+        if (img_nan) return gmin & 0xFFFF;                     // uint16(NaN) + gray_min
         const double q = __dmul_rn(__ddiv_rn((double)v, (double)gmax), 400.0);
         return ((int)q + gmin) & 0xFFFF;
     };
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(NU_THREADS) nuclei_normalise_kernel(const T* _
     {
         const double num = (double)(tid - pmin), den = (double)(pmax - pmin), span = (double)((gmax2 - gmin2) & 0xFFFF);
         const double t = __dadd_rn(__dmul_rn(__ddiv_rn(num, den), span), (double)gmin2);
-        s_lut_p[tid] = (tid >= pmin && tid <= pmax) ? (unsigned short)(int)rint(t) : (unsigned short)0;
+        s_lut_p[tid] = (!prm_nan && tid >= pmin && tid <= pmax) ? (unsigned short)(int)rint(t) : (unsigned short)0;
     }
     __syncthreads();
     const int rows = c.sy * c.sz;

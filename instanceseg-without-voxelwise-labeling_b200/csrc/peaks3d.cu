@@ -549,8 +549,8 @@ __device__ __forceinline__ void pw_outputs(const uint32_t (&m9p)[PW_R][4], const
 // Work unit of a warp = (z chunk, 128-voxel strip, pair of rows); adjacent warps take adjacent row pairs.
 // Per trip: issue the loads of plane z + 2, emit plane z from the planes already in registers (this hides the
 // load latency), then turn the loaded rows into plane z + 2 in the registers plane z just vacated.
-template <bool HIST>
-__global__ void __launch_bounds__(PW_THREADS, PW_MINB)
+template <bool HIST, int MINB>
+__global__ void __launch_bounds__(PW_THREADS, MINB)
 peaks_scan3w_kernel(const float* __restrict__ in, int S, int H, int W, int nstrips, int nrowg, int nzc, int tz, PeakWs ws) {
     __shared__ uint32_t s_hist[PK_BINS1];
     const int ba = blockIdx.y;
@@ -1042,7 +1042,12 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         static const int variant = getenv("B200SEG_PEAKS_VARIANT") ? atoi(getenv("B200SEG_PEAKS_VARIANT")) : 0;
         B200_CHECK_ARG((long long)H * W < (1ll << 31) - 256, "peaks3d: H * W too large");
         const bool wide = variant < 10 && (W % 128) == 0 && (((uintptr_t)input) & 15) == 0;
-        const int xs = wide ? 128 : 32, R = wide ? PW_R : 4, minb = wide ? PW_MINB : 2, nw = wide ? PW_NW : PK_NW;
+        // big batches (many maps per call) run a little faster at 4 resident CTAs per SM despite a few spilled registers
+        const bool wide0 = variant < 10 && (W % 128) == 0;
+        const long long units_guess = (long long)BA * ((W + 127) / 128) * ((H + PW_R - 1) / PW_R) * ((S + 15) / 16);
+        const bool dense4 = variant == 4 || (variant == 0 && wide0 && units_guess >= (long long)sms * 4 * PW_NW * 2 && BA >= 32);
+        const int wminb = dense4 ? 4 : PW_MINB;
+        const int xs = wide ? 128 : 32, R = wide ? PW_R : 4, minb = wide ? wminb : 2, nw = wide ? PW_NW : PK_NW;
         const int nstrips = (W + xs - 1) / xs, nrowg = (H + R - 1) / R;
         // persistent CTAs: 2 resident CTAs per SM in total, spread over the B*A maps
         int per_map = (sms * minb) / BA;                   // never more CTAs than resident slots: a second wave would double the time
@@ -1063,8 +1068,13 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         if ((long long)per_map * nw > units) per_map = (int)((units + nw - 1) / nw);
         dim3 g1((unsigned)per_map, BA);
         if (wide) {
-            if (do_hist) peaks_scan3w_kernel<true><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
-            else peaks_scan3w_kernel<false><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            if (dense4) {
+                if (do_hist) peaks_scan3w_kernel<true, 4><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+                else peaks_scan3w_kernel<false, 4><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            } else {
+                if (do_hist) peaks_scan3w_kernel<true, PW_MINB><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+                else peaks_scan3w_kernel<false, PW_MINB><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            }
         } else if ((W % 32) == 0) peaks_scan3_kernel<4, true, 2><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, do_hist, ws);
         else peaks_scan3_kernel<4, false, 2><<<g1, PK_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, do_hist, ws);
         B200_LAUNCH_CHECK("peaks_scan3_kernel");

@@ -192,7 +192,7 @@ struct BatchStreams {
         return 0;
     }
 };
-static BatchStreams g_batch;
+static BatchStreams g_batch_dev[64];      // one set of streams / events / pinned staging per device ordinal (guarded by the host context's mutex)
 }  // namespace b200seg
 
 extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
@@ -229,6 +229,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     if (e) return e;
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_ARG(dev >= 0 && dev < 64, "postproc_soma_host_batch: device ordinal out of range");
+    BatchStreams& g_batch = g_batch_dev[dev];
     e = g_batch.ensure(dev);
     if (e) return e;
     struct Slot {

@@ -358,10 +358,11 @@ extern "C" int b200seg_soma_binarize_dev(const uint8_t* volumes, int n_volumes, 
     B200_CHECK_ARG(n_volumes <= 65535, "soma_binarize: too many volumes in one call");
     B200_CHECK_ARG((unsigned long long)S * H * W < (1ull << 31), "soma_binarize: volume too large (>= 2^31 voxels)");
     B200_CHECK_ARG(volumes && boxes && prm && crop_off && mask && b_max && status, "soma_binarize: null pointer");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr;
+    int attr_dev;
+    if (attr.needed(&attr_dev)) {
         B200_CUDA(cudaFuncSetAttribute(soma_binarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_CACHE_BYTES));
-        attr_set = true;
+        attr.mark(attr_dev);
     }
     dim3 grid(n_max, n_volumes);
     soma_binarize_kernel<<<grid, SB_THREADS, SB_CACHE_BYTES, stream>>>(volumes, prm, crop_off, n_max, n_volumes, S, H, W,

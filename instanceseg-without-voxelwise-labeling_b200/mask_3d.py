@@ -25,28 +25,35 @@ def _encode_device(mask_t, cap):
 
 def binary_mask_to_rle(binary_mask, cap=1 << 16):
     import torch
+    # any nonzero value is foreground (the reference tests np.where(mask), mask_3d.py:34-40): label values that are
+    # multiples of 256 or float masks in (0, 1) must not vanish in a uint8 cast
     if hasattr(binary_mask, "data_ptr"):
-        m = binary_mask
+        m = (binary_mask != 0)
     else:
-        m = torch.from_numpy(np.ascontiguousarray(binary_mask, dtype=np.uint8))
-    if m.dim() != 3:
-        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % m.dim())    # cython_mask_3d.pyx:19
+        m = torch.from_numpy(np.ascontiguousarray(np.asarray(binary_mask) != 0))
+    if m.dim() not in (2, 3):
+        raise ValueError("Buffer has wrong number of dimensions (expected 2 or 3, got %d)" % m.dim())
+    size = [int(s) for s in m.shape]
+    if m.dim() == 2:
+        # mask_3d.py documents 2-D or 3-D masks: runs follow the Fortran order of the array, which for [H,W] is the
+        # Fortran order of the 3-D array [H,W,1]
+        m = m.unsqueeze(2)
     m = m.to(device="cuda", dtype=torch.uint8).contiguous()
     counts, n = _encode_device(m, int(cap))
     if n > cap:                                               # more runs than the first guess: exact second pass
         counts, n = _encode_device(m, n)
-    return {"counts": [int(v) for v in counts[:n].cpu().numpy()], "size": [int(s) for s in m.shape]}
+    return {"counts": [int(v) for v in counts[:n].cpu().numpy()], "size": size}
 
 
 def rle_to_binary_mask(rle):
     import torch
     counts = np.asarray(rle["counts"], dtype=np.int64)
     size = [int(s) for s in rle["size"]]
-    if len(size) != 3:
-        raise ValueError("rle_to_binary_mask expects a 3D size")
+    if len(size) not in (2, 3):
+        raise ValueError("rle_to_binary_mask expects a 2D or 3D size")
     assert int(counts.sum()) == int(np.prod(size))            # mask_3d.py:53
     L = _lib.lib()
-    S, H, W = size
+    S, H, W = size if len(size) == 3 else (size[0], size[1], 1)
     dev = torch.device("cuda", torch.cuda.current_device())
     c = torch.from_numpy(counts).to(dev)
     mask = torch.empty((S, H, W), dtype=torch.uint8, device=dev)
@@ -54,4 +61,4 @@ def rle_to_binary_mask(rle):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.check(L.b200seg_rle3d_decode_dev(_lib.ptr(c), int(counts.size), _lib.ptr(mask), S, H, W, None, _lib.ptr(ws), ws_bytes,
                                           _lib.current_stream()), "rle3d_decode")
-    return mask.cpu().numpy()
+    return mask.cpu().numpy().reshape(size)

@@ -583,17 +583,20 @@ def scipy_resize_reflect_antialias(image, out_shape):
 
 # ------------------------------------------------------------------------------- nuclei per-instance chain
 def nuclei_normalise(box_img, box_prm):
-    """tools/binarization_nuclei.py:111-121 (numpy 1.x scalar semantics for gray_range: no wrap-around).  Raises
-    ZeroDivisionError where the reference divides 0 by 0 and carries on with NaN-derived values."""
+    """tools/binarization_nuclei.py:111-121 (numpy 1.x scalar semantics for gray_range: no wrap-around).
+    Where the script divides 0 by 0 (gray_max == 0 under the stretch, or a constant PRM crop) numpy yields NaN, warns, and
+    the following `.astype(np.uint16)` turns NaN into 0 on x86-64 / aarch64; the script carries on with those zeros, and so
+    does this restatement (round 1 reported status 7 there instead)."""
     g_lo, g_hi = box_img.min(), box_img.max()
     if int(g_hi) - int(g_lo) + 1 < 400:
         if g_hi == 0:
-            raise ZeroDivisionError("gray_max == 0")
-        box_img = (box_img.astype(float) / g_hi * 400).astype(np.uint16) + g_lo
+            box_img = np.zeros(box_img.shape, np.uint16) + g_lo          # uint16(NaN) == 0, + gray_min (== 0 here)
+        else:
+            box_img = (box_img.astype(float) / g_hi * 400).astype(np.uint16) + g_lo
     g_lo, g_hi = box_img.min(), box_img.max()
     p = box_prm.astype(float)
     if p.max() == p.min():
-        raise ZeroDivisionError("constant PRM crop")
+        return box_img.astype(np.uint16), np.zeros(box_prm.shape, np.uint16)     # round(NaN * span + gray_min) -> uint16 -> 0
     span = (int(g_hi) - int(g_lo)) & 0xFFFF
     box_prm = np.round((p - p.min()) / (p.max() - p.min()) * span + g_lo).astype(np.uint16)
     return box_img.astype(np.uint16), box_prm
@@ -637,8 +640,6 @@ def binarize_nuclei(volume, boxes, prm_crops):
             except ValueError:
                 raise RuntimeError(5)
             m = ndi.binary_erosion(ndi.binary_dilation(~outside, structure=cross), structure=cross, border_value=True)
-        except ZeroDivisionError:
-            st = 7
         except RuntimeError as e:
             st = int(e.args[0])
         region = seg[z1:z2 + 1, y1:y2 + 1, x1:x2 + 1]

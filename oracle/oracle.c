@@ -27,9 +27,11 @@
 /* ------------------------------------------------------------------------------------------
  * 3D NMS -- lib/utils/cython_nms_3d.pyx:39-96 (nms_3d), :102-159 (nms_3d_volume)
  * dets [n,7] = x1,y1,z1,x2,y2,z2,score (fp32, C-contiguous).
- * Tie rule (documented deviation: numpy's default argsort is unstable and platform dependent,
- * cython_nms_3d.pyx:49): key descending, original index ascending; NaN keys sort first
- * (numpy sorts NaN last ascending, then the reference reverses).
+ * Tie rule: the reference visits `scores.argsort()[::-1]` (cython_nms_3d.pyx:49).  numpy's default argsort is an
+ * introsort (insertion sort below 17 elements, where it IS stable; unstable and build dependent above), so equal keys come
+ * out in ascending index order and the reversal puts the HIGHER index first.  That is the rule here: key descending, original
+ * index DESCENDING -- identical to the reference wherever numpy's sort is stable, documented deviation elsewhere.  NaN keys
+ * sort first (numpy sorts NaN last ascending, then the reference reverses).
  * keep_out receives the kept ORIGINAL indices in ascending order (np.where(suppressed==0), :96).
  * ------------------------------------------------------------------------------------------ */
 typedef struct { float key; int idx; } sort_item;
@@ -43,7 +45,7 @@ static int cmp_desc(const void* pa, const void* pb) {
         if (a->key > b->key) return -1;
         if (a->key < b->key) return 1;
     }
-    return (a->idx > b->idx) - (a->idx < b->idx);
+    return (a->idx < b->idx) - (a->idx > b->idx);      /* equal keys: higher original index first */
 }
 
 static inline float f_max(float a, float b) { return a >= b ? a : b; }   /* cython_nms_3d.pyx:30-31 */
