@@ -535,10 +535,19 @@ def run_ours(args, rank, world, local_rank):
     ev_chain, ev_gather = torch.cuda.Event(), torch.cuda.Event()
     with_peaks = [True]
 
-    def step():
+    graphs = {}                                             # with_peaks -> captured CUDA graph of the rank's kernels of one step
+
+    def step_body():
         if with_peaks[0]:
             plan.run(maps)                                      # peak list, count, aggregation stay on the device
         pp.run(vols, dets, boxes, prm, crop_off, NMS_THRESH)
+
+    def step():
+        g_ = graphs.get(with_peaks[0])
+        if g_ is not None:
+            g_.replay()                                         # one launch for the memsets + ~15 kernels of the step
+        else:
+            step_body()
         if world > 1:
             main = torch.cuda.current_stream()
             main.wait_event(ev_gather)                      # the previous gather has finished reading `snap`
@@ -578,18 +587,46 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    torch.cuda.synchronize()
+    l_a = b200seg.launch_count()
+    step_body()
+    launches_per_step = b200seg.launch_count() - l_a            # kernels of this library per step (memsets not counted)
+    with_peaks[0] = False
+    step_body()
+    with_peaks[0] = True
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        # the chain is allocation-free and never synchronises, so a step is capturable: the launch-bound part of a step
+        # (15 small launches at 8 volumes per rank) collapses into one graph launch
+        try:
+            for wp in (True, False):
+                with_peaks[0] = wp
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    step_body()
+                graphs[wp] = g_
+        except Exception as e:                                  # capture unsupported: stay eager, say so
+            graphs.clear()
+            sys.stderr.write("bench: CUDA graph capture failed (%s), running eager\n" % e)
+        with_peaks[0] = True
+        for _ in range(2):
+            step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                                     # before the barrier: spawning nvidia-smi must not skew rank 0
-    l0 = b200seg.launch_count()
     # The timed region is K steps between barriers (max over ranks).  One block of K steps of this workload lasts only
     # milliseconds, so the block is repeated until >= 0.5 s have been timed; ms_per_step is the mean over all blocks.
     blocks = [timed_block(args.steps)]
     while sum(blocks) < args.min_timed_ms and len(blocks) < 200:
         blocks.append(timed_block(args.steps))
-    launches = b200seg.launch_count() - l0
     ms_step = sum(blocks) / (len(blocks) * args.steps)
-    lt = torch.tensor([launches // len(blocks)], dtype=torch.int64, device=dev)
+    ms_eager = None
+    if graphs:                                              # the same K steps launched kernel by kernel, for the record
+        saved = dict(graphs); graphs.clear()
+        step()
+        ms_eager = timed_block(args.steps) / args.steps
+        graphs.update(saved)
+    lt = torch.tensor([launches_per_step * args.steps], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
     value = n_global * V / (ms_step * 1e-3) / 1e9
@@ -769,6 +806,7 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world, vpr),
                 "timed_blocks": len(blocks), "timed_region_s": sum(blocks) / 1e3,
+                "cuda_graph": bool(graphs), "ms_per_step_eager": ms_eager, "kernel_launches_per_step": int(launches_per_step),
                 "value_without_peaks": n_global * V / (ms_nopeaks * 1e-3) / 1e9, "ms_per_step_without_peaks": ms_nopeaks,
                 "parity_checked": checked, "peaks_parity_checked": peaks_checked, "exchange_checked": exchange_ok,
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
@@ -795,6 +833,7 @@ def main():
     ap.add_argument("--parity-volumes", type=int, default=8, help="volumes of this run checked against the oracle chain")
     ap.add_argument("--min-timed-ms", type=float, default=500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a captured CUDA graph")
     ap.add_argument("--seed-base", type=int, default=2000, help="seed of the first synthetic volume (volume i of rank r: base + r*vpr + i)")
     ap.add_argument("--chain-only", action="store_true", help="profiling aid: time only the device-resident chain")
     ap.add_argument("--ops-only", action="store_true", help="profiling aid: only the per-operator timings (RoIAlign3D, peaks, IoU, NMS)")

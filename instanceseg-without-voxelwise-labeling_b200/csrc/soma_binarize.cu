@@ -114,53 +114,72 @@ __device__ __forceinline__ void soma_binarize_cta(SomaShared& sh, uint2* c_img, 
     };
 
     // ---- pass A: stream the crop once: raw min/max + fill the shared-memory cache ------------------
+    // The PRM crop comes first: an instance without a positive PRM voxel is skipped by the script before it touches the
+    // image (binarization_soma.py:74-76) -- about half of the NMS survivors of a volume (duplicates / false boxes) -- so the
+    // image rows of such a crop are never read from HBM.
     int rmin_i, rmax_i, rmin_p, rmax_p;
+    auto minmax8 = [&](uint2 w, unsigned int& mn, unsigned int& mx) {
+        if (SMALL) {                                               // replicate byte 0 into the invalid bytes
+            const unsigned int f0 = (w.x & 0xFFu) * 0x01010101u;
+            const unsigned int v0 = sx >= 4 ? 0xFFFFFFFFu : ((1u << (8 * sx)) - 1u);
+            const unsigned int v1 = sx <= 4 ? 0u : ((1u << (8 * (sx - 4))) - 1u);
+            w.x = (w.x & v0) | (f0 & ~v0); w.y = (w.y & v1) | (f0 & ~v1);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned int a = h ? w.y : w.x;
+            const unsigned int ae = __byte_perm(a, 0u, 0x4240), ao = __byte_perm(a, 0u, 0x4341);   // even / odd bytes
+            mn = __vimin3_u16x2(mn, ae, ao); mx = __vimax3_u16x2(mx, ae, ao);
+        }
+    };
+    auto block_minmax = [&](unsigned int mn2, unsigned int mx2, int slot, int& mn_out, int& mx_out) {
+        const int mn = warp_min((int)min(mn2 & 0xFFFFu, mn2 >> 16)), mx = warp_max((int)max(mx2 & 0xFFFFu, mx2 >> 16));
+        if (lane == 0) { sh.red[slot][warp] = mn; sh.red[slot + 1][warp] = mx; }
+        __syncthreads();
+        if (warp == 0) {
+            int a = lane < SB_NW ? sh.red[slot][lane] : 255, b = lane < SB_NW ? sh.red[slot + 1][lane] : 0;
+            a = warp_min(a); b = warp_max(b);
+            if (lane == 0) { sh.bcast[slot] = a; sh.bcast[slot + 1] = b; }
+        }
+        __syncthreads();
+        mn_out = sh.bcast[slot]; mx_out = sh.bcast[slot + 1];
+    };
     {
-        unsigned int mn_i = 0x00FF00FFu, mx_i = 0u, mn_p = 0x00FF00FFu, mx_p = 0u;     // two 16-bit lanes each
+        unsigned int mn_p = 0x00FF00FFu, mx_p = 0u;                // two 16-bit lanes each
 #pragma unroll 2
         for (int idx = tid; idx < n_items; idx += SB_THREADS) {
             unsigned int ioff, poff; int u_lo;
             decode(idx, ioff, poff, u_lo);
-            uint2 wi, wp;
-            fetch(ioff, poff, wi, wp);
-            if (idx < ncache) { c_img[idx] = wi; c_prm[idx] = wp; }
-            if (SMALL) {                                           // replicate byte 0 into the invalid bytes
-                const unsigned int fi = (wi.x & 0xFFu) * 0x01010101u, fp = (wp.x & 0xFFu) * 0x01010101u;
-                const unsigned int v0 = sx >= 4 ? 0xFFFFFFFFu : ((1u << (8 * sx)) - 1u);
-                const unsigned int v1 = sx <= 4 ? 0u : ((1u << (8 * (sx - 4))) - 1u);
-                wi.x = (wi.x & v0) | (fi & ~v0); wi.y = (wi.y & v1) | (fi & ~v1);
-                wp.x = (wp.x & v0) | (fp & ~v0); wp.y = (wp.y & v1) | (fp & ~v1);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned int a = h ? wi.y : wi.x, b = h ? wp.y : wp.x;
-                const unsigned int ae = __byte_perm(a, 0u, 0x4240), ao = __byte_perm(a, 0u, 0x4341);   // even / odd bytes
-                const unsigned int be = __byte_perm(b, 0u, 0x4240), bo = __byte_perm(b, 0u, 0x4341);
-                mn_i = __vimin3_u16x2(mn_i, ae, ao); mx_i = __vimax3_u16x2(mx_i, ae, ao);
-                mn_p = __vimin3_u16x2(mn_p, be, bo); mx_p = __vimax3_u16x2(mx_p, be, bo);
-            }
+            uint2 wp;
+            if (FAST && !SMALL) wp = load8_fs(prm_crop, poff);
+            else wp = load8_bytes(prm_crop, poff, 0, SMALL ? sx : 8);
+            if (idx < ncache) c_prm[idx] = wp;
+            minmax8(wp, mn_p, mx_p);
         }
-        rmin_i = warp_min((int)min(mn_i & 0xFFFFu, mn_i >> 16)); rmax_i = warp_max((int)max(mx_i & 0xFFFFu, mx_i >> 16));
-        rmin_p = warp_min((int)min(mn_p & 0xFFFFu, mn_p >> 16)); rmax_p = warp_max((int)max(mx_p & 0xFFFFu, mx_p >> 16));
-        if (lane == 0) { sh.red[0][warp] = rmin_i; sh.red[1][warp] = rmax_i; sh.red[2][warp] = rmin_p; sh.red[3][warp] = rmax_p; }
-        __syncthreads();
-        if (warp == 0) {
-            int a = lane < SB_NW ? sh.red[0][lane] : 255, b = lane < SB_NW ? sh.red[1][lane] : 0;
-            int c = lane < SB_NW ? sh.red[2][lane] : 255, d = lane < SB_NW ? sh.red[3][lane] : 0;
-            a = warp_min(a); b = warp_max(b); c = warp_min(c); d = warp_max(d);
-            if (lane == 0) { sh.bcast[0] = a; sh.bcast[1] = b; sh.bcast[2] = c; sh.bcast[3] = d; }
-        }
-        __syncthreads();
-        rmin_i = sh.bcast[0]; rmax_i = sh.bcast[1]; rmin_p = sh.bcast[2]; rmax_p = sh.bcast[3];
+        block_minmax(mn_p, mx_p, 2, rmin_p, rmax_p);
     }
-
-    // ---- normalisation tables (binarization_soma.py:85-91) and value range (otsu.py:201) -----------
-    const int gray_max = rmax_i, prm_max = rmax_p;
-    if (prm_max == 0) {                                   // no positive PRM voxel: instance skipped (:74-76)
+    if (rmax_p == 0) {                                    // no positive PRM voxel: instance skipped (:74-76)
         for (int j = tid; j < n; j += SB_THREADS) mout[j] = 0;
         if (tid == 0) { status_out[inst] = 3; b_max_out[inst] = 0; }
         return;
     }
+    {
+        unsigned int mn_i = 0x00FF00FFu, mx_i = 0u;
+#pragma unroll 2
+        for (int idx = tid; idx < n_items; idx += SB_THREADS) {
+            unsigned int ioff, poff; int u_lo;
+            decode(idx, ioff, poff, u_lo);
+            uint2 wi;
+            if (FAST && !SMALL) wi = load8_fs(img_vol, ioff);
+            else wi = load8_bytes(img_vol, ioff, 0, SMALL ? sx : 8);
+            if (idx < ncache) c_img[idx] = wi;
+            minmax8(wi, mn_i, mx_i);
+        }
+        block_minmax(mn_i, mx_i, 0, rmin_i, rmax_i);
+    }
+
+    // ---- normalisation tables (binarization_soma.py:85-91) and value range (otsu.py:201) -----------
+    const int gray_max = rmax_i, prm_max = rmax_p;
     {
         // np.clip(v / gray_max * 300, 0, 300) + 30 -> astype(uint16) (truncation)
         double f = gray_max > 0 ? __dmul_rn(__ddiv_rn((double)tid, (double)gray_max), 300.0) : 0.0;
