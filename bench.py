@@ -457,6 +457,30 @@ def bench_ops(torch, peak, with_cpu=True):
     ops["generate_proposals_14x16x40x40_top1000"] = {"us": ms * 1e3, "anchors_per_s": n_ / (ms * 1e-3),
                                                      "note": "latency bound: 5 select passes + collect + rank/decode + compact + 3 NMS launches + gather; "
                                                              "score and delta maps stay on the device"}
+    # BASELINE configs[1]: device-resident Mask R-CNN tile flow (proposals -> RoIAlign3D -> stand-in box head -> box_results ->
+    # mask RoIAlign3D -> stand-in mask head -> segm_results) on one 64x200x200 tile, eager and as ONE CUDA graph
+    from b200seg.maskrcnn_flow import TileFlow
+    flow = TileFlow(tile=(64, 200, 200), C=256, dets_per_im=300, seed=1)
+    A_f, (S8, H8, W8) = 35, (8, 25, 25)
+    nf = A_f * S8 * H8 * W8
+    f_feat = torch.from_numpy(rng_e.standard_normal((1, 256, S8, H8, W8)).astype(np.float32)).to(dev)
+    f_sc = torch.from_numpy((rng_e.permutation(nf).astype(np.float32) / np.float32(nf)).reshape(1, A_f, S8, H8, W8)).to(dev)
+    f_dl = torch.from_numpy((rng_e.standard_normal((1, 6 * A_f, S8, H8, W8)) * 0.2).astype(np.float32)).to(dev)
+    l_f0 = b200seg.launch_count()
+    f_out = flow.run(f_feat, f_sc, f_dl)
+    l_f = b200seg.launch_count() - l_f0
+    ms_eager = time_op(torch, lambda: flow.run(f_feat, f_sc, f_dl), 10, flush)
+    fg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(fg):
+        f_out = flow.run(f_feat, f_sc, f_dl)
+    ms_graph = time_op(torch, fg.replay, 20, flush)
+    nd_f = int(f_out["n_dets"][0])
+    ops["maskrcnn_tile_flow_64x200x200"] = {
+        "ms_eager": ms_eager, "ms_cuda_graph": ms_graph, "tiles_per_s": 1e3 / ms_graph, "dets": nd_f, "rois": int(f_out["n_rois"][0]),
+        "dets_per_s": nd_f / (ms_graph * 1e-3), "b200seg_kernel_launches": int(l_f), "volume_59x350x640_ms": 18 * ms_graph,
+        "note": "synthetic features / RPN maps, random-init stand-in heads (the PyTorch model is not the product); 18 such tiles cover a "
+                "59x350x640 volume at TEST.CROP_OVLP 100 (core/test.py:86-93); checked against box_results / segm_results in the GPU tests"}
+    del flow, fg, f_out
     # NMS (latency bound: report microseconds)
     for n in (50, 1000):
         d_np = synth.random_dets(rng, n, extent=(256, 256, 64))

@@ -1120,3 +1120,58 @@ def test_dropin_reference_call_sites_through_the_shim(b2, golden):
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_maskrcnn_tile_flow_matches_the_reference_named_steps(b2, torch_):
+    """BASELINE configs[1]: the device-resident tile flow (proposals -> RoIAlign3D -> box head -> box_results -> mask RoIAlign ->
+    segm_results, fixed capacities, no host round trip) gives what the reference-named host functions give on the same
+    scores / boxes / masks: box_results.box_results_with_nms_and_limit (golden-pinned) and segm.segm_results (golden-pinned);
+    and the flow is capturable as ONE CUDA graph whose replay reproduces the eager result."""
+    from b200seg.maskrcnn_flow import TileFlow
+    from b200seg.box_results import box_results_with_nms_and_limit
+    from b200seg import segm
+    torch = torch_
+    flow = TileFlow(tile=(64, 200, 200), C=64, dets_per_im=40, seed=3)       # a small detection limit makes the limit step bite
+    rng = np.random.default_rng(12)
+    A, (S8, H8, W8) = 35, (8, 25, 25)
+    feat = torch.from_numpy(rng.standard_normal((1, 64, S8, H8, W8)).astype(np.float32)).cuda()
+    n_ = A * S8 * H8 * W8
+    sc = torch.from_numpy((rng.permutation(n_).astype(np.float32) / np.float32(n_)).reshape(1, A, S8, H8, W8)).cuda()
+    dl = torch.from_numpy((rng.standard_normal((1, 6 * A, S8, H8, W8)) * 0.2).astype(np.float32)).cuda()
+    out = flow.run(feat, sc, dl)
+    torch.cuda.synchronize()
+    n_rois, n_dets = int(out["n_rois"][0]), int(out["n_dets"][0])
+    assert 100 < n_rois <= 1000 and 0 < n_dets <= 40
+    # box_results on the host from the very same scores / boxes (rows of the valid proposals only)
+    scores = out["scores"][:n_rois].cpu().numpy()
+    boxes = np.concatenate([np.zeros((n_rois, 6), np.float32), out["boxes"][:n_rois].cpu().numpy()], axis=1)
+    s_h, b_h, cls_boxes, _ = box_results_with_nms_and_limit(scores, boxes, num_classes=2, score_thresh=0.05, nms=0.15, detections_per_im=40)
+    dets = out["dets"][:n_dets].cpu().numpy()
+    assert len(cls_boxes[1]) == n_dets and np.array_equal(dets, cls_boxes[1])
+    assert not out["dets"][n_dets:].any()
+    # segm_results on the host from the very same masks / boxes
+    masks = out["masks"][:n_dets].cpu().numpy()
+    segs = segm.segm_results(cls_boxes, masks, b_h, 64, 200, 200, num_classes=2, resolution=14, cls_specific_mask=False, thresh_binarize=0.5)
+    off = out["crop_off"].cpu().numpy()
+    crops = out["crops"][:int(off[-1])].cpu().numpy()
+    bi = out["boxes_i32"].cpu().numpy()
+    assert off[n_dets] == off[-1] and off[-1] > 0
+    for d in range(n_dets):
+        x0, y0, z0 = np.maximum(bi[d, :3], 0)
+        x1, y1, z1 = np.minimum(bi[d, 3:] + 1, [200, 200, 64])
+        vol = np.zeros((64, 200, 200), np.uint8)
+        if off[d + 1] > off[d]:
+            vol[z0:z1, y0:y1, x0:x1] = crops[off[d]:off[d + 1]].reshape(z1 - z0, y1 - y0, x1 - x0)
+        assert np.array_equal(vol, segs[1][d]), d
+    # one CUDA graph for the whole tile
+    ref = {k: out[k].clone() for k in ("dets", "n_dets", "masks", "crop_off")}
+    ref_crops = out["crops"][:int(off[-1])].clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out2 = flow.run(feat, sc, dl)
+    out2["dets"].zero_(); out2["crops"][:int(off[-1])].zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(out2[k], ref[k]), k
+    assert torch.equal(out2["crops"][:int(off[-1])], ref_crops)
