@@ -17,6 +17,7 @@
 // first voxel wins (what a stable argsort()[-1] returns).  A mask without foreground makes the reference raise
 // (IndexError on the empty bincount); here it is reported as status 5 and nothing is pasted.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200seg {
 
@@ -189,7 +190,7 @@ constexpr int CC_DONE_BIT = 0x40000000;
 // supported, 2 no foreground, 3 empty centre row, 4 not converged, 5 no majority
 __device__ unsigned long long ccf_counts[8];
 __device__ __forceinline__ void ccf_count(int tid, int k) { if (tid == 0) atomicAdd(&ccf_counts[k], 1ull); }
-constexpr int CCF_WARPS = 4, CCF_ROWS = 1152;                 // rows per instance kept in shared memory (mask + fill words)
+constexpr int CCF_ROWS = 1152;                 // rows per instance kept in shared memory (mask + fill words)
 constexpr int CCF_MAX_PAIRS = 6;                              // forward + backward sweeps before a (maze-like) mask is handed on
 
 __device__ __forceinline__ unsigned long long ccf_fill_row(unsigned long long s, unsigned long long m) {
@@ -214,6 +215,7 @@ __device__ __forceinline__ unsigned long long ccf_seeds(unsigned long long own3,
     return (nb | (nb << 1) | (nb >> 1)) & mm;
 }
 
+template <int CCF_WARPS>
 __global__ void __launch_bounds__(CCF_WARPS * 32)
 largest_cc_fill_kernel(uint8_t* __restrict__ mask, const int64_t* __restrict__ crop_off, int n_crops,
                        const int32_t* __restrict__ det_off, const int32_t* __restrict__ boxes,
@@ -621,11 +623,18 @@ extern "C" int b200seg_largest_cc_ex_dev(uint8_t* masks, const int64_t* crop_off
         static OncePerDevice fill_attr;
         int fill_dev;
         if (fill_attr.needed(&fill_dev)) {
-            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+            B200_CUDA(cudaFuncSetAttribute(largest_cc_fill_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
             fill_attr.mark(fill_dev);
         }
         dim3 fgrid(n_max, n_volumes);
-        largest_cc_fill_kernel<<<fgrid, CCF_WARPS * 32, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+        static const int ccf_warps = getenv("B200SEG_CCF_WARPS") ? atoi(getenv("B200SEG_CCF_WARPS")) : 4;
+        if (ccf_warps == 1) largest_cc_fill_kernel<1><<<fgrid, 32, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+        else if (ccf_warps == 2) largest_cc_fill_kernel<2><<<fgrid, 64, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+        else if (ccf_warps == 8) largest_cc_fill_kernel<8><<<fgrid, 256, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
+        else largest_cc_fill_kernel<4><<<fgrid, 128, fill_smem, stream>>>(masks, crop_off, n_max, det_off, boxes, order, n_valid, status, scratch, total_mask_bytes);
         B200_LAUNCH_CHECK("largest_cc_fill_kernel");
     }
     unsigned int* work_counter = reinterpret_cast<unsigned int*>(scratch + total_mask_bytes);       // inside the 64 spare words

@@ -37,7 +37,9 @@ struct PeakWs {
     uint32_t* hist3;      // [BA][256]    key bits 7..0 of the members of the level-2 bin
     uint32_t* ticket;     // [BA][4]      per-map CTA tickets of the scan / refine<2> / refine<3> kernels
     uint32_t* gticket;    // [4]          finalize: work-item ticket, done counter
-    unsigned long long* look;   // [BA * nchunks]  look-back state of the chained scan (flag << 62 | count)
+    unsigned long long* look;   // [BA * nchunks]  per work item: READY flag | number of peaks (chained scan of the finalize kernel)
+    unsigned long long* map_tot;// [BA]  READY flag | peaks of the whole map, published by the map's last finishing work item
+    uint32_t* map_cnt;    // [BA]  finished work items per map
     uint32_t* bits;       // [BA][words]
     unsigned long long* sel;    // [BA][2]  (prefix, remaining rank) handed from one radix level to the next
     uint32_t* list;       // [BA][list_cap]  low 20 key bits of the members of the level-1 bin (list mode)
@@ -64,6 +66,8 @@ static PeakWs peak_layout(void* base, int BA, long long V) {
     w.gticket = (uint32_t*)take(16);
     w.list_n = (uint32_t*)take((size_t)BA * 4);
     w.look = (unsigned long long*)take((size_t)BA * w.nchunks * 8);
+    w.map_tot = (unsigned long long*)take((size_t)BA * 8);
+    w.map_cnt = (uint32_t*)take((size_t)BA * 4);
     w.bits = (uint32_t*)take((size_t)BA * w.words * 4);
     w.zero_bytes = (size_t)(p - (char*)base);
     w.sel = (unsigned long long*)take((size_t)BA * 2 * 8);
@@ -908,6 +912,7 @@ peaks_finalize_kernel(const float* __restrict__ in, int BA, int A, int H, int W,
     if (lane == 0) s_sum[warp] = sum;
     __syncthreads();
     volatile unsigned long long* look = ws.look;
+    volatile unsigned long long* map_tot = ws.map_tot;
     if (tid == 0) {
         uint32_t T = 0; float t = 0.f;
 #pragma unroll
@@ -915,12 +920,21 @@ peaks_finalize_kernel(const float* __restrict__ in, int BA, int A, int H, int W,
         ws.chunk_cnt[item] = T;
         ws.chunk_sum[item] = t;
         look[item] = LB_READY | (unsigned long long)T;     // the count is the whole message: one 64-bit store
+        __threadfence();
+        if (atomicAdd(ws.map_cnt + ba, 1u) == (uint32_t)(ws.nchunks - 1)) {     // last work item of this map: publish the map's total
+            __threadfence();
+            unsigned long long tot = 0;
+            for (int j = 0; j < ws.nchunks; ++j) tot += look[(size_t)ba * ws.nchunks + j] & LB_MASK;
+            map_tot[ba] = LB_READY | tot;
+        }
     }
-    // output offset = sum of the counts of all predecessors (spin until each has been published)
+    // output offset = peaks of all earlier maps (one word per map, published by the map's last item) + peaks of the earlier
+    // items of this map; a few hundred words read by the whole CTA in parallel, spinning until each has been published
     unsigned long long part = 0;
-    for (int j = tid; j < item; j += PK_THREADS) {
+    for (int j = tid; j < ba + chunk; j += PK_THREADS) {
+        volatile unsigned long long* src = j < ba ? map_tot + j : look + ((size_t)ba * ws.nchunks + (j - ba));
         unsigned long long st;
-        do { st = look[j]; } while (!(st & LB_READY));
+        do { st = *src; } while (!(st & LB_READY));
         part += st & LB_MASK;
     }
 #pragma unroll
