@@ -768,8 +768,10 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = n_global * V * e2e_steps / float(dt.item()) / 1e9
     e2e_launches = (b200seg.launch_count() - l1) // e2e_steps
-    h2d = sum(c["volume"].nbytes + c["dets"].nbytes + c["boxes"].nbytes + c["prm"].nbytes + c["crop_off"].nbytes + 8 for c in cases)
-    d2h = sum(2 * V + 4 + c["dets"].shape[0] * 13 for c in cases)
+    from b200seg.binarization import host_batch_traffic
+    h2d, d2h = host_batch_traffic()                  # bytes the library actually moved over the link in the last step
+    h2d_dense = sum(c["volume"].nbytes + c["dets"].nbytes + c["boxes"].nbytes + c["prm"].nbytes + c["crop_off"].nbytes + 8 for c in cases)
+    d2h_dense = sum(2 * V + 4 + c["dets"].shape[0] * 13 for c in cases)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity of THIS run's workload against the oracle (and the CPU baselines, which are the same computation) ----
@@ -836,6 +838,9 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "Gvox/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "gpu_launches": int(e2e_launches), "steps": e2e_steps,
+                        "h2d_bytes_if_everything_were_copied": h2d_dense, "d2h_bytes_if_dense": d2h_dense,
+                        "transfer": "volume by DMA; PRM crops of the NMS survivors by zero-copy gather from the pinned buffer; label "
+                                    "volume as compacted non-zero 16-byte groups, zero fill + scatter by host threads",
                         "note": "binarization chain through b200seg_postproc_soma_host_batch; the peak finder's input is the network's "
                                 "response map, which never exists on the host in the reference flow (peak_response_mapping_3d.py:150)"},
                 "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,

@@ -48,7 +48,9 @@ int b200seg_version(void);
 long long b200seg_launch_count(void);
 /* Profiling knobs (no effect on results unless stated).  "peaks_stop_after" = k: b200seg_peaks3d_dev returns after its
  * first k kernel launches (0 = memset only, 99 = the whole op, the default), so that a caller can time the op kernel by
- * kernel with CUDA events; outputs are incomplete while k < 99.  Unknown names return B200SEG_EINVAL. */
+ * kernel with CUDA events; outputs are incomplete while k < 99.  "host_batch_mode" (default 3) selects the transfer
+ * scheme of b200seg_postproc_soma_host_batch, same results either way: bit 0 = label volumes come back compacted,
+ * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather).  Unknown names return B200SEG_EINVAL. */
 int b200seg_set_option(const char* name, int value);
 
 /* ----------------------------------------------------------------------------------------------
@@ -326,9 +328,16 @@ int b200seg_generate_proposals_dev(const float* scores, const float* deltas, con
                                    float* rois, float* probs, int64_t* keep_idx, int32_t* counts,
                                    void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
-/* A batch of equally shaped volumes, HOST buffers in and out, pipelined over three streams so that the upload
- * of volume v+1, the kernels of volume v and the download of volume v-1 overlap (pass pinned buffers).
- * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host. */
+/* A batch of equally shaped volumes, HOST buffers in and out (the per-volume loop of tools/my_subprocess.py:56 over
+ * tools/binarization_soma.py:57-104).  Pipelined over four device slots: the raw volume travels by DMA, the PRM crops of
+ * the NMS survivors are pulled by a gather kernel straight from the caller's buffer when it is pinned and 16-byte
+ * aligned (else the whole packed array is copied), and the label volume comes back as its non-zero 16-byte groups,
+ * which a pool of host threads (B200SEG_HOST_THREADS, default min(16, cores / LOCAL_WORLD_SIZE)) scatters into the
+ * caller's volume after zero-filling it (a volume with more than 1/8 of its groups labelled is copied densely).
+ * seg[v] may be pageable; pass pinned volumes / prm for full overlap.
+ * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host.
+ * b200seg_postproc_soma_host_batch_traffic reports the bytes the last successful call moved over the link. */
+void b200seg_postproc_soma_host_batch_traffic(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
                                      const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
                                      const int32_t* const* boxes, const uint8_t* const* prm,

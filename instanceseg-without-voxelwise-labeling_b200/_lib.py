@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200seg_postproc_soma_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200seg_postproc_soma_host_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200seg_postproc_soma_host_batch_traffic": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "b200seg_postproc_soma_host": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, C.POINTER(C.c_int),
                                         _vp, _vp, _vp, _vp]),
 }

@@ -216,6 +216,18 @@ def postproc_soma_host(volume, dets, boxes, prm, crop_off, nms_thresh, seg_out=N
                 survive=alive, scores=scores.astype(np.float32))
 
 
+def host_batch_traffic():
+    """(h2d_bytes, d2h_bytes) the last successful postproc_soma_host_batch call moved over the link."""
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    _lib.lib().b200seg_postproc_soma_host_batch_traffic(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def set_host_batch_mode(mode):
+    """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops (default 3)."""
+    _lib.check(_lib.lib().b200seg_set_option(b"host_batch_mode", int(mode)), "set_option")
+
+
 def postproc_soma_host_batch(cases, nms_thresh, seg_out=None, keep_largest_cc=True):
     """numpy in / numpy out for a BATCH of equally shaped volumes (one C call; uploads, kernels and downloads of
     consecutive volumes overlap on three streams -- pass pinned arrays for real overlap).

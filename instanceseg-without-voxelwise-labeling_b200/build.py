@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200seg.so")
-SOURCES = ["api.cu", "nms3d.cu", "iou3d.cu", "roialign3d.cu", "peaks3d.cu", "otsu2d.cu", "soma_binarize.cu", "largest_cc.cu", "paste.cu", "rle3d.cu", "mask_iou.cu", "prefilter.cu", "proposals.cu", "segm_paste.cu", "nuclei.cu", "eval.cu", "pipeline.cu"]
+SOURCES = ["api.cu", "nms3d.cu", "iou3d.cu", "roialign3d.cu", "peaks3d.cu", "otsu2d.cu", "soma_binarize.cu", "largest_cc.cu", "paste.cu", "rle3d.cu", "mask_iou.cu", "prefilter.cu", "proposals.cu", "segm_paste.cu", "nuclei.cu", "eval.cu", "pipeline.cu", "host_batch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int opt_host_batch_mode();            // b200seg_set_option("host_batch_mode"): bit 0 compacted label download, bit 1 PRM gather
 int opt_peaks_stop_after();          // profiling knob: peaks3d stops after its first k kernels (99 = run all)
 
 #define B200_CHECK_ARG(cond, ...)                         \
@@ -74,6 +75,20 @@ struct Carver {
     template <typename T> T* take(size_t n) { T* r = (T*)p; p += align_up(n * sizeof(T), 256); return r; }
     static size_t need(size_t bytes) { return align_up(bytes, 256); }
 };
+
+// carving of the workspace of b200seg_postproc_soma_dev (pipeline.cu) and the part of the chain that follows the NMS
+struct SomaChainWs {
+    uint16_t* ids;
+    char* paste_ws; size_t paste_ws_bytes;
+    char* cc_ws; size_t cc_ws_bytes;
+    char* nms_ws; size_t nms_ws_bytes;
+};
+SomaChainWs soma_chain_ws(void* workspace, size_t workspace_bytes, int n_volumes, int n_max, int S, int H, int W, long long cc_bytes);
+int postproc_soma_after_nms(const uint8_t* volumes, int n_volumes, int S, int H, int W, const int32_t* det_off_dev, int n_max,
+                            int total, const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, long long prm_bytes,
+                            int keep_largest_cc, uint16_t* seg, const int32_t* keep_count, const int32_t* rank_order,
+                            uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive, uint16_t* ids,
+                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream);
 
 // ---- device helpers -------------------------------------------------------------------------
 

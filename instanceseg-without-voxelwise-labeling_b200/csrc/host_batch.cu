@@ -1,0 +1,476 @@
+// host_batch.cu -- HOST-buffer entry point of the binarization chain for a BATCH of equally shaped volumes
+// (tools/binarization_soma.py:57-104 per volume; the per-volume loop of tools/my_subprocess.py:56).
+//
+// The reference hands numpy arrays in and gets the uint16 label volume back, so the PCIe link and the host memory bound
+// this entry point, not the kernels (a few percent of a transfer).  Round-2 layout, per volume:
+//   up     the raw volume and the small per-detection arrays travel by DMA (stream `in`); the packed PRM crops do NOT:
+//          the NMS runs first and a gather kernel then pulls only the crops of its survivors straight out of the
+//          caller's pinned buffer over the link (zero copy; pageable or unaligned buffers fall back to a plain copy);
+//   device NMS -> gather -> binarize -> largest component -> paste (stream `comp`), then the label volume is compacted
+//          into its non-zero 16-byte groups (8 voxels): group index + payload, a few percent of the volume;
+//   down   only the compacted groups and the per-detection bookkeeping travel (stream `out`); a pool of host threads
+//          zero-fills the caller's label volumes while the GPU works and scatters the groups into them.
+//          A volume whose labels cover more than an eighth of the groups is copied densely instead.
+// Six device slots; the host thread sizes the download of a volume (it needs the group count) two volumes after it has
+// enqueued its upload, so that the upload queue never runs dry, and hands finished downloads to the pool one volume later.
+#include "common.cuh"
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <sched.h>
+#include <stdlib.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
+namespace b200seg {
+
+// ---- device side -------------------------------------------------------------------------------------------------
+// non-zero 16-byte groups of the label volume, unordered: idx_out[k] = group index, val_out[k] = its 8 labels.
+// `count` keeps counting past `cap` (the host then takes the dense path).
+__global__ void __launch_bounds__(256)
+seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned int cap,
+                   uint32_t* __restrict__ idx_out, uint4* __restrict__ val_out, uint32_t* __restrict__ count) {
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int per_cta = 256u * 4u;
+    for (unsigned int base = blockIdx.x * per_cta; base < ngroups; base += gridDim.x * per_cta) {      // CTA-uniform trip count
+        uint4 v[4];
+        unsigned int gi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gi[j] = base + j * 256u + threadIdx.x;
+            v[j] = gi[j] < ngroups ? ld_stream_u4(seg + gi[j]) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool nz = (v[j].x | v[j].y | v[j].z | v[j].w) != 0u;
+            const unsigned int m = __ballot_sync(0xffffffffu, nz);
+            if (m == 0u) continue;                                  // warp-uniform
+            unsigned int b = 0;
+            if (lane == 0) b = atomicAdd(count, (unsigned int)__popc(m));
+            b = __shfl_sync(0xffffffffu, b, 0);
+            const unsigned int pos = b + __popc(m & ((1u << lane) - 1u));
+            if (nz && pos < cap) { idx_out[pos] = gi[j]; val_out[pos] = v[j]; }
+        }
+    }
+}
+
+// PRM crops of the NMS survivors: host-mapped (pinned) source -> device copy with the same packing.
+// grid (n_max): CTA r moves the crop of visit rank r.  src and dst share the offset, both bases are 16-byte aligned.
+__global__ void __launch_bounds__(256)
+prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ crop_off,
+                  const int32_t* __restrict__ rank_order, const int32_t* __restrict__ keep_count) {
+    const int r = blockIdx.x;
+    if (r >= keep_count[0]) return;
+    const int inst = rank_order[r];
+    const long long a = crop_off[inst], b = crop_off[inst + 1];
+    long long a16 = (a + 15) & ~15ll, b16 = b & ~15ll;
+    if (a16 > b16) { a16 = b; b16 = b; }                            // crop shorter than one aligned group
+    for (long long i = a + threadIdx.x; i < a16; i += 256) dst[i] = src[i];
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + a16);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + a16);
+    const long long n4 = (b16 - a16) >> 4;
+    long long i = threadIdx.x;
+    for (; i + 3 * 256 < n4; i += 4 * 256) {                        // four 16-byte reads over the link in flight per thread
+        const uint4 v0 = ld_stream_u4(s4 + i), v1 = ld_stream_u4(s4 + i + 256), v2 = ld_stream_u4(s4 + i + 512), v3 = ld_stream_u4(s4 + i + 768);
+        d4[i] = v0; d4[i + 256] = v1; d4[i + 512] = v2; d4[i + 768] = v3;
+    }
+    for (; i < n4; i += 256) d4[i] = ld_stream_u4(s4 + i);
+    for (long long k = b16 + threadIdx.x; k < b; k += 256) dst[k] = src[k];
+}
+
+// Zero fill with non-temporal stores: the label volumes are far larger than the caches and are not read again by this
+// thread, so the lines need not be fetched before they are overwritten (half the memory traffic of a plain memset
+// whenever the C library's own streaming threshold is not reached).
+static void zero_stream(char* dst, size_t bytes) {
+#if defined(__x86_64__)
+    static const bool plain = getenv("B200SEG_HB_PLAIN_MEMSET") != nullptr;
+    if (!plain && bytes >= 4096) {
+        const size_t head = (size_t)((64 - ((uintptr_t)dst & 63)) & 63);
+        if (head) { memset(dst, 0, head); dst += head; bytes -= head; }
+        const __m128i z = _mm_setzero_si128();
+        size_t i = 0;
+        for (; i + 64 <= bytes; i += 64) {
+            _mm_stream_si128((__m128i*)(dst + i), z); _mm_stream_si128((__m128i*)(dst + i + 16), z);
+            _mm_stream_si128((__m128i*)(dst + i + 32), z); _mm_stream_si128((__m128i*)(dst + i + 48), z);
+        }
+        _mm_sfence();
+        if (i < bytes) memset(dst + i, 0, bytes - i);
+        return;
+    }
+#endif
+    memset(dst, 0, bytes);
+}
+
+// ---- host side: worker pool -------------------------------------------------------------------------------------
+struct HostPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    int n_threads = 0;
+    pid_t pid = 0;
+    void ensure() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (n_threads > 0 && pid == getpid()) return;              // a forked child starts its own threads
+        pid = getpid();
+        q.clear();
+        int want = 0;
+        if (const char* e = getenv("B200SEG_HOST_THREADS")) want = atoi(e);
+        if (want <= 0) {
+            int hw = (int)std::thread::hardware_concurrency();
+            if (hw <= 0) hw = 4;
+            int share = 1;
+            if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;   // ranks of one box share its cores
+            want = hw / share;
+            if (want > 16) want = 16;
+            if (want < 2) want = 2;
+        }
+        n_threads = want;
+        for (int i = 0; i < want; ++i) std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [this] { return !q.empty(); });
+                job = std::move(q.front());
+                q.pop_front();
+            }
+            job();
+        }
+    }
+    void push(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+        cv.notify_one();
+    }
+};
+// never destroyed: its threads are detached and wait on the condition variable until the process ends (destroying a
+// condition variable with waiters blocks in glibc)
+static HostPool& g_pool = *new HostPool;
+
+constexpr int HB_SLOTS = 6;
+constexpr int HB_LAG_A = 2;            // the download of volume v is sized and enqueued while volume v + HB_LAG_A is being enqueued
+constexpr int HB_LAG_B = 3;            // ... and handed to the pool one step later
+constexpr int HB_ZERO_PARTS = 4;
+
+struct BatchStreams {
+    cudaStream_t in = nullptr, out = nullptr, out2 = nullptr;   // uploads | bookkeeping downloads | label downloads
+    cudaEvent_t in_done[HB_SLOTS] = {}, comp_done[HB_SLOTS] = {}, cnt_done[HB_SLOTS] = {}, out_done[HB_SLOTS] = {};
+    int device = -1;
+    char* pinned = nullptr;           // grow-only pinned staging: per-volume bookkeeping + per-slot compacted groups
+    size_t pinned_cap = 0;
+    int ensure_pinned(size_t bytes) {
+        if (bytes <= pinned_cap) return 0;
+        if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinned_cap = 0; }
+        const size_t want = align_up(bytes + (bytes >> 2), 1 << 16);
+        B200_CUDA(cudaHostAlloc((void**)&pinned, want, cudaHostAllocDefault));
+        pinned_cap = want;
+        return 0;
+    }
+    int ensure(int dev) {
+        if (device == dev && in) return 0;
+        if (in) {
+            cudaStreamDestroy(in); cudaStreamDestroy(out); cudaStreamDestroy(out2);
+            for (int k = 0; k < HB_SLOTS; ++k) {
+                cudaEventDestroy(in_done[k]); cudaEventDestroy(comp_done[k]); cudaEventDestroy(cnt_done[k]); cudaEventDestroy(out_done[k]);
+            }
+        }
+        B200_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&out2, cudaStreamNonBlocking));
+        for (int k = 0; k < HB_SLOTS; ++k) {
+            B200_CUDA(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&comp_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&cnt_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
+        }
+        device = dev;
+        return 0;
+    }
+};
+static BatchStreams g_batch_dev[64];      // one set per device ordinal (guarded by the host context's mutex)
+static std::atomic<unsigned long long> g_last_h2d{0}, g_last_d2h{0};
+
+// device pointer of a host buffer the GPU can read in place (pinned / registered and 16-byte aligned), else null
+static const uint8_t* mapped_device_pointer(const void* host) {
+    if (!host || (((uintptr_t)host) & 15)) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (const uint8_t*)at.devicePointer;
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" void b200seg_postproc_soma_host_batch_traffic(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_last_h2d.load();
+    if (d2h_bytes) *d2h_bytes = g_last_d2h.load();
+}
+
+extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
+                                                const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
+                                                const int32_t* const* boxes, const uint8_t* const* prm,
+                                                const int64_t* const* crop_off, float nms_thresh, int keep_largest_cc,
+                                                uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
+                                                int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive) {
+    B200_CHECK_ARG(n_volumes >= 0 && S > 0 && H > 0 && W > 0, "postproc_soma_host_batch: bad sizes");
+    if (n_volumes == 0) return 0;
+    B200_CHECK_ARG(volumes && n_dets && seg && n_keep, "postproc_soma_host_batch: null pointer");
+    int n_max = 0;
+    size_t prm_max = 0;
+    for (int v = 0; v < n_volumes; ++v) {
+        const int n = n_dets[v];
+        B200_CHECK_ARG(n >= 0 && volumes[v] && seg[v], "postproc_soma_host_batch: bad volume %d", v);
+        B200_CHECK_ARG(n == 0 || (dets && boxes && prm && crop_off && rank_order && b_max && status && survive &&
+                                  dets[v] && boxes[v] && prm[v] && crop_off[v] && rank_order[v] && b_max[v] && status[v] && survive[v]),
+                       "postproc_soma_host_batch: null pointer for volume %d", v);
+        if (n > n_max) n_max = n;
+        if (n > 0 && (size_t)crop_off[v][n] > prm_max) prm_max = (size_t)crop_off[v][n];
+    }
+    B200_CHECK_ARG(n_max < 65535, "postproc_soma_host_batch: more than 65534 instances per volume do not fit uint16 labels");
+    const size_t V = (size_t)S * H * W;
+    B200_CHECK_ARG(V < (1ull << 34), "postproc_soma_host_batch: volume too large");
+    HostCtx& hc = host_ctx();
+    std::lock_guard<std::mutex> lock(hc.mu);
+    const size_t nn = n_max > 0 ? n_max : 1;
+    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n_max, S, H, W, keep_largest_cc ? (long long)prm_max : 0);
+    const int NB = n_volumes < HB_SLOTS ? n_volumes : HB_SLOTS;
+    // compacted form: only when the volume splits into whole 16-byte groups
+    const int mode = opt_host_batch_mode();
+    const bool sparse = (V % 8) == 0 && (mode & 1);
+    const size_t ngroups = V / 8;
+    size_t cap = ngroups / 8;
+    if (cap < 4096) cap = 4096;
+    if (cap > ngroups) cap = ngroups;
+    if (!sparse) cap = 0;
+    const size_t slot_bytes = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
+                              2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(8) +
+                              3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(cap * 4 + 16) + Carver::need(cap * 16 + 16) +
+                              Carver::need(ws_bytes);
+    int e = hc.ensure(slot_bytes * NB);
+    if (e) return e;
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CHECK_ARG(dev >= 0 && dev < 64, "postproc_soma_host_batch: device ordinal out of range");
+    BatchStreams& g_batch = g_batch_dev[dev];
+    e = g_batch.ensure(dev);
+    if (e) return e;
+    struct Slot {
+        uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
+        int64_t* keep; int32_t* cnt; int32_t* rank; int32_t* bmax; int32_t* stat; uint8_t* surv; uint32_t* gidx; uint4* gval; void* ws;
+    } slot[HB_SLOTS];
+    for (int k = 0; k < NB; ++k) {
+        Carver cv(hc.buf + slot_bytes * k);
+        Slot& s = slot[k];
+        s.vol = cv.take<uint8_t>(V); s.seg = cv.take<uint16_t>(V); s.dets = cv.take<float>(nn * 7); s.off = cv.take<int32_t>(2);
+        s.boxes = cv.take<int32_t>(nn * 6); s.prm = cv.take<uint8_t>(prm_max + 16); s.mask = cv.take<uint8_t>(prm_max + 16);
+        s.coff = cv.take<int64_t>(nn + 1); s.keep = cv.take<int64_t>(nn); s.cnt = cv.take<int32_t>(2); s.rank = cv.take<int32_t>(nn);
+        s.bmax = cv.take<int32_t>(nn); s.stat = cv.take<int32_t>(nn); s.surv = cv.take<uint8_t>(nn);
+        s.gidx = cv.take<uint32_t>(cap + 4); s.gval = cv.take<uint4>(cap + 1); s.ws = cv.p;
+    }
+    // pinned staging: [per-volume bookkeeping] [per-slot group indices | group payloads]
+    size_t small_bytes = 0;
+    for (int v = 0; v < n_volumes; ++v) small_bytes += align_up(16 + 13 * (size_t)n_dets[v], 16);
+    small_bytes = align_up(small_bytes, 256);
+    const size_t stage_bytes = align_up(cap * 4, 256) + align_up(cap * 16, 256);
+    e = g_batch.ensure_pinned(small_bytes + stage_bytes * NB);
+    if (e) return e;
+    g_pool.ensure();
+
+    cudaStream_t s_in = g_batch.in, s_comp = hc.stream, s_out = g_batch.out, s_out2 = g_batch.out2;
+    // host-side state shared with the pool (kept alive until every job has run)
+    struct Shared {
+        std::vector<std::atomic<int>> zero_left;                  // per volume: zero-fill parts still running
+        std::atomic<int> slot_busy[HB_SLOTS];                     // staging slot still being scattered
+        std::atomic<int> pending{0};                              // jobs pushed and not finished
+        explicit Shared(int nv) : zero_left(nv) {}
+    };
+    Shared* sh = new Shared(n_volumes);
+    for (int k = 0; k < HB_SLOTS; ++k) sh->slot_busy[k].store(0);
+    // zero-fill of the label volumes starts now (it does not depend on the GPU)
+    for (int v = 0; v < n_volumes; ++v) {
+        sh->zero_left[v].store(HB_ZERO_PARTS);
+        const size_t bytes = V * 2, part = align_up((bytes + HB_ZERO_PARTS - 1) / HB_ZERO_PARTS, 4096);
+        for (int p = 0; p < HB_ZERO_PARTS; ++p) {
+            const size_t lo = (size_t)p * part < bytes ? (size_t)p * part : bytes;
+            const size_t hi = lo + part < bytes ? lo + part : bytes;
+            char* dst = (char*)seg[v] + lo;
+            sh->pending.fetch_add(1);
+            g_pool.push([sh, v, dst, lo, hi] {
+                if (hi > lo) zero_stream(dst, hi - lo);
+                sh->zero_left[v].fetch_sub(1, std::memory_order_release);
+                sh->pending.fetch_sub(1, std::memory_order_release);
+            });
+        }
+    }
+    static const bool trace = getenv("B200SEG_HB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    const auto t_start = now();
+    double w_cnt = 0, w_slot = 0, w_out = 0, w_zero = 0, w_tail = 0;
+    std::vector<int32_t> offs(2 * (size_t)n_volumes);            // per-volume {0, n} pairs, alive until the copies have run
+    for (int v = 0; v < n_volumes; ++v) { offs[2 * v] = 0; offs[2 * v + 1] = n_dets[v]; }
+    std::vector<size_t> small_off(n_volumes);
+    { size_t o = 0; for (int v = 0; v < n_volumes; ++v) { small_off[v] = o; o += align_up(16 + 13 * (size_t)n_dets[v], 16); } }
+    std::vector<uint32_t> n_groups(n_volumes, 0u);               // compacted groups per volume (0xFFFFFFFF = dense copy)
+    unsigned long long h2d = 0, d2h = 0;
+    int rc = 0;
+#define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
+    for (int step = 0; step < n_volumes + HB_LAG_B; ++step) {
+        // ---- enqueue volume `step`: uploads, chain, compaction, download of the bookkeeping ------------------------
+        if (step < n_volumes) {
+            const int v = step, k = v % NB;
+            Slot& s = slot[k];
+            const int n = n_dets[v];
+            const size_t pbytes = n > 0 ? (size_t)crop_off[v][n] : 0;
+            const uint8_t* prm_mapped = (n > 0 && (mode & 2)) ? mapped_device_pointer(prm[v]) : nullptr;
+            if (v >= NB) B200_BATCH(cudaStreamWaitEvent(s_in, g_batch.out_done[k], 0));     // slot free again
+            B200_BATCH(cudaMemcpyAsync(s.vol, volumes[v], V, cudaMemcpyHostToDevice, s_in));
+            B200_BATCH(cudaMemcpyAsync(s.off, offs.data() + 2 * v, 8, cudaMemcpyHostToDevice, s_in));
+            h2d += V + 8;
+            if (n > 0) {
+                B200_BATCH(cudaMemcpyAsync(s.dets, dets[v], (size_t)n * 28, cudaMemcpyHostToDevice, s_in));
+                B200_BATCH(cudaMemcpyAsync(s.boxes, boxes[v], (size_t)n * 24, cudaMemcpyHostToDevice, s_in));
+                B200_BATCH(cudaMemcpyAsync(s.coff, crop_off[v], (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s_in));
+                h2d += (size_t)n * 52 + (size_t)(n + 1) * 8;
+                if (!prm_mapped) { B200_BATCH(cudaMemcpyAsync(s.prm, prm[v], pbytes, cudaMemcpyHostToDevice, s_in)); h2d += pbytes; }
+            }
+            B200_BATCH(cudaEventRecord(g_batch.in_done[k], s_in));
+            B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.in_done[k], 0));
+            {
+                const long long cc_bytes = keep_largest_cc ? (long long)pbytes : 0;
+                const SomaChainWs L = soma_chain_ws(s.ws, ws_bytes, 1, n, S, H, W, cc_bytes);
+                int ce = b200seg_nms3d_dev(s.dets, s.off, 1, n, nms_thresh, 0, s.keep, s.cnt, s.rank, L.nms_ws, L.nms_ws_bytes, s_comp);
+                if (ce) { rc = ce; goto done; }
+                if (prm_mapped) {
+                    prm_gather_kernel<<<n, 256, 0, s_comp>>>(prm_mapped, s.prm, s.coff, s.rank, s.cnt);
+                    count_launch();
+                    B200_BATCH(cudaGetLastError());
+                }
+                ce = postproc_soma_after_nms(s.vol, 1, S, H, W, s.off, n, n, s.boxes, s.prm, s.coff, (long long)pbytes, keep_largest_cc,
+                                             s.seg, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, L.ids, L.paste_ws, L.paste_ws_bytes,
+                                             L.cc_ws, L.cc_ws_bytes, s_comp);
+                if (ce) { rc = ce; goto done; }
+                if (sparse) {
+                    B200_BATCH(cudaMemsetAsync(s.cnt + 1, 0, 4, s_comp));
+                    unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);
+                    const unsigned int lim = (unsigned int)num_sms() * 16u;
+                    if (grid > lim) grid = lim;
+                    seg_compact_kernel<<<grid, 256, 0, s_comp>>>((const uint4*)s.seg, (unsigned int)ngroups, (unsigned int)cap,
+                                                                 s.gidx, s.gval, (uint32_t*)(s.cnt + 1));
+                    count_launch();
+                    B200_BATCH(cudaGetLastError());
+                }
+            }
+            B200_BATCH(cudaEventRecord(g_batch.comp_done[k], s_comp));
+            B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.comp_done[k], 0));
+            char* st = g_batch.pinned + small_off[v];          // [keep count | group count | pad to 16 | rank n*4 | b_max n*4 | status n*4 | survive n]
+            B200_BATCH(cudaMemcpyAsync(st, s.cnt, 8, cudaMemcpyDeviceToHost, s_out));
+            d2h += 8;
+            if (n > 0) {
+                B200_BATCH(cudaMemcpyAsync(st + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 4, s.bmax, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 8, s.stat, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 12, s.surv, (size_t)n, cudaMemcpyDeviceToHost, s_out));
+                d2h += (size_t)n * 13;
+            }
+            B200_BATCH(cudaEventRecord(g_batch.cnt_done[k], s_out));
+        }
+        // ---- volume `step - HB_LAG_A`: its group count is known -> size and enqueue the download of the label data --------
+        if (step >= HB_LAG_A && step - HB_LAG_A < n_volumes) {
+            const int v = step - HB_LAG_A, k = v % NB;
+            Slot& s = slot[k];
+            { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.cnt_done[k])); w_cnt += ms_since(t); }
+            uint32_t ng = 0xFFFFFFFFu;
+            if (sparse) { memcpy(&ng, g_batch.pinned + small_off[v] + 4, 4); if (ng > cap) ng = 0xFFFFFFFFu; }
+            n_groups[v] = ng;
+            if (ng == 0xFFFFFFFFu) {                               // dense: the DMA must not race the zero fill
+                { const auto t = now(); while (sh->zero_left[v].load(std::memory_order_acquire) > 0) sched_yield(); w_zero += ms_since(t); }
+                B200_BATCH(cudaMemcpyAsync(seg[v], s.seg, V * 2, cudaMemcpyDeviceToHost, s_out2));
+                d2h += V * 2;
+            } else if (ng > 0) {
+                { const auto t = now(); while (sh->slot_busy[k].load(std::memory_order_acquire)) sched_yield(); w_slot += ms_since(t); }   // staging slot scattered by now
+                char* stage = g_batch.pinned + small_bytes + stage_bytes * k;
+                B200_BATCH(cudaMemcpyAsync(stage, s.gidx, (size_t)ng * 4, cudaMemcpyDeviceToHost, s_out2));
+                B200_BATCH(cudaMemcpyAsync(stage + align_up(cap * 4, 256), s.gval, (size_t)ng * 16, cudaMemcpyDeviceToHost, s_out2));
+                d2h += (size_t)ng * 20;
+            }
+            B200_BATCH(cudaEventRecord(g_batch.out_done[k], s_out2));   // (the kernels of this volume finished before cnt_done)
+            // traffic of the gathered PRM crops: the crops of the survivors (known from the visit order now on the host)
+            const int n = n_dets[v];
+            if (n > 0 && (mode & 2) && mapped_device_pointer(prm[v])) {
+                int32_t kc = 0;
+                memcpy(&kc, g_batch.pinned + small_off[v], 4);
+                const int32_t* ro = (const int32_t*)(g_batch.pinned + small_off[v] + 16);
+                for (int r = 0; r < kc && r < n; ++r) h2d += (unsigned long long)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]);
+            }
+        }
+        // ---- volume `step - HB_LAG_B`: its download has been enqueued one step ago -> wait for it, hand it to the pool ----
+        if (step >= HB_LAG_B) {
+            const int v = step - HB_LAG_B, k = v % NB;
+            const uint32_t ng = n_groups[v];
+            if (ng != 0xFFFFFFFFu && ng > 0) {
+                { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.out_done[k])); w_out += ms_since(t); }
+                const char* stage = g_batch.pinned + small_bytes + stage_bytes * k;
+                const uint32_t* gi = (const uint32_t*)stage;
+                const char* gv = stage + align_up(cap * 4, 256);
+                char* dst = (char*)seg[v];
+                sh->slot_busy[k].store(1, std::memory_order_release);
+                sh->pending.fetch_add(1);
+                g_pool.push([sh, v, k, gi, gv, dst, ng] {
+                    while (sh->zero_left[v].load(std::memory_order_acquire) > 0) sched_yield();
+                    for (uint32_t i = 0; i < ng; ++i) memcpy(dst + (size_t)gi[i] * 16, gv + (size_t)i * 16, 16);
+                    sh->slot_busy[k].store(0, std::memory_order_release);
+                    sh->pending.fetch_sub(1, std::memory_order_release);
+                });
+            }
+        }
+    }
+done:
+#undef B200_BATCH
+    {
+        // drain all three streams even on error: the slots, `offs` and the staging must not be reused while copies are in flight
+        const cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_comp), e3 = cudaStreamSynchronize(s_out),
+                          e4 = cudaStreamSynchronize(s_out2);
+        const auto t_tail = now();
+        while (sh->pending.load(std::memory_order_acquire) > 0) sched_yield();
+        w_tail = ms_since(t_tail);
+        delete sh;
+        if (rc == 0) {
+            if (e1 != cudaSuccess) rc = check_cuda(e1, "cudaStreamSynchronize(in)");
+            else if (e2 != cudaSuccess) rc = check_cuda(e2, "cudaStreamSynchronize(compute)");
+            else if (e3 != cudaSuccess) rc = check_cuda(e3, "cudaStreamSynchronize(out)");
+            else if (e4 != cudaSuccess) rc = check_cuda(e4, "cudaStreamSynchronize(out2)");
+        }
+    }
+    if (rc == 0) {                                          // hand the staged small outputs to the caller
+        for (int v = 0; v < n_volumes; ++v) {
+            const size_t n = (size_t)n_dets[v];
+            const char* st = g_batch.pinned + small_off[v];
+            memcpy(&n_keep[v], st, 4);
+            if (n > 0) {
+                memcpy(rank_order[v], st + 16, n * 4);
+                memcpy(b_max[v], st + 16 + n * 4, n * 4);
+                memcpy(status[v], st + 16 + n * 8, n * 4);
+                memcpy(survive[v], st + 16 + n * 12, n);
+            }
+        }
+        g_last_h2d.store(h2d);
+        g_last_d2h.store(d2h);
+        if (trace)
+            fprintf(stderr, "[b200seg host_batch] %d volumes, %d pool threads: %.2f ms; host waits: group count %.2f, staging slot %.2f, "
+                            "download %.2f, zero fill (dense) %.2f, pool tail %.2f ms; up %.1f MB, down %.1f MB\n",
+                    n_volumes, g_pool.n_threads, ms_since(t_start), w_cnt, w_slot, w_out, w_zero, w_tail, h2d / 1e6, d2h / 1e6);
+    }
+    return rc;
+}

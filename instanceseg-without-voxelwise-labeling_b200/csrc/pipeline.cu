@@ -20,6 +20,51 @@ __global__ void iota_u16_kernel(uint16_t* p, int n) {
 
 }  // namespace b200seg
 
+namespace b200seg {
+
+SomaChainWs soma_chain_ws(void* workspace, size_t workspace_bytes, int n_volumes, int n_max, int S, int H, int W, long long cc_bytes) {
+    SomaChainWs L;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    L.ids = (uint16_t*)ws;
+    L.paste_ws = ws + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256);
+    L.paste_ws_bytes = align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256);
+    L.cc_ws = L.paste_ws + L.paste_ws_bytes;
+    L.cc_ws_bytes = cc_bytes > 0 ? align_up(b200seg_largest_cc_workspace_bytes(cc_bytes), 256) : 0;
+    L.nms_ws = L.cc_ws + L.cc_ws_bytes;
+    L.nms_ws_bytes = workspace_bytes - (size_t)(L.nms_ws - (char*)workspace);
+    return L;
+}
+
+// Everything of the chain that follows the NMS (shared with the pipelined host entry point of host_batch.cu, which runs
+// the NMS first and then fetches only the PRM crops of the survivors).
+int postproc_soma_after_nms(const uint8_t* volumes, int n_volumes, int S, int H, int W, const int32_t* det_off_dev, int n_max,
+                            int total, const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, long long prm_bytes,
+                            int keep_largest_cc, uint16_t* seg, const int32_t* keep_count, const int32_t* rank_order,
+                            uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive, uint16_t* ids,
+                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream) {
+    int e = 0;
+    if (n_max > 0) {
+        iota_u16_kernel<<<(n_max + 255) / 256, 256, 0, stream>>>(ids, n_max);
+        B200_LAUNCH_CHECK("iota_u16_kernel");
+        B200_CUDA(cudaMemsetAsync(status, 0xFF, sizeof(int32_t) * (size_t)total, stream));   // -1 = not visited (suppressed)
+        B200_CUDA(cudaMemsetAsync(survive, 0, (size_t)total, stream));
+        B200_CUDA(cudaMemsetAsync(b_max, 0, sizeof(int32_t) * (size_t)total, stream));            // suppressed detections report 0
+        // one launch for the instances of every volume: grid (n_max, n_volumes)
+        e = b200seg_soma_binarize_dev(volumes, n_volumes, S, H, W, det_off_dev, n_max, boxes, prm, crop_off,
+                                      rank_order, keep_count, masks, b_max, status, stream);
+        if (e) return e;
+        if (keep_largest_cc) {                               // binarization_soma.py:97-99
+            e = b200seg_largest_cc_dev(masks, crop_off, prm_bytes, n_volumes, det_off_dev, n_max, boxes, rank_order, keep_count,
+                                       status, cc_ws, cc_ws_bytes, stream);
+            if (e) return e;
+        }
+    }
+    return b200seg_paste_labels_dev(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
+                                    rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream);
+}
+
+}  // namespace b200seg
+
 using namespace b200seg;
 
 extern "C" size_t b200seg_postproc_soma_workspace_bytes(int n_volumes, int n_max, int S, int H, int W, long long cc_mask_bytes) {
@@ -55,36 +100,18 @@ extern "C" int b200seg_postproc_soma_dev(const uint8_t* volumes, int n_volumes, 
         set_error("postproc_soma: workspace too small");
         return B200SEG_EWORKSPACE;
     }
-    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    uint16_t* ids = (uint16_t*)ws;
-    char* paste_ws = ws + align_up((size_t)(n_max > 0 ? n_max : 1) * 2, 256);
-    const size_t paste_ws_bytes = align_up(b200seg_paste_labels_workspace_bytes(n_volumes, S, H, W, n_max), 256);
-    char* cc_ws = paste_ws + paste_ws_bytes;
-    const size_t cc_ws_bytes = cc_bytes > 0 ? align_up(b200seg_largest_cc_workspace_bytes(cc_bytes), 256) : 0;
-    char* nms_ws = cc_ws + cc_ws_bytes;
-    const size_t nms_ws_bytes = workspace_bytes - (size_t)(nms_ws - (char*)workspace);
+    const SomaChainWs L = soma_chain_ws(workspace, workspace_bytes, n_volumes, n_max, S, H, W, cc_bytes);
+    uint16_t* ids = L.ids;
+    char* paste_ws = L.paste_ws; const size_t paste_ws_bytes = L.paste_ws_bytes;
+    char* cc_ws = L.cc_ws; const size_t cc_ws_bytes = L.cc_ws_bytes;
+    char* nms_ws = L.nms_ws; const size_t nms_ws_bytes = L.nms_ws_bytes;
 
     int e = b200seg_nms3d_dev(dets, det_off_dev, n_volumes, n_max, nms_thresh, 0, keep, keep_count, rank_order,
                               nms_ws, nms_ws_bytes, stream);
     if (e) return e;
-    if (n_max > 0) {
-        iota_u16_kernel<<<(n_max + 255) / 256, 256, 0, stream>>>(ids, n_max);
-        B200_LAUNCH_CHECK("iota_u16_kernel");
-        B200_CUDA(cudaMemsetAsync(status, 0xFF, sizeof(int32_t) * (size_t)total, stream));   // -1 = not visited (suppressed)
-        B200_CUDA(cudaMemsetAsync(survive, 0, (size_t)total, stream));
-        B200_CUDA(cudaMemsetAsync(b_max, 0, sizeof(int32_t) * (size_t)total, stream));            // suppressed detections report 0
-        // one launch for the instances of every volume: grid (n_max, n_volumes)
-        e = b200seg_soma_binarize_dev(volumes, n_volumes, S, H, W, det_off_dev, n_max, boxes, prm, crop_off,
-                                      rank_order, keep_count, masks, b_max, status, stream);
-        if (e) return e;
-        if (keep_largest_cc) {                               // binarization_soma.py:97-99
-            e = b200seg_largest_cc_dev(masks, crop_off, prm_bytes, n_volumes, det_off_dev, n_max, boxes, rank_order, keep_count,
-                                       status, cc_ws, cc_ws_bytes, stream);
-            if (e) return e;
-        }
-    }
-    return b200seg_paste_labels_dev(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
-                                    rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream);
+    return postproc_soma_after_nms(volumes, n_volumes, S, H, W, det_off_dev, n_max, total, boxes, prm, crop_off, prm_bytes,
+                                   keep_largest_cc, seg, keep_count, rank_order, masks, b_max, status, survive, ids,
+                                   paste_ws, paste_ws_bytes, cc_ws, cc_ws_bytes, stream);
 }
 
 // HOST-buffer entry point for ONE volume: what a drop-in binarization call site binds to.
@@ -154,175 +181,3 @@ extern "C" int b200seg_postproc_soma_host(const uint8_t* volume, int S, int H, i
     return 0;
 }
 
-// HOST-buffer entry point for a BATCH of equally shaped volumes: the same chain as above, software-pipelined
-// over three streams (H2D | kernels | D2H) and three device slots, so that the upload of volume v+1, the
-// kernels of volume v and the download of volume v-1 overlap (PCIe is full duplex; the chain itself takes a
-// few percent of a transfer).  Pass pinned host buffers for real overlap; pageable memory still works
-// (the copies then serialise inside the driver).  Returns when every output is in host memory.
-namespace b200seg {
-struct BatchStreams {
-    cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t in_done[3] = {nullptr, nullptr, nullptr}, comp_done[3] = {nullptr, nullptr, nullptr},
-                out_done[3] = {nullptr, nullptr, nullptr};
-    int device = -1;
-    char* pinned = nullptr;           // grow-only pinned staging for the small per-volume outputs
-    size_t pinned_cap = 0;
-    int ensure_pinned(size_t bytes) {
-        if (bytes <= pinned_cap) return 0;
-        if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinned_cap = 0; }
-        const size_t want = align_up(bytes + (bytes >> 1), 1 << 16);
-        B200_CUDA(cudaHostAlloc((void**)&pinned, want, cudaHostAllocDefault));
-        pinned_cap = want;
-        return 0;
-    }
-    int ensure(int dev) {
-        if (device == dev && in) return 0;
-        if (in) {
-            cudaStreamDestroy(in); cudaStreamDestroy(out);
-            for (int k = 0; k < 3; ++k) { cudaEventDestroy(in_done[k]); cudaEventDestroy(comp_done[k]); cudaEventDestroy(out_done[k]); }
-        }
-        B200_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
-        B200_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
-        for (int k = 0; k < 3; ++k) {
-            B200_CUDA(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
-            B200_CUDA(cudaEventCreateWithFlags(&comp_done[k], cudaEventDisableTiming));
-            B200_CUDA(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
-        }
-        device = dev;
-        return 0;
-    }
-};
-static BatchStreams g_batch_dev[64];      // one set of streams / events / pinned staging per device ordinal (guarded by the host context's mutex)
-}  // namespace b200seg
-
-extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int W,
-                                                const uint8_t* const* volumes, const float* const* dets, const int32_t* n_dets,
-                                                const int32_t* const* boxes, const uint8_t* const* prm,
-                                                const int64_t* const* crop_off, float nms_thresh, int keep_largest_cc,
-                                                uint16_t* const* seg, int32_t* n_keep, int32_t* const* rank_order,
-                                                int32_t* const* b_max, int32_t* const* status, uint8_t* const* survive) {
-    B200_CHECK_ARG(n_volumes >= 0 && S > 0 && H > 0 && W > 0, "postproc_soma_host_batch: bad sizes");
-    if (n_volumes == 0) return 0;
-    B200_CHECK_ARG(volumes && n_dets && seg && n_keep, "postproc_soma_host_batch: null pointer");
-    int n_max = 0;
-    size_t prm_max = 0;
-    for (int v = 0; v < n_volumes; ++v) {
-        const int n = n_dets[v];
-        B200_CHECK_ARG(n >= 0 && volumes[v] && seg[v], "postproc_soma_host_batch: bad volume %d", v);
-        B200_CHECK_ARG(n == 0 || (dets && boxes && prm && crop_off && rank_order && b_max && status && survive &&
-                                  dets[v] && boxes[v] && prm[v] && crop_off[v] && rank_order[v] && b_max[v] && status[v] && survive[v]),
-                       "postproc_soma_host_batch: null pointer for volume %d", v);
-        if (n > n_max) n_max = n;
-        if (n > 0 && (size_t)crop_off[v][n] > prm_max) prm_max = (size_t)crop_off[v][n];
-    }
-    B200_CHECK_ARG(n_max < 65535, "postproc_soma_host_batch: more than 65534 instances per volume do not fit uint16 labels");
-    HostCtx& hc = host_ctx();
-    std::lock_guard<std::mutex> lock(hc.mu);
-    const size_t V = (size_t)S * H * W;
-    const size_t nn = n_max > 0 ? n_max : 1;
-    const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n_max, S, H, W, keep_largest_cc ? (long long)prm_max : 0);
-    const int NB = n_volumes < 3 ? n_volumes : 3;
-    const size_t slot_bytes = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
-                              2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(4) +
-                              3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(ws_bytes);
-    int e = hc.ensure(slot_bytes * NB);
-    if (e) return e;
-    int dev = 0;
-    B200_CUDA(cudaGetDevice(&dev));
-    B200_CHECK_ARG(dev >= 0 && dev < 64, "postproc_soma_host_batch: device ordinal out of range");
-    BatchStreams& g_batch = g_batch_dev[dev];
-    e = g_batch.ensure(dev);
-    if (e) return e;
-    struct Slot {
-        uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
-        int64_t* keep; int32_t* cnt; int32_t* rank; int32_t* bmax; int32_t* stat; uint8_t* surv; void* ws;
-    } slot[3];
-    for (int k = 0; k < NB; ++k) {
-        Carver cv(hc.buf + slot_bytes * k);
-        Slot& s = slot[k];
-        s.vol = cv.take<uint8_t>(V); s.seg = cv.take<uint16_t>(V); s.dets = cv.take<float>(nn * 7); s.off = cv.take<int32_t>(2);
-        s.boxes = cv.take<int32_t>(nn * 6); s.prm = cv.take<uint8_t>(prm_max + 16); s.mask = cv.take<uint8_t>(prm_max + 16);
-        s.coff = cv.take<int64_t>(nn + 1); s.keep = cv.take<int64_t>(nn); s.cnt = cv.take<int32_t>(1); s.rank = cv.take<int32_t>(nn);
-        s.bmax = cv.take<int32_t>(nn); s.stat = cv.take<int32_t>(nn); s.surv = cv.take<uint8_t>(nn); s.ws = cv.p;
-    }
-    // small outputs go through pinned staging: a device-to-host copy into pageable memory would block the host
-    // thread until the volume is finished and serialise the whole pipeline
-    size_t small_bytes = 0;
-    for (int v = 0; v < n_volumes; ++v) small_bytes += align_up(16 + 13 * (size_t)n_dets[v], 16);
-    e = g_batch.ensure_pinned(small_bytes);
-    if (e) return e;
-    cudaStream_t s_in = g_batch.in, s_comp = hc.stream, s_out = g_batch.out;
-    size_t small_off = 0;
-    // per-volume {0, n} offset pairs must stay alive until their asynchronous copies have run
-    int32_t* offs = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)n_volumes);
-    if (!offs) { set_error("postproc_soma_host_batch: out of host memory"); return B200SEG_EINVAL; }
-    for (int v = 0; v < n_volumes; ++v) { offs[2 * v] = 0; offs[2 * v + 1] = n_dets[v]; }
-    int rc = 0;
-#define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
-    for (int v = 0; v < n_volumes; ++v) {
-        const int k = v % NB;
-        Slot& s = slot[k];
-        const int n = n_dets[v];
-        if (v >= NB) B200_BATCH(cudaStreamWaitEvent(s_in, g_batch.out_done[k], 0));     // slot free again
-        B200_BATCH(cudaMemcpyAsync(s.vol, volumes[v], V, cudaMemcpyHostToDevice, s_in));
-        B200_BATCH(cudaMemcpyAsync(s.off, offs + 2 * v, 8, cudaMemcpyHostToDevice, s_in));
-        if (n > 0) {
-            B200_BATCH(cudaMemcpyAsync(s.dets, dets[v], (size_t)n * 28, cudaMemcpyHostToDevice, s_in));
-            B200_BATCH(cudaMemcpyAsync(s.boxes, boxes[v], (size_t)n * 24, cudaMemcpyHostToDevice, s_in));
-            B200_BATCH(cudaMemcpyAsync(s.prm, prm[v], (size_t)crop_off[v][n], cudaMemcpyHostToDevice, s_in));
-            B200_BATCH(cudaMemcpyAsync(s.coff, crop_off[v], (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s_in));
-        }
-        B200_BATCH(cudaEventRecord(g_batch.in_done[k], s_in));
-        B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.in_done[k], 0));
-        {
-            const int32_t off[2] = {0, n};
-            const int ce = b200seg_postproc_soma_dev(s.vol, 1, S, H, W, s.dets, s.off, off, s.boxes, s.prm, s.coff,
-                                                     n > 0 ? (long long)crop_off[v][n] : 0, nms_thresh, keep_largest_cc, s.seg,
-                                                     s.keep, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, s.ws, ws_bytes, s_comp);
-            if (ce) { rc = ce; goto done; }
-        }
-        B200_BATCH(cudaEventRecord(g_batch.comp_done[k], s_comp));
-        B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.comp_done[k], 0));
-        B200_BATCH(cudaMemcpyAsync(seg[v], s.seg, V * 2, cudaMemcpyDeviceToHost, s_out));
-        {
-            char* st = g_batch.pinned + small_off;          // [cnt | pad to 16 | rank n*4 | b_max n*4 | status n*4 | survive n]
-            B200_BATCH(cudaMemcpyAsync(st, s.cnt, 4, cudaMemcpyDeviceToHost, s_out));
-            if (n > 0) {
-                B200_BATCH(cudaMemcpyAsync(st + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 4, s.bmax, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 8, s.stat, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 12, s.surv, (size_t)n, cudaMemcpyDeviceToHost, s_out));
-            }
-            small_off += align_up(16 + 13 * (size_t)n, 16);
-        }
-        B200_BATCH(cudaEventRecord(g_batch.out_done[k], s_out));
-    }
-done:
-#undef B200_BATCH
-    {
-        // drain all three streams even on error: the slots and `offs` must not be reused while copies are in flight
-        const cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_comp), e3 = cudaStreamSynchronize(s_out);
-        free(offs);
-        if (rc == 0) {
-            if (e1 != cudaSuccess) rc = check_cuda(e1, "cudaStreamSynchronize(in)");
-            else if (e2 != cudaSuccess) rc = check_cuda(e2, "cudaStreamSynchronize(compute)");
-            else if (e3 != cudaSuccess) rc = check_cuda(e3, "cudaStreamSynchronize(out)");
-        }
-    }
-    if (rc == 0) {                                          // hand the staged small outputs to the caller
-        size_t o = 0;
-        for (int v = 0; v < n_volumes; ++v) {
-            const size_t n = (size_t)n_dets[v];
-            const char* st = g_batch.pinned + o;
-            memcpy(&n_keep[v], st, 4);
-            if (n > 0) {
-                memcpy(rank_order[v], st + 16, n * 4);
-                memcpy(b_max[v], st + 16 + n * 4, n * 4);
-                memcpy(status[v], st + 16 + n * 8, n * 4);
-                memcpy(survive[v], st + 16 + n * 12, n);
-            }
-            o += align_up(16 + 13 * n, 16);
-        }
-    }
-    return rc;
-}

@@ -373,6 +373,59 @@ def test_postproc_host_batch_matches_single_volume_calls(b2):
     assert outs[-1]["n_keep"] == 0 and not outs[-1]["seg"].any()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
+    """Every transfer scheme of the batch entry point (dense / compacted label download x whole-array / gathered PRM
+    upload) returns the same outputs; pinned inputs make the zero-copy gather path eligible, a volume whose size is
+    not a multiple of 8 voxels and an odd-aligned PRM buffer exercise the fallbacks."""
+    from b200seg import synth
+    from b200seg.binarization import set_host_batch_mode, host_batch_traffic
+    from helpers import oracle_chain
+    cases = [synth.postproc_case(700 + i, shape=(24, 80, 96), n_blobs=5 + 2 * i, n_dup=4, n_false=3) for i in range(7)]
+    pin = lambda a: torch_.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    keep = []
+    pinned = []
+    for i, c in enumerate(cases):
+        d = dict(c)
+        for k in ("volume", "dets", "boxes", "crop_off"):
+            t = pin(c[k]); keep.append(t); d[k] = t.numpy()
+        if i == 3:                                  # pinned but not 16-byte aligned: whole-array copy
+            t = torch_.empty(c["prm"].size + 1, dtype=torch_.uint8).pin_memory(); keep.append(t)
+            t[1:] = torch_.from_numpy(c["prm"]); d["prm"] = t.numpy()[1:]
+        elif i == 4:                                # pageable
+            d["prm"] = c["prm"].copy()
+        else:
+            t = pin(c["prm"]); keep.append(t); d["prm"] = t.numpy()
+        pinned.append(d)
+    try:
+        set_host_batch_mode(mode)
+        segs = [np.full(c["volume"].shape, 0xABCD, np.uint16) for c in cases]      # stale contents must be overwritten
+        outs = b2.postproc_soma_host_batch(pinned, 0.23, seg_out=segs)
+        h2d, d2h = host_batch_traffic()
+    finally:
+        set_host_batch_mode(3)
+    dense_down = sum(c["volume"].size * 2 for c in cases)
+    full_up = sum(c["volume"].size + c["prm"].size for c in cases)
+    assert (d2h < dense_down // 2) if (mode & 1) else (d2h >= dense_down)
+    assert (h2d < full_up) if (mode & 2) else (h2d >= full_up)
+    for c, o in zip(cases, outs):
+        ref = oracle_chain(c, 0.23)
+        assert np.array_equal(o["seg"], ref["seg"])
+        assert np.array_equal(o["rank_order"], ref["order"])
+        assert np.array_equal(o["survive"], ref["survive"])
+
+
+def test_postproc_host_batch_odd_volume_size(b2):
+    """S*H*W not a multiple of 8: the compacted download does not apply, the dense copy does."""
+    from b200seg import synth
+    from helpers import oracle_chain
+    cases = [synth.postproc_case(720 + i, shape=(9, 35, 37), n_blobs=3, n_dup=1, n_false=1, sigma_xy=(2, 4), sigma_z=(1, 2)) for i in range(3)]
+    outs = b2.postproc_soma_host_batch(cases, 0.23)
+    for c, o in zip(cases, outs):
+        ref = oracle_chain(c, 0.23)
+        assert np.array_equal(o["seg"], ref["seg"])
+
+
 def test_postproc_batched_device_and_fullsize_properties(b2, torch_):
     """Two 128x512x512 volumes (BASELINE config 3/5 size) through the device chain:
     volume 0 is checked voxel-exact against the oracle, both against size-independent properties."""
