@@ -719,7 +719,7 @@ def run_ours(args, rank, world, local_rank):
            "peaks_median": 4 * Vm,                                   # the second read of the map (8 B / voxel in total)
            "peaks_emit": Vm // 8 + 4 * n_pk + 40 * n_pk}             # mask read, candidate values, int64 rows written
     names = {"paste": "paste_labels_kernel", "otsu": "soma_binarize_kernel", "cc": "largest_cc_fill_kernel", "nms": "nms3d (3 kernels)",
-             "peaks_scan": "peaks_scan3w_kernel", "peaks_median": "peaks_collect_kernel", "peaks_emit": "peaks_finalize_kernel"}
+             "peaks_scan": "peaks_scan3f_kernel", "peaks_median": "peaks_sample_kernel + peaks_interval_kernel", "peaks_emit": "peaks_finalize_kernel"}
     tot_prof = max(sum(prof.values()), 1e-9)
     kernels = {k: {"kernel": names[k], "ms_per_step": prof[k], "share": prof[k] / tot_prof,
                    "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (prof[k] * 1e-3) / 1e9 if prof[k] > 0 else None}

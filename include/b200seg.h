@@ -130,6 +130,10 @@ int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int H, int W, i
 int b200seg_peaks3d_bwd_dev(const int64_t* peaks, const int32_t* n_peaks, int cap,
                             const float* grad_agg, float* grad_in,
                             int B, int A, int S, int H, int W, b200seg_stream_t stream);
+/* Maps (since the library was loaded) whose sampled median interval missed and that took the slow exact selection inside
+ * peaks3d (statistics; the result is exact either way).  "peaks_median_mode" option: 0 = automatic (sampled interval for
+ * maps of 2^16..2^21 elements, level-1 histogram otherwise), 1 = histogram path only, 2 = force the miss. */
+int b200seg_peaks3d_fallback_count(unsigned long long* count);
 
 /* ----------------------------------------------------------------------------------------------
  * 2D-Otsu binarization -- replaces tools/otsu.py:199-284 (otsu_py_2d_fast, k = -1), batched over

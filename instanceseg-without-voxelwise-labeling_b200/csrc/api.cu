@@ -67,6 +67,8 @@ static std::atomic<int> g_peaks_stop_after{99};
 int opt_peaks_stop_after() { return g_peaks_stop_after.load(std::memory_order_relaxed); }
 void opt_set_peaks_stop_after(int v) { g_peaks_stop_after.store(v, std::memory_order_relaxed); }
 
+static std::atomic<int> g_peaks_median_mode{0};
+int opt_peaks_median_mode() { return g_peaks_median_mode.load(std::memory_order_relaxed); }
 static std::atomic<int> g_host_batch_mode{3};
 int opt_host_batch_mode() { return g_host_batch_mode.load(std::memory_order_relaxed); }
 
@@ -82,6 +84,7 @@ extern "C" int b200seg_set_option(const char* name, int value) {
     B200_CHECK_ARG(name, "set_option: null name");
     if (!strcmp(name, "peaks_stop_after")) { opt_set_peaks_stop_after(value); return 0; }
     // bit 0: compacted label download (else dense copies), bit 1: zero-copy gather of the surviving PRM crops (else whole array)
+    if (!strcmp(name, "peaks_median_mode")) { g_peaks_median_mode.store(value, std::memory_order_relaxed); return 0; }
     if (!strcmp(name, "host_batch_mode")) { g_host_batch_mode.store(value, std::memory_order_relaxed); return 0; }
     set_error("set_option: unknown option '%s'", name);
     return B200SEG_EINVAL;

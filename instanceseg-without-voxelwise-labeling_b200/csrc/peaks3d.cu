@@ -44,6 +44,8 @@ struct PeakWs {
     unsigned long long* sel;    // [BA][2]  (prefix, remaining rank) handed from one radix level to the next
     uint32_t* list;       // [BA][list_cap]  low 20 key bits of the members of the level-1 bin (list mode)
     uint32_t* list_n;     // [BA]  (zeroed per call)
+    struct PeakIv* iv;    // [BA]  sampled interval of the median (interval path)
+    struct PeakIvCnt* ivcnt;   // [BA]  exact counters of the interval pass (zeroed per call)
     long long list_cap;
     uint32_t* chunk_cnt;  // [BA][nchunks]
     float* chunk_sum;     // [BA][nchunks]
@@ -65,6 +67,7 @@ static PeakWs peak_layout(void* base, int BA, long long V) {
     w.ticket = (uint32_t*)take((size_t)BA * 4 * 4);
     w.gticket = (uint32_t*)take(16);
     w.list_n = (uint32_t*)take((size_t)BA * 4);
+    w.ivcnt = (PeakIvCnt*)take((size_t)BA * 16);
     w.look = (unsigned long long*)take((size_t)BA * w.nchunks * 8);
     w.map_tot = (unsigned long long*)take((size_t)BA * 8);
     w.map_cnt = (uint32_t*)take((size_t)BA * 4);
@@ -74,6 +77,7 @@ static PeakWs peak_layout(void* base, int BA, long long V) {
     w.chunk_cnt = (uint32_t*)take((size_t)BA * w.nchunks * 4);
     w.chunk_sum = (float*)take((size_t)BA * w.nchunks * 4);
     w.thr = (float*)take((size_t)BA * 4);
+    w.iv = (PeakIv*)take((size_t)BA * 16);
     // member list of the level-1 bin: room for a quarter of the map (a map whose median bin holds more falls back to
     // full passes over the map, decided on the device)
     w.list_cap = V < 65536 ? V : (V / 4 < 65536 ? 65536 : (V / 4 > 131072 ? 131072 : V / 4));
@@ -633,6 +637,183 @@ peaks_scan3w_kernel(const float* __restrict__ in, int S, int H, int W, int nstri
     if (HIST) flush_level1<PW_THREADS>(s_hist, ba, V, ws);
 }
 
+// ---- window 3, wide rows, FLOAT domain (round 2) ----------------------------------------------------------------------
+// Same strip / register-marching layout as peaks_scan3w_kernel, but without ordered keys and without the histogram:
+// the maxima are taken with the NaN-propagating three-input float maximum of sm_100 (FMNMX3.NAN), so that with
+// Kb / Ka = maxima over the 13 neighbours that come earlier / later in the window scan
+//     v not NaN:  peak <=> Kb < v and Ka <= v     (a NaN neighbour makes Kb / Ka NaN and both compares false; v = -inf
+//                                                  fails Kb < v because Kb >= -inf; -0 == +0 as in the key order)
+//     v NaN:      peak <=> Ka is not NaN          (the LAST NaN of a window wins the ATen arg-max)
+// Three instructions per loaded element (key conversion) and the per-voxel shared-memory histogram update are gone; the
+// exact median now comes from peaks_sample_kernel + peaks_interval_kernel.
+__device__ __forceinline__ float fmax3n(float a, float b, float c) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+struct PFRaw { float4 v[PW_R + 2]; float h[PW_R + 2]; };
+struct PFPlane {
+    float k[PW_R][4], le[PW_R], re[PW_R];       // centre rows: values, left neighbour of element 0, right neighbour of element 3
+    float m3[PW_R + 2][4], m9[PW_R][4];
+};
+
+__device__ __forceinline__ void pf_load(PFRaw& rw, const float* __restrict__ pz, bool z_ok, const int (&roff)[PW_R + 2],
+                                        uint32_t rows, bool all_rows, bool h_ok, int hoff) {
+    const float4 ninf4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    if (z_ok && all_rows) {                                 // the common case carries no initialisation moves
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            const float* q;
+            asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(q) : "r"(roff[j]), "l"(pz));
+            rw.v[j] = __ldg(reinterpret_cast<const float4*>(q));
+            rw.h[j] = -CUDART_INF_F;
+            if (h_ok) rw.h[j] = __ldg(q + hoff);
+        }
+    } else if (z_ok) {
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            rw.v[j] = ninf4; rw.h[j] = -CUDART_INF_F;
+            if ((rows >> j) & 1u) {                         // warp-uniform
+                const float* q;
+                asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(q) : "r"(roff[j]), "l"(pz));
+                rw.v[j] = __ldg(reinterpret_cast<const float4*>(q));
+                if (h_ok) rw.h[j] = __ldg(q + hoff);
+            }
+        }
+    } else {                                                // warp-uniform: the -inf padding plane
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) { rw.v[j] = ninf4; rw.h[j] = -CUDART_INF_F; }
+    }
+}
+
+// returns (warp-uniform) whether some value of the plane's PW_R + 2 rows (with the x halo) is NaN
+__device__ __forceinline__ bool pf_process(PFPlane& pl, const PFRaw& rw, int lane) {
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < PW_R + 2; ++j) {
+        const float k0 = rw.v[j].x, k1 = rw.v[j].y, k2 = rw.v[j].z, k3 = rw.v[j].w;
+        float le = __shfl_up_sync(0xffffffffu, k3, 1), re = __shfl_down_sync(0xffffffffu, k0, 1);
+        le = lane == 0 ? rw.h[j] : le;
+        re = lane == 31 ? rw.h[j] : re;
+        pl.m3[j][0] = fmax3n(le, k0, k1);
+        pl.m3[j][1] = fmax3n(k0, k1, k2);
+        pl.m3[j][2] = fmax3n(k1, k2, k3);
+        pl.m3[j][3] = fmax3n(k2, k3, re);
+        mx = fmax3n(mx, pl.m3[j][0], pl.m3[j][3]);          // covers le, k0..k3, re
+        if (j >= 1 && j <= PW_R) {
+            pl.k[j - 1][0] = k0; pl.k[j - 1][1] = k1; pl.k[j - 1][2] = k2; pl.k[j - 1][3] = k3;
+            pl.le[j - 1] = le; pl.re[j - 1] = re;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pl.m9[i][e] = fmax3n(pl.m3[i][e], pl.m3[i + 1][e], pl.m3[i + 2][e]);
+    return __any_sync(0xffffffffu, mx != mx);
+}
+
+template <bool SLOW>
+__device__ __forceinline__ void pf_outputs(const float (&m9p)[PW_R][4], const PFPlane& cur, const PFPlane& nxt,
+                                           uint32_t rowmask, int lane, int mywoff, int w32, uint32_t* __restrict__ bz) {
+#pragma unroll
+    for (int i = 0; i < PW_R; ++i) {
+        if (!((rowmask >> i) & 1u)) continue;               // warp-uniform: row y0 + i is outside the map
+        uint32_t nib = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float left = e == 0 ? cur.le[i] : cur.k[i][e - 1], right = e == 3 ? cur.re[i] : cur.k[i][e + 1];
+            const float kb = fmax3n(m9p[i][e], cur.m3[i][e], left);
+            const float ka = fmax3n(nxt.m9[i][e], cur.m3[i + 2][e], right);
+            const float v = cur.k[i][e];
+            bool peak = (kb < v) & (ka <= v);
+            if (SLOW) peak = (v != v) ? !(ka != ka) : peak;
+            nib |= peak ? (1u << e) : 0u;
+        }
+        uint32_t w = nib << (4 * (lane & 7));               // 8 lanes = one 32-voxel word of the mask
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0) bz[mywoff + i * w32] = w;
+    }
+}
+
+// grid (ctas per map, BA); W % 128 == 0, maps 16-byte aligned, H * W < 2^31 (checked by the launcher).
+template <int MINB>
+__global__ void __launch_bounds__(PW_THREADS, MINB)
+peaks_scan3f_kernel(const float* __restrict__ in, int S, int H, int W, int nstrips, int nrowg, int nzc, int tz, PeakWs ws) {
+    const int ba = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    const long long V = (long long)S * (long long)HW;
+    const float* vol = in + (size_t)ba * V;
+    uint32_t* bits = ws.bits + (size_t)ba * ws.words;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w32 = W >> 5;
+    const size_t HW32 = HW >> 5;
+    const int nunits = nstrips * nrowg * nzc;
+    for (int unit = blockIdx.x * PW_NW + warp; unit < nunits; unit += gridDim.x * PW_NW) {
+        const int rowg = unit % nrowg;
+        const int t = unit / nrowg;
+        const int strip = t % nstrips, zc = t / nstrips;
+        const int x0 = strip * 128, y0 = rowg * PW_R, z0 = zc * tz, z1 = min(S, z0 + tz);
+        const bool h_ok = (lane == 0 && x0 > 0) || (lane == 31 && x0 + 128 < W);
+        const int hoff = lane == 0 ? -1 : 4;
+        int roff[PW_R + 2];
+        uint32_t rows = 0;                                  // bit j: row y0 - 1 + j is inside the map
+#pragma unroll
+        for (int j = 0; j < PW_R + 2; ++j) {
+            const int gy = y0 - 1 + j;
+            roff[j] = gy * W + x0 + 4 * lane;
+            if (gy >= 0 && gy < H) rows |= 1u << j;
+        }
+        const bool all_rows = rows == (1u << (PW_R + 2)) - 1u;
+        const uint32_t rowmask = rows >> 1;                 // bit i: centre row y0 + i
+        const int mywoff = ((y0 * W + x0) >> 5) + (lane >> 3);
+
+        PFRaw rw;
+        PFPlane pa, pb;
+        float m9p[PW_R][4];
+        uint32_t nanbits;                                   // bit 0: plane z - 1, bit 1: plane z, bit 2: plane z + 1 holds a NaN
+        pf_load(rw, vol + (ptrdiff_t)(z0 - 1) * (ptrdiff_t)HW, z0 >= 1, roff, rows, all_rows, h_ok, hoff);
+        nanbits = pf_process(pa, rw, lane) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m9p[i][e] = pa.m9[i][e];
+        pf_load(rw, vol + (size_t)z0 * HW, true, roff, rows, all_rows, h_ok, hoff);
+        nanbits |= pf_process(pa, rw, lane) ? 2u : 0u;
+        pf_load(rw, vol + (size_t)(z0 + 1) * HW, z0 + 1 < S, roff, rows, all_rows, h_ok, hoff);
+        nanbits |= pf_process(pb, rw, lane) ? 4u : 0u;
+        int z = z0;
+        const float* pz = vol + (size_t)(z0 + 2) * HW;     // plane z + 2
+        uint32_t* bz = bits + (size_t)z0 * HW32;            // first mask word of plane z
+        while (true) {                                      // two planes per trip: pa / pb swap roles
+            const bool more = z + 1 < z1;                   // plane z + 2 is needed (as the next plane of plane z + 1)
+            if (more) pf_load(rw, pz, z + 2 < S, roff, rows, all_rows, h_ok, hoff);
+            if (nanbits) pf_outputs<true>(m9p, pa, pb, rowmask, lane, mywoff, w32, bz);     // warp-uniform
+            else pf_outputs<false>(m9p, pa, pb, rowmask, lane, mywoff, w32, bz);
+            if (!more) break;
+#pragma unroll
+            for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m9p[i][e] = pa.m9[i][e];
+            nanbits = (nanbits >> 1) | (pf_process(pa, rw, lane) ? 4u : 0u);
+            ++z; pz += HW; bz += HW32;
+            const bool more2 = z + 1 < z1;
+            if (more2) pf_load(rw, pz, z + 2 < S, roff, rows, all_rows, h_ok, hoff);
+            if (nanbits) pf_outputs<true>(m9p, pb, pa, rowmask, lane, mywoff, w32, bz);
+            else pf_outputs<false>(m9p, pb, pa, rowmask, lane, mywoff, w32, bz);
+            if (!more2) break;
+#pragma unroll
+            for (int i = 0; i < PW_R; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m9p[i][e] = pb.m9[i][e];
+            nanbits = (nanbits >> 1) | (pf_process(pb, rw, lane) ? 4u : 0u);
+            ++z; pz += HW; bz += HW32;
+        }
+    }
+}
+
 // LEVEL 2: bins = key bits 19..8 of elements whose top 12 bits match the level-1 bin.
 // LEVEL 3: bins = key bits 7..0 of elements whose top 24 bits match.  The prefix and the remaining rank come from
 // ws.sel (written by the last CTA of the previous level); the last CTA of this level writes the next one, and at
@@ -850,6 +1031,258 @@ peaks_collect_kernel(const float* __restrict__ in, long long V, PeakWs ws, float
     }
 }
 
+// ---- exact median by sampled interval (round 2; maps of 2^16 .. 2^21 elements) -----------------------------------------
+// peaks_sample_kernel: one CTA per map sorts a stratified sample of PK_NS keys and publishes the sample order statistics
+//   PK_ND ranks (5 sigma of the sample median's rank) below / above the middle as the interval [lo, hi]; it holds the map's
+//   median unless the sample is wildly unrepresentative (probability ~3e-7 per map for any distribution), and about 8 % of the map.
+//   Values that repeat in the sample next to lo / hi mark heavy ties (flag bits): their copies are then counted instead of listed.
+// peaks_interval_kernel: ONE streaming pass over the map counts the keys below lo exactly and lists the keys inside the
+//   interval (per-warp shared-memory stages, one global atomic per flush, no block barrier in the loop).  The last CTA of the
+//   map verifies count_below <= rank < count_below + count_inside -- which makes the result exact, not probabilistic -- and
+//   selects the median from the list (radix select on key - lo); if the check fails, or the list overflowed, the same CTA
+//   falls back to a full three-level radix select over the map (slow, never seen on continuous data).
+__device__ unsigned long long pk_fallbacks;           // maps whose sampled interval missed the median (b200seg_peaks3d_fallback_count)
+constexpr int PK_NS = 4096, PK_ND = 160;
+constexpr int PK_IV_THREADS = 512, PK_IV_NW = PK_IV_THREADS / 32;
+constexpr int PK_IV_WSTAGE = 1024;                      // list entries a warp stages before it flushes (a round adds at most 512)
+constexpr uint32_t PK_TIE_LO = 1u, PK_TIE_HI = 2u, PK_FORCE_FAIL = 4u;
+
+struct PeakIv { uint32_t lo, hi, flags, pad; };
+struct PeakIvCnt { uint32_t n_lt, n_eqlo, n_eqhi, has_nan; };
+
+__global__ void __launch_bounds__(512)
+peaks_sample_kernel(const float* __restrict__ in, long long V, PeakWs ws, int force_fail) {
+    __shared__ uint32_t s_h[2][PK_BINS1];
+    __shared__ unsigned long long s_tmp[512 / 32 + 2];
+    const int ba = blockIdx.x, tid = threadIdx.x;
+    const float* vol = in + (size_t)ba * V;
+    const uint32_t st = (uint32_t)(V / PK_NS);              // stratum length (V >= 16 * PK_NS)
+    uint32_t key[PK_NS / 512];
+#pragma unroll
+    for (int u = 0; u < PK_NS / 512; ++u) {                 // independent gathers: one element per stratum
+        const int i = tid + u * 512;
+        const uint32_t h = ((uint32_t)i * 2654435761u) >> 7;    // fixed pseudo-random offset inside the stratum
+        key[u] = fkey(__ldg(vol + (size_t)i * st + (h % st)));
+    }
+    // three radix levels (12 + 12 + 8 bits) for the two ranks at once: exact order statistics and their multiplicity
+    uint32_t pre[2] = {0u, 0u};
+    unsigned long long rk[2] = {(unsigned long long)(PK_NS / 2 - PK_ND), (unsigned long long)(PK_NS / 2 + PK_ND)};
+    uint32_t mult[2] = {0u, 0u};
+#pragma unroll
+    for (int level = 0; level < 3; ++level) {
+        const int nb = level < 2 ? PK_BINS1 : 256;
+        const int sh_pre = level == 0 ? 32 : (level == 1 ? 20 : 8), sh_bin = level == 0 ? 20 : (level == 1 ? 8 : 0);
+        const bool same = level > 0 && pre[0] == pre[1];    // both ranks still in one bin: one histogram serves both
+        __syncthreads();
+        for (int i = tid; i < nb; i += 512) { s_h[0][i] = 0u; s_h[1][i] = 0u; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PK_NS / 512; ++u) {
+            const uint32_t k = key[u], bin = (k >> sh_bin) & (uint32_t)(nb - 1);
+            if (level == 0) atomicAdd(&s_h[0][bin], 1u);
+            else {
+                if ((k >> sh_pre) == pre[0]) atomicAdd(&s_h[0][bin], 1u);
+                if (!same && (k >> sh_pre) == pre[1]) atomicAdd(&s_h[1][bin], 1u);
+            }
+        }
+        __syncthreads();
+        const int which1 = (level == 0 || same) ? 0 : 1;
+        int b0, b1; unsigned long long r0, r1;
+        select_bin_smem<512>(s_h[0], nb, rk[0], s_tmp, &b0, &r0);
+        select_bin_smem<512>(s_h[which1], nb, rk[1], s_tmp, &b1, &r1);
+        mult[0] = s_h[0][b0]; mult[1] = s_h[which1][b1];
+        pre[0] = (level == 0 ? 0u : pre[0] << (level == 1 ? 12 : 8)) | (uint32_t)b0;
+        pre[1] = (level == 0 ? 0u : pre[1] << (level == 1 ? 12 : 8)) | (uint32_t)b1;
+        rk[0] = r0; rk[1] = r1;
+    }
+    if (tid == 0) {
+        PeakIv iv;
+        iv.lo = pre[0]; iv.hi = pre[1];
+        // a value that repeats inside a 4096-element sample is a heavy tie of the map
+        iv.flags = (mult[0] >= 2u ? PK_TIE_LO : 0u) | (mult[1] >= 2u ? PK_TIE_HI : 0u) | (force_fail ? PK_FORCE_FAIL : 0u);
+        iv.pad = 0u;
+        ws.iv[ba] = iv;
+    }
+}
+
+// Radix select of the element of ascending rank `rank` among get(0..n-1) (uint32 values below 2^top_bits), 12 bits per
+// level, by ONE CTA; s_hist has PK_BINS1 entries.  Must be called by all NT threads.
+template <int NT, typename F>
+__device__ uint32_t cta_select_u32(F get, long long n, unsigned long long rank, int top_bits, uint32_t* s_hist, unsigned long long* s_tmp) {
+    uint32_t prefix = 0u;
+    int shift = top_bits;                                   // candidates: x >> shift == prefix (everything while shift == 32)
+    while (shift > 0) {
+        const int nb = shift < 12 ? shift : 12, s2 = shift - nb;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (1 << nb); i += NT) s_hist[i] = 0u;
+        __syncthreads();
+        {
+            long long i = threadIdx.x;
+            for (; i + 7ll * NT < n; i += 8ll * NT) {           // eight independent loads in flight per thread
+                uint32_t x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = get(i + (long long)u * NT);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (shift >= 32 || (x[u] >> shift) == prefix) atomicAdd(&s_hist[(x[u] >> s2) & ((1u << nb) - 1u)], 1u);
+            }
+            for (; i < n; i += NT) {
+                const uint32_t x = get(i);
+                if (shift >= 32 || (x >> shift) == prefix) atomicAdd(&s_hist[(x >> s2) & ((1u << nb) - 1u)], 1u);
+            }
+        }
+        __syncthreads();
+        int bin; unsigned long long r2;
+        select_bin_smem<NT>(s_hist, 1 << nb, rank, s_tmp, &bin, &r2);
+        prefix = (shift >= 32 ? 0u : (prefix << nb)) | (uint32_t)bin;
+        rank = r2;
+        shift = s2;
+    }
+    return prefix;
+}
+
+// One streaming pass over (this CTA's share of) a map.  Matches are queued per LANE (slot s of lane l lives at
+// s_stage_w[s * 32 + l]: conflict free, no prefix sum and no key recomputation per match); a warp flushes its 32 queues
+// with one prefix sum and one global atomic when some lane could overflow in the next round.
+constexpr int PK_IV_QCAP = PK_IV_WSTAGE / 32;           // 32 slots per lane
+
+template <bool TIES>
+__device__ __forceinline__ void interval_stream(const float* __restrict__ vol, long long V, uint32_t lo, uint32_t hi, uint32_t flags,
+                                                uint32_t* s_stage_w, uint32_t* __restrict__ list, uint32_t* __restrict__ list_n,
+                                                long long list_cap, uint32_t& n_lt, uint32_t& n_eqlo, uint32_t& n_eqhi, uint32_t& mx) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t w = hi - lo;
+    const bool tlo = TIES && (flags & PK_TIE_LO), thi = TIES && (flags & PK_TIE_HI) && w != 0u;
+    const bool vec = ((((uintptr_t)vol) & 15) == 0);
+    const long long nvec = vec ? (V >> 2) : 0;
+    const long long stride = (long long)gridDim.x * PK_IV_THREADS;
+    uint32_t* q = s_stage_w + lane;                         // next free slot of my queue
+    uint32_t qn = 0;
+    auto flush = [&]() {
+        uint32_t incl = qn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += a; }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(list_n, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - qn;
+        for (uint32_t s2 = 0; s2 < qn; ++s2)
+            if ((long long)(base + s2) < list_cap) list[base + s2] = s_stage_w[s2 * 32 + lane];
+        qn = 0;
+        q = s_stage_w + lane;
+    };
+    auto element = [&](uint32_t raw) {
+        const uint32_t key = fkey(__uint_as_float(raw));
+        const uint32_t t = key - lo;
+        n_lt += key < lo ? 1u : 0u;
+        bool in = t <= w;                                   // lo <= key <= hi (a key below lo wraps far above w)
+        if (TIES) {
+            if (tlo) { n_eqlo += t == 0u ? 1u : 0u; in = in && t != 0u; }
+            if (thi) { n_eqhi += t == w ? 1u : 0u; in = in && t != w; }
+        }
+        mx = max(mx, key);
+        if (in) { *q = key; q += 32; ++qn; }
+    };
+    {
+        // loop conditions are evaluated on the warp's first index so that every lane makes the same trips (the warp votes inside)
+        long long ib = (long long)blockIdx.x * PK_IV_THREADS + (tid & ~31);
+        for (; ib + 31 + 3 * stride < nvec; ib += 4 * stride) {            // full rounds: 4 independent 128-bit loads in flight
+            const long long i = ib + lane;
+            uint4 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = ld_stream_u4(vol + ((i + j * stride) << 2));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { element(u[j].x); element(u[j].y); element(u[j].z); element(u[j].w); }
+            if (__any_sync(0xffffffffu, qn > (uint32_t)(PK_IV_QCAP - 16))) flush();
+        }
+        for (; ib < nvec; ib += stride) {
+            const long long i = ib + lane;
+            if (i < nvec) {
+                const uint4 u = ld_stream_u4(vol + (i << 2));
+                element(u.x); element(u.y); element(u.z); element(u.w);
+            }
+            if (__any_sync(0xffffffffu, qn > (uint32_t)(PK_IV_QCAP - 16))) flush();
+        }
+    }
+    // unaligned maps / tails
+    for (long long ib = (nvec << 2) + (long long)blockIdx.x * PK_IV_THREADS + (tid & ~31); ib < V; ib += stride) {
+        const long long i = ib + lane;
+        if (i < V) element(__float_as_uint(vol[i]));
+        if (__any_sync(0xffffffffu, qn > (uint32_t)(PK_IV_QCAP - 16))) flush();
+    }
+    if (__any_sync(0xffffffffu, qn > 0u)) flush();
+}
+
+__global__ void __launch_bounds__(PK_IV_THREADS, 2)
+peaks_interval_kernel(const float* __restrict__ in, long long V, PeakWs ws, float* __restrict__ thr_out) {
+    extern __shared__ __align__(16) uint32_t s_dyn[];       // PK_IV_NW warp stages; reused as the histogram of the finishing step
+    __shared__ unsigned long long s_tmp[PK_IV_THREADS / 32 + 2];
+    __shared__ uint32_t s_red[4][PK_IV_NW];
+    __shared__ int s_flag;
+    const int ba = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* vol = in + (size_t)ba * V;
+    const PeakIv iv = ws.iv[ba];
+    uint32_t* list = ws.list + (size_t)ba * (size_t)ws.list_cap;
+    uint32_t n_lt = 0, n_eqlo = 0, n_eqhi = 0, mx = 0;
+    if (iv.flags & (PK_TIE_LO | PK_TIE_HI))
+        interval_stream<true>(vol, V, iv.lo, iv.hi, iv.flags, s_dyn + warp * PK_IV_WSTAGE, list, ws.list_n + ba, ws.list_cap, n_lt, n_eqlo, n_eqhi, mx);
+    else
+        interval_stream<false>(vol, V, iv.lo, iv.hi, iv.flags, s_dyn + warp * PK_IV_WSTAGE, list, ws.list_n + ba, ws.list_cap, n_lt, n_eqlo, n_eqhi, mx);
+    // CTA totals -> the map's counters
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        n_lt += __shfl_xor_sync(0xffffffffu, n_lt, o); n_eqlo += __shfl_xor_sync(0xffffffffu, n_eqlo, o);
+        n_eqhi += __shfl_xor_sync(0xffffffffu, n_eqhi, o); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_red[0][warp] = n_lt; s_red[1][warp] = n_eqlo; s_red[2][warp] = n_eqhi; s_red[3][warp] = mx; }
+    __syncthreads();
+    PeakIvCnt* cnt = ws.ivcnt + ba;
+    if (tid == 0) {
+        uint32_t a = 0, b = 0, c = 0, m = 0;
+        for (int i = 0; i < PK_IV_NW; ++i) { a += s_red[0][i]; b += s_red[1][i]; c += s_red[2][i]; m = max(m, s_red[3][i]); }
+        if (a) atomicAdd(&cnt->n_lt, a);
+        if (b) atomicAdd(&cnt->n_eqlo, b);
+        if (c) atomicAdd(&cnt->n_eqhi, c);
+        if (m == KEY_NAN) atomicOr(&cnt->has_nan, 1u);
+        __threadfence();
+        s_flag = (atomicAdd(ws.ticket + ba * 4 + 1, 1u) == gridDim.x - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    // ---- last CTA of the map: verify the interval and finish the selection ---------------------------------------
+    uint32_t* s_hist = s_dyn;
+    const unsigned long long k = (unsigned long long)((V - 1) / 2);
+    const unsigned long long lt = __ldcg(&cnt->n_lt), eqlo = __ldcg(&cnt->n_eqlo), eqhi = __ldcg(&cnt->n_eqhi);
+    const unsigned long long nl = __ldcg(ws.list_n + ba);
+    const bool has_nan = __ldcg(&cnt->has_nan) != 0u;
+    uint32_t key = 0u;
+    int how;                                                // 0: lo, 1: from the list, 2: hi, 3: fall back
+    if (iv.flags & PK_FORCE_FAIL) how = 3;
+    else if (k < lt) how = 3;
+    else if (k < lt + eqlo) how = 0;
+    else if (k < lt + eqlo + nl) how = (long long)nl <= ws.list_cap ? 1 : 3;
+    else if (k < lt + eqlo + nl + eqhi) how = 2;
+    else how = 3;
+    if (has_nan) how = 0;                                   // the threshold is NaN whatever the interval says
+    if (how == 0) key = iv.lo;
+    else if (how == 2) key = iv.hi;
+    else if (how == 1) {
+        const uint32_t lo = iv.lo, w = iv.hi - iv.lo;
+        const int bits_w = 32 - __clz(w | 1u);
+        key = lo + cta_select_u32<PK_IV_THREADS>([&](long long i) { return __ldcg(list + i) - lo; }, (long long)nl, k - lt - eqlo,
+                                                 bits_w, s_hist, s_tmp);
+    } else {
+        key = cta_select_u32<PK_IV_THREADS>([&](long long i) { return fkey(__ldg(vol + i)); }, V, k, 32, s_hist, s_tmp);
+        if (tid == 0) atomicAdd(&pk_fallbacks, 1ull);       // statistics: maps that took the fallback
+    }
+    if (tid == 0) {
+        const float thr = has_nan ? CUDART_NAN_F : key_to_float(key);
+        ws.thr[ba] = thr;
+        if (thr_out) thr_out[ba] = thr;
+    }
+}
+
 // One launch for filter + count + scan + emit.  Work item = PK_ITEM_WORDS consecutive words of one map's candidate
 // mask (4 per thread), items ordered (map, chunk) = the lexicographic order of the output rows.  A CTA draws its item
 // by ticket, so every predecessor of a running item is running or finished; an item publishes its count as soon as
@@ -1049,7 +1482,12 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
     B200_CHECK_ARG((long long)BA * ws.nchunks < (1ll << 31), "peaks3d: too many work items");
     B200_CUDA(cudaMemsetAsync(base, 0, ws.zero_bytes, stream));
     const int sms = num_sms();
-    const int do_hist = filter_mode == 1;
+    // exact median: sampled interval + one streaming pass for maps of 2^16 .. 2^21 elements, else the level-1 histogram of
+    // the scan + list / refinement passes (option "peaks_median_mode": 0 auto, 1 always the histogram path, 2 auto with the
+    // interval forced to miss, which exercises the fallback selection)
+    const int median_mode = opt_peaks_median_mode();
+    const bool interval = filter_mode == 1 && median_mode != 1 && V >= 16ll * PK_NS && V <= (1ll << 21);
+    const int do_hist = filter_mode == 1 && !interval;
     const int stop_after = opt_peaks_stop_after();        // profiling aid (b200seg_set_option): run only the first k kernels
     if (stop_after < 1) return 0;
     if (win == 3) {
@@ -1060,7 +1498,9 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         const bool wide0 = variant < 10 && (W % 128) == 0;
         const long long units_guess = (long long)BA * ((W + 127) / 128) * ((H + PW_R - 1) / PW_R) * ((S + 15) / 16);
         const bool dense4 = variant == 4 || (variant == 0 && wide0 && units_guess >= (long long)sms * 4 * PW_NW * 2 && BA >= 32);
-        const int wminb = dense4 ? 4 : PW_MINB;
+        const bool fdom = wide && !do_hist && variant != 7;           // float-domain kernel (no histogram)
+        const int fminb = variant == 5 ? 5 : (variant == 3 ? 3 : 4);
+        const int wminb = fdom ? fminb : (dense4 ? 4 : PW_MINB);
         const int xs = wide ? 128 : 32, R = wide ? PW_R : 4, minb = wide ? wminb : 2, nw = wide ? PW_NW : PK_NW;
         const int nstrips = (W + xs - 1) / xs, nrowg = (H + R - 1) / R;
         // persistent CTAs: 2 resident CTAs per SM in total, spread over the B*A maps
@@ -1081,7 +1521,11 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         B200_CHECK_ARG(units < (1ll << 31), "peaks3d: too many work units");
         if ((long long)per_map * nw > units) per_map = (int)((units + nw - 1) / nw);
         dim3 g1((unsigned)per_map, BA);
-        if (wide) {
+        if (fdom) {
+            if (fminb == 5) peaks_scan3f_kernel<5><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            else if (fminb == 3) peaks_scan3f_kernel<3><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+            else peaks_scan3f_kernel<4><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
+        } else if (wide) {
             if (dense4) {
                 if (do_hist) peaks_scan3w_kernel<true, 4><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
                 else peaks_scan3w_kernel<false, 4><<<g1, PW_THREADS, 0, stream>>>(input, S, H, W, nstrips, nrowg, nzc, tz, ws);
@@ -1105,7 +1549,26 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
         B200_LAUNCH_CHECK("peaks_scan_kernel");
     }
     if (stop_after < 2) return 0;
-    if (filter_mode == 1) {
+    if (interval) {
+        peaks_sample_kernel<<<BA, 512, 0, stream>>>(input, V, ws, median_mode == 2);
+        B200_LAUNCH_CHECK("peaks_sample_kernel");
+        if (stop_after < 3) return 0;
+        static OncePerDevice iv_attr;
+        int iv_dev;
+        constexpr int iv_smem = PK_IV_NW * PK_IV_WSTAGE * 4;
+        if (iv_attr.needed(&iv_dev)) {
+            B200_CUDA(cudaFuncSetAttribute(peaks_interval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, iv_smem));
+            iv_attr.mark(iv_dev);
+        }
+        // CTAs per map: enough to fill the machine twice over when the batch is small, one fat CTA per map when it is large
+        long long want = (V / 4 + (long long)PK_IV_THREADS * 16 - 1) / ((long long)PK_IV_THREADS * 16);     // >= 4 rounds per thread
+        long long lim = ((long long)sms * 2 + BA - 1) / BA;
+        int gi = (int)(want < 1 ? 1 : (want > lim ? lim : want));
+        if (gi < 1) gi = 1;
+        dim3 g2(gi, BA);
+        peaks_interval_kernel<<<g2, PK_IV_THREADS, iv_smem, stream>>>(input, V, ws, thr_out);
+        B200_LAUNCH_CHECK("peaks_interval_kernel");
+    } else if (filter_mode == 1) {
         // a few fat CTAs per map: the fixed cost per CTA (clear + publish a 4096-bin histogram) must stay small
         // against its share of the stream
         long long want = (V / 4 + (long long)PK_RF_THREADS * 8 - 1) / ((long long)PK_RF_THREADS * 8);
@@ -1123,6 +1586,12 @@ extern "C" int b200seg_peaks3d_dev(const float* input, int B, int A, int S, int 
     peaks_finalize_kernel<<<BA * ws.nchunks, PK_THREADS, 0, stream>>>(input, BA, A, H, W, V, filter_mode, thr_in, ws, peaks, cap,
                                                                      n_peaks, agg, thr_out);
     B200_LAUNCH_CHECK("peaks_finalize_kernel");
+    return 0;
+}
+
+extern "C" int b200seg_peaks3d_fallback_count(unsigned long long* count) {
+    B200_CHECK_ARG(count, "peaks3d_fallback_count: null pointer");
+    B200_CUDA(cudaMemcpyFromSymbol(count, pk_fallbacks, sizeof(unsigned long long)));
     return 0;
 }
 

@@ -19,6 +19,21 @@ def median_filter(input):
     return thr.contiguous().view(b, c, 1, 1, 1)
 
 
+def set_median_mode(mode):
+    """Exact-median strategy of the fused "median" filter: 0 automatic (sampled interval for maps of 2^16..2^21 elements,
+    level-1 histogram otherwise), 1 histogram path only, 2 sampled interval forced to miss (exercises the slow exact
+    selection).  Results are identical in every mode."""
+    _lib.check(_lib.lib().b200seg_set_option(b"peaks_median_mode", int(mode)), "set_option")
+
+
+def median_fallback_count():
+    """Maps whose sampled interval missed the median since the library was loaded (they took the slow exact selection)."""
+    import ctypes as C
+    n = C.c_ulonglong(0)
+    _lib.check(_lib.lib().b200seg_peaks3d_fallback_count(C.byref(n)), "peaks3d_fallback_count")
+    return int(n.value)
+
+
 class PeaksPlan(object):
     """Pre-allocated, allocation-free and sync-free form of the op for a fixed input shape (what the batched chain and
     bench.py use): `run(input)` enqueues one memset + four kernels on the current stream and returns device buffers

@@ -542,6 +542,44 @@ def test_peaks_aligned_rows_nan_signs_and_plateaus(b2, torch_):
                     assert np.array_equal(thr.cpu().numpy(), othr, equal_nan=True), (t, thr, othr)
 
 
+def test_peaks_sampled_interval_median_ties_and_fallback(b2, torch_):
+    """Maps of 2^16..2^21 elements take the sampled-interval median (one streaming pass); the threshold and the peak list
+    stay exact for continuous data, heavy ties at the median (ReLU-like zeros, binary and few-level maps, constant maps),
+    NaNs, -inf tails, and when the interval is forced to miss (slow exact selection) -- all three strategies agree."""
+    from b200seg.peak_stimulation_3d import peaks_forward, set_median_mode, median_fallback_count
+    rng = np.random.default_rng(404)
+    shapes = [(1, 2, 16, 64, 64), (1, 3, 8, 96, 128), (2, 1, 32, 128, 128), (1, 1, 17, 61, 67), (1, 2, 16, 128, 256)]
+    maps = []
+    for t, shp in enumerate(shapes):
+        x = rng.normal(size=shp).astype(np.float32)
+        maps.append(("normal", x))
+        maps.append(("relu", np.maximum(x - (0.05 if t % 2 else -0.05), 0).astype(np.float32)))     # ~52 % / ~48 % exact zeros
+        maps.append(("binary", (x > 0.01).astype(np.float32)))
+        maps.append(("levels", np.round(x * 1.5).astype(np.float32) * 0.25))
+        c = np.full(shp, 0.375, np.float32); c.flat[rng.integers(0, c.size, 50)] = 1.0
+        maps.append(("constant", c))
+        n = x.copy(); n.flat[rng.integers(0, n.size, 3)] = np.nan
+        maps.append(("nan", n))
+        m = x.copy(); m.flat[rng.integers(0, m.size, m.size // 3)] = -np.inf; m[m > 1.0] = np.inf
+        maps.append(("inf", m))
+        maps.append(("tiny", (x * 1e-42).astype(np.float32)))                                      # denormals and signed zeros
+    before = median_fallback_count()
+    try:
+        for name, x in maps:
+            op, oagg, othr = oracle.peak_stimulation_3d(x, win_size=3, filter_mode="median")
+            for mode in (0, 1, 2):
+                set_median_mode(mode)
+                p, agg, thr = peaks_forward(torch_.from_numpy(x).cuda(), 3, 1)
+                assert np.array_equal(thr.cpu().numpy(), othr, equal_nan=True), (name, x.shape, mode, thr, othr)
+                assert np.array_equal(p.cpu().numpy(), op), (name, x.shape, mode)
+    finally:
+        set_median_mode(0)
+    # mode 2 forces one fallback per map without a NaN (a NaN decides the threshold before the selection); mode 0 must not
+    # add any on these inputs
+    forced = sum(int((~np.isnan(x).reshape(x.shape[0] * x.shape[1], -1).any(axis=1)).sum()) for _, x in maps)
+    assert median_fallback_count() - before == forced, (median_fallback_count() - before, forced)
+
+
 def test_peaks_full_resolution_map(b2, torch_):
     """(1,1,128,512,512) fp32 map (BASELINE config 3, full-resolution variant): exact peak list and threshold vs the oracle."""
     from b200seg import synth
