@@ -107,25 +107,13 @@ struct __align__(16) FwdShared {
     int lo[3], hi[3];
 };
 
-template <typename T, int PT>
-__global__ void __launch_bounds__(RA_THREADS)
-roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out,
-                      int C, int S, int H, int W, int Ps, int Ph, int Pw, float scale, int sr, int layout) {
-    extern __shared__ __align__(16) float s_buf[];
-    __shared__ FwdShared sh;
-    const int r = blockIdx.x;
-    const int c0 = blockIdx.y * RA_CC;
-    const int nc = min(RA_CC, C - c0);
+// Table building shared by both forward kernels (block level, RA_THREADS threads).  On return sh.lo / sh.hi hold the
+// footprint, and -- unless the footprint is empty or `tables` is false -- sh.w the dense axis tables with 1/count
+// folded into the z table when count is a power of two.  Returns true when every sample falls outside the volume.
+__device__ __forceinline__ bool fwd_ranges(FwdShared& sh, const AxisP (&ax)[3], const int (&Pa)[3]) {
     const int tid = threadIdx.x;
-
-    AxisP ax[3];
-    int batch; float count;
-    roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, -1.0, ax[0], ax[1], ax[2], batch, count);
-    const int Pa[3] = {Ps, Ph, Pw};
-
-    // ---- axis tables: footprint range, then dense W[f][p] ------------------------------------------
     if (tid < 3) { sh.lo[tid] = 0x7fffffff; sh.hi[tid] = -1; }
-    for (int i = tid; i < 3 * RA_FMAX * 16; i += RA_THREADS) (&sh.w[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 3 * RA_FMAX * 16; i += (int)blockDim.x) (&sh.w[0][0][0])[i] = 0.f;
     __syncthreads();
     if (tid < 3 * 16) {
         const int a = tid >> 4, p = tid & 15;
@@ -139,55 +127,12 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
         }
     }
     __syncthreads();
-    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
-    const int Fz = sh.hi[0] - zlo + 1, Fy = sh.hi[1] - ylo + 1, Fx = sh.hi[2] - xlo + 1;
-    const bool empty = sh.hi[0] < 0 || sh.hi[1] < 0 || sh.hi[2] < 0;
-    const size_t P3 = (size_t)Ps * Ph * Pw;
-    T* out_r = out + ((size_t)r * C + c0) * P3;
-    if (empty) {                                        // every sample falls outside: zeros
-        for (size_t i = tid; i < (size_t)nc * P3; i += RA_THREADS) out_r[i] = from_f<T>(0.f);
-        return;
-    }
-    const T* feat_b = feat + ((size_t)batch * C + c0) * S * H * W;
-    // per-warp buffers of the separable path (floats): A = stage [rows][RSx] + T1 [rows][PT] (reused as the output
-    // staging area [P3]), B = T2 [Fz][PT][PT]
-    const int rows = Fz * Fy;
-    const int RSx = Fx | 1;                               // odd row stride: conflict-free column walks
-    const int sizeA = max(rows * (RSx + PT), (int)((P3 + 3) & ~(size_t)3));
-    const int need = sizeA + Fz * PT * PT;
-    const bool separable = Fz <= RA_FMAX && Fy <= RA_FMAX && Fx <= RA_FMAX && need <= FwdCfg<PT>::SMEM_FLOATS;
-    if (!separable) {
-        // direct evaluation (reference arithmetic), coalesced over the output span of this CTA
-        for (size_t idx = tid; idx < (size_t)nc * P3; idx += RA_THREADS) {
-            const int c = (int)(idx / P3);
-            const int e = (int)(idx % P3);
-            int ps, ph, pw;
-            if (layout == 0) { ps = e % Ps; pw = (e / Ps) % Pw; ph = e / (Ps * Pw); }
-            else { pw = e % Pw; ph = (e / Pw) % Ph; ps = e / (Pw * Ph); }
-            const T* data = feat_b + (size_t)c * S * H * W;
-            float acc = 0.f;
-            for (int iz = 0; iz < ax[0].g; ++iz) {
-                const Tap tz = axis_sample(ax[0], ps, iz);
-                for (int iy = 0; iy < ax[1].g; ++iy) {
-                    const Tap ty = axis_sample(ax[1], ph, iy);
-                    for (int ix = 0; ix < ax[2].g; ++ix) {
-                        const Tap tx = axis_sample(ax[2], pw, ix);
-                        if (!(tz.valid && ty.valid && tx.valid)) continue;
-                        const T* p0 = data + ((size_t)tz.low * H + ty.low) * W;
-                        const T* p1 = data + ((size_t)tz.low * H + ty.high) * W;
-                        const T* p2 = data + ((size_t)tz.high * H + ty.low) * W;
-                        const T* p3 = data + ((size_t)tz.high * H + ty.high) * W;
-                        acc += tz.h * ty.h * tx.h * to_f(p0[tx.low]) + tz.h * ty.h * tx.l * to_f(p0[tx.high]) +
-                               tz.h * ty.l * tx.h * to_f(p1[tx.low]) + tz.h * ty.l * tx.l * to_f(p1[tx.high]) +
-                               tz.l * ty.h * tx.h * to_f(p2[tx.low]) + tz.l * ty.h * tx.l * to_f(p2[tx.high]) +
-                               tz.l * ty.l * tx.h * to_f(p3[tx.low]) + tz.l * ty.l * tx.l * to_f(p3[tx.high]);
-                    }
-                }
-            }
-            out_r[idx] = from_f<T>(acc / count);
-        }
-        return;
-    }
+    return sh.hi[0] < 0 || sh.hi[1] < 0 || sh.hi[2] < 0;
+}
+
+// footprints of at most RA_FMAX voxels per axis only.  Ends with a block barrier.
+__device__ __forceinline__ void fwd_tables(FwdShared& sh, const AxisP (&ax)[3], const int (&Pa)[3], float count, bool pow2) {
+    const int tid = threadIdx.x;
     if (tid < 3 * 16) {
         const int a = tid >> 4, p = tid & 15;
         if (p < Pa[a]) {
@@ -198,20 +143,59 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
             }
         }
     }
-    const int icount = ax[0].g * ax[1].g * ax[2].g;
-    const bool pow2 = (icount & (icount - 1)) == 0;       // sr = 2: count = 8 -> scaling by 1/count is exact
     __syncthreads();
-    if (pow2) for (int i = tid; i < RA_FMAX * 16; i += RA_THREADS) (&sh.w[0][0][0])[i] *= 1.0f / count;
-    // offset of every footprint row (z, y) inside one channel volume
-    for (int row = tid; row < rows; row += RA_THREADS) {
-        const int z = row / Fy, y = row - z * Fy;
-        sh.row_off[row] = ((zlo + z) * H + (ylo + y)) * W + xlo;
-    }
+    if (pow2) for (int i = tid; i < RA_FMAX * 16; i += (int)blockDim.x) (&sh.w[0][0][0])[i] *= 1.0f / count;
     __syncthreads();
+}
 
-    // ---- from here on every warp works on its own channels; no block barrier ------------------------
+// direct evaluation (reference arithmetic) of nc channels of one RoI, coalesced over the output span
+template <typename T>
+__device__ __forceinline__ void fwd_direct(const T* __restrict__ feat_b, T* __restrict__ out_r, const AxisP (&ax)[3], int nc,
+                                           int S, int H, int W, int Ps, int Ph, int Pw, int layout, float count) {
+    const size_t P3 = (size_t)Ps * Ph * Pw;
+    for (size_t idx = threadIdx.x; idx < (size_t)nc * P3; idx += blockDim.x) {
+        const int c = (int)(idx / P3);
+        const int e = (int)(idx % P3);
+        int ps, ph, pw;
+        if (layout == 0) { ps = e % Ps; pw = (e / Ps) % Pw; ph = e / (Ps * Pw); }
+        else { pw = e % Pw; ph = (e / Pw) % Ph; ps = e / (Pw * Ph); }
+        const T* data = feat_b + (size_t)c * S * H * W;
+        float acc = 0.f;
+        for (int iz = 0; iz < ax[0].g; ++iz) {
+            const Tap tz = axis_sample(ax[0], ps, iz);
+            for (int iy = 0; iy < ax[1].g; ++iy) {
+                const Tap ty = axis_sample(ax[1], ph, iy);
+                for (int ix = 0; ix < ax[2].g; ++ix) {
+                    const Tap tx = axis_sample(ax[2], pw, ix);
+                    if (!(tz.valid && ty.valid && tx.valid)) continue;
+                    const T* p0 = data + ((size_t)tz.low * H + ty.low) * W;
+                    const T* p1 = data + ((size_t)tz.low * H + ty.high) * W;
+                    const T* p2 = data + ((size_t)tz.high * H + ty.low) * W;
+                    const T* p3 = data + ((size_t)tz.high * H + ty.high) * W;
+                    acc += tz.h * ty.h * tx.h * to_f(p0[tx.low]) + tz.h * ty.h * tx.l * to_f(p0[tx.high]) +
+                           tz.h * ty.l * tx.h * to_f(p1[tx.low]) + tz.h * ty.l * tx.l * to_f(p1[tx.high]) +
+                           tz.l * ty.h * tx.h * to_f(p2[tx.low]) + tz.l * ty.h * tx.l * to_f(p2[tx.high]) +
+                           tz.l * ty.l * tx.h * to_f(p3[tx.low]) + tz.l * ty.l * tx.l * to_f(p3[tx.high]);
+                }
+            }
+        }
+        out_r[idx] = from_f<T>(acc / count);
+    }
+}
+
+// Generic separable path (footprints up to RA_FMAX voxels per axis, pooled sizes up to 16): nc (<= RA_CC) channels of one
+// RoI, every warp on its own channels, no block barrier inside.  Needs the tables of fwd_tables and, behind them,
+// sh.row_off (filled by the caller + one block barrier).
+template <typename T, int PT>
+__device__ __forceinline__ void fwd_generic_warps(float* s_buf, const FwdShared& sh, const T* __restrict__ feat_b,
+                                                  T* __restrict__ out_r, int nc, int S, int H, int W, int Ps, int Ph, int Pw,
+                                                  int layout, int Fz, int Fy, int Fx, int need, int sizeA, float count, bool pow2) {
+    const int tid = threadIdx.x;
+    const size_t P3 = (size_t)Ps * Ph * Pw;
+    const int rows = Fz * Fy;
+    const int RSx = Fx | 1;                               // odd row stride: conflict-free column walks
     const int lane = tid & 31, warp = tid >> 5;
-    const int n_active = min(RA_THREADS / 32, FwdCfg<PT>::SMEM_FLOATS / need);
+    const int n_active = min((int)blockDim.x / 32, FwdCfg<PT>::SMEM_FLOATS / need);
     if (warp >= n_active) return;
     float* bufA = s_buf + (size_t)warp * need;            // stage [rows][RSx], then T1 [rows][PT] behind it; later out [P3]
     float* sT1 = bufA + rows * RSx;
@@ -305,6 +289,373 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
                 o[i] = from_f<T>(v0); o[i + 32] = from_f<T>(v1); o[i + 64] = from_f<T>(v2); o[i + 96] = from_f<T>(v3);
             }
             for (; i < n3; i += 32) o[i] = from_f<T>(bufA[i]);
+        }
+    }
+}
+
+// Generic forward kernel: pooled sizes 9..16 (the mask head's 14^3) -- and the body the fast kernel below falls back to.
+// cpb = channels per CTA (a multiple of RA_CC).
+template <typename T, int PT>
+__device__ __forceinline__ void fwd_generic_cta(float* s_buf, FwdShared& sh, const T* __restrict__ feat_b, T* __restrict__ out_r,
+                                                const AxisP (&ax)[3], const int (&Pa)[3], int ncta, int S, int H, int W,
+                                                int layout, float count) {
+    const int tid = threadIdx.x;
+    const int Ps = Pa[0], Ph = Pa[1], Pw = Pa[2];
+    const size_t P3 = (size_t)Ps * Ph * Pw;
+    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
+    const int Fz = sh.hi[0] - zlo + 1, Fy = sh.hi[1] - ylo + 1, Fx = sh.hi[2] - xlo + 1;
+    // per-warp buffers of the separable path (floats): A = stage [rows][RSx] + T1 [rows][PT] (reused as the output
+    // staging area [P3]), B = T2 [Fz][PT][PT]
+    const int rows = Fz * Fy;
+    const int RSx = Fx | 1;
+    const int sizeA = max(rows * (RSx + PT), (int)((P3 + 3) & ~(size_t)3));
+    const int need = sizeA + Fz * PT * PT;
+    const bool separable = Fz <= RA_FMAX && Fy <= RA_FMAX && Fx <= RA_FMAX && need <= FwdCfg<PT>::SMEM_FLOATS;
+    if (!separable) {
+        fwd_direct<T>(feat_b, out_r, ax, ncta, S, H, W, Ps, Ph, Pw, layout, count);
+        return;
+    }
+    const int icount = ax[0].g * ax[1].g * ax[2].g;
+    const bool pow2 = (icount & (icount - 1)) == 0;       // sr = 2: count = 8 -> scaling by 1/count is exact
+    fwd_tables(sh, ax, Pa, count, pow2);
+    for (int row = tid; row < rows; row += (int)blockDim.x) {   // offset of every footprint row (z, y) inside one channel volume
+        const int z = row / Fy, y = row - z * Fy;
+        sh.row_off[row] = ((zlo + z) * H + (ylo + y)) * W + xlo;
+    }
+    __syncthreads();
+    const size_t SHW = (size_t)S * H * W;
+    for (int c0 = 0; c0 < ncta; c0 += RA_CC)
+        fwd_generic_warps<T, PT>(s_buf, sh, feat_b + (size_t)c0 * SHW, out_r + (size_t)c0 * P3, min(RA_CC, ncta - c0), S, H, W,
+                                 Ps, Ph, Pw, layout, Fz, Fy, Fx, need, sizeA, count, pow2);
+}
+
+template <typename T, int PT>
+__global__ void __launch_bounds__(RA_THREADS)
+roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out,
+                      int C, int S, int H, int W, int Ps, int Ph, int Pw, float scale, int sr, int layout) {
+    extern __shared__ __align__(16) float s_buf[];
+    __shared__ FwdShared sh;
+    const int r = blockIdx.x;
+    const int c0 = blockIdx.y * RA_CC;
+    const int nc = min(RA_CC, C - c0);
+    AxisP ax[3];
+    int batch; float count;
+    roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, -1.0, ax[0], ax[1], ax[2], batch, count);
+    const int Pa[3] = {Ps, Ph, Pw};
+    const bool empty = fwd_ranges(sh, ax, Pa);
+    const size_t P3 = (size_t)Ps * Ph * Pw;
+    T* out_r = out + ((size_t)r * C + c0) * P3;
+    if (empty) {                                        // every sample falls outside: zeros
+        for (size_t i = threadIdx.x; i < (size_t)nc * P3; i += RA_THREADS) out_r[i] = from_f<T>(0.f);
+        return;
+    }
+    const T* feat_b = feat + ((size_t)batch * C + c0) * S * H * W;
+    fwd_generic_cta<T, PT>(s_buf, sh, feat_b, out_r, ax, Pa, nc, S, H, W, layout, count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, fast path: pooled sizes <= 8 (the box head's 7^3) and footprints of <= 8 voxels per axis
+// ------------------------------------------------------------------------------------------------
+// The generic kernel above spends most of its issue slots on shared-memory traffic (one weight-row load per feature
+// value) and on half-empty warps (25..49 items over 32 lanes).  Here the lanes of a warp are CHANNELS, so the axis
+// weights are warp-uniform scalars that live in REGISTERS and every lane runs the same dense little contraction with
+// all indices static (measured on B200: a shared-memory load costs the same whether its 32 lanes read 32 or 256 distinct
+// bytes, and a 128-bit load costs 4.3x a 32-bit one -- profiles/exp/lds_patterns.cu -- so broadcast weight loads are as
+// expensive as data loads and have to go):
+//   * a warp task = (RoI, 16 channels).  lane = (channel pair cp = lane & 7, pw pair g = lane >> 3); a staged voxel holds
+//     its 16 channels contiguously, so one 64-bit shared load yields the packed operand (ch 2cp, ch 2cp+1) of an FFMA2 whose
+//     other operand is a scalar weight (FFMA2's .F32 broadcast form): two FMAs per issue slot, no register shuffling.
+//   * phase A walks the footprint plane by plane along the axis that is contracted LAST (y in the reference's (H,W,S) bin
+//     order, z in layout 1).  Planes arrive through cp.async into a double buffer; per
+//     footprint row the x contraction feeds a dense scatter into the bins of the second axis (U[p2][pw pair], 16 packed
+//     accumulators); the finished plane goes to shared memory as columns [channel][pw, p2].
+//   * phase B: lane = column (4 per lane, packed in pairs); the last contraction runs down the planes and every store
+//     instruction writes 32 consecutive output elements -- in both bin orders the column index IS the fast part of the
+//     output index, which is why the pass order depends on the layout.
+// A CTA owns one RoI (tables built once) and up to `cpb` = 64 channels; as many warps as fit the shared-memory pool work on
+// 16-channel groups, the others retire.  RoIs that do not qualify take the generic body above inside the same launch.
+constexpr int RF_THREADS = 192;         // 6 warps, 2 CTAs per SM: 168 registers per thread
+constexpr int RF_POOL_FLOATS = 25600;   // 100 KB: two CTAs per SM
+constexpr int RF_G = 16;                // channels per warp task
+constexpr int RF_CHS = 20;              // floats per staged voxel (16 channels + pad: staging stores are conflict-free)
+constexpr int RF_F = 8;                 // max footprint voxels per axis
+
+struct __align__(16) FastShared {
+    float w2[RF_F][8];                  // second axis: [footprint voxel][bin]
+    float w3[RF_F][8];                  // last axis
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// acc += (w, w) * v   (scalar weight, packed pair of channels / columns)
+__device__ __forceinline__ unsigned long long fma2s(float w, unsigned long long v, unsigned long long acc) {
+    return fma2(pack2(w, w), v, acc);
+}
+
+// rows of one staged plane: x contraction + dense scatter into the bins of the second axis (processing rows in pairs
+// inside one basic block -- four x chains instead of two -- was measured: no gain, the kernel is not FFMA2-latency bound)
+template <int FX>
+__device__ __forceinline__ void fast_plane_rows(const float* __restrict__ stage, int F2, const float (&wx)[RF_F][2],
+                                                const float (&w2)[RF_F][8], unsigned long long (&U)[8][2]) {
+#pragma unroll
+    for (int f2 = 0; f2 < RF_F; ++f2) {
+        if (f2 < F2) {                                                     // warp-uniform
+            const float* rowp = stage + f2 * FX * RF_CHS;
+            unsigned long long t0 = 0ull, t1 = 0ull;
+#pragma unroll
+            for (int x = 0; x < FX; ++x) {
+                const unsigned long long v = *reinterpret_cast<const unsigned long long*>(rowp + x * RF_CHS);
+                t0 = fma2s(wx[x][0], v, t0);
+                t1 = fma2s(wx[x][1], v, t1);
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                U[p][0] = fma2s(w2[f2][p], t0, U[p][0]);
+                U[p][1] = fma2s(w2[f2][p], t1, U[p][1]);
+            }
+        }
+    }
+}
+
+// phase B for one warp task: columns [0, NQ) of the column buffer, F3N planes deep
+template <typename T, int F3N>
+__device__ __forceinline__ void fast_columns(const float* __restrict__ ubuf, const FastShared& fs, T* __restrict__ og,
+                                             int NQ, int NC, int UST, int P3, int P3n, int lane) {
+    float w3[F3N][8];
+#pragma unroll
+    for (int f = 0; f < F3N; ++f) {
+        const float4 a = *reinterpret_cast<const float4*>(&fs.w3[f][0]), b = *reinterpret_cast<const float4*>(&fs.w3[f][4]);
+        w3[f][0] = a.x; w3[f][1] = a.y; w3[f][2] = a.z; w3[f][3] = a.w;
+        w3[f][4] = b.x; w3[f][5] = b.y; w3[f][6] = b.z; w3[f][7] = b.w;
+    }
+    int q0 = 0;
+    for (; q0 + 64 < NQ; q0 += 128) {                      // 4 columns per lane
+        unsigned long long acc[8][2];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) { acc[p][0] = 0ull; acc[p][1] = 0ull; }
+        // columns beyond the buffer are clamped (their results are never stored)
+        const int o0 = q0 + lane, o1 = q0 + 32 + lane;
+        const int o2 = min(q0 + 64 + lane, UST - 1), o3 = min(q0 + 96 + lane, UST - 1);
+#pragma unroll
+        for (int f3 = 0; f3 < F3N; ++f3) {
+            const float* up = ubuf + f3 * UST;
+            const unsigned long long v01 = pack2(up[o0], up[o1]);
+            const unsigned long long v23 = pack2(up[o2], up[o3]);
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                acc[p][0] = fma2s(w3[f3][p], v01, acc[p][0]);
+                acc[p][1] = fma2s(w3[f3][p], v23, acc[p][1]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + 32 * i + lane;
+            if (q < NQ) {
+                const int ch = q / NC;                     // NC is a compile-time constant for the model's pooled sizes
+                T* o = og + (ch * P3 + (q - ch * NC));
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    if (p < P3n) {
+                        const float v = (i & 1) ? hi2(acc[p][i >> 1]) : lo2(acc[p][i >> 1]);
+                        o[p * NC] = from_f<T>(v);
+                    }
+                }
+            }
+        }
+    }
+    for (; q0 < NQ; q0 += 64) {                            // tail: 2 columns per lane
+        unsigned long long acc[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) acc[p] = 0ull;
+        const int o0 = min(q0 + lane, UST - 1), o1 = min(q0 + 32 + lane, UST - 1);
+#pragma unroll
+        for (int f3 = 0; f3 < F3N; ++f3) {
+            const float* up = ubuf + f3 * UST;
+            const unsigned long long v01 = pack2(up[o0], up[o1]);
+#pragma unroll
+            for (int p = 0; p < 8; ++p) acc[p] = fma2s(w3[f3][p], v01, acc[p]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = q0 + 32 * i + lane;
+            if (q < NQ) {
+                const int ch = q / NC;
+                T* o = og + (ch * P3 + (q - ch * NC));
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    if (p < P3n) o[p * NC] = from_f<T>(i ? hi2(acc[p]) : lo2(acc[p]));
+                }
+            }
+        }
+    }
+}
+
+// PC > 0: cubic pooled size known at compile time (Ps == Ph == Pw == PC): all column strides and loop bounds are constants.
+// L0: the reference's (H,W,S) bin order (layout 0); otherwise (S,H,W) (layout 1).
+template <typename T, int PC, bool L0>
+__global__ void __launch_bounds__(RF_THREADS, 2)
+roialign3d_fwd_fast_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out,
+                           int C, int S, int H, int W, int Ps_, int Ph_, int Pw_, float scale, int sr, int cpb) {
+    extern __shared__ __align__(16) float s_buf[];
+    __shared__ FwdShared sh;
+    __shared__ FastShared fs;
+    const int Ps = PC > 0 ? PC : Ps_, Ph = PC > 0 ? PC : Ph_, Pw = PC > 0 ? PC : Pw_;
+    const int r = blockIdx.x;
+    const int c_begin = blockIdx.y * cpb;
+    const int ncta = min(cpb, C - c_begin);
+    const int tid = threadIdx.x;
+    constexpr int layout = L0 ? 0 : 1;
+
+    AxisP ax[3];
+    int batch; float count;
+    roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, -1.0, ax[0], ax[1], ax[2], batch, count);
+    const int Pa[3] = {Ps, Ph, Pw};
+    const bool empty = fwd_ranges(sh, ax, Pa);
+    const int P3 = Ps * Ph * Pw;
+    T* out_r = out + ((size_t)r * C + c_begin) * P3;
+    if (empty) {
+        for (size_t i = tid; i < (size_t)ncta * P3; i += RF_THREADS) out_r[i] = from_f<T>(0.f);
+        return;
+    }
+    const size_t SHW = (size_t)S * H * W;
+    const T* feat_b = feat + ((size_t)batch * C + c_begin) * SHW;
+    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
+    const int Fz = sh.hi[0] - zlo + 1, Fy = sh.hi[1] - ylo + 1, Fx = sh.hi[2] - xlo + 1;
+    // axis roles: 1 = x (contracted first), 2 = scattered in registers, 3 = contracted last (slowest output index)
+    constexpr int a2 = L0 ? 0 : 1, a3 = L0 ? 1 : 0;
+    const int F2 = L0 ? Fz : Fy, F3 = L0 ? Fy : Fz;
+    const int P2 = Pa[a2], P3n = Pa[a3];
+    const int NC = Pw * P2;                                // columns per channel
+    const int UST = RF_G * NC;                             // floats per plane of the column buffer
+    const int stage_f = F2 * Fx * RF_CHS;
+    const int need = 2 * stage_f + F3 * UST;
+    const int icount = ax[0].g * ax[1].g * ax[2].g;
+    const bool pow2 = (icount & (icount - 1)) == 0;        // sr = 2: count = 8 -> 1/count folds into the z table exactly
+    const bool fast = pow2 && Fz <= RF_F && Fy <= RF_F && Fx <= RF_F && need <= RF_POOL_FLOATS;
+    if (!fast) {
+        fwd_generic_cta<T, 8>(s_buf, sh, feat_b, out_r, ax, Pa, ncta, S, H, W, layout, count);
+        return;
+    }
+    // (building the tables per warp with shuffles instead -- no block barrier at all -- was measured 7 % slower)
+    fwd_tables(sh, ax, Pa, count, true);
+    if (tid < 2 * RF_F * 8) {
+        const int which = tid >> 6, f = (tid >> 3) & 7, p = tid & 7;
+        (which ? fs.w3 : fs.w2)[f][p] = sh.w[which ? a3 : a2][f][p];
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_active = min(RF_THREADS / 32, RF_POOL_FLOATS / need);
+    if (warp >= n_active) return;
+    float* stage = s_buf + (size_t)warp * need;
+    float* ubuf = stage + 2 * stage_f;
+    const int cp = lane & 7, g = lane >> 3;
+    float wx[RF_F][2];
+#pragma unroll
+    for (int x = 0; x < RF_F; ++x) { wx[x][0] = sh.w[2][x][2 * g]; wx[x][1] = sh.w[2][x][2 * g + 1]; }
+    float w2[RF_F][8];
+#pragma unroll
+    for (int f = 0; f < RF_F; ++f) {
+        const float4 a = *reinterpret_cast<const float4*>(&fs.w2[f][0]), b = *reinterpret_cast<const float4*>(&fs.w2[f][4]);
+        w2[f][0] = a.x; w2[f][1] = a.y; w2[f][2] = a.z; w2[f][3] = a.w;
+        w2[f][4] = b.x; w2[f][5] = b.y; w2[f][6] = b.z; w2[f][7] = b.w;
+    }
+    // staging geometry: lane = (x = lane & 7, channel slot li = lane >> 3): channels li, li+4, li+8, li+12 of every row
+    const int lx = lane & 7, li = lane >> 3;
+    const int row_stride = L0 ? H * W : W;                 // global step between rows of a plane (axis 2)
+    const int plane_stride = L0 ? W : H * W;               // global step between planes (axis 3)
+    const int org = (zlo * H + ylo) * W + xlo + lx;
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)(lx * RF_CHS + li) * 4u;
+    const unsigned row_bytes = (unsigned)(Fx * RF_CHS) * 4u;
+    const int groups = (ncta + RF_G - 1) / RF_G;
+
+    for (int grp = warp; grp < groups; grp += n_active) {
+        const int ncg = min(RF_G, ncta - grp * RF_G);
+        const T* fg = feat_b + ((size_t)grp * RF_G + li) * SHW + org;
+        // planes arrive through cp.async (4-byte copies: rows start at arbitrary x) into a double buffer
+        auto issue_plane = [&](int k) {
+            if (lx < Fx) {
+                const T* s = fg + (size_t)k * plane_stride;
+                unsigned d = stage_s + (unsigned)((k & 1) * stage_f) * 4u;
+                if (ncg == RF_G) {
+#pragma unroll 2
+                    for (int f2 = 0; f2 < F2; ++f2, s += row_stride, d += row_bytes) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            if constexpr (sizeof(T) == 4) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d + 16u * c4), "l"(s + (size_t)(4 * c4) * SHW) : "memory");
+                            } else {
+                                const float v = to_f(s[(size_t)(4 * c4) * SHW]);
+                                asm volatile("st.shared.f32 [%0], %1;" :: "r"(d + 16u * c4), "f"(v) : "memory");
+                            }
+                        }
+                    }
+                } else {
+                    for (int f2 = 0; f2 < F2; ++f2, s += row_stride, d += row_bytes) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            if (li + 4 * c4 < ncg) {
+                                const float v = to_f(s[(size_t)(4 * c4) * SHW]);
+                                asm volatile("st.shared.f32 [%0], %1;" :: "r"(d + 16u * c4), "f"(v) : "memory");
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        __syncwarp();
+        issue_plane(0);
+        for (int k = 0; k < F3; ++k) {
+            if (k + 1 < F3) { issue_plane(k + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
+            unsigned long long U[8][2];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) { U[p][0] = 0ull; U[p][1] = 0ull; }
+            const float* st = stage + (k & 1) * stage_f + 2 * cp;
+            switch (Fx) {
+                case 1: fast_plane_rows<1>(st, F2, wx, w2, U); break;
+                case 2: fast_plane_rows<2>(st, F2, wx, w2, U); break;
+                case 3: fast_plane_rows<3>(st, F2, wx, w2, U); break;
+                case 4: fast_plane_rows<4>(st, F2, wx, w2, U); break;
+                case 5: fast_plane_rows<5>(st, F2, wx, w2, U); break;
+                case 6: fast_plane_rows<6>(st, F2, wx, w2, U); break;
+                case 7: fast_plane_rows<7>(st, F2, wx, w2, U); break;
+                default: fast_plane_rows<8>(st, F2, wx, w2, U); break;
+            }
+            // finished plane -> columns [channel][L0 ? pw * P2 + p2 : p2 * Pw + pw]
+            float* up = ubuf + k * UST + (2 * cp) * NC;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int pw = 2 * g + j;
+                if (pw < Pw) {
+                    float* upc = up + (L0 ? pw * P2 : pw);
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        if (p < P2) {
+                            const int col = L0 ? p : p * Pw;
+                            upc[col] = lo2(U[p][j]);
+                            upc[NC + col] = hi2(U[p][j]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- phase B: last contraction down the planes, lane = 4 columns, coalesced stores ---------------------
+        T* og = out_r + (size_t)grp * RF_G * P3;
+        const int NQ = ncg * NC;
+        switch (F3) {
+            case 1: fast_columns<T, 1>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 2: fast_columns<T, 2>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 3: fast_columns<T, 3>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 4: fast_columns<T, 4>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 5: fast_columns<T, 5>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 6: fast_columns<T, 6>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 7: fast_columns<T, 7>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            default: fast_columns<T, 8>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
         }
     }
 }
@@ -561,18 +912,29 @@ template <typename T>
 static int launch_fwd(const void* features, const float* rois, void* output, int C, int S, int H, int W, int R,
                       int Ps, int Ph, int Pw, float scale, int sr, int layout, cudaStream_t stream) {
     const int pmax = Ps > Ph ? (Ps > Pw ? Ps : Pw) : (Ph > Pw ? Ph : Pw);
-    dim3 grid(R, (C + RA_CC - 1) / RA_CC);
     if (pmax <= 8) {
-        const size_t smem = FwdCfg<8>::SMEM_FLOATS * sizeof(float);
-        B200_CUDA(cudaFuncSetAttribute(roialign3d_fwd_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roialign3d_fwd_kernel<T, 8><<<grid, RA_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W,
-                                                                        Ps, Ph, Pw, scale, sr, layout);
-    } else {
-        const size_t smem = FwdCfg<16>::SMEM_FLOATS * sizeof(float);
-        B200_CUDA(cudaFuncSetAttribute(roialign3d_fwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roialign3d_fwd_kernel<T, 16><<<grid, RA_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W,
-                                                                         Ps, Ph, Pw, scale, sr, layout);
+        int cpb = C <= 64 ? C : 64;                                    // channels per CTA (one RoI per CTA); 64 / 128 / 256 measured: 127 / 133 / 150 us
+        cpb = (cpb + RA_CC - 1) / RA_CC * RA_CC;
+        dim3 grid(R, (C + cpb - 1) / cpb);
+        const size_t smem = RF_POOL_FLOATS * sizeof(float);
+        const bool cubic7 = Ps == 7 && Ph == 7 && Pw == 7;             // the box head's pooled size
+        auto launch = [&](auto kern) -> int {
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, RF_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W, Ps, Ph, Pw, scale, sr, cpb);
+            return 0;
+        };
+        int e;
+        if (cubic7) e = layout == 0 ? launch(roialign3d_fwd_fast_kernel<T, 7, true>) : launch(roialign3d_fwd_fast_kernel<T, 7, false>);
+        else e = layout == 0 ? launch(roialign3d_fwd_fast_kernel<T, 0, true>) : launch(roialign3d_fwd_fast_kernel<T, 0, false>);
+        if (e) return e;
+        B200_LAUNCH_CHECK("roialign3d_fwd_fast_kernel");
+        return 0;
     }
+    dim3 grid(R, (C + RA_CC - 1) / RA_CC);
+    const size_t smem = FwdCfg<16>::SMEM_FLOATS * sizeof(float);
+    B200_CUDA(cudaFuncSetAttribute(roialign3d_fwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roialign3d_fwd_kernel<T, 16><<<grid, RA_THREADS, smem, stream>>>((const T*)features, rois, (T*)output, C, S, H, W,
+                                                                     Ps, Ph, Pw, scale, sr, layout);
     B200_LAUNCH_CHECK("roialign3d_fwd_kernel");
     return 0;
 }

@@ -720,7 +720,10 @@ def test_roialign_layout_shw_is_adjoint_and_bf16(b2, torch_):
     r = torch_.from_numpy(rois).cuda()
     ref = roialign3d_forward(f, r, 7, 7, 7, 0.25, 2, layout=0)
     shw = roialign3d_forward(f, r, 7, 7, 7, 0.25, 2, layout=1)
-    assert torch_.equal(shw, ref.permute(0, 1, 4, 2, 3).contiguous())      # (H,W,S) storage vs (S,H,W)
+    # (H,W,S) storage vs (S,H,W): the same bins; the two layouts contract the axes in different orders (the last pass is the
+    # one whose bin index is the slowest output index), so they agree to rounding, not bit for bit
+    ok, err = _close(shw.cpu().numpy(), ref.permute(0, 1, 4, 2, 3).contiguous().cpu().numpy(), rel=2e-6)
+    assert ok, err
     # <A x, g> == <x, A^T g> for the self-consistent layout
     fx = f.clone().double().float().requires_grad_(True)
     y = RoIAlignFunction_3d(7, 7, 7, 0.25, 2, layout="shw")(fx, r)
