@@ -754,19 +754,34 @@ def run_ours(args, rank, world, local_rank):
     def e2e_step():
         # one C call for the rank's batch: uploads, kernels and downloads of consecutive volumes overlap
         return b200seg.postproc_soma_host_batch(e2e_cases, NMS_THRESH, seg_out=e2e_segs)
+    from b200seg.binarization import set_host_batch_out
+    e2e_steps = max(2, min(args.steps, int(np.ceil(640.0 / max(vpr, 1)))))         # about 10 passes over 64 volumes at most
+
+    def e2e_timed(n_steps):
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(n_steps):
+            e2e_step()
+        barrier()
+        dt_ = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+        return n_global * V * n_steps / float(dt_.item()) / 1e9
+
+    # (a) label buffers of unknown content: the library zero-fills every volume on the host (2 B/voxel of host memory traffic)
+    set_host_batch_out(0)
     for _ in range(2):
         e2e_out = e2e_step()
-    e2e_steps = max(2, min(args.steps, int(np.ceil(640.0 / max(vpr, 1)))))         # about 10 passes over 64 volumes at most
-    barrier()
+    e2e_dense_fill = e2e_timed(max(2, e2e_steps // 2))
+    # (b) the headline: the same pinned label buffers are reused step after step and the library is told so -- it clears
+    # the voxels it wrote last time instead of whole volumes.  Same bytes in the buffers afterwards (parity-checked below
+    # against the oracle on THESE buffers); the reference allocates a lazily-zero np.zeros per volume (binarization_soma.py:57).
+    set_host_batch_out(2)
+    for _ in range(2):
+        e2e_out = e2e_step()
     l1 = b200seg.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = n_global * V * e2e_steps / float(dt.item()) / 1e9
+    e2e_val = e2e_timed(e2e_steps)
+    set_host_batch_out(0)
     e2e_launches = (b200seg.launch_count() - l1) // e2e_steps
     from b200seg.binarization import host_batch_traffic
     h2d, d2h = host_batch_traffic()                  # bytes the library actually moved over the link in the last step
@@ -839,8 +854,13 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_val, "unit": "Gvox/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "gpu_launches": int(e2e_launches), "steps": e2e_steps,
                         "h2d_bytes_if_everything_were_copied": h2d_dense, "d2h_bytes_if_dense": d2h_dense,
+                        "value_dense_fill": e2e_dense_fill,
+                        "label_buffers": "value: the pinned label buffers are reused every step and the call is told that they still hold "
+                                         "its previous result (b200seg_set_option host_batch_out=2: only the voxels written last time are "
+                                         "cleared); value_dense_fill: buffers of unknown content, every volume zero-filled on the host "
+                                         "(host_batch_out=0).  Identical bytes either way; both parity-checked against the oracle",
                         "transfer": "volume by DMA; PRM crops of the NMS survivors by zero-copy gather from the pinned buffer; label "
-                                    "volume as compacted non-zero 16-byte groups, zero fill + scatter by host threads",
+                                    "volume as compacted non-zero 16-byte groups, scattered by host threads",
                         "note": "binarization chain through b200seg_postproc_soma_host_batch; the peak finder's input is the network's "
                                 "response map, which never exists on the host in the reference flow (peak_response_mapping_3d.py:150)"},
                 "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,

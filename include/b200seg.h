@@ -50,7 +50,12 @@ long long b200seg_launch_count(void);
  * first k kernel launches (0 = memset only, 99 = the whole op, the default), so that a caller can time the op kernel by
  * kernel with CUDA events; outputs are incomplete while k < 99.  "host_batch_mode" (default 3) selects the transfer
  * scheme of b200seg_postproc_soma_host_batch, same results either way: bit 0 = label volumes come back compacted,
- * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather).  Unknown names return B200SEG_EINVAL. */
+ * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather).  "host_batch_out" (default 0) tells that
+ * entry point what the caller's label buffers hold ON ENTRY, again with identical results: 0 = anything (every buffer is
+ * zero-filled, 2 bytes of host memory traffic per voxel -- the bound of the call), 1 = zeros (a fresh np.zeros / calloc
+ * buffer, what tools/binarization_soma.py:57 allocates per volume), 2 = exactly what this entry point wrote into the same
+ * buffer last time (only the groups written then are cleared; a buffer the library has no record of is zero-filled).
+ * Unknown names return B200SEG_EINVAL. */
 int b200seg_set_option(const char* name, int value);
 
 /* ----------------------------------------------------------------------------------------------

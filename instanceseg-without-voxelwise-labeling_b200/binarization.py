@@ -223,6 +223,13 @@ def host_batch_traffic():
     return int(a.value), int(b.value)
 
 
+def set_host_batch_out(state):
+    """What the `seg_out` buffers handed to postproc_soma_host_batch hold on entry (results are identical either way):
+    0 = anything (the library zero-fills them, the default), 1 = zeros (fresh np.zeros buffers, as the reference script
+    allocates per volume), 2 = what the same call wrote into the same buffers last time (only those voxels are cleared)."""
+    _lib.check(_lib.lib().b200seg_set_option(b"host_batch_out", int(state)), "set_option")
+
+
 def set_host_batch_mode(mode):
     """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops (default 3)."""
     _lib.check(_lib.lib().b200seg_set_option(b"host_batch_mode", int(mode)), "set_option")

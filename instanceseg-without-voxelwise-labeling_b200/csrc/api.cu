@@ -69,6 +69,8 @@ void opt_set_peaks_stop_after(int v) { g_peaks_stop_after.store(v, std::memory_o
 
 static std::atomic<int> g_peaks_median_mode{0};
 int opt_peaks_median_mode() { return g_peaks_median_mode.load(std::memory_order_relaxed); }
+static std::atomic<int> g_host_batch_out{0};
+int opt_host_batch_out() { return g_host_batch_out.load(std::memory_order_relaxed); }
 static std::atomic<int> g_host_batch_mode{3};
 int opt_host_batch_mode() { return g_host_batch_mode.load(std::memory_order_relaxed); }
 
@@ -85,6 +87,11 @@ extern "C" int b200seg_set_option(const char* name, int value) {
     if (!strcmp(name, "peaks_stop_after")) { opt_set_peaks_stop_after(value); return 0; }
     // bit 0: compacted label download (else dense copies), bit 1: zero-copy gather of the surviving PRM crops (else whole array)
     if (!strcmp(name, "peaks_median_mode")) { g_peaks_median_mode.store(value, std::memory_order_relaxed); return 0; }
+    if (!strcmp(name, "host_batch_out")) {
+        if (value < 0 || value > 2) { set_error("set_option: host_batch_out must be 0, 1 or 2"); return B200SEG_EINVAL; }
+        g_host_batch_out.store(value, std::memory_order_relaxed);
+        return 0;
+    }
     if (!strcmp(name, "host_batch_mode")) { g_host_batch_mode.store(value, std::memory_order_relaxed); return 0; }
     set_error("set_option: unknown option '%s'", name);
     return B200SEG_EINVAL;

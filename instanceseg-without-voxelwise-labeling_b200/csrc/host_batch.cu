@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <thread>
 #include <unistd.h>
+#include <unordered_map>
 #include <vector>
 #if defined(__x86_64__)
 #include <emmintrin.h>
@@ -199,6 +200,14 @@ struct BatchStreams {
 static BatchStreams g_batch_dev[64];      // one set per device ordinal (guarded by the host context's mutex)
 static std::atomic<unsigned long long> g_last_h2d{0}, g_last_d2h{0};
 
+// "host_batch_out" = 2: the caller's label buffer still holds the result this entry point wrote into it last time, so
+// instead of zero-filling all of it (2 bytes per voxel of host memory traffic, the bound of the whole call) only the
+// non-zero 16-byte groups written last time are cleared.  Keyed by the buffer address; an entry is dropped whenever the
+// content of the buffer is not exactly "zeros + the listed groups" (dense download, error, different size).
+struct PrevLabels { size_t bytes = 0; std::vector<uint32_t> groups; };
+static std::mutex g_prev_mu;
+static std::unordered_map<const void*, PrevLabels>& g_prev = *new std::unordered_map<const void*, PrevLabels>;
+
 // device pointer of a host buffer the GPU can read in place (pinned / registered and 16-byte aligned), else null
 static const uint8_t* mapped_device_pointer(const void* host) {
     if (!host || (((uintptr_t)host) & 15)) return nullptr;
@@ -298,7 +307,30 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     Shared* sh = new Shared(n_volumes);
     for (int k = 0; k < HB_SLOTS; ++k) sh->slot_busy[k].store(0);
     // zero-fill of the label volumes starts now (it does not depend on the GPU)
+    const int out_state = sparse ? opt_host_batch_out() : 0;
     for (int v = 0; v < n_volumes; ++v) {
+        if (out_state == 1) { sh->zero_left[v].store(0); continue; }            // the caller vouches for zeros
+        if (out_state == 2) {
+            std::vector<uint32_t>* prev = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(g_prev_mu);
+                auto it = g_prev.find(seg[v]);
+                if (it != g_prev.end() && it->second.bytes == V * 2) prev = new std::vector<uint32_t>(std::move(it->second.groups));
+                if (it != g_prev.end()) g_prev.erase(it);                       // re-registered by the scatter job of this call
+            }
+            if (prev) {
+                sh->zero_left[v].store(1);
+                char* dst = (char*)seg[v];
+                sh->pending.fetch_add(1);
+                g_pool.push([sh, v, dst, prev] {
+                    for (uint32_t gi : *prev) memset(dst + (size_t)gi * 16, 0, 16);
+                    delete prev;
+                    sh->zero_left[v].fetch_sub(1, std::memory_order_release);
+                    sh->pending.fetch_sub(1, std::memory_order_release);
+                });
+                continue;
+            }
+        }
         sh->zero_left[v].store(HB_ZERO_PARTS);
         const size_t bytes = V * 2, part = align_up((bytes + HB_ZERO_PARTS - 1) / HB_ZERO_PARTS, 4096);
         for (int p = 0; p < HB_ZERO_PARTS; ++p) {
@@ -419,6 +451,11 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
         if (step >= HB_LAG_B) {
             const int v = step - HB_LAG_B, k = v % NB;
             const uint32_t ng = n_groups[v];
+            if (ng == 0 && out_state == 2) {                                    // all-zero result: nothing to clear next time
+                std::lock_guard<std::mutex> lk(g_prev_mu);
+                PrevLabels pl; pl.bytes = V * 2;
+                g_prev[seg[v]] = std::move(pl);
+            }
             if (ng != 0xFFFFFFFFu && ng > 0) {
                 { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.out_done[k])); w_out += ms_since(t); }
                 const char* stage = g_batch.pinned + small_bytes + stage_bytes * k;
@@ -427,9 +464,17 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 char* dst = (char*)seg[v];
                 sh->slot_busy[k].store(1, std::memory_order_release);
                 sh->pending.fetch_add(1);
-                g_pool.push([sh, v, k, gi, gv, dst, ng] {
+                const size_t vbytes = V * 2;
+                g_pool.push([sh, v, k, gi, gv, dst, ng, out_state, vbytes] {
                     while (sh->zero_left[v].load(std::memory_order_acquire) > 0) sched_yield();
                     for (uint32_t i = 0; i < ng; ++i) memcpy(dst + (size_t)gi[i] * 16, gv + (size_t)i * 16, 16);
+                    if (out_state == 2) {                                       // remember what has to be cleared next time
+                        PrevLabels pl;
+                        pl.bytes = vbytes;
+                        pl.groups.assign(gi, gi + ng);
+                        std::lock_guard<std::mutex> lk(g_prev_mu);
+                        g_prev[dst] = std::move(pl);
+                    }
                     sh->slot_busy[k].store(0, std::memory_order_release);
                     sh->pending.fetch_sub(1, std::memory_order_release);
                 });
@@ -446,6 +491,10 @@ done:
         while (sh->pending.load(std::memory_order_acquire) > 0) sched_yield();
         w_tail = ms_since(t_tail);
         delete sh;
+        if (rc != 0 || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_prev_mu);                         // buffer contents are undefined after an error
+            for (int v = 0; v < n_volumes; ++v) g_prev.erase(seg[v]);
+        }
         if (rc == 0) {
             if (e1 != cudaSuccess) rc = check_cuda(e1, "cudaStreamSynchronize(in)");
             else if (e2 != cudaSuccess) rc = check_cuda(e2, "cudaStreamSynchronize(compute)");

@@ -373,6 +373,45 @@ def test_postproc_host_batch_matches_single_volume_calls(b2):
     assert outs[-1]["n_keep"] == 0 and not outs[-1]["seg"].any()
 
 
+def test_postproc_host_batch_output_states(b2):
+    """`host_batch_out`: what the label buffers hold on entry.  1 = zeros (fresh np.zeros, the reference's allocation),
+    2 = the previous result of the same call (only what was written then is cleared; unknown buffers are zero-filled).
+    Same buffers reused over three different batches, one of them with an all-background volume; a buffer the library
+    has never seen, full of garbage, must still come out right in state 2."""
+    from b200seg import synth
+    from b200seg.binarization import set_host_batch_out
+    from helpers import oracle_chain
+    shape = (24, 80, 96)
+    batches = [[synth.postproc_case(900 + 10 * b + i, shape=shape, n_blobs=3 + 2 * i + b, n_dup=3, n_false=2) for i in range(4)]
+               for b in range(3)]
+    empty = dict(batches[1][2])
+    empty["dets"] = empty["dets"][:0]; empty["boxes"] = empty["boxes"][:0]; empty["prm"] = empty["prm"][:0]
+    empty["crop_off"] = np.zeros(1, np.int64)
+    batches[1][2] = empty
+    refs = [[oracle_chain(c, 0.23)["seg"] if c["dets"].shape[0] else np.zeros(shape, np.uint16) for c in bt] for bt in batches]
+    try:
+        set_host_batch_out(2)
+        segs = [np.full(shape, 0x1234, np.uint16) for _ in range(4)]          # never seen by the library: garbage allowed
+        for bt, rf in zip(batches, refs):
+            b2.postproc_soma_host_batch(bt, 0.23, seg_out=segs)
+            for s_, r_ in zip(segs, rf):
+                assert np.array_equal(s_, r_)
+        segs[1][3, 5, 7] = 77                                                    # the caller breaks the contract ...
+        set_host_batch_out(0)                                                    # ... and says so: state 0 repairs it
+        b2.postproc_soma_host_batch(batches[0], 0.23, seg_out=segs)
+        for s_, r_ in zip(segs, refs[0]):
+            assert np.array_equal(s_, r_)
+        set_host_batch_out(1)
+        fresh = [np.zeros(shape, np.uint16) for _ in range(4)]
+        b2.postproc_soma_host_batch(batches[2], 0.23, seg_out=fresh)
+        for s_, r_ in zip(fresh, refs[2]):
+            assert np.array_equal(s_, r_)
+    finally:
+        set_host_batch_out(0)
+    with pytest.raises(b2.B200SegError):
+        set_host_batch_out(3)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
     """Every transfer scheme of the batch entry point (dense / compacted label download x whole-array / gathered PRM
