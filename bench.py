@@ -561,10 +561,28 @@ def run_ours(args, rank, world, local_rank):
 
     graphs = {}                                             # with_peaks -> captured CUDA graph of the rank's kernels of one step
 
+    # The peak finder and the binarization chain of a step share no data (the peak finder reads the response maps, the
+    # chain the volumes / detections / PRM crops), and neither fills the GPU on its own (occupancy 19 % in the scan,
+    # barrier / latency stalls in the emit pass and in the per-instance kernels): they run as two branches of the step --
+    # fork / join on events, captured into the same CUDA graph -- unless --no-overlap asks for the serial order.
+    peak_stream = torch.cuda.Stream(device=dev)
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
     def step_body():
+        overlap = with_peaks[0] and not args.no_overlap
         if with_peaks[0]:
-            plan.run(maps)                                      # peak list, count, aggregation stay on the device
+            if overlap:
+                cur = torch.cuda.current_stream()
+                ev_fork.record(cur)
+                peak_stream.wait_event(ev_fork)
+                with torch.cuda.stream(peak_stream):
+                    plan.run(maps)                              # peak list, count, aggregation stay on the device
+                    ev_join.record(peak_stream)
+            else:
+                plan.run(maps)
         pp.run(vols, dets, boxes, prm, crop_off, NMS_THRESH)
+        if overlap:
+            torch.cuda.current_stream().wait_event(ev_join)
 
     def step():
         g_ = graphs.get(with_peaks[0])
@@ -649,6 +667,14 @@ def run_ours(args, rank, world, local_rank):
         saved = dict(graphs); graphs.clear()
         step()
         ms_eager = timed_block(args.steps) / args.steps
+        graphs.update(saved)
+    ms_serial = None
+    if not args.no_overlap:                                 # the same steps with the two branches one after the other (eager)
+        saved = dict(graphs); graphs.clear()
+        args.no_overlap = True
+        step()
+        ms_serial = timed_block(args.steps) / args.steps
+        args.no_overlap = False
         graphs.update(saved)
     lt = torch.tensor([launches_per_step * args.steps], dtype=torch.int64, device=dev)
     if world > 1:
@@ -847,7 +873,7 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world, vpr),
                 "timed_blocks": len(blocks), "timed_region_s": sum(blocks) / 1e3,
-                "cuda_graph": bool(graphs), "ms_per_step_eager": ms_eager, "kernel_launches_per_step": int(launches_per_step),
+                "cuda_graph": bool(graphs), "peaks_and_chain_overlap": not args.no_overlap, "ms_per_step_eager": ms_eager, "ms_per_step_serial_eager": ms_serial, "kernel_launches_per_step": int(launches_per_step),
                 "value_without_peaks": n_global * V / (ms_nopeaks * 1e-3) / 1e9, "ms_per_step_without_peaks": ms_nopeaks,
                 "parity_checked": checked, "peaks_parity_checked": peaks_checked, "exchange_checked": exchange_ok,
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
@@ -882,6 +908,7 @@ def main():
     ap.add_argument("--parity-volumes", type=int, default=8, help="volumes of this run checked against the oracle chain")
     ap.add_argument("--min-timed-ms", type=float, default=500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the peak finder and the chain of a step one after the other instead of as two concurrent branches")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a captured CUDA graph")
     ap.add_argument("--seed-base", type=int, default=2000, help="seed of the first synthetic volume (volume i of rank r: base + r*vpr + i)")
     ap.add_argument("--chain-only", action="store_true", help="profiling aid: time only the device-resident chain")
