@@ -43,7 +43,8 @@ __device__ __forceinline__ Tap axis_sample(const AxisP& a, int p, int i) {
     Tap t;
     // fma(p, bin, start) + ((i+.5)*bin)/g : the contraction nvcc applies to the reference kernel
     float c = __fadd_rn(__fmaf_rn((float)p, a.bin, a.start), __fdiv_rn(__fmul_rn(i + .5f, a.bin), (float)a.g));
-    t.valid = !((double)c < a.guard || c > (float)a.dim);
+    // -1.0 is a float: (double)c < -1.0 <=> c < -1.0f, which keeps the forward's samples off the fp64 pipe
+    t.valid = a.guard == -1.0 ? !(c < -1.0f || c > (float)a.dim) : !((double)c < a.guard || c > (float)a.dim);
     if (c <= 0) c = 0;
     int low = (int)c;
     if (low >= a.dim - 1) { t.high = t.low = a.dim - 1; c = (float)t.low; }
@@ -372,9 +373,15 @@ roialign3d_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois
 //   * phase B: lane = column (4 per lane, packed in pairs); the last contraction runs down the planes and every store
 //     instruction writes 32 consecutive output elements -- in both bin orders the column index IS the fast part of the
 //     output index, which is why the pass order depends on the layout.
-// A CTA owns one RoI (tables built once) and up to `cpb` = 64 channels; as many warps as fit the shared-memory pool work on
-// 16-channel groups, the others retire.  RoIs that do not qualify take the generic body above inside the same launch.
+// A CTA owns one RoI (tables built once by warp 0: lane = (axis, bin), ranges by shuffles, every lane accumulates its own
+// table column in registers -- one block barrier) and up to `cpb` = 96 channels = six 16-channel tasks.  A task belongs to a
+// TEAM of two warps: they take alternate planes in phase A (each with its own staging double buffer) and alternate blocks of
+// 128 columns in phase B, with named barriers in between -- twice the issue streams on the same column buffer.  This was the
+// one change that moved the kernel (0.121 -> 0.108 ms): it is bound by the latency of a task's dependent phases and by how
+// many tasks fit the shared memory of an SM, not by issue slots or bandwidth.  As many teams as fit the pool
+// work at a time, the other warps retire.  RoIs that do not qualify take the generic body above inside the same launch.
 constexpr int RF_THREADS = 192;         // 6 warps, 2 CTAs per SM: 168 registers per thread
+constexpr int RF_TEAM = 2;              // warps per task (3 measured: same time)
 constexpr int RF_POOL_FLOATS = 25600;   // 100 KB: two CTAs per SM
 constexpr int RF_G = 16;                // channels per warp task
 constexpr int RF_CHS = 20;              // floats per staged voxel (16 channels + pad: staging stores are conflict-free)
@@ -421,7 +428,7 @@ __device__ __forceinline__ void fast_plane_rows(const float* __restrict__ stage,
 // phase B for one warp task: columns [0, NQ) of the column buffer, F3N planes deep
 template <typename T, int F3N>
 __device__ __forceinline__ void fast_columns(const float* __restrict__ ubuf, const FastShared& fs, T* __restrict__ og,
-                                             int NQ, int NC, int UST, int P3, int P3n, int lane) {
+                                             int NQ, int NC, int UST, int P3, int P3n, int lane, int half) {
     float w3[F3N][8];
 #pragma unroll
     for (int f = 0; f < F3N; ++f) {
@@ -429,13 +436,13 @@ __device__ __forceinline__ void fast_columns(const float* __restrict__ ubuf, con
         w3[f][0] = a.x; w3[f][1] = a.y; w3[f][2] = a.z; w3[f][3] = a.w;
         w3[f][4] = b.x; w3[f][5] = b.y; w3[f][6] = b.z; w3[f][7] = b.w;
     }
-    int q0 = 0;
-    for (; q0 + 64 < NQ; q0 += 128) {                      // 4 columns per lane
+    // the two warps of a pair take alternate blocks of 128 columns
+    for (int q0 = half * 128; q0 < NQ; q0 += RF_TEAM * 128) {   // 4 columns per lane
         unsigned long long acc[8][2];
 #pragma unroll
         for (int p = 0; p < 8; ++p) { acc[p][0] = 0ull; acc[p][1] = 0ull; }
         // columns beyond the buffer are clamped (their results are never stored)
-        const int o0 = q0 + lane, o1 = q0 + 32 + lane;
+        const int o0 = min(q0 + lane, UST - 1), o1 = min(q0 + 32 + lane, UST - 1);
         const int o2 = min(q0 + 64 + lane, UST - 1), o3 = min(q0 + 96 + lane, UST - 1);
 #pragma unroll
         for (int f3 = 0; f3 < F3N; ++f3) {
@@ -464,31 +471,6 @@ __device__ __forceinline__ void fast_columns(const float* __restrict__ ubuf, con
             }
         }
     }
-    for (; q0 < NQ; q0 += 64) {                            // tail: 2 columns per lane
-        unsigned long long acc[8];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) acc[p] = 0ull;
-        const int o0 = min(q0 + lane, UST - 1), o1 = min(q0 + 32 + lane, UST - 1);
-#pragma unroll
-        for (int f3 = 0; f3 < F3N; ++f3) {
-            const float* up = ubuf + f3 * UST;
-            const unsigned long long v01 = pack2(up[o0], up[o1]);
-#pragma unroll
-            for (int p = 0; p < 8; ++p) acc[p] = fma2s(w3[f3][p], v01, acc[p]);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int q = q0 + 32 * i + lane;
-            if (q < NQ) {
-                const int ch = q / NC;
-                T* o = og + (ch * P3 + (q - ch * NC));
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    if (p < P3n) o[p * NC] = from_f<T>(i ? hi2(acc[p]) : lo2(acc[p]));
-                }
-            }
-        }
-    }
 }
 
 // PC > 0: cubic pooled size known at compile time (Ps == Ph == Pw == PC): all column strides and loop bounds are constants.
@@ -511,45 +493,86 @@ roialign3d_fwd_fast_kernel(const T* __restrict__ feat, const float* __restrict__
     int batch; float count;
     roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, -1.0, ax[0], ax[1], ax[2], batch, count);
     const int Pa[3] = {Ps, Ph, Pw};
-    const bool empty = fwd_ranges(sh, ax, Pa);
     const int P3 = Ps * Ph * Pw;
     T* out_r = out + ((size_t)r * C + c_begin) * P3;
-    if (empty) {
+    const size_t SHW = (size_t)S * H * W;
+    const T* feat_b = feat + ((size_t)batch * C + c_begin) * SHW;
+    constexpr int a2 = L0 ? 0 : 1, a3 = L0 ? 1 : 0;        // axis roles: x first, a2 scattered in registers, a3 last
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // ---- footprint and axis tables: warp 0 alone, lane = (axis, bin); ranges by shuffles, every lane accumulates its own
+    //      table column in registers (same order per element as fwd_tables) and writes it once: ONE block barrier instead of
+    //      the five of fwd_ranges + fwd_tables, no zero fill, no shared-memory atomics ------------------------------------
+    if (warp == 0) {
+        const int ta = min(lane >> 3, 2), tp = lane & 7;
+        const AxisP mine = ta == 0 ? ax[0] : (ta == 1 ? ax[1] : ax[2]);
+        const int myP = ta == 0 ? Ps : (ta == 1 ? Ph : Pw);
+        const bool t_on = lane < 24 && tp < myP;
+        int lo = 0x7fffffff, hi = -1;
+        if (t_on) {
+            for (int i = 0; i < mine.g; ++i) {
+                const Tap t = axis_sample(mine, tp, i);
+                if (t.valid) { lo = min(lo, t.low); hi = max(hi, t.high); }
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+        float wcol[RF_F];                                  // column tp of this lane's axis table: W[f][tp], f = footprint voxel
+#pragma unroll
+        for (int f = 0; f < RF_F; ++f) wcol[f] = 0.f;
+        if (t_on) {
+            for (int i = 0; i < mine.g; ++i) {
+                const Tap t = axis_sample(mine, tp, i);
+                if (t.valid) {
+                    const int il = t.low - lo, ih = t.high - lo;
+#pragma unroll
+                    for (int f = 0; f < RF_F; ++f) { if (il == f) wcol[f] += t.h; if (ih == f) wcol[f] += t.l; }
+                }
+            }
+        }
+        const float zs = ta == 0 ? 1.0f / count : 1.0f;    // only used when count is a power of two (fast path): exact
+        if (lane < 24) {
+            float* dst = ta == 2 ? &sh.w[2][0][tp] : (ta == a2 ? &fs.w2[0][tp] : &fs.w3[0][tp]);
+            const int fstride = ta == 2 ? 16 : 8;
+#pragma unroll
+            for (int f = 0; f < RF_F; ++f) dst[f * fstride] = wcol[f] * zs;
+            if (tp == 0) { sh.lo[ta] = lo; sh.hi[ta] = hi; }
+        }
+    }
+    __syncthreads();
+    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
+    if (sh.hi[0] < 0 || sh.hi[1] < 0 || sh.hi[2] < 0) {   // every sample falls outside: zeros
         for (size_t i = tid; i < (size_t)ncta * P3; i += RF_THREADS) out_r[i] = from_f<T>(0.f);
         return;
     }
-    const size_t SHW = (size_t)S * H * W;
-    const T* feat_b = feat + ((size_t)batch * C + c_begin) * SHW;
-    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
     const int Fz = sh.hi[0] - zlo + 1, Fy = sh.hi[1] - ylo + 1, Fx = sh.hi[2] - xlo + 1;
-    // axis roles: 1 = x (contracted first), 2 = scattered in registers, 3 = contracted last (slowest output index)
-    constexpr int a2 = L0 ? 0 : 1, a3 = L0 ? 1 : 0;
     const int F2 = L0 ? Fz : Fy, F3 = L0 ? Fy : Fz;
     const int P2 = Pa[a2], P3n = Pa[a3];
     const int NC = Pw * P2;                                // columns per channel
     const int UST = RF_G * NC;                             // floats per plane of the column buffer
     const int stage_f = F2 * Fx * RF_CHS;
-    const int need = 2 * stage_f + F3 * UST;
+    const int need = 2 * RF_TEAM * stage_f + F3 * UST;     // a double-buffered staging area per warp of the team
     const int icount = ax[0].g * ax[1].g * ax[2].g;
     const bool pow2 = (icount & (icount - 1)) == 0;        // sr = 2: count = 8 -> 1/count folds into the z table exactly
     const bool fast = pow2 && Fz <= RF_F && Fy <= RF_F && Fx <= RF_F && need <= RF_POOL_FLOATS;
-    if (!fast) {
+    if (!fast) {                                           // CTA-uniform: the generic body rebuilds its own (larger) tables
+        __syncthreads();
+        fwd_ranges(sh, ax, Pa);
         fwd_generic_cta<T, 8>(s_buf, sh, feat_b, out_r, ax, Pa, ncta, S, H, W, layout, count);
         return;
     }
-    // (building the tables per warp with shuffles instead -- no block barrier at all -- was measured 7 % slower)
-    fwd_tables(sh, ax, Pa, count, true);
-    if (tid < 2 * RF_F * 8) {
-        const int which = tid >> 6, f = (tid >> 3) & 7, p = tid & 7;
-        (which ? fs.w3 : fs.w2)[f][p] = sh.w[which ? a3 : a2][f][p];
-    }
-    __syncthreads();
 
-    const int lane = tid & 31, warp = tid >> 5;
-    const int n_active = min(RF_THREADS / 32, RF_POOL_FLOATS / need);
-    if (warp >= n_active) return;
-    float* stage = s_buf + (size_t)warp * need;
-    float* ubuf = stage + 2 * stage_f;
+    // a task (RoI, 16 channels) belongs to a PAIR of warps: alternate planes in phase A, alternate column blocks in phase B,
+    // named barriers in between -- twice the issue streams on the same shared memory
+    const int pair = warp / RF_TEAM, half = warp - pair * RF_TEAM;
+    const int n_active = min(RF_THREADS / (32 * RF_TEAM), RF_POOL_FLOATS / need);
+    if (pair >= n_active) return;
+    float* stage = s_buf + (size_t)pair * need + half * 2 * stage_f;
+    float* ubuf = s_buf + (size_t)pair * need + 2 * RF_TEAM * stage_f;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(1 + pair), "n"(32 * RF_TEAM) : "memory"); };
     const int cp = lane & 7, g = lane >> 3;
     float wx[RF_F][2];
 #pragma unroll
@@ -570,14 +593,14 @@ roialign3d_fwd_fast_kernel(const T* __restrict__ feat, const float* __restrict__
     const unsigned row_bytes = (unsigned)(Fx * RF_CHS) * 4u;
     const int groups = (ncta + RF_G - 1) / RF_G;
 
-    for (int grp = warp; grp < groups; grp += n_active) {
+    for (int grp = pair; grp < groups; grp += n_active) {
         const int ncg = min(RF_G, ncta - grp * RF_G);
         const T* fg = feat_b + ((size_t)grp * RF_G + li) * SHW + org;
         // planes arrive through cp.async (4-byte copies: rows start at arbitrary x) into a double buffer
-        auto issue_plane = [&](int k) {
+        auto issue_plane = [&](int k, int it_) {
             if (lx < Fx) {
                 const T* s = fg + (size_t)k * plane_stride;
-                unsigned d = stage_s + (unsigned)((k & 1) * stage_f) * 4u;
+                unsigned d = stage_s + (unsigned)((it_ & 1) * stage_f) * 4u;
                 if (ncg == RF_G) {
 #pragma unroll 2
                     for (int f2 = 0; f2 < F2; ++f2, s += row_stride, d += row_bytes) {
@@ -606,15 +629,15 @@ roialign3d_fwd_fast_kernel(const T* __restrict__ feat, const float* __restrict__
             cp_async_commit();
         };
         __syncwarp();
-        issue_plane(0);
-        for (int k = 0; k < F3; ++k) {
-            if (k + 1 < F3) { issue_plane(k + 1); cp_async_wait<1>(); }
+        if (half < F3) issue_plane(half, 0);
+        for (int k = half, it = 0; k < F3; k += RF_TEAM, ++it) {
+            if (k + RF_TEAM < F3) { issue_plane(k + RF_TEAM, it + 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncwarp();
             unsigned long long U[8][2];
 #pragma unroll
             for (int p = 0; p < 8; ++p) { U[p][0] = 0ull; U[p][1] = 0ull; }
-            const float* st = stage + (k & 1) * stage_f + 2 * cp;
+            const float* st = stage + (it & 1) * stage_f + 2 * cp;
             switch (Fx) {
                 case 1: fast_plane_rows<1>(st, F2, wx, w2, U); break;
                 case 2: fast_plane_rows<2>(st, F2, wx, w2, U); break;
@@ -644,19 +667,21 @@ roialign3d_fwd_fast_kernel(const T* __restrict__ feat, const float* __restrict__
             }
             __syncwarp();
         }
+        pair_sync();                                       // all planes of the task are in the column buffer
         // ---- phase B: last contraction down the planes, lane = 4 columns, coalesced stores ---------------------
         T* og = out_r + (size_t)grp * RF_G * P3;
         const int NQ = ncg * NC;
         switch (F3) {
-            case 1: fast_columns<T, 1>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 2: fast_columns<T, 2>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 3: fast_columns<T, 3>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 4: fast_columns<T, 4>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 5: fast_columns<T, 5>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 6: fast_columns<T, 6>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            case 7: fast_columns<T, 7>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
-            default: fast_columns<T, 8>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane); break;
+            case 1: fast_columns<T, 1>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 2: fast_columns<T, 2>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 3: fast_columns<T, 3>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 4: fast_columns<T, 4>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 5: fast_columns<T, 5>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 6: fast_columns<T, 6>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            case 7: fast_columns<T, 7>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
+            default: fast_columns<T, 8>(ubuf, fs, og, NQ, NC, UST, P3, P3n, lane, half); break;
         }
+        pair_sync();                                       // the column buffer is free again
     }
 }
 
@@ -913,7 +938,7 @@ static int launch_fwd(const void* features, const float* rois, void* output, int
                       int Ps, int Ph, int Pw, float scale, int sr, int layout, cudaStream_t stream) {
     const int pmax = Ps > Ph ? (Ps > Pw ? Ps : Pw) : (Ph > Pw ? Ph : Pw);
     if (pmax <= 8) {
-        int cpb = C <= 64 ? C : 64;                                    // channels per CTA (one RoI per CTA); 64 / 128 / 256 measured: 127 / 133 / 150 us
+        int cpb = C <= 96 ? C : 96;                                    // channels per CTA (one RoI per CTA): six tasks for three teams of two warps
         cpb = (cpb + RA_CC - 1) / RA_CC * RA_CC;
         dim3 grid(R, (C + cpb - 1) / cpb);
         const size_t smem = RF_POOL_FLOATS * sizeof(float);

@@ -706,6 +706,9 @@ def _elementwise_rel(a, b, q=0.9999):
     ((1, 3, 16, 40, 40), 12, 0.25, 7, 0, (10, 160)),       # adaptive sampling (sr=0), large footprints
     ((1, 2, 20, 64, 64), 6, 1.0, 7, 2, (30, 64)),          # footprint > 16 voxels: direct path
     ((1, 33, 4, 8, 8), 9, 0.5, 3, 1, (2, 12)),             # P=3, sr=1, channel tail
+    ((1, 20, 8, 24, 24), 24, 0.125, 7, 3, (10, 50)),       # sr=3: count 27 is not a power of two -> generic body inside the fast kernel
+    ((1, 6, 16, 48, 48), 10, 0.5, 7, 2, (20, 28)),         # footprints of 11..16 voxels with P=7: generic separable body inside the fast kernel
+    ((2, 40, 8, 32, 32), 48, 0.125, 8, 2, (10, 50)),       # P=8 (no padding bin), channel groups of 16 + 8
 ])
 def test_roialign_fwd_bwd_vs_oracle(b2, torch_, shape, R, scale, P, sr, side):
     from b200seg import synth
