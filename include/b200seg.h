@@ -103,6 +103,10 @@ int b200seg_iou3d_host(const float* boxes, long long N, const float* query, long
  * ---------------------------------------------------------------------------------------------- */
 /* workspace of the backward: per-RoI footprint boxes + per-axis adjoint tables (R x (S+H+W) x 8|16 floats) */
 size_t b200seg_roialign3d_workspace_bytes(int R, int S, int H, int W, int P_max);
+/* workspace that also enables the round-2 backward for pooled sizes <= 8 (per-RoI footprint gradients, one slot of
+ * 8^3 voxels x 16 channels per (RoI, channel group): R x ceil(C/16) x 32 KB); b200seg_roialign3d_bwd_dev picks the path by
+ * the size it is handed -- a workspace of the smaller size above keeps the round-1 kernel, same results to rounding */
+size_t b200seg_roialign3d_bwd_workspace_bytes(int R, int C, int S, int H, int W, int P_max);
 int b200seg_roialign3d_fwd_dev(const void* features, int dtype, const float* rois, void* output,
                                int B, int C, int S, int H, int W, int R,
                                int Ps, int Ph, int Pw, float spatial_scale, int sampling_ratio,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200seg_iou3d_dev": (_i, [_vp, _ll, _vp, _ll, _vp, _vp]),
     "b200seg_iou3d_host": (_i, [_vp, _ll, _vp, _ll, _vp]),
     "b200seg_roialign3d_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "b200seg_roialign3d_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "b200seg_roialign3d_fwd_dev": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "b200seg_roialign3d_bwd_dev": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "b200seg_peaks3d_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -920,11 +920,466 @@ roialign3d_bwd_kernel(const T* __restrict__ gout, const RoiBox* __restrict__ box
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, fast path (round 2): pooled sizes <= 8, footprints <= 8 voxels per axis, power-of-two sample counts
+// ------------------------------------------------------------------------------------------------
+// Two launches, still deterministic and atomics-free:
+//   1. roialign3d_bwd_roi_kernel -- the forward's fast kernel run backwards, per RoI: lanes are channels, a task = (RoI, 16
+//      channels) worked by a team of two warps.  Phase B^T: lane = 4 columns (ph, pw) of grad_out (coalesced loads, the
+//      reference reads grad_out in (S,H,W) order in both layouts), contraction with the z table into Fz planes of the column
+//      buffer.  Phase A^T per plane: lane = (channel pair, pw pair) reads its columns, per footprint row the y table gives
+//      t[pw], the x table the lane's partial of every footprint voxel (its two pw bins only); the partials of the four pw
+//      pairs go to shared memory and are summed while the plane is written out -- the FOOTPRINT GRADIENT of the RoI,
+//      dF[r][channel group][z][y][x][16 channels], 64-byte runs, into the caller's workspace (a fixed slot of 8^3 voxels
+//      per (RoI, channel group)).
+//   2. roialign3d_bwd_gather_kernel -- owner computes: a CTA owns an 8^3 feature tile x 16 channels, lists the RoIs that hit
+//      the tile in index order and adds their footprint gradients voxel by voxel into a shared-memory tile (one RoI after
+//      the other: fixed summation order), then writes every grad_in element exactly once, x fastest.  RoIs that do not
+//      qualify for the fast path are evaluated directly from the per-axis adjoint tables at this point (rare).
+// Against the round-1 kernel (every tile re-ran the three contractions of every RoI it touches, 2.5 visits per RoI, one
+// channel per warp) the contraction work is done once per RoI with full lanes; the price is the footprint-gradient round
+// trip through HBM (about 0.6 x the size of grad_out on the BASELINE shapes).
+constexpr int RG_SLOT = RF_F * RF_F * RF_F * RF_G;     // floats per (RoI, channel group) slot of the footprint gradient
+
+struct __align__(16) BwdRoi {      // one per RoI, written by the first channel slab's CTA of roialign3d_bwd_roi_kernel
+    int lo[3], hi[3];              // footprint (inclusive), hi < lo when no valid sample on that axis
+    int batch;
+    int fast;                      // 1: footprint gradient in the workspace; 0: direct evaluation from the tables
+};
+
+__device__ __forceinline__ unsigned long long mul2s(float w, unsigned long long v) {
+    unsigned long long d;
+    const unsigned long long ww = pack2(w, w);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(ww), "l"(v));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long shfl_xor2(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+// Column buffer of the backward: plane stride UB (a multiple of 128 columns, so that phase B^T stores whole blocks without
+// guards); inside a plane channel PAIRS are interleaved -- element (channel ch, column col) sits at
+// ((ch >> 1) * NC + col) * 2 + (ch & 1) -- so that phase A^T fetches its packed operand with one 64-bit load.
+
+// phase B^T for one warp of a team: columns [0, NQ) in blocks of 128, alternate blocks per warp.  PCC > 0: Ps known.
+template <typename T, int F3N, int PCC>
+__device__ __forceinline__ void bwd_fast_columns(float* __restrict__ ubuf, const FastShared& fs, const T* __restrict__ gg,
+                                                 int NQ, int NC, int UB, int P3, int P3n, int lane, int half) {
+    float w3[F3N][8];
+#pragma unroll
+    for (int f = 0; f < F3N; ++f) {
+        const float4 a = *reinterpret_cast<const float4*>(&fs.w3[f][0]), b = *reinterpret_cast<const float4*>(&fs.w3[f][4]);
+        w3[f][0] = a.x; w3[f][1] = a.y; w3[f][2] = a.z; w3[f][3] = a.w;
+        w3[f][4] = b.x; w3[f][5] = b.y; w3[f][6] = b.z; w3[f][7] = b.w;
+    }
+    constexpr int NP = PCC > 0 ? PCC : 8;
+    for (int q0 = half * 128; q0 < NQ; q0 += RF_TEAM * 128) {
+        unsigned long long g01[NP], g23[NP];
+        int dsto[4];
+        {
+            float gv[NP][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = min(q0 + 32 * i + lane, NQ - 1);     // clamped: columns past the end repeat the last one (never read back)
+                const int ch = q / NC, col = q - ch * NC;
+                const T* o = gg + (ch * P3 + col);
+                dsto[i] = ((ch >> 1) * NC + col) * 2 + (ch & 1);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) gv[p][i] = (PCC > 0 || p < P3n) ? to_f(o[p * NC]) : 0.f;
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) { g01[p] = pack2(gv[p][0], gv[p][1]); g23[p] = pack2(gv[p][2], gv[p][3]); }
+        }
+        const bool last = q0 + 128 > NQ;                           // warp-uniform: only the last block has columns to skip
+#pragma unroll
+        for (int f3 = 0; f3 < F3N; ++f3) {
+            unsigned long long a01 = mul2s(w3[f3][0], g01[0]), a23 = mul2s(w3[f3][0], g23[0]);
+#pragma unroll
+            for (int p = 1; p < NP; ++p) {
+                a01 = fma2s(w3[f3][p], g01[p], a01);
+                a23 = fma2s(w3[f3][p], g23[p], a23);
+            }
+            float* up = ubuf + f3 * UB;
+            if (!last) {
+                up[dsto[0]] = lo2(a01); up[dsto[1]] = hi2(a01); up[dsto[2]] = lo2(a23); up[dsto[3]] = hi2(a23);
+            } else {
+                if (q0 + lane < NQ) up[dsto[0]] = lo2(a01);
+                if (q0 + 32 + lane < NQ) up[dsto[1]] = hi2(a01);
+                if (q0 + 64 + lane < NQ) up[dsto[2]] = lo2(a23);
+                if (q0 + 96 + lane < NQ) up[dsto[3]] = hi2(a23);
+            }
+        }
+    }
+}
+
+// phase A^T rows of one plane: t[pw] from the columns, then this lane's partial (its two pw bins) of every voxel of the row;
+// the partials of the four pw pairs (lanes 8 apart) are summed by a butterfly reduce-scatter over groups of four voxels, so
+// that lane (cp, g) ends up with voxel 4 m + g of the row for channels (2cp, 2cp+1): one coalesced 64-bit store per group.
+template <int FX>
+__device__ __forceinline__ void bwd_fast_plane_rows(float* __restrict__ dplane, int F2, int g, const float (&wx)[RF_F][2],
+                                                    const float (&w2)[RF_F][8], const unsigned long long (&U)[8][2], bool st_ok) {
+#pragma unroll
+    for (int f2 = 0; f2 < RF_F; ++f2) {
+        if (f2 < F2) {                                                     // warp-uniform
+            unsigned long long t0 = mul2s(w2[f2][0], U[0][0]), t1 = mul2s(w2[f2][0], U[0][1]);
+#pragma unroll
+            for (int p = 1; p < 8; ++p) {
+                t0 = fma2s(w2[f2][p], U[p][0], t0);
+                t1 = fma2s(w2[f2][p], U[p][1], t1);
+            }
+            float* rowp = dplane + f2 * FX * RF_G;
+#pragma unroll
+            for (int m = 0; m < (FX + 3) / 4; ++m) {
+                unsigned long long d[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int x = 4 * m + e;
+                    d[e] = x < FX ? fma2s(wx[x][1], t1, mul2s(wx[x][0], t0)) : 0ull;
+                }
+                // step 1 (lanes 16 apart): g < 2 keeps voxels 0,1, g >= 2 keeps voxels 2,3
+                const bool up2 = (g & 2) != 0;
+                const unsigned long long s0 = up2 ? d[0] : d[2], s1 = up2 ? d[1] : d[3];       // what the partner wants
+                const unsigned long long k0 = up2 ? d[2] : d[0], k1 = up2 ? d[3] : d[1];
+                const unsigned long long e0 = add2(k0, shfl_xor2(s0, 16)), e1 = add2(k1, shfl_xor2(s1, 16));
+                // step 2 (lanes 8 apart): even g keeps the first of its two voxels, odd g the second
+                const bool up1 = (g & 1) != 0;
+                const unsigned long long s = up1 ? e0 : e1, k = up1 ? e1 : e0;
+                const unsigned long long tot = add2(k, shfl_xor2(s, 8));
+                const int x = 4 * m + g;
+                if (x < FX && st_ok) *reinterpret_cast<unsigned long long*>(rowp + x * RF_G) = tot;
+            }
+        }
+    }
+}
+
+// grid (R, channel slabs).  boxes / flags for the gather pass are written by the CTAs of slab 0.
+template <typename T, int PC>
+__global__ void __launch_bounds__(RF_THREADS, 2)
+roialign3d_bwd_roi_kernel(const T* __restrict__ gout, const float* __restrict__ rois, BwdRoi* __restrict__ broi,
+                          float* __restrict__ tables, float* __restrict__ dF,
+                          int C, int S, int H, int W, int Ps_, int Ph_, int Pw_, float scale, int sr, double zguard, int cpb) {
+    extern __shared__ __align__(16) float s_buf[];
+    __shared__ FwdShared sh;
+    __shared__ FastShared fs;
+    const int Ps = PC > 0 ? PC : Ps_, Ph = PC > 0 ? PC : Ph_, Pw = PC > 0 ? PC : Pw_;
+    const int r = blockIdx.x;
+    const int c_begin = blockIdx.y * cpb;
+    const int ncta = min(cpb, C - c_begin);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    AxisP ax[3];
+    int batch; float count;
+    roi_axes(rois + (size_t)r * 7, scale, sr, Ps, Ph, Pw, S, H, W, zguard, ax[0], ax[1], ax[2], batch, count);
+    const int P3 = Ps * Ph * Pw;
+    // axis roles (grad_out is read in (S,H,W) order): x first, y scattered in registers (a2 = 1), z last (a3 = 0)
+    if (warp == 0) {
+        const int ta = min(lane >> 3, 2), tp = lane & 7;
+        const AxisP mine = ta == 0 ? ax[0] : (ta == 1 ? ax[1] : ax[2]);
+        const int myP = ta == 0 ? Ps : (ta == 1 ? Ph : Pw);
+        const bool t_on = lane < 24 && tp < myP;
+        int lo = 0x7fffffff, hi = -1;
+        if (t_on) {
+            for (int i = 0; i < mine.g; ++i) {
+                const Tap t = axis_sample(mine, tp, i);
+                if (t.valid) { lo = min(lo, t.low); hi = max(hi, t.high); }
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+        float wcol[RF_F];
+#pragma unroll
+        for (int f = 0; f < RF_F; ++f) wcol[f] = 0.f;
+        if (t_on) {
+            for (int i = 0; i < mine.g; ++i) {
+                const Tap t = axis_sample(mine, tp, i);
+                if (t.valid) {
+                    const int il = t.low - lo, ih = t.high - lo;
+#pragma unroll
+                    for (int f = 0; f < RF_F; ++f) { if (il == f) wcol[f] += t.h; if (ih == f) wcol[f] += t.l; }
+                }
+            }
+        }
+        const float zs = ta == 0 ? 1.0f / count : 1.0f;    // only used when count is a power of two: exact
+        if (lane < 24) {
+            float* dst = ta == 2 ? &sh.w[2][0][tp] : (ta == 1 ? &fs.w2[0][tp] : &fs.w3[0][tp]);
+            const int fstride = ta == 2 ? 16 : 8;
+#pragma unroll
+            for (int f = 0; f < RF_F; ++f) dst[f * fstride] = wcol[f] * zs;
+            if (tp == 0) { sh.lo[ta] = lo; sh.hi[ta] = hi; }
+        }
+    }
+    __syncthreads();
+    const int zlo = sh.lo[0], ylo = sh.lo[1], xlo = sh.lo[2];
+    const bool empty = sh.hi[0] < 0 || sh.hi[1] < 0 || sh.hi[2] < 0;
+    const int Fz = sh.hi[0] - zlo + 1, Fy = sh.hi[1] - ylo + 1, Fx = sh.hi[2] - xlo + 1;
+    const int F2 = Fy, F3 = Fz;
+    const int P2 = Ph, P3n = Ps;
+    const int NC = Ph * Pw;                                // columns per channel
+    const int UB = (RF_G * NC + 127) & ~127;               // floats per plane of the column buffer
+    const int need = F3 * UB;
+    const int icount = ax[0].g * ax[1].g * ax[2].g;
+    const bool pow2 = (icount & (icount - 1)) == 0;
+    const bool fast = !empty && pow2 && Fz <= RF_F && Fy <= RF_F && Fx <= RF_F && need <= RF_POOL_FLOATS;
+    if (blockIdx.y == 0) {
+        if (tid == 0) {
+            BwdRoi b;
+            for (int a = 0; a < 3; ++a) { b.lo[a] = sh.lo[a]; b.hi[a] = empty ? sh.lo[a] - 1 : sh.hi[a]; }
+            b.batch = batch; b.fast = fast ? 1 : 0;
+            broi[r] = b;
+        }
+        if (!fast && !empty) {
+            // direct evaluation in the gather pass needs the adjoint tables over the whole extent: W[axis][voxel][bin], 8 bins
+            float* tab = tables + (size_t)r * (S + H + W) * 8;
+            for (int i = tid; i < (S + H + W) * 8; i += RF_THREADS) tab[i] = 0.f;
+            __syncthreads();
+            if (tid < 24) {
+                const int a = tid >> 3, p = tid & 7;
+                const int Pa = a == 0 ? Ps : (a == 1 ? Ph : Pw);
+                const int seg = a == 0 ? 0 : (a == 1 ? S : S + H);
+                const AxisP mine = a == 0 ? ax[0] : (a == 1 ? ax[1] : ax[2]);
+                if (p < Pa) {
+                    float* col = tab + (size_t)seg * 8 + p;
+                    for (int i = 0; i < mine.g; ++i) {                     // one thread per column: no races
+                        const Tap t = axis_sample(mine, p, i);
+                        if (!t.valid) continue;
+                        col[(size_t)t.low * 8] += t.h;
+                        col[(size_t)t.high * 8] += t.l;
+                    }
+                }
+            }
+        }
+    }
+    if (!fast) return;
+
+    const int pair = warp / RF_TEAM, half = warp - pair * RF_TEAM;
+    const int n_active = min(RF_THREADS / (32 * RF_TEAM), RF_POOL_FLOATS / need);
+    if (pair >= n_active) return;
+    float* ubuf = s_buf + (size_t)pair * need;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(1 + pair), "n"(32 * RF_TEAM) : "memory"); };
+    const int cp = lane & 7, g = lane >> 3;
+    float wx[RF_F][2];
+#pragma unroll
+    for (int x = 0; x < RF_F; ++x) { wx[x][0] = sh.w[2][x][2 * g]; wx[x][1] = sh.w[2][x][2 * g + 1]; }
+    float w2[RF_F][8];
+#pragma unroll
+    for (int f = 0; f < RF_F; ++f) {
+        const float4 a = *reinterpret_cast<const float4*>(&fs.w2[f][0]), b = *reinterpret_cast<const float4*>(&fs.w2[f][4]);
+        w2[f][0] = a.x; w2[f][1] = a.y; w2[f][2] = a.z; w2[f][3] = a.w;
+        w2[f][4] = b.x; w2[f][5] = b.y; w2[f][6] = b.z; w2[f][7] = b.w;
+    }
+    const int groups = (ncta + RF_G - 1) / RF_G;
+    const int NG = (C + RF_G - 1) / RF_G;
+    const int plane_vox = F2 * Fx;
+    // this lane's columns in a plane: channel pair cp, pw = 2g + j (the bin 7 of a 7-bin axis carries zero weights: its index
+    // is clamped to a valid column instead of guarded), all ph bins
+    int ucol[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) ucol[j] = (cp * NC + min(2 * g + j, Pw - 1)) * 2;
+
+    for (int grp = pair; grp < groups; grp += n_active) {
+        const int ncg = min(RF_G, ncta - grp * RF_G);
+        const T* gg = gout + ((size_t)r * C + c_begin + grp * RF_G) * P3;
+        const int NQ = ncg * NC;
+        if (ncg < RF_G) {                                  // tail group: absent channels must read zeros, not stale shared memory
+            for (int i = lane + 32 * half; i < F3 * UB; i += 32 * RF_TEAM) ubuf[i] = 0.f;
+            pair_sync();
+        }
+        switch (F3) {
+            case 1: bwd_fast_columns<T, 1, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 2: bwd_fast_columns<T, 2, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 3: bwd_fast_columns<T, 3, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 4: bwd_fast_columns<T, 4, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 5: bwd_fast_columns<T, 5, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 6: bwd_fast_columns<T, 6, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            case 7: bwd_fast_columns<T, 7, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+            default: bwd_fast_columns<T, 8, PC>(ubuf, fs, gg, NQ, NC, UB, P3, P3n, lane, half); break;
+        }
+        pair_sync();                                       // every plane of the column buffer is complete
+        float* slot = dF + ((size_t)r * NG + (c_begin / RF_G + grp)) * RG_SLOT + 2 * cp;
+        const bool st_ok = 2 * cp < ncg;                   // (channel counts are even in practice; an odd tail writes one spare float inside the slot)
+        for (int k = half; k < F3; k += RF_TEAM) {
+            unsigned long long U[8][2];
+            const float* up = ubuf + k * UB;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    U[p][j] = *reinterpret_cast<const unsigned long long*>(up + ucol[j] + min(p, P2 - 1) * (2 * Pw));
+            float* dplane = slot + (size_t)k * plane_vox * RF_G;
+            switch (Fx) {
+                case 1: bwd_fast_plane_rows<1>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 2: bwd_fast_plane_rows<2>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 3: bwd_fast_plane_rows<3>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 4: bwd_fast_plane_rows<4>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 5: bwd_fast_plane_rows<5>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 6: bwd_fast_plane_rows<6>(dplane, F2, g, wx, w2, U, st_ok); break;
+                case 7: bwd_fast_plane_rows<7>(dplane, F2, g, wx, w2, U, st_ok); break;
+                default: bwd_fast_plane_rows<8>(dplane, F2, g, wx, w2, U, st_ok); break;
+            }
+        }
+        pair_sync();                                       // the column buffer is free again
+    }
+}
+
+// grid (tiles of one batch element, channel groups, B); block 256 = 16 row slots x 16 channels.
+// A thread owns, for its channel, the four tile rows (z, y) with z mod 4 == sz and y mod 4 == sy -- 32 voxels, accumulated
+// in REGISTERS over the RoIs of the tile's list in index order (no barrier inside the list walk, fixed summation order),
+// and finally written as four runs of 8 consecutive x (two 128-bit stores per row for fp32).
+constexpr int RGT = 8;                                     // tile edge
+constexpr int RG_LIST = 256;                               // RoIs listed per round
+template <typename T, int PC>
+__global__ void __launch_bounds__(256)
+roialign3d_bwd_gather_kernel(const T* __restrict__ gout, const BwdRoi* __restrict__ broi, const float* __restrict__ tables,
+                             const float* __restrict__ rois, const float* __restrict__ dF, T* __restrict__ gin,
+                             int C, int S, int H, int W, int R, int Ps_, int Ph_, int Pw_, float scale, int sr,
+                             int tiles_x, int tiles_y) {
+    __shared__ int s_list[RG_LIST];
+    __shared__ BwdRoi s_box[RG_LIST];
+    __shared__ int s_wcnt[8];
+    const int Ps = PC > 0 ? PC : Ps_, Ph = PC > 0 ? PC : Ph_, Pw = PC > 0 ? PC : Pw_;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, cg = blockIdx.y, b = blockIdx.z;
+    const int t0[3] = {(tile / (tiles_x * tiles_y)) * RGT, ((tile / tiles_x) % tiles_y) * RGT, (tile % tiles_x) * RGT};
+    const int t1[3] = {min(t0[0] + RGT, S) - 1, min(t0[1] + RGT, H) - 1, min(t0[2] + RGT, W) - 1};
+    const int NG = (C + RF_G - 1) / RF_G;
+    const int ncg = min(RF_G, C - cg * RF_G);
+    const int c = tid & 15, slot = tid >> 4;               // channel, row slot
+    const int sz = slot >> 2, sy = slot & 3;
+    const int P3 = Ps * Ph * Pw;
+    const bool c_ok = c < ncg;
+    float acc[4][RGT];                                     // rows (sz + 4 i, sy + 4 j), i, j in {0, 1}: index 2 i + j
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int x = 0; x < RGT; ++x) acc[q][x] = 0.f;
+
+    for (int r0 = 0; r0 < R; r0 += RG_LIST) {
+        __syncthreads();                                   // everybody is done with the previous list
+        const int rn = min(RG_LIST, R - r0);
+        bool hit = false;
+        BwdRoi mine;
+        if (tid < rn) {
+            mine = broi[r0 + tid];
+            hit = mine.batch == b;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) hit = hit && mine.hi[a] >= mine.lo[a] && mine.hi[a] >= t0[a] && mine.lo[a] <= t1[a];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, n_list = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) before += s_wcnt[w]; n_list += s_wcnt[w]; }
+        if (hit) { const int pos = before + __popc(m & ((1u << lane) - 1u)); s_list[pos] = r0 + tid; s_box[pos] = mine; }
+        __syncthreads();
+        for (int k = 0; k < n_list; ++k) {                 // RoIs in index order: fixed summation order per voxel
+            const int r = s_list[k];
+            const BwdRoi bx = s_box[k];
+            const int Fy = bx.hi[1] - bx.lo[1] + 1, Fx = bx.hi[2] - bx.lo[2] + 1;
+            const int xa = max(bx.lo[2], t0[2]), xb = min(bx.hi[2], t1[2]);      // x range inside the tile (not empty: the RoI hits the tile)
+            if (bx.fast) {
+                const float* base = dF + ((size_t)r * NG + cg) * RG_SLOT + c;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gz = t0[0] + sz + 4 * (q >> 1), gy = t0[1] + sy + 4 * (q & 1);
+                    if (gz < bx.lo[0] || gz > bx.hi[0] || gy < bx.lo[1] || gy > bx.hi[1] || !c_ok) continue;
+                    const float* row = base + (size_t)(((gz - bx.lo[0]) * Fy + (gy - bx.lo[1])) * Fx - bx.lo[2] + t0[2]) * RF_G;
+#pragma unroll
+                    for (int x = 0; x < RGT; ++x) {
+                        const int gx = t0[2] + x;
+                        if (gx >= xa && gx <= xb) acc[q][x] += row[x * RF_G];
+                    }
+                }
+            } else if (c_ok) {
+                // direct evaluation from the per-axis adjoint tables (RoIs with large footprints or odd sample counts)
+                const float* tab = tables + (size_t)r * (S + H + W) * 8;
+                const T* gc = gout + ((size_t)r * C + cg * RF_G + c) * P3;
+                const float* roi = rois + (size_t)r * 7;
+                const float rs = fmaxf(roi[6] * scale - roi[3] * scale, 1.f), rw = fmaxf(roi[4] * scale - roi[1] * scale, 1.f),
+                            rh = fmaxf(roi[5] * scale - roi[2] * scale, 1.f);
+                const int gz_ = sr > 0 ? sr : (int)ceilf(rs / Ps), gy_ = sr > 0 ? sr : (int)ceilf(rh / Ph), gx_ = sr > 0 ? sr : (int)ceilf(rw / Pw);
+                const float inv_count = 1.0f / (float)(gz_ * gy_ * gx_);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gz = t0[0] + sz + 4 * (q >> 1), gy = t0[1] + sy + 4 * (q & 1);
+                    if (gz < bx.lo[0] || gz > bx.hi[0] || gy < bx.lo[1] || gy > bx.hi[1]) continue;
+                    const float* wz = tab + (size_t)gz * 8, *wy = tab + (size_t)(S + gy) * 8;
+#pragma unroll
+                    for (int x = 0; x < RGT; ++x) {
+                        const int gx = t0[2] + x;
+                        if (gx < xa || gx > xb) continue;
+                        const float* wxp = tab + (size_t)(S + H + gx) * 8;
+                        float a3 = 0.f;
+                        for (int ps = 0; ps < Ps; ++ps) {
+                            const float a = wz[ps];
+                            if (a == 0.f) continue;
+                            float s2 = 0.f;
+                            for (int ph = 0; ph < Ph; ++ph) {
+                                const float bq = wy[ph];
+                                if (bq == 0.f) continue;
+                                float s1 = 0.f;
+                                for (int pw = 0; pw < Pw; ++pw) s1 = fmaf(wxp[pw], to_f(gc[(ps * Ph + ph) * Pw + pw]), s1);
+                                s2 = fmaf(bq, s1, s2);
+                            }
+                            a3 = fmaf(a, s2, a3);
+                        }
+                        acc[q][x] += a3 * inv_count;
+                    }
+                }
+            }
+        }
+    }
+    // every grad_in element of the tile is written exactly once: four runs of 8 consecutive x per thread
+    if (c_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int gz = t0[0] + sz + 4 * (q >> 1), gy = t0[1] + sy + 4 * (q & 1);
+            if (gz >= S || gy >= H) continue;
+            T* dst = gin + ((((size_t)b * C + cg * RF_G + c) * S + gz) * H + gy) * W + t0[2];
+            if (sizeof(T) == 4 && t0[2] + RGT <= W && (W & 3) == 0) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < RGT; ++x) if (t0[2] + x < W) dst[x] = from_f<T>(acc[q][x]);
+            }
+        }
+    }
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
 
 static size_t bwd_table_floats(int R, int S, int H, int W, int PT) { return (size_t)R * (size_t)(S + H + W) * PT; }
+
+// layout of the fast backward's workspace: [BwdRoi x R] [adjoint tables R x (S+H+W) x 8] [footprint gradients R x NG x slot]
+static size_t bwd_fast_bytes(int R, int C, int S, int H, int W, size_t* off_tables, size_t* off_df) {
+    const size_t r = R > 0 ? R : 1;
+    const size_t ng = (size_t)(C + RF_G - 1) / RF_G;
+    size_t o = align_up(r * sizeof(BwdRoi), 256);
+    if (off_tables) *off_tables = o;
+    o += align_up(r * (size_t)(S + H + W) * 8 * sizeof(float), 256);
+    if (off_df) *off_df = o;
+    o += align_up(r * ng * (size_t)RG_SLOT * sizeof(float), 256);
+    return o + 256;
+}
+
+extern "C" size_t b200seg_roialign3d_bwd_workspace_bytes(int R, int C, int S, int H, int W, int P_max) {
+    const size_t base = b200seg_roialign3d_workspace_bytes(R, S, H, W, P_max);
+    if (P_max > 8 || C <= 0 || S <= 0 || H <= 0 || W <= 0) return base;
+    const size_t fastb = bwd_fast_bytes(R, C, S, H, W, nullptr, nullptr);
+    return fastb > base ? fastb : base;
+}
 
 extern "C" size_t b200seg_roialign3d_workspace_bytes(int R, int S, int H, int W, int P_max) {
     const int PT = P_max <= 8 ? 8 : 16;
@@ -1026,6 +1481,41 @@ extern "C" int b200seg_roialign3d_bwd_dev(const void* grad_out, int dtype, const
         return B200SEG_EWORKSPACE;
     }
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (pmax <= 8 && B <= 65535 && (C + RF_G - 1) / RF_G <= 65535) {
+        size_t off_tables = 0, off_df = 0;
+        const size_t need = bwd_fast_bytes(R, C, S, H, W, &off_tables, &off_df);
+        if (workspace_bytes >= need) {                      // sized with b200seg_roialign3d_bwd_workspace_bytes: two-launch fast path
+            BwdRoi* broi = (BwdRoi*)ws;
+            float* tables = (float*)(ws + off_tables);
+            float* dF = (float*)(ws + off_df);
+            const double zguard = layout == 0 ? -0.1 : -1.0;
+            const bool cubic7 = Ps == 7 && Ph == 7 && Pw == 7;
+            const int tiles_x = (W + RGT - 1) / RGT, tiles_y = (H + RGT - 1) / RGT, tiles_z = (S + RGT - 1) / RGT;
+            auto run = [&](auto kroi, auto kgather, auto tag) -> int {
+                using T = decltype(tag);
+                if (R > 0) {
+                    int cpb = C <= 96 ? C : 96;
+                    cpb = (cpb + RF_G - 1) / RF_G * RF_G;
+                    dim3 grid(R, (C + cpb - 1) / cpb);
+                    const size_t smem = RF_POOL_FLOATS * sizeof(float);
+                    B200_CUDA(cudaFuncSetAttribute(kroi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kroi<<<grid, RF_THREADS, smem, stream>>>((const T*)grad_out, rois, broi, tables, dF, C, S, H, W, Ps, Ph, Pw,
+                                                             spatial_scale, sampling_ratio, zguard, cpb);
+                    B200_LAUNCH_CHECK("roialign3d_bwd_roi_kernel");
+                }
+                dim3 g2(tiles_x * tiles_y * tiles_z, (C + RF_G - 1) / RF_G, B);
+                kgather<<<g2, 256, 0, stream>>>((const T*)grad_out, broi, tables, rois, dF, (T*)grad_in, C, S, H, W, R, Ps, Ph, Pw,
+                                                spatial_scale, sampling_ratio, tiles_x, tiles_y);
+                B200_LAUNCH_CHECK("roialign3d_bwd_gather_kernel");
+                return 0;
+            };
+            if (dtype == B200SEG_F32)
+                return cubic7 ? run(roialign3d_bwd_roi_kernel<float, 7>, roialign3d_bwd_gather_kernel<float, 7>, float())
+                              : run(roialign3d_bwd_roi_kernel<float, 0>, roialign3d_bwd_gather_kernel<float, 0>, float());
+            return cubic7 ? run(roialign3d_bwd_roi_kernel<__nv_bfloat16, 7>, roialign3d_bwd_gather_kernel<__nv_bfloat16, 7>, __nv_bfloat16())
+                          : run(roialign3d_bwd_roi_kernel<__nv_bfloat16, 0>, roialign3d_bwd_gather_kernel<__nv_bfloat16, 0>, __nv_bfloat16());
+        }
+    }
     RoiBox* boxes = (RoiBox*)ws;
     float* tables = (float*)(ws + align_up((size_t)(R > 0 ? R : 1) * sizeof(RoiBox), 256));
     // layout 0 keeps the reference's backward z guard (-0.1); layout 1 is the exact adjoint (-1.0)

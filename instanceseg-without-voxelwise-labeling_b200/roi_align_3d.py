@@ -42,7 +42,7 @@ def roialign3d_backward(grad_out, rois, feature_size, scale, sr, layout=0):
     R, _, Ps, Ph, Pw = grad_out.shape
     L = _lib.lib()
     grad_in = torch.empty((B, Cc, S, H, W), dtype=grad_out.dtype, device=grad_out.device)
-    ws_bytes = L.b200seg_roialign3d_workspace_bytes(R, S, H, W, max(Ps, Ph, Pw))
+    ws_bytes = L.b200seg_roialign3d_bwd_workspace_bytes(R, Cc, S, H, W, max(Ps, Ph, Pw))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad_out.device)
     _lib.check(L.b200seg_roialign3d_bwd_dev(
         _lib.ptr(grad_out), _DT[grad_out.dtype], _lib.ptr(rois), _lib.ptr(grad_in), B, Cc, S, H, W, R,
