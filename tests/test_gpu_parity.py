@@ -732,6 +732,37 @@ def test_roialign_fwd_bwd_vs_oracle(b2, torch_, shape, R, scale, P, sr, side):
     assert torch_.equal(f.grad, f2.grad)
 
 
+def test_roialign_backward_paths_agree(b2, torch_):
+    """The backward picks its path by the workspace it is handed: b200seg_roialign3d_bwd_workspace_bytes enables the
+    two-launch path (per-RoI footprint gradients + gather), the smaller b200seg_roialign3d_workspace_bytes keeps the
+    tile kernel.  Both are deterministic and agree with the oracle and with each other to rounding; the mix of
+    qualifying and non-qualifying RoIs (large footprints) exercises the direct evaluation inside the gather pass."""
+    from b200seg import synth, _lib
+    feat, rois = synth.roialign_case(77, feat_shape=(2, 24, 10, 40, 40), n_rois=60, scale=0.25, side=(8, 70), frac_outside=0.1)
+    rois[0, 1:] = [-50, -50, -50, -40, -40, -40]
+    g = np.random.default_rng(3).standard_normal((60, 24, 7, 7, 7)).astype(np.float32)
+    ref = oracle.roialign3d_bwd(g, rois, feat.shape, 0.25, 2)
+    L = _lib.lib()
+    gd, rd = torch_.from_numpy(g).cuda(), torch_.from_numpy(rois).cuda()
+    B, C, S, H, W = feat.shape
+    outs = []
+    for nbytes in (L.b200seg_roialign3d_workspace_bytes(60, S, H, W, 7), L.b200seg_roialign3d_bwd_workspace_bytes(60, C, S, H, W, 7)):
+        ws = torch_.empty(nbytes, dtype=torch_.uint8, device="cuda")
+        res = []
+        for _ in range(2):
+            gi = torch_.full(feat.shape, float("nan"), dtype=torch_.float32, device="cuda")
+            _lib.check(L.b200seg_roialign3d_bwd_dev(_lib.ptr(gd), 0, _lib.ptr(rd), _lib.ptr(gi), B, C, S, H, W, 60, 7, 7, 7, 0.25, 2, 0,
+                                                    _lib.ptr(ws), nbytes, _lib.current_stream()), "bwd")
+            res.append(gi)
+        assert torch_.equal(res[0], res[1])
+        ok, err = _close(res[0].cpu().numpy(), ref, floor="max")
+        assert ok, err
+        outs.append(res[0])
+    assert L.b200seg_roialign3d_bwd_workspace_bytes(60, C, S, H, W, 7) > L.b200seg_roialign3d_workspace_bytes(60, S, H, W, 7)
+    ok, err = _close(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rel=2e-6, floor="max")
+    assert ok, err
+
+
 def test_roialign_vs_reference_cuda_kernels(b2, torch_):
     """Same inputs through the reference's own .cu (compiled unmodified for sm_100a)."""
     from b200seg import synth
