@@ -48,9 +48,11 @@ int b200seg_version(void);
 long long b200seg_launch_count(void);
 /* Profiling knobs (no effect on results unless stated).  "peaks_stop_after" = k: b200seg_peaks3d_dev returns after its
  * first k kernel launches (0 = memset only, 99 = the whole op, the default), so that a caller can time the op kernel by
- * kernel with CUDA events; outputs are incomplete while k < 99.  "host_batch_mode" (default 3) selects the transfer
+ * kernel with CUDA events; outputs are incomplete while k < 99.  "host_batch_mode" (default 7) selects the transfer
  * scheme of b200seg_postproc_soma_host_batch, same results either way: bit 0 = label volumes come back compacted,
- * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather).  "host_batch_out" (default 0) tells that
+ * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather), bit 2 = the raw volume is not
+ * copied either: the NMS runs first, host threads pack the image crops of its survivors (the only voxels the chain reads)
+ * into a pinned buffer and that buffer travels instead.  "host_batch_out" (default 0) tells that
  * entry point what the caller's label buffers hold ON ENTRY, again with identical results: 0 = anything (every buffer is
  * zero-filled, 2 bytes of host memory traffic per voxel -- the bound of the call), 1 = zeros (a fresh np.zeros / calloc
  * buffer, what tools/binarization_soma.py:57 allocates per volume), 2 = exactly what this entry point wrote into the same

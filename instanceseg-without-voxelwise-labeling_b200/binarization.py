@@ -231,7 +231,8 @@ def set_host_batch_out(state):
 
 
 def set_host_batch_mode(mode):
-    """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops (default 3)."""
+    """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops, bit 2: the image
+    crops of the NMS survivors travel packed by host threads, the raw volume is never copied (default 7)."""
     _lib.check(_lib.lib().b200seg_set_option(b"host_batch_mode", int(mode)), "set_option")
 
 

@@ -71,7 +71,7 @@ static std::atomic<int> g_peaks_median_mode{0};
 int opt_peaks_median_mode() { return g_peaks_median_mode.load(std::memory_order_relaxed); }
 static std::atomic<int> g_host_batch_out{0};
 int opt_host_batch_out() { return g_host_batch_out.load(std::memory_order_relaxed); }
-static std::atomic<int> g_host_batch_mode{3};
+static std::atomic<int> g_host_batch_mode{7};
 int opt_host_batch_mode() { return g_host_batch_mode.load(std::memory_order_relaxed); }
 
 }  // namespace b200seg

@@ -67,13 +67,21 @@ seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned
 // grid (n_max): CTA r moves the crop of visit rank r.  src and dst share the offset, both bases are 16-byte aligned.
 __global__ void __launch_bounds__(256)
 prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ crop_off,
-                  const int32_t* __restrict__ rank_order, const int32_t* __restrict__ keep_count) {
+                  const int32_t* __restrict__ rank_order, const int32_t* __restrict__ keep_count,
+                  const uint8_t* __restrict__ all_zero) {
     const int r = blockIdx.x;
     if (r >= keep_count[0]) return;
     const int inst = rank_order[r];
     const long long a = crop_off[inst], b = crop_off[inst + 1];
     long long a16 = (a + 15) & ~15ll, b16 = b & ~15ll;
     if (a16 > b16) { a16 = b; b16 = b; }                            // crop shorter than one aligned group
+    if (all_zero && all_zero[r]) {                                  // the host saw no positive voxel in this crop: nothing to fetch
+        for (long long i = a + threadIdx.x; i < a16; i += 256) dst[i] = 0;
+        uint4* z4 = reinterpret_cast<uint4*>(dst + a16);
+        for (long long i = threadIdx.x; i < ((b16 - a16) >> 4); i += 256) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (long long k = b16 + threadIdx.x; k < b; k += 256) dst[k] = 0;
+        return;
+    }
     for (long long i = a + threadIdx.x; i < a16; i += 256) dst[i] = src[i];
     const uint4* s4 = reinterpret_cast<const uint4*>(src + a16);
     uint4* d4 = reinterpret_cast<uint4*>(dst + a16);
@@ -85,6 +93,54 @@ prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, co
     }
     for (; i < n4; i += 256) d4[i] = ld_stream_u4(s4 + i);
     for (long long k = b16 + threadIdx.x; k < b; k += 256) dst[k] = src[k];
+}
+
+// Image crops of the NMS survivors, packed by host threads (box-shaped, visit order, back to back) -> the rows of the device
+// copy of the volume they came from.  The chain reads the image only inside the boxes of the instances it binarizes
+// (binarization_soma.py:78-94), so with "host_batch_mode" bit 2 the 33.5 MB volume never crosses the link: the NMS runs
+// first, its visit order comes back (a few hundred bytes), host threads copy the survivors' box rows into one pinned
+// buffer (about 2.5 MB per volume) and that buffer travels by DMA.  Fetching the rows in place over the link instead (a
+// gather kernel reading the pinned volume) was measured: 29-byte rows become 32-byte read requests and the link delivers
+// 9 GB/s of them, less than the DMA of the whole volume.  The rest of the device volume keeps stale bytes nobody reads.
+// grid (n_max): CTA r moves the box of visit rank r; one warp per row.
+__global__ void __launch_bounds__(256)
+img_unpack_kernel(const uint8_t* __restrict__ pack, const int64_t* __restrict__ pk_off, const uint8_t* __restrict__ all_zero,
+                  uint8_t* __restrict__ dst, int H, int W, const int32_t* __restrict__ boxes,
+                  const int32_t* __restrict__ rank_order, const int32_t* __restrict__ keep_count) {
+    const int r = blockIdx.x;
+    if (r >= keep_count[0]) return;
+    // an instance without a positive PRM voxel is skipped by the script before it touches the image (:74-76): the host did
+    // not pack its crop (the bytes of its slot are stale) and it must not overwrite rows it shares with other boxes
+    if (all_zero[r]) return;
+    const int inst = rank_order[r];
+    const int32_t* bx = boxes + (size_t)inst * 6;
+    const int x1 = bx[0], y1 = bx[1], z1 = bx[2];
+    const int sx = bx[3] - x1 + 1, sy = bx[4] - y1 + 1, sz = bx[5] - z1 + 1;
+    if (sx <= 0 || sy <= 0 || sz <= 0) return;
+    const uint8_t* src = pack + pk_off[r];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t HW = (size_t)H * W;
+    const int rows = sz * sy;
+    for (int row0 = warp; row0 < rows; row0 += 8 * 4) {        // four rows in flight per warp
+        uint8_t v[4];
+        size_t off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = min(row0 + 8 * u, rows - 1);
+            const int z = row / sy, y = row - z * sy;
+            off[u] = (size_t)(z1 + z) * HW + (size_t)(y1 + y) * W + x1;
+            v[u] = lane < sx ? src[(size_t)row * sx + lane] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (lane < sx && row0 + 8 * u < rows) dst[off[u] + lane] = v[u];
+        if (sx > 32) {                                          // wide boxes: the rest of the rows
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = row0 + 8 * u;
+                if (row < rows) for (int x = 32 + lane; x < sx; x += 32) dst[off[u] + x] = src[(size_t)row * sx + x];
+            }
+        }
+    }
 }
 
 // Zero fill with non-temporal stores: the label volumes are far larger than the caches and are not read again by this
@@ -116,6 +172,7 @@ struct HostPool {
     std::condition_variable cv;
     std::deque<std::function<void()>> q;
     int n_threads = 0;
+    int cap = 16;
     pid_t pid = 0;
     void ensure() {
         std::lock_guard<std::mutex> lk(mu);
@@ -130,7 +187,7 @@ struct HostPool {
             int share = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;   // ranks of one box share its cores
             want = hw / share;
-            if (want > 16) want = 16;
+            if (want > cap) want = cap;
             if (want < 2) want = 2;
         }
         n_threads = want;
@@ -156,15 +213,20 @@ struct HostPool {
 // never destroyed: its threads are detached and wait on the condition variable until the process ends (destroying a
 // condition variable with waiters blocks in glibc)
 static HostPool& g_pool = *new HostPool;
+static HostPool& g_pack_pool = *new HostPool;      // packs image crops: short jobs that must not queue behind the zero fills
 
-constexpr int HB_SLOTS = 6;
+constexpr int HB_SLOTS = 8;
 constexpr int HB_LAG_A = 2;            // the download of volume v is sized and enqueued while volume v + HB_LAG_A is being enqueued
 constexpr int HB_LAG_B = 3;            // ... and handed to the pool one step later
 constexpr int HB_ZERO_PARTS = 4;
+constexpr int HB_LAG_N = 4;            // packed-image mode: the chain of volume v is enqueued while the NMS of volume v + HB_LAG_N is
 
 struct BatchStreams {
     cudaStream_t in = nullptr, out = nullptr, out2 = nullptr;   // uploads | bookkeeping downloads | label downloads
+    cudaStream_t comp2 = nullptr, comp3 = nullptr;              // more compute streams: consecutive volumes overlap on the GPU
+    cudaStream_t nms = nullptr;                                 // high priority: the NMS of a volume must not queue behind the chains of others
     cudaEvent_t in_done[HB_SLOTS] = {}, comp_done[HB_SLOTS] = {}, cnt_done[HB_SLOTS] = {}, out_done[HB_SLOTS] = {};
+    cudaEvent_t nmsc_done[HB_SLOTS] = {}, nms_done[HB_SLOTS] = {}, pack_done[HB_SLOTS] = {};
     int device = -1;
     char* pinned = nullptr;           // grow-only pinned staging: per-volume bookkeeping + per-slot compacted groups
     size_t pinned_cap = 0;
@@ -179,16 +241,27 @@ struct BatchStreams {
     int ensure(int dev) {
         if (device == dev && in) return 0;
         if (in) {
-            cudaStreamDestroy(in); cudaStreamDestroy(out); cudaStreamDestroy(out2);
+            cudaStreamDestroy(in); cudaStreamDestroy(out); cudaStreamDestroy(out2); cudaStreamDestroy(comp2); cudaStreamDestroy(comp3); cudaStreamDestroy(nms);
             for (int k = 0; k < HB_SLOTS; ++k) {
                 cudaEventDestroy(in_done[k]); cudaEventDestroy(comp_done[k]); cudaEventDestroy(cnt_done[k]); cudaEventDestroy(out_done[k]);
+                cudaEventDestroy(nmsc_done[k]); cudaEventDestroy(nms_done[k]); cudaEventDestroy(pack_done[k]);
             }
         }
         B200_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
         B200_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
         B200_CUDA(cudaStreamCreateWithFlags(&out2, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&comp2, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&comp3, cudaStreamNonBlocking));
+        {
+            int lo_p = 0, hi_p = 0;
+            B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            B200_CUDA(cudaStreamCreateWithPriority(&nms, cudaStreamNonBlocking, hi_p));
+        }
         for (int k = 0; k < HB_SLOTS; ++k) {
             B200_CUDA(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&nmsc_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&nms_done[k], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&pack_done[k], cudaEventDisableTiming));
             B200_CUDA(cudaEventCreateWithFlags(&comp_done[k], cudaEventDisableTiming));
             B200_CUDA(cudaEventCreateWithFlags(&cnt_done[k], cudaEventDisableTiming));
             B200_CUDA(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
@@ -262,7 +335,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     if (cap < 4096) cap = 4096;
     if (cap > ngroups) cap = ngroups;
     if (!sparse) cap = 0;
-    const size_t slot_bytes = Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
+    const bool pack_mode = (mode & 4) != 0;                   // image crops of the NMS survivors packed by host threads, no DMA of the volume
+    const size_t slot_bytes = (pack_mode ? Carver::need(prm_max + 16) + Carver::need(nn * 8) + Carver::need(nn) : 0) + Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
                               2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(8) +
                               3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(cap * 4 + 16) + Carver::need(cap * 16 + 16) +
                               Carver::need(ws_bytes);
@@ -275,12 +349,14 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     e = g_batch.ensure(dev);
     if (e) return e;
     struct Slot {
-        uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
+        uint8_t* pack; int64_t* pk_off; uint8_t* pk_zero; uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
         int64_t* keep; int32_t* cnt; int32_t* rank; int32_t* bmax; int32_t* stat; uint8_t* surv; uint32_t* gidx; uint4* gval; void* ws;
     } slot[HB_SLOTS];
     for (int k = 0; k < NB; ++k) {
         Carver cv(hc.buf + slot_bytes * k);
         Slot& s = slot[k];
+        s.pack = nullptr; s.pk_off = nullptr; s.pk_zero = nullptr;
+        if (pack_mode) { s.pack = cv.take<uint8_t>(prm_max + 16); s.pk_off = cv.take<int64_t>(nn); s.pk_zero = cv.take<uint8_t>(nn); }
         s.vol = cv.take<uint8_t>(V); s.seg = cv.take<uint16_t>(V); s.dets = cv.take<float>(nn * 7); s.off = cv.take<int32_t>(2);
         s.boxes = cv.take<int32_t>(nn * 6); s.prm = cv.take<uint8_t>(prm_max + 16); s.mask = cv.take<uint8_t>(prm_max + 16);
         s.coff = cv.take<int64_t>(nn + 1); s.keep = cv.take<int64_t>(nn); s.cnt = cv.take<int32_t>(2); s.rank = cv.take<int32_t>(nn);
@@ -292,11 +368,19 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     for (int v = 0; v < n_volumes; ++v) small_bytes += align_up(16 + 13 * (size_t)n_dets[v], 16);
     small_bytes = align_up(small_bytes, 256);
     const size_t stage_bytes = align_up(cap * 4, 256) + align_up(cap * 16, 256);
-    e = g_batch.ensure_pinned(small_bytes + stage_bytes * NB);
+    // packed-image mode, per slot: [keep count | pad to 16 | visit order n*4] [offsets n*8 | all-zero-PRM flags n] [packed crops]
+    const size_t nmsst_bytes = align_up(16 + nn * 4, 256), pkoff_bytes = align_up(nn * 8, 256) + align_up(nn, 256);
+    const size_t pack_bytes = pack_mode ? nmsst_bytes + pkoff_bytes + align_up(prm_max + 16, 256) : 0;
+    e = g_batch.ensure_pinned(small_bytes + (stage_bytes + pack_bytes) * NB);
     if (e) return e;
     g_pool.ensure();
+    if (pack_mode) g_pack_pool.ensure();
+    char* const pack_base = g_batch.pinned + small_bytes + stage_bytes * NB;
 
-    cudaStream_t s_in = g_batch.in, s_comp = hc.stream, s_out = g_batch.out, s_out2 = g_batch.out2;
+    cudaStream_t s_in = g_batch.in, s_out = g_batch.out, s_out2 = g_batch.out2;
+    // the kernels of one volume are small (a dozen launches of a few hundred CTAs): volumes rotate over three compute streams
+    // so that the chains of consecutive volumes overlap on the GPU
+    const cudaStream_t comp_streams[3] = {hc.stream, g_batch.comp2, g_batch.comp3};
     // host-side state shared with the pool (kept alive until every job has run)
     struct Shared {
         std::vector<std::atomic<int>> zero_left;                  // per volume: zero-fill parts still running
@@ -349,7 +433,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
     const auto t_start = now();
-    double w_cnt = 0, w_slot = 0, w_out = 0, w_zero = 0, w_tail = 0;
+    double w_cnt = 0, w_slot = 0, w_out = 0, w_zero = 0, w_tail = 0, w_nms = 0, w_pack = 0;
     std::vector<int32_t> offs(2 * (size_t)n_volumes);            // per-volume {0, n} pairs, alive until the copies have run
     for (int v = 0; v < n_volumes; ++v) { offs[2 * v] = 0; offs[2 * v + 1] = n_dets[v]; }
     std::vector<size_t> small_off(n_volumes);
@@ -358,18 +442,24 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     unsigned long long h2d = 0, d2h = 0;
     int rc = 0;
 #define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
-    for (int step = 0; step < n_volumes + HB_LAG_B; ++step) {
-        // ---- enqueue volume `step`: uploads, chain, compaction, download of the bookkeeping ------------------------
+    const int lag_n = pack_mode ? HB_LAG_N : 0;               // stage A (NMS) runs lag_n volumes ahead of stage B, stage P lag_n - 1
+    std::atomic<int> pack_left[HB_SLOTS];                       // packing jobs of the slot's volume still running
+    int pack_kc[HB_SLOTS] = {};
+    size_t pack_total[HB_SLOTS] = {};
+    for (int k = 0; k < HB_SLOTS; ++k) pack_left[k].store(0);
+    for (int step = 0; step < n_volumes + lag_n + HB_LAG_B; ++step) {
+        // ---- stage A, volume `step`: uploads of the small arrays (and of the volume unless it travels packed), NMS -------
         if (step < n_volumes) {
             const int v = step, k = v % NB;
+            const cudaStream_t s_comp = pack_mode ? g_batch.nms : comp_streams[v % 3];   // (stage A only enqueues the NMS)
             Slot& s = slot[k];
             const int n = n_dets[v];
             const size_t pbytes = n > 0 ? (size_t)crop_off[v][n] : 0;
             const uint8_t* prm_mapped = (n > 0 && (mode & 2)) ? mapped_device_pointer(prm[v]) : nullptr;
             if (v >= NB) B200_BATCH(cudaStreamWaitEvent(s_in, g_batch.out_done[k], 0));     // slot free again
-            B200_BATCH(cudaMemcpyAsync(s.vol, volumes[v], V, cudaMemcpyHostToDevice, s_in));
+            if (!pack_mode && n > 0) { B200_BATCH(cudaMemcpyAsync(s.vol, volumes[v], V, cudaMemcpyHostToDevice, s_in)); h2d += V; }
             B200_BATCH(cudaMemcpyAsync(s.off, offs.data() + 2 * v, 8, cudaMemcpyHostToDevice, s_in));
-            h2d += V + 8;
+            h2d += 8;
             if (n > 0) {
                 B200_BATCH(cudaMemcpyAsync(s.dets, dets[v], (size_t)n * 28, cudaMemcpyHostToDevice, s_in));
                 B200_BATCH(cudaMemcpyAsync(s.boxes, boxes[v], (size_t)n * 24, cudaMemcpyHostToDevice, s_in));
@@ -384,12 +474,114 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 const SomaChainWs L = soma_chain_ws(s.ws, ws_bytes, 1, n, S, H, W, cc_bytes);
                 int ce = b200seg_nms3d_dev(s.dets, s.off, 1, n, nms_thresh, 0, s.keep, s.cnt, s.rank, L.nms_ws, L.nms_ws_bytes, s_comp);
                 if (ce) { rc = ce; goto done; }
-                if (prm_mapped) {
-                    prm_gather_kernel<<<n, 256, 0, s_comp>>>(prm_mapped, s.prm, s.coff, s.rank, s.cnt);
+            }
+            if (pack_mode) B200_BATCH(cudaEventRecord(g_batch.nmsc_done[k], s_comp));
+            if (pack_mode && n > 0) {                         // the visit order comes back right away: the host packs by it
+                char* nst = pack_base + pack_bytes * k;
+                B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.nmsc_done[k], 0));
+                B200_BATCH(cudaMemcpyAsync(nst, s.cnt, 4, cudaMemcpyDeviceToHost, s_out));
+                B200_BATCH(cudaMemcpyAsync(nst + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+                B200_BATCH(cudaEventRecord(g_batch.nms_done[k], s_out));
+                d2h += 4 + (size_t)n * 4;
+            }
+        }
+        // ---- stage P, volume `step - lag_n + 1`: its visit order is back -> hand the packing of its image crops to the pool ----
+        const int sp = step - lag_n + 1;
+        if (pack_mode && sp >= 0 && sp < n_volumes && n_dets[sp] > 0) {
+            const int v = sp, k = v % NB;
+            const int n = n_dets[v];
+            char* nst = pack_base + pack_bytes * k;
+            int64_t* pko = (int64_t*)(nst + nmsst_bytes);
+            uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+            uint8_t* pk = (uint8_t*)(nst + nmsst_bytes + pkoff_bytes);
+            // the previous user of this slot's pinned buffers was volume v - NB: its copies were issued long ago; make sure they are done
+            if (v >= NB) B200_BATCH(cudaEventSynchronize(g_batch.pack_done[k]));
+            { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.nms_done[k])); w_nms += ms_since(t); }
+            int32_t kc = 0;
+            memcpy(&kc, nst, 4);
+            if (kc > n) kc = n;
+            if (kc < 0) kc = 0;
+            const int32_t* ro = (const int32_t*)(nst + 16);
+            size_t total = 0;
+            for (int r = 0; r < kc; ++r) { pko[r] = (int64_t)total; total += (size_t)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]); }
+            pack_kc[k] = kc; pack_total[k] = total;
+            const int njobs = kc < 1 ? 0 : (kc < 4 * g_pack_pool.n_threads ? (kc + 3) / 4 : g_pack_pool.n_threads * 2);
+            pack_left[k].store(njobs);
+            const uint8_t* vol = volumes[v];
+            const uint8_t* prm_h = prm[v];
+            const int64_t* co = crop_off[v];
+            const int32_t* bxs = boxes[v];
+            std::atomic<int>* left = &pack_left[k];
+            for (int j = 0; j < njobs; ++j) {
+                const int r0 = (int)((long long)kc * j / njobs), r1 = (int)((long long)kc * (j + 1) / njobs);
+                g_pack_pool.push([=] {
+                    for (int r = r0; r < r1; ++r) {
+                        const int i = ro[r];
+                        const int32_t* bx = bxs + (size_t)i * 6;
+                        const int sx = bx[3] - bx[0] + 1, sy = bx[4] - bx[1] + 1, sz = bx[5] - bx[2] + 1;
+                        pkz[r] = 1;
+                        if (sx <= 0 || sy <= 0 || sz <= 0) continue;
+                        // skipped by the script (no positive PRM voxel): its image is never read, nothing to pack
+                        const uint8_t* pc = prm_h + co[i];
+                        const size_t pn = (size_t)(co[i + 1] - co[i]);
+                        size_t q = 0;
+                        unsigned long long acc = 0;
+                        for (; q + 8 <= pn && !acc; q += 8) { unsigned long long w; memcpy(&w, pc + q, 8); acc |= w; }
+                        for (; q < pn && !acc; ++q) acc |= pc[q];
+                        pkz[r] = acc ? 0 : 1;
+                        if (!acc) continue;
+                        uint8_t* d = pk + pko[r];
+                        for (int z = 0; z < sz; ++z) {
+                            const uint8_t* row = vol + ((size_t)(bx[2] + z) * H + bx[1]) * W + bx[0];
+                            for (int y = 0; y < sy; ++y, row += W, d += sx) memcpy(d, row, (size_t)sx);
+                        }
+                    }
+                    left->fetch_sub(1, std::memory_order_release);
+                });
+            }
+        }
+        const int sb = step - lag_n;
+        // ---- stage B, volume `sb`: (packed image crops,) PRM gather, chain, compaction, download of the bookkeeping -------
+        if (sb >= 0 && sb < n_volumes) {
+            const int v = sb, k = v % NB;
+            const cudaStream_t s_comp = comp_streams[v % 3];
+            Slot& s = slot[k];
+            const int n = n_dets[v];
+            const size_t pbytes = n > 0 ? (size_t)crop_off[v][n] : 0;
+            const uint8_t* prm_mapped = (n > 0 && (mode & 2)) ? mapped_device_pointer(prm[v]) : nullptr;
+            if (pack_mode) B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.nmsc_done[k], 0));   // the NMS ran on its own stream
+            const uint8_t* zero_flags = nullptr;
+            if (pack_mode && n > 0) {
+                char* nst = pack_base + pack_bytes * k;
+                int64_t* pko = (int64_t*)(nst + nmsst_bytes);
+                uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+                uint8_t* pk = (uint8_t*)(nst + nmsst_bytes + pkoff_bytes);
+                { const auto tp = now(); while (pack_left[k].load(std::memory_order_acquire) > 0) sched_yield(); w_pack += ms_since(tp); }
+                const int kc = pack_kc[k];
+                if (kc > 0) {
+                    B200_BATCH(cudaMemcpyAsync(s.pk_off, pko, (size_t)kc * 8, cudaMemcpyHostToDevice, s_in));
+                    B200_BATCH(cudaMemcpyAsync(s.pk_zero, pkz, (size_t)kc, cudaMemcpyHostToDevice, s_in));
+                    B200_BATCH(cudaMemcpyAsync(s.pack, pk, pack_total[k], cudaMemcpyHostToDevice, s_in));
+                    h2d += (size_t)kc * 9 + pack_total[k];
+                    zero_flags = s.pk_zero;
+                }
+                B200_BATCH(cudaEventRecord(g_batch.pack_done[k], s_in));
+                B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.pack_done[k], 0));
+                if (kc > 0) {
+                    img_unpack_kernel<<<n, 256, 0, s_comp>>>(s.pack, s.pk_off, s.pk_zero, s.vol, H, W, s.boxes, s.rank, s.cnt);
                     count_launch();
                     B200_BATCH(cudaGetLastError());
                 }
-                ce = postproc_soma_after_nms(s.vol, 1, S, H, W, s.off, n, n, s.boxes, s.prm, s.coff, (long long)pbytes, keep_largest_cc,
+            }
+            if (prm_mapped) {                                 // PRM crops of the survivors, fetched in place (zero fill where the host saw only zeros)
+                prm_gather_kernel<<<n, 256, 0, s_comp>>>(prm_mapped, s.prm, s.coff, s.rank, s.cnt, zero_flags);
+                count_launch();
+                B200_BATCH(cudaGetLastError());
+            }
+            {
+                const long long cc_bytes = keep_largest_cc ? (long long)pbytes : 0;
+                const SomaChainWs L = soma_chain_ws(s.ws, ws_bytes, 1, n, S, H, W, cc_bytes);
+                int ce = postproc_soma_after_nms(s.vol, 1, S, H, W, s.off, n, n, s.boxes, s.prm, s.coff, (long long)pbytes, keep_largest_cc,
                                              s.seg, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, L.ids, L.paste_ws, L.paste_ws_bytes,
                                              L.cc_ws, L.cc_ws_bytes, s_comp);
                 if (ce) { rc = ce; goto done; }
@@ -418,9 +610,9 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             }
             B200_BATCH(cudaEventRecord(g_batch.cnt_done[k], s_out));
         }
-        // ---- volume `step - HB_LAG_A`: its group count is known -> size and enqueue the download of the label data --------
-        if (step >= HB_LAG_A && step - HB_LAG_A < n_volumes) {
-            const int v = step - HB_LAG_A, k = v % NB;
+        // ---- volume `sb - HB_LAG_A`: its group count is known -> size and enqueue the download of the label data --------
+        if (sb >= HB_LAG_A && sb - HB_LAG_A < n_volumes) {
+            const int v = sb - HB_LAG_A, k = v % NB;
             Slot& s = slot[k];
             { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.cnt_done[k])); w_cnt += ms_since(t); }
             uint32_t ng = 0xFFFFFFFFu;
@@ -444,12 +636,14 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 int32_t kc = 0;
                 memcpy(&kc, g_batch.pinned + small_off[v], 4);
                 const int32_t* ro = (const int32_t*)(g_batch.pinned + small_off[v] + 16);
-                for (int r = 0; r < kc && r < n; ++r) h2d += (unsigned long long)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]);
+                const uint8_t* pkz = pack_mode ? (const uint8_t*)(pack_base + pack_bytes * k + nmsst_bytes + align_up(nn * 8, 256)) : nullptr;
+                for (int r = 0; r < kc && r < n; ++r)
+                    if (!pkz || !pkz[r]) h2d += (unsigned long long)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]);
             }
         }
-        // ---- volume `step - HB_LAG_B`: its download has been enqueued one step ago -> wait for it, hand it to the pool ----
-        if (step >= HB_LAG_B) {
-            const int v = step - HB_LAG_B, k = v % NB;
+        // ---- volume `sb - HB_LAG_B`: its download has been enqueued one step ago -> wait for it, hand it to the pool ----
+        if (sb >= HB_LAG_B && sb - HB_LAG_B < n_volumes) {
+            const int v = sb - HB_LAG_B, k = v % NB;
             const uint32_t ng = n_groups[v];
             if (ng == 0 && out_state == 2) {                                    // all-zero result: nothing to clear next time
                 std::lock_guard<std::mutex> lk(g_prev_mu);
@@ -485,9 +679,13 @@ done:
 #undef B200_BATCH
     {
         // drain all three streams even on error: the slots, `offs` and the staging must not be reused while copies are in flight
-        const cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_comp), e3 = cudaStreamSynchronize(s_out),
+        cudaError_t e2 = cudaStreamSynchronize(comp_streams[0]);
+        for (int q = 1; q < 3; ++q) { const cudaError_t eq = cudaStreamSynchronize(comp_streams[q]); if (e2 == cudaSuccess) e2 = eq; }
+        { const cudaError_t eq = cudaStreamSynchronize(g_batch.nms); if (e2 == cudaSuccess) e2 = eq; }
+        const cudaError_t e1 = cudaStreamSynchronize(s_in), e3 = cudaStreamSynchronize(s_out),
                           e4 = cudaStreamSynchronize(s_out2);
         const auto t_tail = now();
+        for (int k = 0; k < HB_SLOTS; ++k) while (pack_left[k].load(std::memory_order_acquire) > 0) sched_yield();   // (only after an error)
         while (sh->pending.load(std::memory_order_acquire) > 0) sched_yield();
         w_tail = ms_since(t_tail);
         delete sh;
@@ -518,8 +716,8 @@ done:
         g_last_d2h.store(d2h);
         if (trace)
             fprintf(stderr, "[b200seg host_batch] %d volumes, %d pool threads: %.2f ms; host waits: group count %.2f, staging slot %.2f, "
-                            "download %.2f, zero fill (dense) %.2f, pool tail %.2f ms; up %.1f MB, down %.1f MB\n",
-                    n_volumes, g_pool.n_threads, ms_since(t_start), w_cnt, w_slot, w_out, w_zero, w_tail, h2d / 1e6, d2h / 1e6);
+                            "download %.2f, zero fill (dense) %.2f, pool tail %.2f, visit order %.2f, packing %.2f ms; up %.1f MB, down %.1f MB\n",
+                    n_volumes, g_pool.n_threads, ms_since(t_start), w_cnt, w_slot, w_out, w_zero, w_tail, w_nms, w_pack, h2d / 1e6, d2h / 1e6);
     }
     return rc;
 }

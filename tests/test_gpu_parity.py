@@ -412,10 +412,11 @@ def test_postproc_host_batch_output_states(b2):
         set_host_batch_out(3)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 7])
 def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
     """Every transfer scheme of the batch entry point (dense / compacted label download x whole-array / gathered PRM
-    upload) returns the same outputs; pinned inputs make the zero-copy gather path eligible, a volume whose size is
+    upload; mode 7 also sends the image crops of the NMS survivors packed by host threads instead of the volume) returns
+    the same outputs; pinned inputs make the zero-copy gather path eligible, a volume whose size is
     not a multiple of 8 voxels and an odd-aligned PRM buffer exercise the fallbacks."""
     from b200seg import synth
     from b200seg.binarization import set_host_batch_mode, host_batch_traffic
@@ -442,7 +443,7 @@ def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
         outs = b2.postproc_soma_host_batch(pinned, 0.23, seg_out=segs)
         h2d, d2h = host_batch_traffic()
     finally:
-        set_host_batch_mode(3)
+        set_host_batch_mode(7)
     dense_down = sum(c["volume"].size * 2 for c in cases)
     full_up = sum(c["volume"].size + c["prm"].size for c in cases)
     assert (d2h < dense_down // 2) if (mode & 1) else (d2h >= dense_down)
