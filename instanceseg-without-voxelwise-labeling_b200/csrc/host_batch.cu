@@ -1,18 +1,23 @@
 // host_batch.cu -- HOST-buffer entry point of the binarization chain for a BATCH of equally shaped volumes
 // (tools/binarization_soma.py:57-104 per volume; the per-volume loop of tools/my_subprocess.py:56).
 //
-// The reference hands numpy arrays in and gets the uint16 label volume back, so the PCIe link and the host memory bound
-// this entry point, not the kernels (a few percent of a transfer).  Round-2 layout, per volume:
-//   up     the raw volume and the small per-detection arrays travel by DMA (stream `in`); the packed PRM crops do NOT:
-//          the NMS runs first and a gather kernel then pulls only the crops of its survivors straight out of the
-//          caller's pinned buffer over the link (zero copy; pageable or unaligned buffers fall back to a plain copy);
-//   device NMS -> gather -> binarize -> largest component -> paste (stream `comp`), then the label volume is compacted
-//          into its non-zero 16-byte groups (8 voxels): group index + payload, a few percent of the volume;
-//   down   only the compacted groups and the per-detection bookkeeping travel (stream `out`); a pool of host threads
-//          zero-fills the caller's label volumes while the GPU works and scatters the groups into them.
-//          A volume whose labels cover more than an eighth of the groups is copied densely instead.
-// Six device slots; the host thread sizes the download of a volume (it needs the group count) two volumes after it has
-// enqueued its upload, so that the upload queue never runs dry, and hands finished downloads to the pool one volume later.
+// The reference hands numpy arrays in and gets the uint16 label volume back, so the PCIe link, the host memory and the
+// latency of a dozen small launches per volume bound this entry point, not the kernels.  Layout, per volume:
+//   stage A  (four volumes ahead) the small per-detection arrays travel by DMA, the NMS runs on its own high-priority stream
+//            and its visit order comes straight back (a few hundred bytes);
+//   stage P  (one step before the chain) a pool of host threads packs the image crops of the NMS survivors that have a
+//            positive PRM voxel -- the only voxels of the raw volume the chain ever reads -- into a pinned buffer
+//            ("host_batch_mode" bit 2; without it the whole 33.5 MB volume travels by DMA);
+//   stage B  the packed crops travel by DMA and an unpack kernel restores their rows in the device volume; the PRM crops of
+//            the same survivors are pulled straight out of the caller's pinned buffer by a gather kernel (zero copy; all-zero
+//            crops are zero-filled on the device instead; pageable or unaligned buffers fall back to a plain copy); then
+//            binarize -> largest component -> paste, and the label volume is compacted into its non-zero 16-byte groups
+//            (8 voxels): group index + payload, a few percent of the volume.  Volumes rotate over three compute streams;
+//   down     only the compacted groups and the per-detection bookkeeping travel; a second pool of host threads prepares the
+//            caller's label volumes (zero fill, or nothing / an undo list: "host_batch_out") and scatters the groups.
+//            A volume whose labels cover more than an eighth of the groups is copied densely instead.
+// Eight device slots; the host thread sizes the download of a volume (it needs the group count) two volumes after it has
+// enqueued its chain and hands finished downloads to the pool one volume later.
 #include "common.cuh"
 
 #include <atomic>
@@ -186,7 +191,7 @@ struct HostPool {
             if (hw <= 0) hw = 4;
             int share = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;   // ranks of one box share its cores
-            want = hw / share;
+            want = hw / share / 2;                                  // two pools (fill / scatter and packing) share the cores
             if (want > cap) want = cap;
             if (want < 2) want = 2;
         }
