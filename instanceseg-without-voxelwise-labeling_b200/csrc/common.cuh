@@ -85,12 +85,20 @@ struct SomaChainWs {
     char* cc_ws; size_t cc_ws_bytes;
     char* nms_ws; size_t nms_ws_bytes;
 };
+// optional second output of the paste kernel: the non-zero 64-byte lines of the (single) label volume (paste.cu)
+struct PasteLines { uint32_t* idx; uint4* val; uint32_t* count; uint32_t cap; };
+bool paste_lines_supported(const uint16_t* seg, int n_volumes, int S, int H, int W);
+int paste_labels_launch(uint16_t* seg, int n_volumes, int S, int H, int W, const int32_t* det_off, int n_max, const int32_t* boxes,
+                        const uint16_t* ids, const uint8_t* masks, const int64_t* mask_off, const int32_t* order,
+                        const int32_t* n_valid, uint8_t* survive, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                        const PasteLines* lines);
 SomaChainWs soma_chain_ws(void* workspace, size_t workspace_bytes, int n_volumes, int n_max, int S, int H, int W, long long cc_bytes);
 int postproc_soma_after_nms(const uint8_t* volumes, int n_volumes, int S, int H, int W, const int32_t* det_off_dev, int n_max,
                             int total, const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, long long prm_bytes,
                             int keep_largest_cc, uint16_t* seg, const int32_t* keep_count, const int32_t* rank_order,
                             uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive, uint16_t* ids,
-                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream);
+                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream,
+                            const PasteLines* lines = nullptr);
 
 // ---- device helpers -------------------------------------------------------------------------
 

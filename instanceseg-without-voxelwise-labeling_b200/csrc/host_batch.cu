@@ -11,11 +11,11 @@
 //   stage B  the packed crops travel by DMA and an unpack kernel restores their rows in the device volume; the PRM crops of
 //            the same survivors are pulled straight out of the caller's pinned buffer by a gather kernel (zero copy; all-zero
 //            crops are zero-filled on the device instead; pageable or unaligned buffers fall back to a plain copy); then
-//            binarize -> largest component -> paste, and the label volume is compacted into its non-zero 16-byte groups
-//            (8 voxels): group index + payload, a few percent of the volume.  Volumes rotate over three compute streams;
-//   down     only the compacted groups and the per-detection bookkeeping travel; a second pool of host threads prepares the
-//            caller's label volumes (zero fill, or nothing / an undo list: "host_batch_out") and scatters the groups.
-//            A volume whose labels cover more than an eighth of the groups is copied densely instead.
+//            binarize -> largest component -> paste, and the label volume is compacted into its non-zero 64-byte lines
+//            (32 voxels): line index + payload, a few percent of the volume.  Volumes rotate over three compute streams;
+//   down     only the compacted lines and the per-detection bookkeeping travel; the pool of host threads prepares the
+//            caller's label volumes (zero fill, or nothing / an undo list: "host_batch_out") and writes the lines with
+//            full-line non-temporal stores.  A volume whose labels cover more than a quarter of the lines is copied densely.
 // Eight device slots; the host thread sizes the download of a volume (it needs the group count) two volumes after it has
 // enqueued its chain and hands finished downloads to the pool one volume later.
 #include "common.cuh"
@@ -39,8 +39,11 @@
 namespace b200seg {
 
 // ---- device side -------------------------------------------------------------------------------------------------
-// non-zero 16-byte groups of the label volume, unordered: idx_out[k] = group index, val_out[k] = its 8 labels.
-// `count` keeps counting past `cap` (the host then takes the dense path).
+// non-zero 64-byte lines of the label volume (4 consecutive 16-byte groups = 32 labels), unordered: idx_out[k] = line index,
+// val_out[4k .. 4k+3] = its groups (groups past the end of the volume read as zero).  A line is the unit the host writes with
+// full-line non-temporal stores: no read-for-ownership of the destination, which is what bounded the 16-byte scatter of
+// round 2.  Loads stay coalesced (lane = group); the four lanes of a quad own one line (base and the 256-group stride are
+// multiples of 4).  `count` keeps counting past `cap` (the host then takes the dense path).
 __global__ void __launch_bounds__(256)
 seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned int cap,
                    uint32_t* __restrict__ idx_out, uint4* __restrict__ val_out, uint32_t* __restrict__ count) {
@@ -59,11 +62,16 @@ seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned
             const bool nz = (v[j].x | v[j].y | v[j].z | v[j].w) != 0u;
             const unsigned int m = __ballot_sync(0xffffffffu, nz);
             if (m == 0u) continue;                                  // warp-uniform
+            const unsigned int lm = (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u;     // bit 4q: quad q holds a non-zero line
             unsigned int b = 0;
-            if (lane == 0) b = atomicAdd(count, (unsigned int)__popc(m));
+            if (lane == 0) b = atomicAdd(count, (unsigned int)__popc(lm));
             b = __shfl_sync(0xffffffffu, b, 0);
-            const unsigned int pos = b + __popc(m & ((1u << lane) - 1u));
-            if (nz && pos < cap) { idx_out[pos] = gi[j]; val_out[pos] = v[j]; }
+            const unsigned int q0 = lane & ~3u;
+            const unsigned int pos = b + __popc(lm & ((1u << q0) - 1u));
+            if (((lm >> q0) & 1u) && pos < cap) {
+                if ((lane & 3u) == 0u) idx_out[pos] = gi[j] >> 2;
+                val_out[(size_t)pos * 4 + (lane & 3u)] = v[j];
+            }
         }
     }
 }
@@ -172,18 +180,22 @@ static void zero_stream(char* dst, size_t bytes) {
 }
 
 // ---- host side: worker pool -------------------------------------------------------------------------------------
+// One pool, two queues.  The crop packing jobs (short, on the critical path of the uploads) go to the urgent queue and
+// are always taken first; zero fills, clears and scatters of the label volumes go to the normal queue.  Every thread
+// serves both, so no core idles while the other kind of work is queued (round 2 had two pools of half the cores each).
 struct HostPool {
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<std::function<void()>> q;
+    std::deque<std::function<void()>> q, q_urgent;
     int n_threads = 0;
-    int cap = 16;
+    int cap = 32;
     pid_t pid = 0;
     void ensure() {
         std::lock_guard<std::mutex> lk(mu);
         if (n_threads > 0 && pid == getpid()) return;              // a forked child starts its own threads
         pid = getpid();
         q.clear();
+        q_urgent.clear();
         int want = 0;
         if (const char* e = getenv("B200SEG_HOST_THREADS")) want = atoi(e);
         if (want <= 0) {
@@ -191,7 +203,11 @@ struct HostPool {
             if (hw <= 0) hw = 4;
             int share = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;   // ranks of one box share its cores
-            want = hw / share / 2;                                  // two pools (fill / scatter and packing) share the cores
+            // One core stays with the thread that drives the GPU.  Beyond a handful of cores a quarter is left idle: with every
+            // core streaming label lines the zero-copy PRM reads of the GPU slow down (15 threads of a 16-core box: 66 Gvox/s,
+            // 8 threads: 73 Gvox/s through this entry point).
+            const int per = hw / share;
+            want = per <= 4 ? per - 1 : per * 3 / 4;
             if (want > cap) want = cap;
             if (want < 2) want = 2;
         }
@@ -203,24 +219,104 @@ struct HostPool {
             std::function<void()> job;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [this] { return !q.empty(); });
-                job = std::move(q.front());
-                q.pop_front();
+                cv.wait(lk, [this] { return !q.empty() || !q_urgent.empty(); });
+                std::deque<std::function<void()>>& src = q_urgent.empty() ? q : q_urgent;
+                job = std::move(src.front());
+                src.pop_front();
             }
             job();
         }
     }
-    void push(std::function<void()> f) {
-        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+    void push(std::function<void()> f, bool urgent = false) {
+        { std::lock_guard<std::mutex> lk(mu); (urgent ? q_urgent : q).push_back(std::move(f)); }
         cv.notify_one();
     }
 };
 // never destroyed: its threads are detached and wait on the condition variable until the process ends (destroying a
 // condition variable with waiters blocks in glibc)
 static HostPool& g_pool = *new HostPool;
-static HostPool& g_pack_pool = *new HostPool;      // packs image crops: short jobs that must not queue behind the zero fills
 
-constexpr int HB_SLOTS = 8;
+// ---- host side: the three loops the pool threads spend their time in ---------------------------------------------------
+// The packing touches one or two cache lines at a time at addresses the hardware prefetchers cannot guess (box rows of a
+// 33 MB volume), so it requests its lines a fixed distance ahead; the label loops write whole lines past the caches.
+constexpr int HB_PF_ROWS = 12;         // image rows requested ahead of the copy
+
+static inline void copy_row(uint8_t* d, const uint8_t* s, int n) {
+#if defined(__x86_64__)
+    if (n >= 16 && n <= 32) {                                       // the common box widths: two overlapping 16-byte moves
+        const __m128i a = _mm_loadu_si128((const __m128i*)s), b = _mm_loadu_si128((const __m128i*)(s + n - 16));
+        _mm_storeu_si128((__m128i*)d, a); _mm_storeu_si128((__m128i*)(d + n - 16), b);
+        return;
+    }
+    if (n > 32 && n <= 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)s), b = _mm_loadu_si128((const __m128i*)(s + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + n - 32)), e = _mm_loadu_si128((const __m128i*)(s + n - 16));
+        _mm_storeu_si128((__m128i*)d, a); _mm_storeu_si128((__m128i*)(d + 16), b);
+        _mm_storeu_si128((__m128i*)(d + n - 32), c); _mm_storeu_si128((__m128i*)(d + n - 16), e);
+        return;
+    }
+    if (n >= 8 && n < 16) {
+        uint64_t a, b;
+        memcpy(&a, s, 8); memcpy(&b, s + n - 8, 8);
+        memcpy(d, &a, 8); memcpy(d + n - 8, &b, 8);
+        return;
+    }
+#endif
+    memcpy(d, s, (size_t)n);
+}
+
+// box rows (sz x sy rows of sx bytes, origin `base`, row pitch W, plane pitch HW) -> d, back to back
+static void pack_box_rows(uint8_t* d, const uint8_t* base, int sx, int sy, int sz, size_t W, size_t HW) {
+    int pz = 0, py = 0;                                             // cursor of the prefetch, HB_PF_ROWS rows ahead of the copy
+    auto request = [&] {
+        if (pz >= sz) return;
+        const uint8_t* r = base + (size_t)pz * HW + (size_t)py * W;
+        __builtin_prefetch(r, 0, 3);
+        __builtin_prefetch(r + sx - 1, 0, 3);
+        if (++py == sy) { py = 0; ++pz; }
+    };
+    for (int i = 0; i < HB_PF_ROWS; ++i) request();
+    for (int z = 0; z < sz; ++z) {
+        const uint8_t* row = base + (size_t)z * HW;
+        for (int y = 0; y < sy; ++y, row += W, d += sx) { request(); copy_row(d, row, sx); }
+    }
+}
+
+// line `li` of a label volume of `vbytes` bytes: 64 bytes, except the last one of a volume that is not a multiple of 64 bytes
+static inline void put_line(char* dst, size_t vbytes, uint32_t li, const char* src, bool aligned) {
+    const size_t off = (size_t)li * 64;
+    if (off >= vbytes) return;
+    const size_t n = vbytes - off < 64 ? vbytes - off : 64;
+#if defined(__x86_64__)
+    if (aligned && n == 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)src), b = _mm_loadu_si128((const __m128i*)(src + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(src + 32)), d = _mm_loadu_si128((const __m128i*)(src + 48));
+        __m128i* o = (__m128i*)(dst + off);
+        _mm_stream_si128(o, a); _mm_stream_si128(o + 1, b); _mm_stream_si128(o + 2, c); _mm_stream_si128(o + 3, d);
+        return;
+    }
+#endif
+    memcpy(dst + off, src, n);
+}
+static inline void fence_lines() {
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
+// The label volume is "zeros + the listed lines", so a listed line is cleared / written as a whole.
+static void clear_lines(char* dst, size_t vbytes, const uint32_t* li, uint32_t nl) {
+    alignas(16) static const char zeros[64] = {0};
+    const bool aligned = (((uintptr_t)dst) & 63) == 0;
+    for (uint32_t i = 0; i < nl; ++i) put_line(dst, vbytes, li[i], zeros, aligned);
+    fence_lines();
+}
+static void scatter_lines(char* dst, size_t vbytes, const uint32_t* li, const char* lv, uint32_t nl) {
+    const bool aligned = (((uintptr_t)dst) & 63) == 0;
+    for (uint32_t i = 0; i < nl; ++i) put_line(dst, vbytes, li[i], lv + (size_t)i * 64, aligned);
+    fence_lines();
+}
+
+constexpr int HB_SLOTS = 12;
 constexpr int HB_LAG_A = 2;            // the download of volume v is sized and enqueued while volume v + HB_LAG_A is being enqueued
 constexpr int HB_LAG_B = 3;            // ... and handed to the pool one step later
 constexpr int HB_ZERO_PARTS = 4;
@@ -280,8 +376,8 @@ static std::atomic<unsigned long long> g_last_h2d{0}, g_last_d2h{0};
 
 // "host_batch_out" = 2: the caller's label buffer still holds the result this entry point wrote into it last time, so
 // instead of zero-filling all of it (2 bytes per voxel of host memory traffic, the bound of the whole call) only the
-// non-zero 16-byte groups written last time are cleared.  Keyed by the buffer address; an entry is dropped whenever the
-// content of the buffer is not exactly "zeros + the listed groups" (dense download, error, different size).
+// non-zero 64-byte lines written last time are cleared.  Keyed by the buffer address; an entry is dropped whenever the
+// content of the buffer is not exactly "zeros + the listed lines" (dense download, error, different size).
 struct PrevLabels { size_t bytes = 0; std::vector<uint32_t> groups; };
 static std::mutex g_prev_mu;
 static std::unordered_map<const void*, PrevLabels>& g_prev = *new std::unordered_map<const void*, PrevLabels>;
@@ -332,18 +428,19 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     const size_t nn = n_max > 0 ? n_max : 1;
     const size_t ws_bytes = b200seg_postproc_soma_workspace_bytes(1, n_max, S, H, W, keep_largest_cc ? (long long)prm_max : 0);
     const int NB = n_volumes < HB_SLOTS ? n_volumes : HB_SLOTS;
-    // compacted form: only when the volume splits into whole 16-byte groups
+    // compacted form: only when the volume splits into whole 16-byte groups (the kernel loads them as uint4)
     const int mode = opt_host_batch_mode();
     const bool sparse = (V % 8) == 0 && (mode & 1);
     const size_t ngroups = V / 8;
-    size_t cap = ngroups / 8;
-    if (cap < 4096) cap = 4096;
-    if (cap > ngroups) cap = ngroups;
+    const size_t nlines = (ngroups + 3) / 4;                  // 64-byte lines (the last one may be partial)
+    size_t cap = nlines / 4;                                  // lines the compacted form may hold
+    if (cap < 16384) cap = 16384;
+    if (cap > nlines) cap = nlines;
     if (!sparse) cap = 0;
     const bool pack_mode = (mode & 4) != 0;                   // image crops of the NMS survivors packed by host threads, no DMA of the volume
     const size_t slot_bytes = (pack_mode ? Carver::need(prm_max + 16) + Carver::need(nn * 8) + Carver::need(nn) : 0) + Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
                               2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(8) +
-                              3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(cap * 4 + 16) + Carver::need(cap * 16 + 16) +
+                              3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(cap * 4 + 16) + Carver::need(cap * 64 + 64) +
                               Carver::need(ws_bytes);
     int e = hc.ensure(slot_bytes * NB);
     if (e) return e;
@@ -366,20 +463,19 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
         s.boxes = cv.take<int32_t>(nn * 6); s.prm = cv.take<uint8_t>(prm_max + 16); s.mask = cv.take<uint8_t>(prm_max + 16);
         s.coff = cv.take<int64_t>(nn + 1); s.keep = cv.take<int64_t>(nn); s.cnt = cv.take<int32_t>(2); s.rank = cv.take<int32_t>(nn);
         s.bmax = cv.take<int32_t>(nn); s.stat = cv.take<int32_t>(nn); s.surv = cv.take<uint8_t>(nn);
-        s.gidx = cv.take<uint32_t>(cap + 4); s.gval = cv.take<uint4>(cap + 1); s.ws = cv.p;
+        s.gidx = cv.take<uint32_t>(cap + 4); s.gval = cv.take<uint4>(cap * 4 + 4); s.ws = cv.p;
     }
-    // pinned staging: [per-volume bookkeeping] [per-slot group indices | group payloads]
+    // pinned staging: [per-volume bookkeeping] [per-slot line indices | line payloads]
     size_t small_bytes = 0;
     for (int v = 0; v < n_volumes; ++v) small_bytes += align_up(16 + 13 * (size_t)n_dets[v], 16);
     small_bytes = align_up(small_bytes, 256);
-    const size_t stage_bytes = align_up(cap * 4, 256) + align_up(cap * 16, 256);
+    const size_t stage_bytes = align_up(cap * 4, 256) + align_up(cap * 64, 256);
     // packed-image mode, per slot: [keep count | pad to 16 | visit order n*4] [offsets n*8 | all-zero-PRM flags n] [packed crops]
     const size_t nmsst_bytes = align_up(16 + nn * 4, 256), pkoff_bytes = align_up(nn * 8, 256) + align_up(nn, 256);
     const size_t pack_bytes = pack_mode ? nmsst_bytes + pkoff_bytes + align_up(prm_max + 16, 256) : 0;
     e = g_batch.ensure_pinned(small_bytes + (stage_bytes + pack_bytes) * NB);
     if (e) return e;
     g_pool.ensure();
-    if (pack_mode) g_pack_pool.ensure();
     char* const pack_base = g_batch.pinned + small_bytes + stage_bytes * NB;
 
     cudaStream_t s_in = g_batch.in, s_out = g_batch.out, s_out2 = g_batch.out2;
@@ -411,8 +507,9 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 sh->zero_left[v].store(1);
                 char* dst = (char*)seg[v];
                 sh->pending.fetch_add(1);
-                g_pool.push([sh, v, dst, prev] {
-                    for (uint32_t gi : *prev) memset(dst + (size_t)gi * 16, 0, 16);
+                const size_t vbytes0 = V * 2;
+                g_pool.push([sh, v, dst, prev, vbytes0] {
+                    clear_lines(dst, vbytes0, prev->data(), (uint32_t)prev->size());
                     delete prev;
                     sh->zero_left[v].fetch_sub(1, std::memory_order_release);
                     sh->pending.fetch_sub(1, std::memory_order_release);
@@ -452,7 +549,12 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     int pack_kc[HB_SLOTS] = {};
     size_t pack_total[HB_SLOTS] = {};
     for (int k = 0; k < HB_SLOTS; ++k) pack_left[k].store(0);
-    for (int step = 0; step < n_volumes + lag_n + HB_LAG_B; ++step) {
+    // chains in flight on the GPU: the host sizes the download of volume v (it needs its line count) while it enqueues volume
+    // v + lag_a, so lag_a + 1 chains can be queued before the host has to wait for one of them
+    static const int lag_env = getenv("B200SEG_HB_LAG") ? atoi(getenv("B200SEG_HB_LAG")) : 0;
+    const int lag_a = lag_env >= 1 && lag_env <= 6 ? lag_env : HB_LAG_A, lag_b = lag_a + (HB_LAG_B - HB_LAG_A);
+    static_assert(HB_LAG_N + 6 + (HB_LAG_B - HB_LAG_A) + 1 <= HB_SLOTS, "a slot must be free again before its next volume arrives");
+    for (int step = 0; step < n_volumes + lag_n + lag_b; ++step) {
         // ---- stage A, volume `step`: uploads of the small arrays (and of the volume unless it travels packed), NMS -------
         if (step < n_volumes) {
             const int v = step, k = v % NB;
@@ -510,7 +612,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             size_t total = 0;
             for (int r = 0; r < kc; ++r) { pko[r] = (int64_t)total; total += (size_t)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]); }
             pack_kc[k] = kc; pack_total[k] = total;
-            const int njobs = kc < 1 ? 0 : (kc < 4 * g_pack_pool.n_threads ? (kc + 3) / 4 : g_pack_pool.n_threads * 2);
+            const int njobs = kc < 1 ? 0 : (kc < 4 * g_pool.n_threads ? (kc + 3) / 4 : g_pool.n_threads * 2);
             pack_left[k].store(njobs);
             const uint8_t* vol = volumes[v];
             const uint8_t* prm_h = prm[v];
@@ -519,7 +621,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             std::atomic<int>* left = &pack_left[k];
             for (int j = 0; j < njobs; ++j) {
                 const int r0 = (int)((long long)kc * j / njobs), r1 = (int)((long long)kc * (j + 1) / njobs);
-                g_pack_pool.push([=] {
+                g_pool.push([=] {
                     for (int r = r0; r < r1; ++r) {
                         const int i = ro[r];
                         const int32_t* bx = bxs + (size_t)i * 6;
@@ -535,14 +637,10 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                         for (; q < pn && !acc; ++q) acc |= pc[q];
                         pkz[r] = acc ? 0 : 1;
                         if (!acc) continue;
-                        uint8_t* d = pk + pko[r];
-                        for (int z = 0; z < sz; ++z) {
-                            const uint8_t* row = vol + ((size_t)(bx[2] + z) * H + bx[1]) * W + bx[0];
-                            for (int y = 0; y < sy; ++y, row += W, d += sx) memcpy(d, row, (size_t)sx);
-                        }
+                        pack_box_rows(pk + pko[r], vol + ((size_t)bx[2] * H + bx[1]) * W + bx[0], sx, sy, sz, (size_t)W, (size_t)H * W);
                     }
                     left->fetch_sub(1, std::memory_order_release);
-                });
+                }, true);
             }
         }
         const int sb = step - lag_n;
@@ -586,12 +684,19 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             {
                 const long long cc_bytes = keep_largest_cc ? (long long)pbytes : 0;
                 const SomaChainWs L = soma_chain_ws(s.ws, ws_bytes, 1, n, S, H, W, cc_bytes);
+                // The paste kernel can emit the compacted lines itself (B200SEG_HB_FUSED_LINES=1) instead of a second pass over the
+                // volume.  Measured through this entry point (64 volumes, same box, alternating runs): 73.9 Gvox/s fused against
+                // 76.4 with the separate pass -- the extra ballots / atomics lengthen the paste kernel by more than the 50 us
+                // streaming kernel they replace, so the separate pass stays the default.
+                static const bool fused_on = getenv("B200SEG_HB_FUSED_LINES") != nullptr;
+                const bool fused_lines = sparse && fused_on && paste_lines_supported(s.seg, 1, S, H, W);
+                const PasteLines pl{s.gidx, s.gval, (uint32_t*)(s.cnt + 1), (uint32_t)cap};
+                if (sparse) B200_BATCH(cudaMemsetAsync(s.cnt + 1, 0, 4, s_comp));
                 int ce = postproc_soma_after_nms(s.vol, 1, S, H, W, s.off, n, n, s.boxes, s.prm, s.coff, (long long)pbytes, keep_largest_cc,
                                              s.seg, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, L.ids, L.paste_ws, L.paste_ws_bytes,
-                                             L.cc_ws, L.cc_ws_bytes, s_comp);
+                                             L.cc_ws, L.cc_ws_bytes, s_comp, fused_lines ? &pl : nullptr);
                 if (ce) { rc = ce; goto done; }
-                if (sparse) {
-                    B200_BATCH(cudaMemsetAsync(s.cnt + 1, 0, 4, s_comp));
+                if (sparse && !fused_lines) {
                     unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);
                     const unsigned int lim = (unsigned int)num_sms() * 16u;
                     if (grid > lim) grid = lim;
@@ -616,8 +721,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             B200_BATCH(cudaEventRecord(g_batch.cnt_done[k], s_out));
         }
         // ---- volume `sb - HB_LAG_A`: its group count is known -> size and enqueue the download of the label data --------
-        if (sb >= HB_LAG_A && sb - HB_LAG_A < n_volumes) {
-            const int v = sb - HB_LAG_A, k = v % NB;
+        if (sb >= lag_a && sb - lag_a < n_volumes) {
+            const int v = sb - lag_a, k = v % NB;
             Slot& s = slot[k];
             { const auto t = now(); B200_BATCH(cudaEventSynchronize(g_batch.cnt_done[k])); w_cnt += ms_since(t); }
             uint32_t ng = 0xFFFFFFFFu;
@@ -631,8 +736,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 { const auto t = now(); while (sh->slot_busy[k].load(std::memory_order_acquire)) sched_yield(); w_slot += ms_since(t); }   // staging slot scattered by now
                 char* stage = g_batch.pinned + small_bytes + stage_bytes * k;
                 B200_BATCH(cudaMemcpyAsync(stage, s.gidx, (size_t)ng * 4, cudaMemcpyDeviceToHost, s_out2));
-                B200_BATCH(cudaMemcpyAsync(stage + align_up(cap * 4, 256), s.gval, (size_t)ng * 16, cudaMemcpyDeviceToHost, s_out2));
-                d2h += (size_t)ng * 20;
+                B200_BATCH(cudaMemcpyAsync(stage + align_up(cap * 4, 256), s.gval, (size_t)ng * 64, cudaMemcpyDeviceToHost, s_out2));
+                d2h += (size_t)ng * 68;
             }
             B200_BATCH(cudaEventRecord(g_batch.out_done[k], s_out2));   // (the kernels of this volume finished before cnt_done)
             // traffic of the gathered PRM crops: the crops of the survivors (known from the visit order now on the host)
@@ -647,8 +752,8 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             }
         }
         // ---- volume `sb - HB_LAG_B`: its download has been enqueued one step ago -> wait for it, hand it to the pool ----
-        if (sb >= HB_LAG_B && sb - HB_LAG_B < n_volumes) {
-            const int v = sb - HB_LAG_B, k = v % NB;
+        if (sb >= lag_b && sb - lag_b < n_volumes) {
+            const int v = sb - lag_b, k = v % NB;
             const uint32_t ng = n_groups[v];
             if (ng == 0 && out_state == 2) {                                    // all-zero result: nothing to clear next time
                 std::lock_guard<std::mutex> lk(g_prev_mu);
@@ -666,7 +771,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 const size_t vbytes = V * 2;
                 g_pool.push([sh, v, k, gi, gv, dst, ng, out_state, vbytes] {
                     while (sh->zero_left[v].load(std::memory_order_acquire) > 0) sched_yield();
-                    for (uint32_t i = 0; i < ng; ++i) memcpy(dst + (size_t)gi[i] * 16, gv + (size_t)i * 16, 16);
+                    scatter_lines(dst, vbytes, gi, gv, ng);
                     if (out_state == 2) {                                       // remember what has to be cleared next time
                         PrevLabels pl;
                         pl.bytes = vbytes;

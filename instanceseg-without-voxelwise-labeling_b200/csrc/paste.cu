@@ -97,11 +97,16 @@ __device__ __forceinline__ unsigned int nonzero_bytes(unsigned int x) {
 __device__ __forceinline__ unsigned int widen01(unsigned int m) { return __byte_perm(m, 0u, 0x1100); }
 __device__ __forceinline__ unsigned int widen23(unsigned int m) { return __byte_perm(m, 0u, 0x3322); }
 
+// LINES (single volume, W % 32 == 0, 16-byte aligned seg): besides the dense label volume the kernel emits the volume's
+// non-zero 64-byte lines (32 labels: the four 8-voxel groups of a quad of lanes) as (line index, payload) pairs in no
+// particular order -- the form the host batch entry point downloads (host_batch.cu).  One global atomic per warp and tile
+// that holds a label; `lines.count` keeps counting past `lines.cap`.
+template <bool LINES>
 __global__ void __launch_bounds__(PASTE_THREADS, 8)
 paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, const uint16_t* __restrict__ ids,
                     const uint8_t* __restrict__ masks, const VBox* __restrict__ vbox_all,
                     const uint32_t* __restrict__ tile_bits_all, uint8_t* __restrict__ survive_all,
-                    const int32_t* __restrict__ det_off, int vec_ok, int vec_mask_ok) {
+                    const int32_t* __restrict__ det_off, int vec_ok, int vec_mask_ok, PasteLines lines) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int lx = tid % (PT_X / 8), ly = tid / (PT_X / 8);
     const int ntiles = g.tiles_x * g.tiles_y * g.tiles_z;
@@ -195,6 +200,33 @@ paste_labels_kernel(uint16_t* __restrict__ seg_all, PasteGeom g, int n_volumes, 
                 }
             }
         }
+        if (LINES) {
+            unsigned int lm[PT_Z], total = 0u;
+#pragma unroll
+            for (int p = 0; p < PT_Z; ++p) {
+                const bool nz = inside && z0 + p < g.S && (lab[p][0] | lab[p][1] | lab[p][2] | lab[p][3]) != 0u;
+                const unsigned int m = __ballot_sync(0xffffffffu, nz);
+                lm[p] = (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u;       // bit 4q: quad q holds a non-zero line
+                total += __popc(lm[p]);
+            }
+            if (total) {                                                          // warp-uniform
+                unsigned int b = 0u;
+                if (lane == 0) b = atomicAdd(lines.count, total);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                const unsigned int q0 = lane & ~3u;
+                const size_t HW = (size_t)g.H * g.W;
+#pragma unroll
+                for (int p = 0; p < PT_Z; ++p) {
+                    if (lm[p] == 0u) continue;
+                    const unsigned int pos = b + __popc(lm[p] & ((1u << q0) - 1u));
+                    b += __popc(lm[p]);
+                    if (((lm[p] >> q0) & 1u) && pos < lines.cap) {
+                        if ((lane & 3u) == 0u) lines.idx[pos] = (uint32_t)(((size_t)(z0 + p) * HW + (size_t)y * g.W + x) >> 5);
+                        lines.val[(size_t)pos * 4 + (lane & 3u)] = make_uint4(lab[p][0], lab[p][1], lab[p][2], lab[p][3]);
+                    }
+                }
+            }
+        }
         if (inside) {
             const size_t HW = (size_t)g.H * g.W;
             uint16_t* dst = seg_all + (size_t)cur_vol * V + (size_t)z0 * HW + (size_t)y * g.W + x;
@@ -238,7 +270,20 @@ extern "C" int b200seg_paste_labels_dev(uint16_t* seg, int n_volumes, int S, int
                                         const uint16_t* ids, const uint8_t* masks, const int64_t* mask_off,
                                         const int32_t* order, const int32_t* n_valid, uint8_t* survive,
                                         void* workspace, size_t workspace_bytes, b200seg_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return b200seg::paste_labels_launch(seg, n_volumes, S, H, W, det_off, n_max, boxes, ids, masks, mask_off, order, n_valid, survive,
+                                        workspace, workspace_bytes, (cudaStream_t)stream_, nullptr);
+}
+
+bool b200seg::paste_lines_supported(const uint16_t* seg, int n_volumes, int S, int H, int W) {
+    return n_volumes == 1 && (W % 32) == 0 && ((((uintptr_t)seg) & 15) == 0) && (((size_t)S * H * W) % 8 == 0);
+}
+
+int b200seg::paste_labels_launch(uint16_t* seg, int n_volumes, int S, int H, int W,
+                                 const int32_t* det_off, int n_max, const int32_t* boxes,
+                                 const uint16_t* ids, const uint8_t* masks, const int64_t* mask_off,
+                                 const int32_t* order, const int32_t* n_valid, uint8_t* survive,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t stream, const PasteLines* lines) {
+    B200_CHECK_ARG(!lines || paste_lines_supported(seg, n_volumes, S, H, W), "paste_labels: line output needs one volume with W %% 32 == 0");
     B200_CHECK_ARG(S > 0 && H > 0 && W > 0 && n_max >= 0 && n_volumes >= 0, "paste_labels: bad sizes");
     if (n_volumes == 0) return 0;
     B200_CHECK_ARG(seg && workspace, "paste_labels: null seg/workspace");
@@ -265,14 +310,20 @@ extern "C" int b200seg_paste_labels_dev(uint16_t* seg, int n_volumes, int S, int
         B200_LAUNCH_CHECK("paste_bin_kernel");
     }
     const int vec_ok = (W % 8 == 0) && ((((uintptr_t)seg) & 15) == 0) && (((size_t)S * H * W) % 8 == 0);
-    static int occ = 0;
+    static int occ = 0, occ_lines = 0;
     if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_labels_kernel, PASTE_THREADS, 0) != cudaSuccess || occ < 1) occ = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_labels_kernel<false>, PASTE_THREADS, 0) != cudaSuccess || occ < 1) occ = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lines, paste_labels_kernel<true>, PASTE_THREADS, 0) != cudaSuccess || occ_lines < 1) occ_lines = 4;
     }
-    long long grid = (long long)num_sms() * occ;
+    long long grid = (long long)num_sms() * (lines ? occ_lines : occ);
     if (grid > (long long)(ntiles * n_volumes)) grid = (long long)(ntiles * n_volumes);
-    paste_labels_kernel<<<(unsigned)grid, PASTE_THREADS, 0, stream>>>(seg, g, n_volumes, ids, masks, vbox, tile_bits, survive,
-                                                                     det_off, vec_ok, (int)((((uintptr_t)masks) & 7) == 0));
+    const int vec_mask_ok = (int)((((uintptr_t)masks) & 7) == 0);
+    if (lines)
+        paste_labels_kernel<true><<<(unsigned)grid, PASTE_THREADS, 0, stream>>>(seg, g, n_volumes, ids, masks, vbox, tile_bits, survive,
+                                                                               det_off, vec_ok, vec_mask_ok, *lines);
+    else
+        paste_labels_kernel<false><<<(unsigned)grid, PASTE_THREADS, 0, stream>>>(seg, g, n_volumes, ids, masks, vbox, tile_bits, survive,
+                                                                                det_off, vec_ok, vec_mask_ok, PasteLines{nullptr, nullptr, nullptr, 0u});
     B200_LAUNCH_CHECK("paste_labels_kernel");
     return 0;
 }

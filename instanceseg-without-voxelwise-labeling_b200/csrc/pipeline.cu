@@ -41,7 +41,8 @@ int postproc_soma_after_nms(const uint8_t* volumes, int n_volumes, int S, int H,
                             int total, const int32_t* boxes, const uint8_t* prm, const int64_t* crop_off, long long prm_bytes,
                             int keep_largest_cc, uint16_t* seg, const int32_t* keep_count, const int32_t* rank_order,
                             uint8_t* masks, int32_t* b_max, int32_t* status, uint8_t* survive, uint16_t* ids,
-                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream) {
+                            void* paste_ws, size_t paste_ws_bytes, void* cc_ws, size_t cc_ws_bytes, cudaStream_t stream,
+                            const PasteLines* lines) {
     int e = 0;
     if (n_max > 0) {
         iota_u16_kernel<<<(n_max + 255) / 256, 256, 0, stream>>>(ids, n_max);
@@ -59,8 +60,8 @@ int postproc_soma_after_nms(const uint8_t* volumes, int n_volumes, int S, int H,
             if (e) return e;
         }
     }
-    return b200seg_paste_labels_dev(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
-                                    rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream);
+    return paste_labels_launch(seg, n_volumes, S, H, W, det_off_dev, n_max, boxes, ids, masks, crop_off,
+                               rank_order, keep_count, survive, paste_ws, paste_ws_bytes, stream, lines);
 }
 
 }  // namespace b200seg
