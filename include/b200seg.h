@@ -52,11 +52,14 @@ long long b200seg_launch_count(void);
  * scheme of b200seg_postproc_soma_host_batch, same results either way: bit 0 = label volumes come back compacted,
  * bit 1 = only the PRM crops of the NMS survivors are fetched (zero-copy gather), bit 2 = the raw volume is not
  * copied either: the NMS runs first, host threads pack the image crops of its survivors (the only voxels the chain reads)
- * into a pinned buffer and that buffer travels instead.  "host_batch_out" (default 0) tells that
+ * into a pinned buffer and that buffer travels instead; bit 3 (with bit 2) = the PRM crops of those survivors are packed into
+ * the same buffer by the host threads instead of being gathered over the link; bits 4 / 5 = the chain is launched for groups
+ * of 2 / 4 volumes instead of one volume at a time (both measured slower on a 16-core host, see host_batch.cu; they pay
+ * where host cores are plentiful).  "host_batch_out" (default 0) tells that
  * entry point what the caller's label buffers hold ON ENTRY, again with identical results: 0 = anything (every buffer is
  * zero-filled, 2 bytes of host memory traffic per voxel -- the bound of the call), 1 = zeros (a fresh np.zeros / calloc
  * buffer, what tools/binarization_soma.py:57 allocates per volume), 2 = exactly what this entry point wrote into the same
- * buffer last time (only the groups written then are cleared; a buffer the library has no record of is zero-filled).
+ * buffer last time (only the 64-byte lines written then are cleared; a buffer the library has no record of is zero-filled).
  * Unknown names return B200SEG_EINVAL. */
 int b200seg_set_option(const char* name, int value);
 
@@ -346,9 +349,9 @@ int b200seg_generate_proposals_dev(const float* scores, const float* deltas, con
 /* A batch of equally shaped volumes, HOST buffers in and out (the per-volume loop of tools/my_subprocess.py:56 over
  * tools/binarization_soma.py:57-104).  Pipelined over four device slots: the raw volume travels by DMA, the PRM crops of
  * the NMS survivors are pulled by a gather kernel straight from the caller's buffer when it is pinned and 16-byte
- * aligned (else the whole packed array is copied), and the label volume comes back as its non-zero 16-byte groups,
+ * aligned (else the whole packed array is copied), and the label volume comes back as its non-zero 64-byte lines,
  * which a pool of host threads (B200SEG_HOST_THREADS, default min(16, cores / LOCAL_WORLD_SIZE)) scatters into the
- * caller's volume after zero-filling it (a volume with more than 1/8 of its groups labelled is copied densely).
+ * caller's volume after zero-filling it (a volume with more than 1/4 of its lines labelled is copied densely).
  * seg[v] may be pageable; pass pinned volumes / prm for full overlap.
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host.
  * b200seg_postproc_soma_host_batch_traffic reports the bytes the last successful call moved over the link. */

@@ -232,7 +232,9 @@ def set_host_batch_out(state):
 
 def set_host_batch_mode(mode):
     """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops, bit 2: the image
-    crops of the NMS survivors travel packed by host threads, the raw volume is never copied (default 7)."""
+    crops of the NMS survivors travel packed by host threads, the raw volume is never copied (default 7); bit 3 (8): their PRM
+    crops travel in the same packed buffer instead of the zero-copy gather; bits 4 / 5 (16 / 32): the chain is launched for
+    groups of 2 / 4 volumes."""
     _lib.check(_lib.lib().b200seg_set_option(b"host_batch_mode", int(mode)), "set_option")
 
 

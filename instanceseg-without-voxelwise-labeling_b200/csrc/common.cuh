@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
-int opt_host_batch_mode();            // b200seg_set_option("host_batch_mode"): bit 0 compacted label download, bit 1 PRM gather
+int opt_host_batch_mode();            // b200seg_set_option("host_batch_mode"): bit 0 compacted label download, bit 1 PRM gather, bit 2 packed image crops, bit 3 packed PRM crops, bits 4 / 5 groups of 2 / 4 volumes per chain launch
 int opt_host_batch_out();             // what the caller's label buffers hold on entry: 0 unknown, 1 zeros, 2 this entry point's previous result
 int opt_peaks_median_mode();          // 0 auto, 1 histogram path only, 2 sampled interval forced to miss (tests the fallback)
 int opt_peaks_stop_after();          // profiling knob: peaks3d stops after its first k kernels (99 = run all)

@@ -79,13 +79,16 @@ seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned
 // PRM crops of the NMS survivors: host-mapped (pinned) source -> device copy with the same packing.
 // grid (n_max): CTA r moves the crop of visit rank r.  src and dst share the offset, both bases are 16-byte aligned.
 __global__ void __launch_bounds__(256)
-prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ crop_off,
+prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ crop_off, long long shift,
                   const int32_t* __restrict__ rank_order, const int32_t* __restrict__ keep_count,
-                  const uint8_t* __restrict__ all_zero) {
+                  const uint8_t* __restrict__ all_zero, const int64_t* __restrict__ src_off) {
     const int r = blockIdx.x;
     if (r >= keep_count[0]) return;
     const int inst = rank_order[r];
-    const long long a = crop_off[inst], b = crop_off[inst + 1];
+    const long long a = crop_off[inst] - shift, b = crop_off[inst + 1] - shift;   // the device copy of the offsets counts from the group's base
+    // src_off: the crops sit back to back in visit order (packed by the host, already on the device), crop r at src_off[r],
+    // which is congruent to `a` modulo 16; else src mirrors dst
+    if (src_off && !(all_zero && all_zero[r])) src += src_off[r] - a;
     long long a16 = (a + 15) & ~15ll, b16 = b & ~15ll;
     if (a16 > b16) { a16 = b; b16 = b; }                            // crop shorter than one aligned group
     if (all_zero && all_zero[r]) {                                  // the host saw no positive voxel in this crop: nothing to fetch
@@ -320,7 +323,9 @@ constexpr int HB_SLOTS = 12;
 constexpr int HB_LAG_A = 2;            // the download of volume v is sized and enqueued while volume v + HB_LAG_A is being enqueued
 constexpr int HB_LAG_B = 3;            // ... and handed to the pool one step later
 constexpr int HB_ZERO_PARTS = 4;
-constexpr int HB_LAG_N = 4;            // packed-image mode: the chain of volume v is enqueued while the NMS of volume v + HB_LAG_N is
+constexpr int HB_GROUP = 4;            // largest number of volumes per chain launch ("host_batch_mode" bits 4 / 5); HB_SLOTS is a multiple of it
+constexpr int HB_LAG_P = 2;            // packed-image mode: the crops of volume v are handed to the pool while the NMS of volume v + HB_LAG_P is enqueued
+constexpr int HB_LAG_N = 5;            // packed-image mode: the chain of volume v is enqueued while the NMS of volume v + HB_LAG_N is
 
 struct BatchStreams {
     cudaStream_t in = nullptr, out = nullptr, out2 = nullptr;   // uploads | bookkeeping downloads | label downloads
@@ -438,11 +443,28 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     if (cap > nlines) cap = nlines;
     if (!sparse) cap = 0;
     const bool pack_mode = (mode & 4) != 0;                   // image crops of the NMS survivors packed by host threads, no DMA of the volume
-    const size_t slot_bytes = (pack_mode ? Carver::need(prm_max + 16) + Carver::need(nn * 8) + Carver::need(nn) : 0) + Carver::need(V) + Carver::need(V * 2) + Carver::need(nn * 28) + Carver::need(8) + Carver::need(nn * 24) +
-                              2 * Carver::need(prm_max + 16) + Carver::need((nn + 1) * 8) + Carver::need(nn * 8) + Carver::need(8) +
-                              3 * Carver::need(nn * 4) + Carver::need(nn) + Carver::need(cap * 4 + 16) + Carver::need(cap * 64 + 64) +
-                              Carver::need(ws_bytes);
-    int e = hc.ensure(slot_bytes * NB);
+    // volumes per chain launch; consecutive slots of a group are adjacent in every array the chain kernels index by volume
+    // ("host_batch_mode" bits 4 / 5: groups of 2 / 4 volumes.  Measured on 64 volumes, same box, alternating runs: 80.6 Gvox/s
+    // with single-volume launches, 78.3 in pairs, 72.6 in fours -- the call is bound by the host's memory traffic and by the
+    // upload direction of the link, not by the kernels, and a group delays the downloads of its first volumes; default 1.)
+    const int G = (mode & 32) ? HB_GROUP : (mode & 16) ? 2 : 1;
+    const int n_groups_dev = (NB + G - 1) / G;
+    const size_t nd = nn + 1;                                 // per-volume stride of the per-detection arrays (one spare entry: crop_off[n])
+    const size_t P = align_up(prm_max + 16, 256);            // per-volume stride of the PRM crops and of the masks
+    const size_t ws_bytes_g = b200seg_postproc_soma_workspace_bytes(G, (int)nd, S, H, W, keep_largest_cc ? (long long)(P * G) : 0);
+    // "host_batch_mode" bit 3 (with bit 2): the PRM crops of the survivors with a positive voxel travel in the same pinned buffer,
+    // behind the image crops, instead of being pulled over the link by the zero-copy gather kernel (16-byte reads reach about a
+    // quarter of the DMA rate).  It takes the wait for the GPU out of the call (12 -> 1-3 ms of 25) and puts the same time into
+    // the host pool, which copies 2.5 MB more per volume: 69.6 against 78.6 Gvox/s on the 16-core box, so it is off by default;
+    // it is the better choice where host cores are plentiful and for pageable PRM buffers (no whole-array copy).
+    const bool prm_packed = pack_mode && (mode & 8);
+    const size_t packbuf_bytes = align_up(prm_max + 16, 256) + (prm_packed ? align_up(prm_max + 32 * nn + 64, 256) : 0);
+    const size_t slot_bytes = (pack_mode ? Carver::need(packbuf_bytes) + 2 * Carver::need(nn * 8) + Carver::need(nn) : 0) + Carver::need(nn * 28) + Carver::need(8) +
+                              Carver::need(nn * 8) + Carver::need(cap * 4 + 16) + Carver::need(cap * 64 + 64) + Carver::need(ws_bytes);
+    const size_t shared_bytes = Carver::need(V * NB) + Carver::need(V * 2 * NB) + 2 * Carver::need(P * NB) + Carver::need(nd * 24 * NB) + Carver::need(nd * 8 * NB) +
+                                3 * Carver::need(nd * 4 * NB) + Carver::need(nd * NB) + 2 * Carver::need(4 * (size_t)HB_SLOTS) + Carver::need(4 * (size_t)(HB_SLOTS + 1)) +
+                                (size_t)n_groups_dev * Carver::need(ws_bytes_g);
+    int e = hc.ensure(slot_bytes * NB + shared_bytes);
     if (e) return e;
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
@@ -451,19 +473,35 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     e = g_batch.ensure(dev);
     if (e) return e;
     struct Slot {
-        uint8_t* pack; int64_t* pk_off; uint8_t* pk_zero; uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
-        int64_t* keep; int32_t* cnt; int32_t* rank; int32_t* bmax; int32_t* stat; uint8_t* surv; uint32_t* gidx; uint4* gval; void* ws;
+        uint8_t* pack; int64_t* pk_off; int64_t* pk_poff; uint8_t* pk_zero; uint8_t* vol; uint16_t* seg; float* dets; int32_t* off; int32_t* boxes; uint8_t* prm; uint8_t* mask; int64_t* coff;
+        int64_t* keep; int32_t* cnt; uint32_t* lines; int32_t* rank; int32_t* bmax; int32_t* stat; uint8_t* surv; uint32_t* gidx; uint4* gval; void* ws;
     } slot[HB_SLOTS];
+    Carver cs(hc.buf + slot_bytes * NB);
+    uint8_t* const vol_all = cs.take<uint8_t>(V * NB);
+    uint16_t* const seg_all = cs.take<uint16_t>(V * NB);
+    uint8_t* const prm_all = cs.take<uint8_t>(P * NB);
+    uint8_t* const mask_all = cs.take<uint8_t>(P * NB);
+    int32_t* const boxes_all = cs.take<int32_t>(nd * 6 * NB);
+    int64_t* const coff_all = cs.take<int64_t>(nd * NB);
+    int32_t* const rank_all = cs.take<int32_t>(nd * NB);
+    int32_t* const bmax_all = cs.take<int32_t>(nd * NB);
+    int32_t* const stat_all = cs.take<int32_t>(nd * NB);
+    uint8_t* const surv_all = cs.take<uint8_t>(nd * NB);
+    int32_t* const keepcnt_all = cs.take<int32_t>(HB_SLOTS);        // NMS survivors per slot: the chain's n_valid[volume]
+    uint32_t* const linecnt_all = cs.take<uint32_t>(HB_SLOTS);      // compacted lines per slot
+    int32_t* const det_off_tab = cs.take<int32_t>(HB_SLOTS + 1);    // {0, nd, 2 nd, ...}: detection offsets inside a group
+    void* group_ws[HB_SLOTS];
+    for (int q = 0; q < n_groups_dev; ++q) group_ws[q] = cs.take<char>(ws_bytes_g);
     for (int k = 0; k < NB; ++k) {
         Carver cv(hc.buf + slot_bytes * k);
         Slot& s = slot[k];
-        s.pack = nullptr; s.pk_off = nullptr; s.pk_zero = nullptr;
-        if (pack_mode) { s.pack = cv.take<uint8_t>(prm_max + 16); s.pk_off = cv.take<int64_t>(nn); s.pk_zero = cv.take<uint8_t>(nn); }
-        s.vol = cv.take<uint8_t>(V); s.seg = cv.take<uint16_t>(V); s.dets = cv.take<float>(nn * 7); s.off = cv.take<int32_t>(2);
-        s.boxes = cv.take<int32_t>(nn * 6); s.prm = cv.take<uint8_t>(prm_max + 16); s.mask = cv.take<uint8_t>(prm_max + 16);
-        s.coff = cv.take<int64_t>(nn + 1); s.keep = cv.take<int64_t>(nn); s.cnt = cv.take<int32_t>(2); s.rank = cv.take<int32_t>(nn);
-        s.bmax = cv.take<int32_t>(nn); s.stat = cv.take<int32_t>(nn); s.surv = cv.take<uint8_t>(nn);
-        s.gidx = cv.take<uint32_t>(cap + 4); s.gval = cv.take<uint4>(cap * 4 + 4); s.ws = cv.p;
+        s.pack = nullptr; s.pk_off = nullptr; s.pk_poff = nullptr; s.pk_zero = nullptr;
+        if (pack_mode) { s.pack = cv.take<uint8_t>(packbuf_bytes); s.pk_off = cv.take<int64_t>(nn); s.pk_poff = cv.take<int64_t>(nn); s.pk_zero = cv.take<uint8_t>(nn); }
+        s.dets = cv.take<float>(nn * 7); s.off = cv.take<int32_t>(2); s.keep = cv.take<int64_t>(nn);
+        s.gidx = cv.take<uint32_t>(cap + 4); s.gval = cv.take<uint4>(cap * 4 + 4); s.ws = cv.p;          // (s.ws: workspace of this volume's NMS)
+        s.vol = vol_all + V * k; s.seg = seg_all + V * k; s.prm = prm_all + P * k; s.mask = mask_all + P * k;
+        s.boxes = boxes_all + nd * 6 * k; s.coff = coff_all + nd * k; s.rank = rank_all + nd * k; s.bmax = bmax_all + nd * k;
+        s.stat = stat_all + nd * k; s.surv = surv_all + nd * k; s.cnt = keepcnt_all + k; s.lines = linecnt_all + k;
     }
     // pinned staging: [per-volume bookkeeping] [per-slot line indices | line payloads]
     size_t small_bytes = 0;
@@ -471,12 +509,15 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     small_bytes = align_up(small_bytes, 256);
     const size_t stage_bytes = align_up(cap * 4, 256) + align_up(cap * 64, 256);
     // packed-image mode, per slot: [keep count | pad to 16 | visit order n*4] [offsets n*8 | all-zero-PRM flags n] [packed crops]
-    const size_t nmsst_bytes = align_up(16 + nn * 4, 256), pkoff_bytes = align_up(nn * 8, 256) + align_up(nn, 256);
-    const size_t pack_bytes = pack_mode ? nmsst_bytes + pkoff_bytes + align_up(prm_max + 16, 256) : 0;
-    e = g_batch.ensure_pinned(small_bytes + (stage_bytes + pack_bytes) * NB);
+    const size_t nmsst_bytes = align_up(16 + nn * 4, 256), pkoff_bytes = 2 * align_up(nn * 8, 256) + align_up(nn, 256);
+    const size_t pack_bytes = pack_mode ? nmsst_bytes + pkoff_bytes + packbuf_bytes : 0;
+    const size_t coffst_bytes = align_up(nd * 8, 256);       // per slot: the volume's crop offsets counted from its group's PRM base
+    e = g_batch.ensure_pinned(small_bytes + (stage_bytes + pack_bytes + coffst_bytes) * NB + 256);
     if (e) return e;
     g_pool.ensure();
     char* const pack_base = g_batch.pinned + small_bytes + stage_bytes * NB;
+    char* const coffst_base = pack_base + pack_bytes * NB;
+    int32_t* const det_tab_host = (int32_t*)(coffst_base + coffst_bytes * NB);
 
     cudaStream_t s_in = g_batch.in, s_out = g_batch.out, s_out2 = g_batch.out2;
     // the kernels of one volume are small (a dozen launches of a few hundred CTAs): volumes rotate over three compute streams
@@ -546,19 +587,24 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
 #define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
     const int lag_n = pack_mode ? HB_LAG_N : 0;               // stage A (NMS) runs lag_n volumes ahead of stage B, stage P lag_n - 1
     std::atomic<int> pack_left[HB_SLOTS];                       // packing jobs of the slot's volume still running
+    std::atomic<int> scan_left[HB_SLOTS];                       // ... and the PRM scans that precede them
     int pack_kc[HB_SLOTS] = {};
     size_t pack_total[HB_SLOTS] = {};
-    for (int k = 0; k < HB_SLOTS; ++k) pack_left[k].store(0);
+    for (int k = 0; k < HB_SLOTS; ++k) { pack_left[k].store(0); scan_left[k].store(0); }
     // chains in flight on the GPU: the host sizes the download of volume v (it needs its line count) while it enqueues volume
     // v + lag_a, so lag_a + 1 chains can be queued before the host has to wait for one of them
     static const int lag_env = getenv("B200SEG_HB_LAG") ? atoi(getenv("B200SEG_HB_LAG")) : 0;
-    const int lag_a = lag_env >= 1 && lag_env <= 6 ? lag_env : HB_LAG_A, lag_b = lag_a + (HB_LAG_B - HB_LAG_A);
-    static_assert(HB_LAG_N + 6 + (HB_LAG_B - HB_LAG_A) + 1 <= HB_SLOTS, "a slot must be free again before its next volume arrives");
+    // (a chain is launched when the last volume of its group arrives: G - 1 more steps for the first one)
+    const int lag_a = (lag_env >= 1 && lag_env <= 2 ? lag_env : HB_LAG_A) + G - 1, lag_b = lag_a + (HB_LAG_B - HB_LAG_A);
+    static_assert(HB_LAG_N + 2 + HB_GROUP - 1 + (HB_LAG_B - HB_LAG_A) + 1 <= HB_SLOTS, "a slot must be free again before its next volume arrives");
+    static_assert(HB_SLOTS % HB_GROUP == 0, "groups must not wrap around the slot ring");
+    for (int j = 0; j <= HB_SLOTS; ++j) det_tab_host[j] = (int32_t)(j * nd);
+    B200_BATCH(cudaMemcpyAsync(det_off_tab, det_tab_host, 4 * (size_t)(HB_SLOTS + 1), cudaMemcpyHostToDevice, s_in));
     for (int step = 0; step < n_volumes + lag_n + lag_b; ++step) {
         // ---- stage A, volume `step`: uploads of the small arrays (and of the volume unless it travels packed), NMS -------
         if (step < n_volumes) {
             const int v = step, k = v % NB;
-            const cudaStream_t s_comp = pack_mode ? g_batch.nms : comp_streams[v % 3];   // (stage A only enqueues the NMS)
+            const cudaStream_t s_comp = pack_mode ? g_batch.nms : comp_streams[(v / G) % 3];   // (stage A only enqueues the NMS; else the group's stream)
             Slot& s = slot[k];
             const int n = n_dets[v];
             const size_t pbytes = n > 0 ? (size_t)crop_off[v][n] : 0;
@@ -570,9 +616,15 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             if (n > 0) {
                 B200_BATCH(cudaMemcpyAsync(s.dets, dets[v], (size_t)n * 28, cudaMemcpyHostToDevice, s_in));
                 B200_BATCH(cudaMemcpyAsync(s.boxes, boxes[v], (size_t)n * 24, cudaMemcpyHostToDevice, s_in));
-                B200_BATCH(cudaMemcpyAsync(s.coff, crop_off[v], (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s_in));
+                {   // crop offsets counted from the PRM base of the volume's group
+                    int64_t* cst = (int64_t*)(coffst_base + coffst_bytes * k);
+                    if (v >= NB) B200_BATCH(cudaEventSynchronize(g_batch.in_done[k]));     // (the copy out of this staging for volume v - NB ran long ago)
+                    const int64_t shift = (int64_t)(P * (size_t)(k % G));
+                    for (int i = 0; i <= n; ++i) cst[i] = crop_off[v][i] + shift;
+                    B200_BATCH(cudaMemcpyAsync(s.coff, cst, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s_in));
+                }
                 h2d += (size_t)n * 52 + (size_t)(n + 1) * 8;
-                if (!prm_mapped) { B200_BATCH(cudaMemcpyAsync(s.prm, prm[v], pbytes, cudaMemcpyHostToDevice, s_in)); h2d += pbytes; }
+                if (!prm_mapped && !prm_packed) { B200_BATCH(cudaMemcpyAsync(s.prm, prm[v], pbytes, cudaMemcpyHostToDevice, s_in)); h2d += pbytes; }
             }
             B200_BATCH(cudaEventRecord(g_batch.in_done[k], s_in));
             B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.in_done[k], 0));
@@ -593,13 +645,14 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             }
         }
         // ---- stage P, volume `step - lag_n + 1`: its visit order is back -> hand the packing of its image crops to the pool ----
-        const int sp = step - lag_n + 1;
+        const int sp = step - HB_LAG_P;                          // (the copies get lag_n - HB_LAG_P steps before stage B needs them)
         if (pack_mode && sp >= 0 && sp < n_volumes && n_dets[sp] > 0) {
             const int v = sp, k = v % NB;
             const int n = n_dets[v];
             char* nst = pack_base + pack_bytes * k;
             int64_t* pko = (int64_t*)(nst + nmsst_bytes);
-            uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+            int64_t* ppo = (int64_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+            uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + 2 * align_up(nn * 8, 256));
             uint8_t* pk = (uint8_t*)(nst + nmsst_bytes + pkoff_bytes);
             // the previous user of this slot's pinned buffers was volume v - NB: its copies were issued long ago; make sure they are done
             if (v >= NB) B200_BATCH(cudaEventSynchronize(g_batch.pack_done[k]));
@@ -609,16 +662,22 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             if (kc > n) kc = n;
             if (kc < 0) kc = 0;
             const int32_t* ro = (const int32_t*)(nst + 16);
-            size_t total = 0;
-            for (int r = 0; r < kc; ++r) { pko[r] = (int64_t)total; total += (size_t)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]); }
-            pack_kc[k] = kc; pack_total[k] = total;
+            pack_kc[k] = kc; pack_total[k] = 0;
+            // Two rounds of jobs.  Round 1 looks for a positive voxel in the PRM crop of every survivor (an instance without one
+            // is skipped by the script before it touches the image, binarization_soma.py:74-76: nothing of it travels).  The
+            // job that finishes last lays out the buffer -- image crops back to back, then the PRM crops, each starting at its
+            // own offset modulo 16 so that the device copy moves aligned 16-byte words -- and hands out round 2, the copies.
             const int njobs = kc < 1 ? 0 : (kc < 4 * g_pool.n_threads ? (kc + 3) / 4 : g_pool.n_threads * 2);
-            pack_left[k].store(njobs);
+            pack_left[k].store(njobs > 0 ? 1 : 0);                 // round 2 not handed out yet
+            scan_left[k].store(njobs);
             const uint8_t* vol = volumes[v];
             const uint8_t* prm_h = prm[v];
             const int64_t* co = crop_off[v];
             const int32_t* bxs = boxes[v];
             std::atomic<int>* left = &pack_left[k];
+            std::atomic<int>* sleft = &scan_left[k];
+            size_t* total_out = &pack_total[k];
+            HostPool* pool = &g_pool;
             for (int j = 0; j < njobs; ++j) {
                 const int r0 = (int)((long long)kc * j / njobs), r1 = (int)((long long)kc * (j + 1) / njobs);
                 g_pool.push([=] {
@@ -628,7 +687,6 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                         const int sx = bx[3] - bx[0] + 1, sy = bx[4] - bx[1] + 1, sz = bx[5] - bx[2] + 1;
                         pkz[r] = 1;
                         if (sx <= 0 || sy <= 0 || sz <= 0) continue;
-                        // skipped by the script (no positive PRM voxel): its image is never read, nothing to pack
                         const uint8_t* pc = prm_h + co[i];
                         const size_t pn = (size_t)(co[i + 1] - co[i]);
                         size_t q = 0;
@@ -636,35 +694,69 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                         for (; q + 8 <= pn && !acc; q += 8) { unsigned long long w; memcpy(&w, pc + q, 8); acc |= w; }
                         for (; q < pn && !acc; ++q) acc |= pc[q];
                         pkz[r] = acc ? 0 : 1;
-                        if (!acc) continue;
-                        pack_box_rows(pk + pko[r], vol + ((size_t)bx[2] * H + bx[1]) * W + bx[0], sx, sy, sz, (size_t)W, (size_t)H * W);
                     }
-                    left->fetch_sub(1, std::memory_order_release);
+                    if (sleft->fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+                    // last scan job: layout + round 2
+                    size_t total = 0;
+                    for (int r = 0; r < kc; ++r) {
+                        pko[r] = (int64_t)total;
+                        if (!pkz[r]) total += (size_t)(co[ro[r] + 1] - co[ro[r]]);
+                    }
+                    if (prm_packed)
+                        for (int r = 0; r < kc; ++r) {
+                            ppo[r] = 0;
+                            if (pkz[r]) continue;
+                            total = ((total + 15) & ~(size_t)15) + ((size_t)co[ro[r]] & 15);
+                            ppo[r] = (int64_t)total;
+                            total += (size_t)(co[ro[r] + 1] - co[ro[r]]);
+                        }
+                    *total_out = total;
+                    left->fetch_add(njobs, std::memory_order_relaxed);
+                    for (int j2 = 0; j2 < njobs; ++j2) {
+                        const int q0 = (int)((long long)kc * j2 / njobs), q1 = (int)((long long)kc * (j2 + 1) / njobs);
+                        pool->push([=] {
+                            for (int r = q0; r < q1; ++r) {
+                                if (pkz[r]) continue;
+                                const int i = ro[r];
+                                const int32_t* bx = bxs + (size_t)i * 6;
+                                const int sx = bx[3] - bx[0] + 1, sy = bx[4] - bx[1] + 1, sz = bx[5] - bx[2] + 1;
+                                pack_box_rows(pk + pko[r], vol + ((size_t)bx[2] * H + bx[1]) * W + bx[0], sx, sy, sz, (size_t)W, (size_t)H * W);
+                                if (prm_packed) memcpy(pk + ppo[r], prm_h + co[i], (size_t)(co[i + 1] - co[i]));
+                            }
+                            left->fetch_sub(1, std::memory_order_release);
+                        }, true);
+                    }
+                    left->fetch_sub(1, std::memory_order_release);             // the round-2 marker
                 }, true);
             }
         }
         const int sb = step - lag_n;
-        // ---- stage B, volume `sb`: (packed image crops,) PRM gather, chain, compaction, download of the bookkeeping -------
+        // ---- stage B, volume `sb`: (packed image crops,) PRM gather; with the last volume of a group: chain of the group,
+        //      compaction and download of the bookkeeping of each of its volumes ---------------------------------------------
         if (sb >= 0 && sb < n_volumes) {
             const int v = sb, k = v % NB;
-            const cudaStream_t s_comp = comp_streams[v % 3];
+            const int g0 = v - v % G, g1 = (g0 + G < n_volumes ? g0 + G : n_volumes) - 1;      // first / last volume of the group
+            const int k0 = g0 % NB, ng_vol = g1 - g0 + 1;
+            const cudaStream_t s_comp = comp_streams[(v / G) % 3];
             Slot& s = slot[k];
             const int n = n_dets[v];
             const size_t pbytes = n > 0 ? (size_t)crop_off[v][n] : 0;
             const uint8_t* prm_mapped = (n > 0 && (mode & 2)) ? mapped_device_pointer(prm[v]) : nullptr;
-            if (pack_mode) B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.nmsc_done[k], 0));   // the NMS ran on its own stream
+            B200_BATCH(cudaStreamWaitEvent(s_comp, pack_mode ? g_batch.nmsc_done[k] : g_batch.in_done[k], 0));   // the NMS ran on its own stream
             const uint8_t* zero_flags = nullptr;
             if (pack_mode && n > 0) {
                 char* nst = pack_base + pack_bytes * k;
                 int64_t* pko = (int64_t*)(nst + nmsst_bytes);
-                uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+                int64_t* ppo = (int64_t*)(nst + nmsst_bytes + align_up(nn * 8, 256));
+            uint8_t* pkz = (uint8_t*)(nst + nmsst_bytes + 2 * align_up(nn * 8, 256));
                 uint8_t* pk = (uint8_t*)(nst + nmsst_bytes + pkoff_bytes);
                 { const auto tp = now(); while (pack_left[k].load(std::memory_order_acquire) > 0) sched_yield(); w_pack += ms_since(tp); }
                 const int kc = pack_kc[k];
                 if (kc > 0) {
                     B200_BATCH(cudaMemcpyAsync(s.pk_off, pko, (size_t)kc * 8, cudaMemcpyHostToDevice, s_in));
                     B200_BATCH(cudaMemcpyAsync(s.pk_zero, pkz, (size_t)kc, cudaMemcpyHostToDevice, s_in));
-                    B200_BATCH(cudaMemcpyAsync(s.pack, pk, pack_total[k], cudaMemcpyHostToDevice, s_in));
+                    if (prm_packed) { B200_BATCH(cudaMemcpyAsync(s.pk_poff, ppo, (size_t)kc * 8, cudaMemcpyHostToDevice, s_in)); h2d += (size_t)kc * 8; }
+                    if (pack_total[k] > 0) B200_BATCH(cudaMemcpyAsync(s.pack, pk, pack_total[k], cudaMemcpyHostToDevice, s_in));
                     h2d += (size_t)kc * 9 + pack_total[k];
                     zero_flags = s.pk_zero;
                 }
@@ -676,49 +768,66 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                     B200_BATCH(cudaGetLastError());
                 }
             }
-            if (prm_mapped) {                                 // PRM crops of the survivors, fetched in place (zero fill where the host saw only zeros)
-                prm_gather_kernel<<<n, 256, 0, s_comp>>>(prm_mapped, s.prm, s.coff, s.rank, s.cnt, zero_flags);
-                count_launch();
-                B200_BATCH(cudaGetLastError());
-            }
-            {
-                const long long cc_bytes = keep_largest_cc ? (long long)pbytes : 0;
-                const SomaChainWs L = soma_chain_ws(s.ws, ws_bytes, 1, n, S, H, W, cc_bytes);
-                // The paste kernel can emit the compacted lines itself (B200SEG_HB_FUSED_LINES=1) instead of a second pass over the
-                // volume.  Measured through this entry point (64 volumes, same box, alternating runs): 73.9 Gvox/s fused against
-                // 76.4 with the separate pass -- the extra ballots / atomics lengthen the paste kernel by more than the 50 us
-                // streaming kernel they replace, so the separate pass stays the default.
-                static const bool fused_on = getenv("B200SEG_HB_FUSED_LINES") != nullptr;
-                const bool fused_lines = sparse && fused_on && paste_lines_supported(s.seg, 1, S, H, W);
-                const PasteLines pl{s.gidx, s.gval, (uint32_t*)(s.cnt + 1), (uint32_t)cap};
-                if (sparse) B200_BATCH(cudaMemsetAsync(s.cnt + 1, 0, 4, s_comp));
-                int ce = postproc_soma_after_nms(s.vol, 1, S, H, W, s.off, n, n, s.boxes, s.prm, s.coff, (long long)pbytes, keep_largest_cc,
-                                             s.seg, s.cnt, s.rank, s.mask, s.bmax, s.stat, s.surv, L.ids, L.paste_ws, L.paste_ws_bytes,
-                                             L.cc_ws, L.cc_ws_bytes, s_comp, fused_lines ? &pl : nullptr);
-                if (ce) { rc = ce; goto done; }
-                if (sparse && !fused_lines) {
-                    unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);
-                    const unsigned int lim = (unsigned int)num_sms() * 16u;
-                    if (grid > lim) grid = lim;
-                    seg_compact_kernel<<<grid, 256, 0, s_comp>>>((const uint4*)s.seg, (unsigned int)ngroups, (unsigned int)cap,
-                                                                 s.gidx, s.gval, (uint32_t*)(s.cnt + 1));
+            if (prm_packed) {                                 // PRM crops of the survivors: packed buffer (on the device by now) -> their own offsets
+                if (n > 0 && pack_kc[k] > 0) {
+                    prm_gather_kernel<<<n, 256, 0, s_comp>>>(s.pack, s.prm, s.coff, (long long)(P * (size_t)(k % G)), s.rank, s.cnt, s.pk_zero, s.pk_poff);
                     count_launch();
                     B200_BATCH(cudaGetLastError());
                 }
+            } else if (prm_mapped) {                          // PRM crops of the survivors, fetched in place (zero fill where the host saw only zeros)
+                prm_gather_kernel<<<n, 256, 0, s_comp>>>(prm_mapped, s.prm, s.coff, (long long)(P * (size_t)(k % G)), s.rank, s.cnt, zero_flags, nullptr);
+                count_launch();
+                B200_BATCH(cudaGetLastError());
             }
-            B200_BATCH(cudaEventRecord(g_batch.comp_done[k], s_comp));
-            B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.comp_done[k], 0));
-            char* st = g_batch.pinned + small_off[v];          // [keep count | group count | pad to 16 | rank n*4 | b_max n*4 | status n*4 | survive n]
-            B200_BATCH(cudaMemcpyAsync(st, s.cnt, 8, cudaMemcpyDeviceToHost, s_out));
-            d2h += 8;
-            if (n > 0) {
-                B200_BATCH(cudaMemcpyAsync(st + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 4, s.bmax, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 8, s.stat, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)n * 12, s.surv, (size_t)n, cudaMemcpyDeviceToHost, s_out));
-                d2h += (size_t)n * 13;
+            if (v == g1) {
+                // every array the chain indexes by volume is strided per slot, so the group is one batched launch: volume j of the
+                // group = slot k0 + j, its detections start at j * nd, its PRM crops / masks at j * P
+                int n_any = 0;
+                for (int u = g0; u <= g1; ++u) n_any = n_dets[u] > n_any ? n_dets[u] : n_any;
+                const long long mask_bytes = (long long)(P * (size_t)ng_vol);
+                const SomaChainWs L = soma_chain_ws(group_ws[k0 / G], ws_bytes_g, ng_vol, (int)nd, S, H, W, keep_largest_cc ? mask_bytes : 0);
+                Slot& s0 = slot[k0];
+                if (sparse) B200_BATCH(cudaMemsetAsync(s0.lines, 0, 4 * (size_t)ng_vol, s_comp));
+                // The paste kernel can emit the compacted lines itself (B200SEG_HB_FUSED_LINES=1, single-volume groups only) instead of
+                // a second pass over the volume.  Measured through this entry point (64 volumes, same box, alternating runs): 73.9
+                // Gvox/s fused against 76.4 with the separate pass -- the extra ballots / atomics lengthen the paste kernel by more
+                // than the 50 us streaming kernel they replace, so the separate pass stays the default.
+                static const bool fused_on = getenv("B200SEG_HB_FUSED_LINES") != nullptr;
+                const bool fused_lines = sparse && fused_on && ng_vol == 1 && paste_lines_supported(s0.seg, 1, S, H, W);
+                const PasteLines pl{s0.gidx, s0.gval, s0.lines, (uint32_t)cap};
+                int ce = postproc_soma_after_nms(s0.vol, ng_vol, S, H, W, det_off_tab, n_any > 0 ? (int)nd : 0, (int)(nd * ng_vol), s0.boxes, s0.prm, s0.coff,
+                                                 mask_bytes, keep_largest_cc, s0.seg, s0.cnt, s0.rank, s0.mask, s0.bmax, s0.stat, s0.surv, L.ids,
+                                                 L.paste_ws, L.paste_ws_bytes, L.cc_ws, L.cc_ws_bytes, s_comp, fused_lines ? &pl : nullptr);
+                if (ce) { rc = ce; goto done; }
+                for (int u = g0; u <= g1 && sparse && !fused_lines; ++u) {
+                    Slot& su = slot[u % NB];
+                    unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);
+                    const unsigned int lim = (unsigned int)num_sms() * 16u;
+                    if (grid > lim) grid = lim;
+                    seg_compact_kernel<<<grid, 256, 0, s_comp>>>((const uint4*)su.seg, (unsigned int)ngroups, (unsigned int)cap,
+                                                                 su.gidx, su.gval, su.lines);
+                    count_launch();
+                    B200_BATCH(cudaGetLastError());
+                }
+                B200_BATCH(cudaEventRecord(g_batch.comp_done[k], s_comp));
+                B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.comp_done[k], 0));
+                for (int u = g0; u <= g1; ++u) {
+                    Slot& su = slot[u % NB];
+                    const int nu = n_dets[u];
+                    char* st = g_batch.pinned + small_off[u];      // [keep count | line count | pad to 16 | rank n*4 | b_max n*4 | status n*4 | survive n]
+                    B200_BATCH(cudaMemcpyAsync(st, su.cnt, 4, cudaMemcpyDeviceToHost, s_out));
+                    B200_BATCH(cudaMemcpyAsync(st + 4, su.lines, 4, cudaMemcpyDeviceToHost, s_out));
+                    d2h += 8;
+                    if (nu > 0) {
+                        B200_BATCH(cudaMemcpyAsync(st + 16, su.rank, (size_t)nu * 4, cudaMemcpyDeviceToHost, s_out));
+                        B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)nu * 4, su.bmax, (size_t)nu * 4, cudaMemcpyDeviceToHost, s_out));
+                        B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)nu * 8, su.stat, (size_t)nu * 4, cudaMemcpyDeviceToHost, s_out));
+                        B200_BATCH(cudaMemcpyAsync(st + 16 + (size_t)nu * 12, su.surv, (size_t)nu, cudaMemcpyDeviceToHost, s_out));
+                        d2h += (size_t)nu * 13;
+                    }
+                    B200_BATCH(cudaEventRecord(g_batch.cnt_done[u % NB], s_out));
+                }
             }
-            B200_BATCH(cudaEventRecord(g_batch.cnt_done[k], s_out));
         }
         // ---- volume `sb - HB_LAG_A`: its group count is known -> size and enqueue the download of the label data --------
         if (sb >= lag_a && sb - lag_a < n_volumes) {
@@ -742,11 +851,11 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             B200_BATCH(cudaEventRecord(g_batch.out_done[k], s_out2));   // (the kernels of this volume finished before cnt_done)
             // traffic of the gathered PRM crops: the crops of the survivors (known from the visit order now on the host)
             const int n = n_dets[v];
-            if (n > 0 && (mode & 2) && mapped_device_pointer(prm[v])) {
+            if (n > 0 && !prm_packed && (mode & 2) && mapped_device_pointer(prm[v])) {
                 int32_t kc = 0;
                 memcpy(&kc, g_batch.pinned + small_off[v], 4);
                 const int32_t* ro = (const int32_t*)(g_batch.pinned + small_off[v] + 16);
-                const uint8_t* pkz = pack_mode ? (const uint8_t*)(pack_base + pack_bytes * k + nmsst_bytes + align_up(nn * 8, 256)) : nullptr;
+                const uint8_t* pkz = pack_mode ? (const uint8_t*)(pack_base + pack_bytes * k + nmsst_bytes + 2 * align_up(nn * 8, 256)) : nullptr;
                 for (int r = 0; r < kc && r < n; ++r)
                     if (!pkz || !pkz[r]) h2d += (unsigned long long)(crop_off[v][ro[r] + 1] - crop_off[v][ro[r]]);
             }

@@ -412,7 +412,7 @@ def test_postproc_host_batch_output_states(b2):
         set_host_batch_out(3)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 7])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 7, 15, 23, 39, 47, 33])
 def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
     """Every transfer scheme of the batch entry point (dense / compacted label download x whole-array / gathered PRM
     upload; mode 7 also sends the image crops of the NMS survivors packed by host threads instead of the volume) returns
@@ -447,7 +447,7 @@ def test_postproc_host_batch_transfer_modes_pinned(b2, torch_, mode):
     dense_down = sum(c["volume"].size * 2 for c in cases)
     full_up = sum(c["volume"].size + c["prm"].size for c in cases)
     assert (d2h < dense_down * 3 // 4) if (mode & 1) else (d2h >= dense_down)     # 64-byte lines: coarse on volumes this small
-    assert (h2d < full_up) if (mode & 2) else (h2d >= full_up)
+    assert (h2d < full_up) if (mode & 6) else (h2d >= full_up)      # bit 1: gathered PRM crops, bit 2: image and PRM crops packed by the host
     for c, o in zip(cases, outs):
         ref = oracle_chain(c, 0.23)
         assert np.array_equal(o["seg"], ref["seg"])
