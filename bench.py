@@ -885,8 +885,9 @@ def run_ours(args, rank, world, local_rank):
                                          "its previous result (b200seg_set_option host_batch_out=2: only the voxels written last time are "
                                          "cleared); value_dense_fill: buffers of unknown content, every volume zero-filled on the host "
                                          "(host_batch_out=0).  Identical bytes either way; both parity-checked against the oracle",
-                        "transfer": "volume by DMA; PRM crops of the NMS survivors by zero-copy gather from the pinned buffer; label "
-                                    "volume as compacted non-zero 16-byte groups, scattered by host threads",
+                        "transfer": "image crops of the NMS survivors with a positive PRM voxel packed by host threads into a pinned buffer "
+                                    "(DMA); their PRM crops by zero-copy gather from the caller's pinned buffer; label volume as compacted "
+                                    "non-zero 64-byte lines, written by host threads with full-line non-temporal stores",
                         "note": "binarization chain through b200seg_postproc_soma_host_batch; the peak finder's input is the network's "
                                 "response map, which never exists on the host in the reference flow (peak_response_mapping_3d.py:150)"},
                 "gpu_launches": int(lt.item()), "kernels": kernels, "ops": ops,

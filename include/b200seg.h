@@ -55,7 +55,9 @@ long long b200seg_launch_count(void);
  * into a pinned buffer and that buffer travels instead; bit 3 (with bit 2) = the PRM crops of those survivors are packed into
  * the same buffer by the host threads instead of being gathered over the link; bits 4 / 5 = the chain is launched for groups
  * of 2 / 4 volumes instead of one volume at a time (both measured slower on a 16-core host, see host_batch.cu; they pay
- * where host cores are plentiful).  "host_batch_out" (default 0) tells that
+ * where host cores are plentiful); bit 6 / bit 8 = pinned label buffers always receive their lines through the staged
+ * download and the host scatter / always in place from the GPU (default: in place when a rank has fewer than 8 host cores
+ * to itself); bit 7 = the visit orders of the NMS share the bookkeeping download stream.  "host_batch_out" (default 0) tells that
  * entry point what the caller's label buffers hold ON ENTRY, again with identical results: 0 = anything (every buffer is
  * zero-filled, 2 bytes of host memory traffic per voxel -- the bound of the call), 1 = zeros (a fresh np.zeros / calloc
  * buffer, what tools/binarization_soma.py:57 allocates per volume), 2 = exactly what this entry point wrote into the same

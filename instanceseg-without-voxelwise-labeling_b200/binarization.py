@@ -234,7 +234,8 @@ def set_host_batch_mode(mode):
     """bit 0: compacted label download, bit 1: zero-copy gather of the surviving PRM crops, bit 2: the image
     crops of the NMS survivors travel packed by host threads, the raw volume is never copied (default 7); bit 3 (8): their PRM
     crops travel in the same packed buffer instead of the zero-copy gather; bits 4 / 5 (16 / 32): the chain is launched for
-    groups of 2 / 4 volumes."""
+    groups of 2 / 4 volumes; bit 6 / bit 8 (64 / 256): pinned label buffers get their lines staged + scattered by host threads /
+    written in place by the GPU (default: by the number of host cores per rank)."""
     _lib.check(_lib.lib().b200seg_set_option(b"host_batch_mode", int(mode)), "set_option")
 
 

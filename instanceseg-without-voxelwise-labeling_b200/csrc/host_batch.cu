@@ -76,6 +76,25 @@ seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned
     }
 }
 
+// Compacted lines -> their place in the caller's label volume (host-mapped pinned memory, 16-byte aligned): posted 64-byte
+// writes over the link instead of a staged download that host threads scatter.  The host side of the staged scheme costs
+// three passes over the line data in host DRAM (DMA write, read, non-temporal write) and a third of the pool's time; here it
+// is one write.  The kernel is bound by the link, not by the SMs, so it is launched with a handful of CTAs on a stream of
+// its own: it runs beside the chains of the following volumes instead of filling the machine with stalled CTAs (a
+// full-grid version that wrote the lines straight from the volume walk took 131 us per volume on the compute stream).
+// The line count stays on the device.  The caller's volume must already be zero (cleared / zero-filled by the pool).
+constexpr int HB_SCATTER_CTAS = 32;
+__global__ void __launch_bounds__(256)
+lines_to_host_kernel(const uint32_t* __restrict__ idx, const uint4* __restrict__ val, const uint32_t* __restrict__ count,
+                     unsigned int cap, unsigned int ngroups, uint4* __restrict__ host_dst) {
+    const unsigned int n = min(*count, cap);
+    const unsigned int q = threadIdx.x & 3u;
+    for (unsigned int i = blockIdx.x * 64u + (threadIdx.x >> 2); i < n; i += gridDim.x * 64u) {
+        const unsigned int g = idx[i] * 4u + q;
+        if (g < ngroups) host_dst[g] = val[(size_t)i * 4 + q];      // the four stores of a quad are one 64-byte line
+    }
+}
+
 // PRM crops of the NMS survivors: host-mapped (pinned) source -> device copy with the same packing.
 // grid (n_max): CTA r moves the crop of visit rank r.  src and dst share the offset, both bases are 16-byte aligned.
 __global__ void __launch_bounds__(256)
@@ -329,6 +348,9 @@ constexpr int HB_LAG_N = 5;            // packed-image mode: the chain of volume
 
 struct BatchStreams {
     cudaStream_t in = nullptr, out = nullptr, out2 = nullptr;   // uploads | bookkeeping downloads | label downloads
+    cudaStream_t out4 = nullptr;                                // line scatter kernels (link bound, a few CTAs)
+    cudaEvent_t scat_done[HB_SLOTS] = {};
+    cudaStream_t out3 = nullptr;                                // visit orders of the NMS (must not queue behind the bookkeeping of older volumes)
     cudaStream_t comp2 = nullptr, comp3 = nullptr;              // more compute streams: consecutive volumes overlap on the GPU
     cudaStream_t nms = nullptr;                                 // high priority: the NMS of a volume must not queue behind the chains of others
     cudaEvent_t in_done[HB_SLOTS] = {}, comp_done[HB_SLOTS] = {}, cnt_done[HB_SLOTS] = {}, out_done[HB_SLOTS] = {};
@@ -347,7 +369,8 @@ struct BatchStreams {
     int ensure(int dev) {
         if (device == dev && in) return 0;
         if (in) {
-            cudaStreamDestroy(in); cudaStreamDestroy(out); cudaStreamDestroy(out2); cudaStreamDestroy(comp2); cudaStreamDestroy(comp3); cudaStreamDestroy(nms);
+            cudaStreamDestroy(in); cudaStreamDestroy(out); cudaStreamDestroy(out2); cudaStreamDestroy(out3); cudaStreamDestroy(out4);
+            for (int k = 0; k < HB_SLOTS; ++k) cudaEventDestroy(scat_done[k]); cudaStreamDestroy(comp2); cudaStreamDestroy(comp3); cudaStreamDestroy(nms);
             for (int k = 0; k < HB_SLOTS; ++k) {
                 cudaEventDestroy(in_done[k]); cudaEventDestroy(comp_done[k]); cudaEventDestroy(cnt_done[k]); cudaEventDestroy(out_done[k]);
                 cudaEventDestroy(nmsc_done[k]); cudaEventDestroy(nms_done[k]); cudaEventDestroy(pack_done[k]);
@@ -356,6 +379,9 @@ struct BatchStreams {
         B200_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
         B200_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
         B200_CUDA(cudaStreamCreateWithFlags(&out2, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&out3, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&out4, cudaStreamNonBlocking));
+        for (int k = 0; k < HB_SLOTS; ++k) B200_CUDA(cudaEventCreateWithFlags(&scat_done[k], cudaEventDisableTiming));
         B200_CUDA(cudaStreamCreateWithFlags(&comp2, cudaStreamNonBlocking));
         B200_CUDA(cudaStreamCreateWithFlags(&comp3, cudaStreamNonBlocking));
         {
@@ -582,6 +608,19 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     std::vector<size_t> small_off(n_volumes);
     { size_t o = 0; for (int v = 0; v < n_volumes; ++v) { small_off[v] = o; o += align_up(16 + 13 * (size_t)n_dets[v], 16); } }
     std::vector<uint32_t> n_groups(n_volumes, 0u);               // compacted groups per volume (0xFFFFFFFF = dense copy)
+    // Lines written in place by the GPU (pinned label buffers only) or staged download + host scatter?  The staged form is a
+    // little faster while the host has cores and memory bandwidth to spare (one rank on a 16-core box: 74.6 against 70.8 Gvox/s);
+    // when the ranks of a box share the host it is the host's DRAM traffic that bounds the call and the in-place form wins
+    // (8 ranks on 32 cores, 8 volumes each: 16.3 against 20.4 ms per call, 132 against 105 Gvox/s in aggregate).  Default: in
+    // place when a rank has fewer than 8 cores to itself; "host_batch_mode" bit 6 forces the staged form, bit 8 the in-place one.
+    bool want_direct = (mode & 256) != 0;
+    if (!(mode & (64 | 256))) {
+        int hw = (int)std::thread::hardware_concurrency(), share = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;
+        want_direct = hw > 0 && hw / share < 8;
+    }
+    std::vector<uint4*> direct(n_volumes, nullptr);             // device view of the caller's label volume where the GPU can write it in place
+    for (int v = 0; v < n_volumes && sparse && want_direct; ++v) direct[v] = (uint4*)mapped_device_pointer(seg[v]);
     unsigned long long h2d = 0, d2h = 0;
     int rc = 0;
 #define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
@@ -637,10 +676,13 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
             if (pack_mode) B200_BATCH(cudaEventRecord(g_batch.nmsc_done[k], s_comp));
             if (pack_mode && n > 0) {                         // the visit order comes back right away: the host packs by it
                 char* nst = pack_base + pack_bytes * k;
-                B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.nmsc_done[k], 0));
-                B200_BATCH(cudaMemcpyAsync(nst, s.cnt, 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaMemcpyAsync(nst + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-                B200_BATCH(cudaEventRecord(g_batch.nms_done[k], s_out));
+                // on its own stream: on the bookkeeping stream it would queue behind the downloads of older volumes, which wait for
+                // their chains -- the NMS would then run only as far ahead as the chains let it ("host_batch_mode" bit 7: as before)
+                const cudaStream_t s_nmsout = (mode & 128) ? s_out : g_batch.out3;
+                B200_BATCH(cudaStreamWaitEvent(s_nmsout, g_batch.nmsc_done[k], 0));
+                B200_BATCH(cudaMemcpyAsync(nst, s.cnt, 4, cudaMemcpyDeviceToHost, s_nmsout));
+                B200_BATCH(cudaMemcpyAsync(nst + 16, s.rank, (size_t)n * 4, cudaMemcpyDeviceToHost, s_nmsout));
+                B200_BATCH(cudaEventRecord(g_batch.nms_done[k], s_nmsout));
                 d2h += 4 + (size_t)n * 4;
             }
         }
@@ -811,6 +853,16 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 }
                 B200_BATCH(cudaEventRecord(g_batch.comp_done[k], s_comp));
                 B200_BATCH(cudaStreamWaitEvent(s_out, g_batch.comp_done[k], 0));
+                for (int u = g0; u <= g1 && sparse; ++u) {
+                    if (!direct[u]) continue;                      // the lines go straight into the caller's (pinned) volume: it must be zero by now
+                    Slot& su = slot[u % NB];
+                    { const auto t = now(); while (sh->zero_left[u].load(std::memory_order_acquire) > 0) sched_yield(); w_zero += ms_since(t); }
+                    B200_BATCH(cudaStreamWaitEvent(g_batch.out4, g_batch.comp_done[k], 0));
+                    lines_to_host_kernel<<<HB_SCATTER_CTAS, 256, 0, g_batch.out4>>>(su.gidx, su.gval, su.lines, (unsigned int)cap, (unsigned int)ngroups, direct[u]);
+                    count_launch();
+                    B200_BATCH(cudaGetLastError());
+                    B200_BATCH(cudaEventRecord(g_batch.scat_done[u % NB], g_batch.out4));
+                }
                 for (int u = g0; u <= g1; ++u) {
                     Slot& su = slot[u % NB];
                     const int nu = n_dets[u];
@@ -845,9 +897,10 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 { const auto t = now(); while (sh->slot_busy[k].load(std::memory_order_acquire)) sched_yield(); w_slot += ms_since(t); }   // staging slot scattered by now
                 char* stage = g_batch.pinned + small_bytes + stage_bytes * k;
                 B200_BATCH(cudaMemcpyAsync(stage, s.gidx, (size_t)ng * 4, cudaMemcpyDeviceToHost, s_out2));
-                B200_BATCH(cudaMemcpyAsync(stage + align_up(cap * 4, 256), s.gval, (size_t)ng * 64, cudaMemcpyDeviceToHost, s_out2));
-                d2h += (size_t)ng * 68;
+                if (!direct[v]) B200_BATCH(cudaMemcpyAsync(stage + align_up(cap * 4, 256), s.gval, (size_t)ng * 64, cudaMemcpyDeviceToHost, s_out2));
+                d2h += (size_t)ng * 68;                            // (direct: the 64-byte payloads crossed the link as the kernel's own writes)
             }
+            if (direct[v]) B200_BATCH(cudaStreamWaitEvent(s_out2, g_batch.scat_done[k], 0));   // the slot's line buffers are free once the scatter kernel is done
             B200_BATCH(cudaEventRecord(g_batch.out_done[k], s_out2));   // (the kernels of this volume finished before cnt_done)
             // traffic of the gathered PRM crops: the crops of the survivors (known from the visit order now on the host)
             const int n = n_dets[v];
@@ -878,9 +931,10 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 sh->slot_busy[k].store(1, std::memory_order_release);
                 sh->pending.fetch_add(1);
                 const size_t vbytes = V * 2;
-                g_pool.push([sh, v, k, gi, gv, dst, ng, out_state, vbytes] {
+                const bool in_place = direct[v] != nullptr;
+                g_pool.push([sh, v, k, gi, gv, dst, ng, out_state, vbytes, in_place] {
                     while (sh->zero_left[v].load(std::memory_order_acquire) > 0) sched_yield();
-                    scatter_lines(dst, vbytes, gi, gv, ng);
+                    if (!in_place) scatter_lines(dst, vbytes, gi, gv, ng);
                     if (out_state == 2) {                                       // remember what has to be cleared next time
                         PrevLabels pl;
                         pl.bytes = vbytes;
@@ -901,6 +955,8 @@ done:
         cudaError_t e2 = cudaStreamSynchronize(comp_streams[0]);
         for (int q = 1; q < 3; ++q) { const cudaError_t eq = cudaStreamSynchronize(comp_streams[q]); if (e2 == cudaSuccess) e2 = eq; }
         { const cudaError_t eq = cudaStreamSynchronize(g_batch.nms); if (e2 == cudaSuccess) e2 = eq; }
+        { const cudaError_t eq = cudaStreamSynchronize(g_batch.out3); if (e2 == cudaSuccess) e2 = eq; }
+        { const cudaError_t eq = cudaStreamSynchronize(g_batch.out4); if (e2 == cudaSuccess) e2 = eq; }
         const cudaError_t e1 = cudaStreamSynchronize(s_in), e3 = cudaStreamSynchronize(s_out),
                           e4 = cudaStreamSynchronize(s_out2);
         const auto t_tail = now();

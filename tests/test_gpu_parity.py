@@ -466,12 +466,15 @@ def test_postproc_host_batch_odd_volume_size(b2):
         assert np.array_equal(o["seg"], ref["seg"])
 
 
-def test_postproc_host_batch_partial_last_line_and_unaligned_buffers(b2):
+@pytest.mark.parametrize("pinned", [False, True])
+def test_postproc_host_batch_partial_last_line_and_unaligned_buffers(b2, torch_, pinned):
     """S*H*W a multiple of 8 but not of 32: the compacted download ends in a partial 64-byte line; label buffers that are
     not 64-byte aligned take the plain-copy form of the line writes.  Every output state, twice (the second call clears
-    what the first one wrote)."""
+    what the first one wrote).  Pinned label buffers are written in place by the GPU (seg_lines_to_host_kernel), pageable ones
+    through the staged download and the host scatter; "host_batch_mode" bit 8 / bit 6 force the in-place / the staged form for
+    pinned buffers (the default picks by the number of host cores per rank)."""
     from b200seg import synth
-    from b200seg.binarization import set_host_batch_out
+    from b200seg.binarization import set_host_batch_out, set_host_batch_mode
     from helpers import oracle_chain
     shape = (9, 36, 38)                                  # 12312 voxels = 1539 groups = 384 lines + 3 groups
     assert (9 * 36 * 38) % 8 == 0 and (9 * 36 * 38) % 32 != 0
@@ -481,13 +484,21 @@ def test_postproc_host_batch_partial_last_line_and_unaligned_buffers(b2):
     V = int(np.prod(shape))
     try:
         for shift in (0, 8):                             # 64-byte aligned / 16-byte aligned only
-            raw = [np.full(V + 64, 0xABCD, np.uint16) for _ in cases]
+            if pinned:
+                keep = [torch_.empty(V + 64, dtype=torch_.int16).pin_memory() for _ in cases]
+                raw = [t.numpy().view(np.uint16) for t in keep]
+                for r in raw:
+                    r[...] = 0xABCD
+            else:
+                raw = [np.full(V + 64, 0xABCD, np.uint16) for _ in cases]
             segs = []
             for r in raw:
                 o = ((-r.ctypes.data) % 64) // 2 + shift
                 segs.append(r[o:o + V].reshape(shape))
-            for state in (0, 2, 2, 1):                   # garbage -> result -> same result kept (twice) -> caller-zeroed
+            # garbage -> result -> same result kept (twice) -> caller-zeroed -> staged form (garbage, kept) -> back to the default form
+            for state, mode in ((0, 7 | 256), (2, 7 | 256), (2, 7 | 256), (1, 7 | 256), (0, 7 | 64), (2, 7 | 64), (2, 7 | 256), (2, 7)):
                 set_host_batch_out(state)
+                set_host_batch_mode(mode)
                 if state == 1:
                     for sg in segs:
                         sg[...] = 0
@@ -499,6 +510,7 @@ def test_postproc_host_batch_partial_last_line_and_unaligned_buffers(b2):
                     assert (r[:off] == 0xABCD).all() and (r[off + V:] == 0xABCD).all(), "wrote outside the label volume"
     finally:
         set_host_batch_out(0)
+        set_host_batch_mode(7)
 
 
 def test_postproc_batched_device_and_fullsize_properties(b2, torch_):
