@@ -47,11 +47,12 @@ namespace b200seg {
 __global__ void __launch_bounds__(256)
 seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned int cap,
                    uint32_t* __restrict__ idx_out, uint4* __restrict__ val_out, uint32_t* __restrict__ count) {
-    const unsigned int lane = threadIdx.x & 31;
+    __shared__ unsigned int s_tot[8], s_base;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int per_cta = 256u * 4u;
     for (unsigned int base = blockIdx.x * per_cta; base < ngroups; base += gridDim.x * per_cta) {      // CTA-uniform trip count
         uint4 v[4];
-        unsigned int gi[4];
+        unsigned int gi[4], lm[4], tot = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             gi[j] = base + j * 256u + threadIdx.x;
@@ -61,18 +62,33 @@ seg_compact_kernel(const uint4* __restrict__ seg, unsigned int ngroups, unsigned
         for (int j = 0; j < 4; ++j) {
             const bool nz = (v[j].x | v[j].y | v[j].z | v[j].w) != 0u;
             const unsigned int m = __ballot_sync(0xffffffffu, nz);
-            if (m == 0u) continue;                                  // warp-uniform
-            const unsigned int lm = (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u;     // bit 4q: quad q holds a non-zero line
-            unsigned int b = 0;
-            if (lane == 0) b = atomicAdd(count, (unsigned int)__popc(lm));
-            b = __shfl_sync(0xffffffffu, b, 0);
+            lm[j] = (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u;     // bit 4q: quad q holds a non-zero line
+            tot += __popc(lm[j]);
+        }
+        // one global atomic per CTA and trip (a volume holds ~10^5 lines: one atomic per warp and row of groups made the
+        // single counter the bound of the kernel); most CTAs see only zeros and skip it
+        if (lane == 0) s_tot[warp] = tot;
+        __syncthreads();
+        unsigned int before = 0u, all = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const unsigned int t = s_tot[w]; all += t; before += w < (int)warp ? t : 0u; }
+        if (all != 0u) {                                            // CTA-uniform
+            if (threadIdx.x == 0) s_base = atomicAdd(count, all);
+            __syncthreads();
+            unsigned int b = s_base + before;
             const unsigned int q0 = lane & ~3u;
-            const unsigned int pos = b + __popc(lm & ((1u << q0) - 1u));
-            if (((lm >> q0) & 1u) && pos < cap) {
-                if ((lane & 3u) == 0u) idx_out[pos] = gi[j] >> 2;
-                val_out[(size_t)pos * 4 + (lane & 3u)] = v[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (lm[j] == 0u) continue;                          // warp-uniform
+                const unsigned int pos = b + __popc(lm[j] & ((1u << q0) - 1u));
+                b += __popc(lm[j]);
+                if (((lm[j] >> q0) & 1u) && pos < cap) {
+                    if ((lane & 3u) == 0u) idx_out[pos] = gi[j] >> 2;
+                    val_out[(size_t)pos * 4 + (lane & 3u)] = v[j];
+                }
             }
         }
+        __syncthreads();                                            // s_tot / s_base are reused by the next trip
     }
 }
 
@@ -843,9 +859,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 if (ce) { rc = ce; goto done; }
                 for (int u = g0; u <= g1 && sparse && !fused_lines; ++u) {
                     Slot& su = slot[u % NB];
-                    unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);
-                    const unsigned int lim = (unsigned int)num_sms() * 16u;
-                    if (grid > lim) grid = lim;
+                    const unsigned int grid = (unsigned int)((ngroups + 1023) / 1024);          // one trip per CTA (the loop covers grids beyond 2^31 groups)
                     seg_compact_kernel<<<grid, 256, 0, s_comp>>>((const uint4*)su.seg, (unsigned int)ngroups, (unsigned int)cap,
                                                                  su.gidx, su.gval, su.lines);
                     count_launch();
