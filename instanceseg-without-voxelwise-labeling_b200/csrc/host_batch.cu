@@ -153,7 +153,9 @@ prm_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, co
 // buffer (about 2.5 MB per volume) and that buffer travels by DMA.  Fetching the rows in place over the link instead (a
 // gather kernel reading the pinned volume) was measured: 29-byte rows become 32-byte read requests and the link delivers
 // 9 GB/s of them, less than the DMA of the whole volume.  The rest of the device volume keeps stale bytes nobody reads.
-// grid (n_max): CTA r moves the box of visit rank r; one warp per row.
+// grid (n_max, HB_UNPACK_PARTS): CTAs (r, 0..parts-1) move the box of visit rank r, a quarter of its rows each (the kernel lasts as
+// long as its largest box: 41 us per volume with one CTA per box); one warp per row.
+constexpr int HB_UNPACK_PARTS = 4;
 __global__ void __launch_bounds__(256)
 img_unpack_kernel(const uint8_t* __restrict__ pack, const int64_t* __restrict__ pk_off, const uint8_t* __restrict__ all_zero,
                   uint8_t* __restrict__ dst, int H, int W, const int32_t* __restrict__ boxes,
@@ -171,8 +173,9 @@ img_unpack_kernel(const uint8_t* __restrict__ pack, const int64_t* __restrict__ 
     const uint8_t* src = pack + pk_off[r];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t HW = (size_t)H * W;
-    const int rows = sz * sy;
-    for (int row0 = warp; row0 < rows; row0 += 8 * 4) {        // four rows in flight per warp
+    const int all_rows = sz * sy;
+    const int r_lo = (int)((long long)all_rows * blockIdx.y / gridDim.y), rows = (int)((long long)all_rows * (blockIdx.y + 1) / gridDim.y);
+    for (int row0 = r_lo + warp; row0 < rows; row0 += 8 * 4) { // four rows in flight per warp
         uint8_t v[4];
         size_t off[4];
 #pragma unroll
@@ -821,7 +824,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 B200_BATCH(cudaEventRecord(g_batch.pack_done[k], s_in));
                 B200_BATCH(cudaStreamWaitEvent(s_comp, g_batch.pack_done[k], 0));
                 if (kc > 0) {
-                    img_unpack_kernel<<<n, 256, 0, s_comp>>>(s.pack, s.pk_off, s.pk_zero, s.vol, H, W, s.boxes, s.rank, s.cnt);
+                    img_unpack_kernel<<<dim3(n, HB_UNPACK_PARTS), 256, 0, s_comp>>>(s.pack, s.pk_off, s.pk_zero, s.vol, H, W, s.boxes, s.rank, s.cnt);
                     count_launch();
                     B200_BATCH(cudaGetLastError());
                 }
