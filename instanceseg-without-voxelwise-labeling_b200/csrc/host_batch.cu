@@ -361,7 +361,6 @@ constexpr int HB_SLOTS = 12;
 constexpr int HB_LAG_A = 2;            // the download of volume v is sized and enqueued while volume v + HB_LAG_A is being enqueued
 constexpr int HB_LAG_B = 3;            // ... and handed to the pool one step later
 constexpr int HB_ZERO_PARTS = 4;
-constexpr int HB_CLEAR_AHEAD = 8;      // the label volume of volume v is cleared / zero-filled from step v - HB_CLEAR_AHEAD on
 constexpr int HB_GROUP = 4;            // largest number of volumes per chain launch ("host_batch_mode" bits 4 / 5); HB_SLOTS is a multiple of it
 constexpr int HB_LAG_P = 2;            // packed-image mode: the crops of volume v are handed to the pool while the NMS of volume v + HB_LAG_P is enqueued
 constexpr int HB_LAG_N = 5;            // packed-image mode: the chain of volume v is enqueued while the NMS of volume v + HB_LAG_N is
@@ -578,13 +577,10 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     };
     Shared* sh = new Shared(n_volumes);
     for (int k = 0; k < HB_SLOTS; ++k) sh->slot_busy[k].store(0);
-    // Zero fill / clear of the label volumes: it does not depend on the GPU, so the first volumes are handed to the pool now and
-    // the others HB_CLEAR_AHEAD steps before their turn.  (All of them at once, as in round 2, put every line write of the call
-    // behind 64 clears in the pool's queue: with few threads the staging slots then stayed busy and the host thread waited.)
+    // zero-fill of the label volumes starts now (it does not depend on the GPU)
     const int out_state = sparse ? opt_host_batch_out() : 0;
-    for (int v = 0; v < n_volumes; ++v) sh->zero_left[v].store(out_state == 1 ? 0 : 1);      // 1 = not cleared yet
-    auto push_clear = [&](int v) {
-        if (out_state == 1) return;                                             // the caller vouches for zeros
+    for (int v = 0; v < n_volumes; ++v) {
+        if (out_state == 1) { sh->zero_left[v].store(0); continue; }            // the caller vouches for zeros
         if (out_state == 2) {
             std::vector<uint32_t>* prev = nullptr;
             {
@@ -604,7 +600,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                     sh->zero_left[v].fetch_sub(1, std::memory_order_release);
                     sh->pending.fetch_sub(1, std::memory_order_release);
                 });
-                return;
+                continue;
             }
         }
         sh->zero_left[v].store(HB_ZERO_PARTS);
@@ -620,8 +616,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 sh->pending.fetch_sub(1, std::memory_order_release);
             });
         }
-    };
-    for (int v = 0; v < n_volumes && v < HB_CLEAR_AHEAD; ++v) push_clear(v);
+    }
     static const bool trace = getenv("B200SEG_HB_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -664,7 +659,6 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     for (int j = 0; j <= HB_SLOTS; ++j) det_tab_host[j] = (int32_t)(j * nd);
     B200_BATCH(cudaMemcpyAsync(det_off_tab, det_tab_host, 4 * (size_t)(HB_SLOTS + 1), cudaMemcpyHostToDevice, s_in));
     for (int step = 0; step < n_volumes + lag_n + lag_b; ++step) {
-        if (step + HB_CLEAR_AHEAD < n_volumes) push_clear(step + HB_CLEAR_AHEAD);
         // ---- stage A, volume `step`: uploads of the small arrays (and of the volume unless it travels packed), NMS -------
         if (step < n_volumes) {
             const int v = step, k = v % NB;
