@@ -3,9 +3,9 @@
 //
 // The reference hands numpy arrays in and gets the uint16 label volume back, so the PCIe link, the host memory and the
 // latency of a dozen small launches per volume bound this entry point, not the kernels.  Layout, per volume:
-//   stage A  (four volumes ahead) the small per-detection arrays travel by DMA, the NMS runs on its own high-priority stream
+//   stage A  (five volumes ahead) the small per-detection arrays travel by DMA, the NMS runs on its own high-priority stream
 //            and its visit order comes straight back (a few hundred bytes);
-//   stage P  (one step before the chain) a pool of host threads packs the image crops of the NMS survivors that have a
+//   stage P  (three steps before the chain) a pool of host threads packs the image crops of the NMS survivors that have a
 //            positive PRM voxel -- the only voxels of the raw volume the chain ever reads -- into a pinned buffer
 //            ("host_batch_mode" bit 2; without it the whole 33.5 MB volume travels by DMA);
 //   stage B  the packed crops travel by DMA and an unpack kernel restores their rows in the device volume; the PRM crops of
@@ -15,8 +15,11 @@
 //            (32 voxels): line index + payload, a few percent of the volume.  Volumes rotate over three compute streams;
 //   down     only the compacted lines and the per-detection bookkeeping travel; the pool of host threads prepares the
 //            caller's label volumes (zero fill, or nothing / an undo list: "host_batch_out") and writes the lines with
-//            full-line non-temporal stores.  A volume whose labels cover more than a quarter of the lines is copied densely.
-// Eight device slots; the host thread sizes the download of a volume (it needs the group count) two volumes after it has
+//            full-line non-temporal stores -- or, for pinned label volumes of ranks that share a host, a small kernel on its
+//            own stream writes the lines in place over the link and only their indices are downloaded.  A volume whose labels
+//            cover more than a quarter of the lines is copied densely.  "host_batch_mode" bits 3-8 select measured
+//            alternatives (PRM crops packed by the host, chain launches for groups of 2 / 4 volumes, ...): include/b200seg.h.
+// Twelve device slots; the host thread sizes the download of a volume (it needs the line count) two volumes after it has
 // enqueued its chain and hands finished downloads to the pool one volume later.
 #include "common.cuh"
 
