@@ -349,12 +349,15 @@ int b200seg_generate_proposals_dev(const float* scores, const float* deltas, con
                                    void* workspace, size_t workspace_bytes, b200seg_stream_t stream);
 
 /* A batch of equally shaped volumes, HOST buffers in and out (the per-volume loop of tools/my_subprocess.py:56 over
- * tools/binarization_soma.py:57-104).  Pipelined over four device slots: the raw volume travels by DMA, the PRM crops of
- * the NMS survivors are pulled by a gather kernel straight from the caller's buffer when it is pinned and 16-byte
+ * tools/binarization_soma.py:57-104).  Pipelined over twelve device slots: the NMS runs ahead and host threads pack the
+ * image crops of its survivors into a pinned buffer that travels by DMA (the raw volume does not), the PRM crops of
+ * the same survivors are pulled by a gather kernel straight from the caller's buffer when it is pinned and 16-byte
  * aligned (else the whole packed array is copied), and the label volume comes back as its non-zero 64-byte lines,
- * which a pool of host threads (B200SEG_HOST_THREADS, default min(16, cores / LOCAL_WORLD_SIZE)) scatters into the
- * caller's volume after zero-filling it (a volume with more than 1/4 of its lines labelled is copied densely).
- * seg[v] may be pageable; pass pinned volumes / prm for full overlap.
+ * which a pool of host threads (B200SEG_HOST_THREADS, default 3/4 of cores / LOCAL_WORLD_SIZE, at most 32) writes into
+ * the caller's volume after zero-filling it -- or which the GPU writes in place when seg[v] is pinned and the host is
+ * shared by several ranks (a volume with more than 1/4 of its lines labelled is copied densely).
+ * seg[v] may be pageable; pass pinned volumes / prm / seg for full overlap.  "host_batch_mode" (b200seg_set_option)
+ * selects the transfer scheme, "host_batch_out" tells what seg[v] holds on entry; results are identical either way.
  * Every array argument has n_volumes entries; per-volume meanings as in b200seg_postproc_soma_host.
  * b200seg_postproc_soma_host_batch_traffic reports the bytes the last successful call moved over the link. */
 void b200seg_postproc_soma_host_batch_traffic(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
