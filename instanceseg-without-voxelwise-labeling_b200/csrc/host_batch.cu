@@ -646,7 +646,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
     unsigned long long h2d = 0, d2h = 0;
     int rc = 0;
 #define B200_BATCH(call) do { int _e = ::b200seg::check_cuda((call), #call); if (_e) { rc = _e; goto done; } } while (0)
-    const int lag_n = pack_mode ? HB_LAG_N : 0;               // stage A (NMS) runs lag_n volumes ahead of stage B, stage P lag_n - 1
+    const int lag_n = pack_mode ? HB_LAG_N : 0;               // stage A (NMS) runs lag_n volumes ahead of stage B, stage P lag_n - HB_LAG_P
     std::atomic<int> pack_left[HB_SLOTS];                       // packing jobs of the slot's volume still running
     std::atomic<int> scan_left[HB_SLOTS];                       // ... and the PRM scans that precede them
     int pack_kc[HB_SLOTS] = {};
@@ -708,7 +708,7 @@ extern "C" int b200seg_postproc_soma_host_batch(int n_volumes, int S, int H, int
                 d2h += 4 + (size_t)n * 4;
             }
         }
-        // ---- stage P, volume `step - lag_n + 1`: its visit order is back -> hand the packing of its image crops to the pool ----
+        // ---- stage P, volume `step - HB_LAG_P`: its visit order is back -> hand the packing of its image crops to the pool ----
         const int sp = step - HB_LAG_P;                          // (the copies get lag_n - HB_LAG_P steps before stage B needs them)
         if (pack_mode && sp >= 0 && sp < n_volumes && n_dets[sp] > 0) {
             const int v = sp, k = v % NB;
